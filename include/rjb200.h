@@ -1,0 +1,224 @@
+/*
+ * rjb200.h -- C ABI of the B200-native spatial-join engine (LSI / PIP / overlay).
+ *
+ * This is the drop-in boundary for RayJoin's operator interfaces.  RayJoin has
+ * no FFI of its own; its seam is three C++ abstract templates plus two CLIs
+ * (paths relative to the RayJoin tree):
+ *
+ *   Context<coord_t, coefficient_t>    src/context.h:16-127
+ *   LSI<CTX>::Init/Query/get_xsects    src/app/lsi.h:7-43
+ *   PIP<CTX>::Init/Query/get_closest_eids   src/app/pip.h:8-38
+ *   MapOverlay<CTX> 6-step protocol    src/app/map_overlay.h:9-56
+ *   load_from / read_pgraph / .bin     src/map/planar_graph.h:41-252
+ *   WriteOutputChain                   src/app/output_chain.h:41-205
+ *
+ * Every entry point below names the reference interface it replaces.  Plain
+ * pointers and sizes only; no C++/torch types cross the boundary; no
+ * exceptions cross it either: every call returns an int status (0 = ok) and
+ * rjb_last_error() gives the message for the calling thread.
+ *
+ * Conventions
+ *   - map ids are 0 / 1 exactly as in RayJoin (query_exec: base map R = 0,
+ *     query map S = 1; polyover_exec: IntersectEdge(0) queries map 0 against
+ *     the index of map 1).
+ *   - edge ids (eid), point ids and chain numbering are RayJoin's:
+ *     edge eid of chain c joins points (eid + c, eid + c + 1)
+ *     (src/map/map.h:200-207).
+ *   - "d_" pointers are device pointers owned by the context, valid until the
+ *     next call of the same kind on that context (mirrors get_xsects()).
+ *   - all calls are synchronous on the context's stream unless noted.
+ */
+#ifndef RJB200_H
+#define RJB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rjb_ctx rjb_ctx;
+
+/* status codes */
+enum {
+  RJB_OK = 0,
+  RJB_ERR_INVALID = 1,        /* bad argument / call order                 */
+  RJB_ERR_CUDA = 2,           /* CUDA runtime error (message has details)  */
+  RJB_ERR_QUEUE_OVERFLOW = 3, /* xsect queue too small (see rjb_lsi)       */
+  RJB_ERR_IO = 4,             /* file could not be read / written / parsed */
+  RJB_ERR_NO_INDEX = 5        /* query before rjb_build_index              */
+};
+
+/* index / execution modes: RayJoin's -mode flag (src/flags.cc:8).  "rt" has
+ * no equivalent on B200 (no RT cores); BRUTE is an all-pairs GPU mode that
+ * exists for testing the exact arithmetic without any index.              */
+enum { RJB_MODE_GRID = 0, RJB_MODE_LBVH = 1, RJB_MODE_BRUTE = 2 };
+
+#define RJB_NO_HIT 0xFFFFFFFFu /* closest_eid of a point with no edge above */
+#define RJB_EXTERIOR_FACE 0    /* src/config.h:8 */
+#define RJB_DONTKNOW (-1)      /* src/config.h:3 */
+
+/* One intersection.  Replaces dev::Intersection<int64_t> (src/algo/lsi.h:9-25,
+ * 48 bytes: x.num,x.den,y.num,y.den,eid[2],mid_point_polygon_id); the
+ * reference always stores denominators == 1 (truncating conversion,
+ * src/util/rational.h:190-192), so they are dropped.                      */
+typedef struct {
+  int64_t x, y;                 /* scaled (internal) coordinates            */
+  uint32_t eid[2];              /* eid[m] = edge of map m                   */
+  int32_t mid_point_polygon_id; /* RJB_DONTKNOW until overlay fills it      */
+  int32_t _pad;
+} rjb_xsect;
+
+/* Scaling<double> (src/map/scaling.h:32-136) as plain data */
+typedef struct {
+  double rx, ry, rrx, rry;
+  double deltax, deltay, ddeltax, ddeltay;
+  int64_t internal_min, internal_max, internal_range;
+} rjb_scaling;
+
+/* ---- lifetime ----------------------------------------------------------- */
+const char* rjb_last_error(void);
+const char* rjb_version(void);
+
+/* Context ctor (src/context.h:31-74): owns one stream and both maps.       */
+int rjb_create(int device, rjb_ctx** out);
+void rjb_destroy(rjb_ctx* ctx);
+
+/* Run all work of this context on an externally owned cudaStream_t
+ * (e.g. torch's current stream) instead of the internal non-blocking one
+ * (src/util/stream.h:13-27).  NULL restores the internal stream.           */
+int rjb_set_stream(rjb_ctx* ctx, void* cuda_stream);
+
+/* ---- maps ---------------------------------------------------------------
+ * PlanarGraph<double> (src/map/planar_graph.h:32-39) handed over as host
+ * SoA: xy = n_points x {x,y} doubles, row_index = n_chains+1 CSR offsets into
+ * points, left/right = face ids per chain.  Host buffers are only read during
+ * the call.  Replaces Context::LoadToDevice -> Map::LoadFrom
+ * (src/context.h:76-88, src/map/map.h:161-233): uploads, scales with
+ * fma + truncation exactly like the device kernel at map.h:171-180, and
+ * derives RayJoin's edge numbering.
+ *
+ * The scaling must be fixed first (rjb_set_bounding_box) because RayJoin
+ * derives it from the union bounding box of both maps (context.h:37-47).   */
+int rjb_set_bounding_box(rjb_ctx* ctx, double min_x, double min_y, double max_x,
+                         double max_y);
+int rjb_get_scaling(const rjb_ctx* ctx, rjb_scaling* out);
+int rjb_set_map(rjb_ctx* ctx, int map_id, const double* xy, uint64_t n_points,
+                const uint32_t* row_index, const int64_t* left,
+                const int64_t* right, uint64_t n_chains);
+/* counts: out[0] = points, out[1] = edges, out[2] = chains */
+int rjb_map_info(const rjb_ctx* ctx, int map_id, uint64_t out[3]);
+/* device views of the loaded map (scaled points as int64 x,y pairs; per-edge
+ * chain id so that p1 = eid + chain) for callers that stay on the GPU       */
+int rjb_map_device_views(const rjb_ctx* ctx, int map_id,
+                         const int64_t** d_points_xy,
+                         const uint32_t** d_edge_chain);
+
+/* ---- index build ---------------------------------------------------------
+ * Replaces UniformGrid::AddMapToGrid (src/grid/uniform_grid.h:131-358) for
+ * RJB_MODE_GRID and FillPrimitivesLBVH + lbvh::bvh::construct
+ * (src/tree/primtive.h:33-57, deps/lbvh/lbvh/bvh.cuh:277-481) for
+ * RJB_MODE_LBVH.  grid_size is RayJoin's -grid_size (ignored for LBVH);
+ * build_ms (optional) receives the device time of the build.               */
+int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
+                    double* build_ms);
+
+/* tuning knobs that have no RayJoin flag (defaults are fine):
+ *   "lbvh_leaf_size"  edges per LBVH leaf, 1..8 (default 4)
+ *   "sort_queries"    1 = visit query edges / points in Morton order       */
+int rjb_set_option(rjb_ctx* ctx, const char* name, int64_t value);
+
+/* ---- LSI ------------------------------------------------------------------
+ * LSI<CTX>::Init + Query + get_xsects (src/app/lsi.h:21-37,
+ * src/app/lsi_lbvh.h:27-98, src/app/lsi_grid.h:97-159).  Queries every edge of
+ * map `query_map_id` against the index of the other map with
+ * e1 = query-side edge, e2 = base-side edge (lsi_lbvh.h:71).  The result
+ * queue holds (|E0|+|E1|) * xsect_factor entries like
+ * src/run_query.cu:226-228; unlike the reference (assert only,
+ * src/util/queue.h:23-39) an overflow is detected: the call returns
+ * RJB_ERR_QUEUE_OVERFLOW, *n_xsects is the number that was needed and no
+ * partial result is exposed.  Result order is unspecified (atomic queue).
+ * n_candidates (optional) = exact-predicate evaluations ("Total tests").    */
+int rjb_lsi(rjb_ctx* ctx, int query_map_id, int mode, double xsect_factor,
+            const rjb_xsect** d_xsects, uint64_t* n_xsects,
+            uint64_t* n_candidates);
+
+/* ---- PIP ------------------------------------------------------------------
+ * PIP<CTX>::Query + get_closest_eids (src/app/pip.h:26-36,
+ * src/app/pip_lbvh.h:25-142, src/app/pip_grid.h:21-77): for each query point
+ * (scaled int64 x,y; or all vertices of map query_map_id when d_points_xy is
+ * NULL, src/run_query.cu:346) the closest edge of the other map above it,
+ * RJB_NO_HIT if none; face id = get_face_id (src/map/map.h:79-87) or
+ * RJB_EXTERIOR_FACE.  d_points_xy is a DEVICE pointer.                      */
+int rjb_pip(rjb_ctx* ctx, int query_map_id, int mode, const int64_t* d_points_xy,
+            uint64_t n_points, const uint32_t** d_closest_eid,
+            const int32_t** d_face_id, uint64_t* n_candidates);
+
+/* host-buffer convenience used by the end-to-end path: unscaled double points
+ * on the host are uploaded, scaled on the device (fma semantics) and queried;
+ * results are copied back into caller buffers (may be NULL).               */
+int rjb_pip_host(rjb_ctx* ctx, int query_map_id, int mode, const double* h_xy,
+                 uint64_t n_points, uint32_t* h_closest_eid, int32_t* h_face_id);
+
+/* ---- overlay ----------------------------------------------------------------
+ * MapOverlay<CTX> protocol (src/app/map_overlay.h:20-30, call order of
+ * src/run_overlay.cu:196-226).  rjb_overlay_run performs Init, BuildIndex (both
+ * maps), IntersectEdge(0), LocateVerticesInOtherMap(0/1) and
+ * ComputeOutputPolygons; phase_ms[6] (optional) receives
+ * {build, lsi, pip0, pip1, polygons, total}.  rjb_overlay_write is
+ * WriteOutputChain (src/app/output_chain.h:41-205), same text format.       */
+int rjb_overlay_run(rjb_ctx* ctx, int mode, uint32_t grid_size,
+                    double xsect_factor, double* phase_ms);
+/* results of the last rjb_overlay_run, device pointers:
+ *  xsects sorted by eid[im] and along the edge, with mid_point_polygon_id
+ *  (xsect_edges_sorted_[im]); closest_eid / point_in_polygon per vertex of
+ *  map im (get_closet_eids / get_point_in_polygon)                          */
+int rjb_overlay_results(const rjb_ctx* ctx, int im, const rjb_xsect** d_xsects,
+                        uint64_t* n_xsects, const uint32_t** d_closest_eid,
+                        const int32_t** d_point_in_polygon);
+int rjb_overlay_write(rjb_ctx* ctx, const char* path);
+
+/* ---- introspection for measurement ------------------------------------------
+ * device times (ms, CUDA events on the context's stream) of the kernels of the
+ * last rjb_lsi / rjb_pip call: out[0] = traversal (or grid-cell) kernel,
+ * out[1] = intersection-point pass.  Replaces the reference's Stopwatch /
+ * -profile sub-stage timers (src/util/stopwatch.h).                            */
+int rjb_last_kernel_ms(const rjb_ctx* ctx, double out[2]);
+/* index of map_id: out[0] = leaves (LBVH) / edge-cell incidences (grid),
+ * out[1] = bytes of the index, out[2] = leaf size / grid size, out[3] = 0      */
+int rjb_index_info(const rjb_ctx* ctx, int map_id, int mode, uint64_t out[4]);
+
+/* ---- transfers --------------------------------------------------------------- */
+int rjb_copy_to_host(rjb_ctx* ctx, const void* d_src, void* h_dst,
+                     uint64_t bytes);
+int rjb_sync(rjb_ctx* ctx);
+
+/* ---- CDB files (host side) ---------------------------------------------------
+ * read_pgraph / serialize_pgraph / deserialize_pgraph / load_from
+ * (src/map/planar_graph.h:41-252).  The returned graph is owned by the
+ * library; arrays stay valid until rjb_graph_free.                           */
+typedef struct {
+  uint64_t n_chains, n_points;
+  const int64_t* chain_id;    /* n_chains */
+  const int64_t* first_point; /* n_chains (as written in the file; unused) */
+  const int64_t* last_point;  /* n_chains */
+  const int64_t* left;        /* n_chains */
+  const int64_t* right;       /* n_chains */
+  const uint32_t* row_index;  /* n_chains + 1 (0 entries for an empty graph) */
+  const double* xy;           /* n_points x 2 */
+  double min_x, min_y, max_x, max_y;
+  void* _owner;
+} rjb_graph;
+
+int rjb_graph_load(const char* path, const char* serialize_prefix,
+                   rjb_graph* out);
+int rjb_graph_read_text(const char* path, rjb_graph* out);
+int rjb_graph_read_bin(const char* path, rjb_graph* out);
+int rjb_graph_write_bin(const rjb_graph* g, const char* path);
+void rjb_graph_free(rjb_graph* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RJB200_H */

@@ -1,0 +1,410 @@
+"""ctypes binding of librjb200.so (include/rjb200.h) and a thin host-side mirror
+of RayJoin's operator interface (Context / LSI / PIP / MapOverlay).
+
+There is no CPU fallback: if the CUDA library is missing or no device is
+present every entry point raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librjb200.so")
+
+MODE_GRID, MODE_LBVH, MODE_BRUTE = 0, 1, 2
+MODES = {"grid": MODE_GRID, "lbvh": MODE_LBVH, "brute": MODE_BRUTE}
+NO_HIT = 0xFFFFFFFF
+ERR_QUEUE_OVERFLOW = 3
+
+# every symbol include/rjb200.h declares (tests check the library exports them)
+EXPORTS = [
+    "rjb_last_error", "rjb_version", "rjb_create", "rjb_destroy", "rjb_set_stream",
+    "rjb_set_bounding_box", "rjb_get_scaling", "rjb_set_map", "rjb_map_info",
+    "rjb_map_device_views", "rjb_build_index", "rjb_set_option", "rjb_lsi", "rjb_pip",
+    "rjb_pip_host", "rjb_overlay_run", "rjb_overlay_results", "rjb_overlay_write",
+    "rjb_last_kernel_ms", "rjb_index_info", "rjb_copy_to_host", "rjb_sync",
+    "rjb_graph_load", "rjb_graph_read_text", "rjb_graph_read_bin", "rjb_graph_write_bin",
+    "rjb_graph_free",
+]
+
+
+class RjbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("rjb error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Xsect(C.Structure):
+    _fields_ = [("x", C.c_int64), ("y", C.c_int64), ("eid", C.c_uint32 * 2),
+                ("mid_point_polygon_id", C.c_int32), ("_pad", C.c_int32)]
+
+
+XSECT_DTYPE = np.dtype([("x", "<i8"), ("y", "<i8"), ("eid", "<u4", (2,)),
+                        ("mid_point_polygon_id", "<i4"), ("_pad", "<i4")])
+assert XSECT_DTYPE.itemsize == C.sizeof(Xsect) == 32
+
+
+class Scaling(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("rx", "ry", "rrx", "rry", "deltax", "deltay", "ddeltax", "ddeltay")] + \
+               [(n, C.c_int64) for n in ("internal_min", "internal_max", "internal_range")]
+
+
+class Graph(C.Structure):
+    _fields_ = [("n_chains", C.c_uint64), ("n_points", C.c_uint64),
+                ("chain_id", C.POINTER(C.c_int64)), ("first_point", C.POINTER(C.c_int64)),
+                ("last_point", C.POINTER(C.c_int64)), ("left", C.POINTER(C.c_int64)),
+                ("right", C.POINTER(C.c_int64)), ("row_index", C.POINTER(C.c_uint32)),
+                ("xy", C.POINTER(C.c_double)), ("min_x", C.c_double), ("min_y", C.c_double),
+                ("max_x", C.c_double), ("max_y", C.c_double), ("_owner", C.c_void_p)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen librjb200.so; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RjbError(-1, "librjb200.so is not built (run python -m rayjoin_b200.build); "
+                               "there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.rjb_last_error.restype = C.c_char_p
+        _lib.rjb_version.restype = C.c_char_p
+        _lib.rjb_destroy.restype = None
+        _lib.rjb_graph_free.restype = None
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RjbError(rc, load_library().rjb_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class PlanarGraph:
+    """Host-side planar graph (reference: PlanarGraph<double>, planar_graph.h:32-39)."""
+
+    def __init__(self, xy, row_index, left, right, chain_id=None, first_point=None,
+                 last_point=None, bbox=None):
+        self.xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        self.row_index = np.ascontiguousarray(row_index, dtype=np.uint32)
+        self.left = np.ascontiguousarray(left, dtype=np.int64)
+        self.right = np.ascontiguousarray(right, dtype=np.int64)
+        n = len(self.left)
+        self.chain_id = np.arange(n, dtype=np.int64) if chain_id is None else \
+            np.ascontiguousarray(chain_id, dtype=np.int64)
+        self.first_point = np.zeros(n, np.int64) if first_point is None else \
+            np.ascontiguousarray(first_point, dtype=np.int64)
+        self.last_point = np.zeros(n, np.int64) if last_point is None else \
+            np.ascontiguousarray(last_point, dtype=np.int64)
+        if bbox is None and len(self.xy):
+            bbox = (self.xy[:, 0].min(), self.xy[:, 1].min(), self.xy[:, 0].max(), self.xy[:, 1].max())
+        self.bbox = bbox
+
+    @property
+    def n_points(self):
+        return len(self.xy)
+
+    @property
+    def n_chains(self):
+        return len(self.left)
+
+    @property
+    def n_edges(self):
+        return self.n_points - self.n_chains
+
+
+def _graph_to_py(g):
+    nc, npnt = g.n_chains, g.n_points
+
+    def arr(p, n, dt):
+        if n == 0:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True)
+    out = PlanarGraph(arr(g.xy, 2 * npnt, np.float64).reshape(-1, 2),
+                      arr(g.row_index, nc + 1 if npnt else 0, np.uint32),
+                      arr(g.left, nc, np.int64), arr(g.right, nc, np.int64),
+                      arr(g.chain_id, nc, np.int64), arr(g.first_point, nc, np.int64),
+                      arr(g.last_point, nc, np.int64),
+                      (g.min_x, g.min_y, g.max_x, g.max_y))
+    return out
+
+
+def load_from(path, serialize_prefix=""):
+    """load_from (planar_graph.h:222-252): .bin cache under serialize_prefix, else text."""
+    lib = load_library()
+    g = Graph()
+    _check(lib.rjb_graph_load(path.encode(), serialize_prefix.encode(), C.byref(g)))
+    try:
+        return _graph_to_py(g)
+    finally:
+        lib.rjb_graph_free(C.byref(g))
+
+
+def read_pgraph(path):
+    lib = load_library()
+    g = Graph()
+    _check(lib.rjb_graph_read_text(path.encode(), C.byref(g)))
+    try:
+        return _graph_to_py(g)
+    finally:
+        lib.rjb_graph_free(C.byref(g))
+
+
+def deserialize_pgraph(path):
+    lib = load_library()
+    g = Graph()
+    _check(lib.rjb_graph_read_bin(path.encode(), C.byref(g)))
+    try:
+        return _graph_to_py(g)
+    finally:
+        lib.rjb_graph_free(C.byref(g))
+
+
+def serialize_pgraph(pg, path):
+    lib = load_library()
+    g = Graph()
+    g.n_chains, g.n_points = pg.n_chains, pg.n_points
+    keep = [pg.chain_id, pg.first_point, pg.last_point, pg.left, pg.right, pg.row_index, pg.xy]
+    g.chain_id = pg.chain_id.ctypes.data_as(C.POINTER(C.c_int64))
+    g.first_point = pg.first_point.ctypes.data_as(C.POINTER(C.c_int64))
+    g.last_point = pg.last_point.ctypes.data_as(C.POINTER(C.c_int64))
+    g.left = pg.left.ctypes.data_as(C.POINTER(C.c_int64))
+    g.right = pg.right.ctypes.data_as(C.POINTER(C.c_int64))
+    g.row_index = pg.row_index.ctypes.data_as(C.POINTER(C.c_uint32))
+    g.xy = pg.xy.ctypes.data_as(C.POINTER(C.c_double))
+    g.min_x, g.min_y, g.max_x, g.max_y = pg.bbox
+    _check(lib.rjb_graph_write_bin(C.byref(g), path.encode()))
+    del keep
+
+
+class Context:
+    """Context (reference src/context.h): owns the stream, both maps and the scaling."""
+
+    def __init__(self, graphs=None, device=0, bbox=None, stream=None):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        _check(self.lib.rjb_create(C.c_int(device), C.byref(self._h)))
+        self.device = device
+        self.graphs = [None, None]
+        if stream is not None:
+            self.set_stream(stream)
+        if graphs is not None:
+            graphs = list(graphs) + [None] * (2 - len(graphs))
+            if bbox is None:
+                boxes = [g.bbox for g in graphs if g is not None and g.n_points]
+                bbox = (min(b[0] for b in boxes), min(b[1] for b in boxes),
+                        max(b[2] for b in boxes), max(b[3] for b in boxes))
+            self.set_bounding_box(*bbox)
+            for im, g in enumerate(graphs):
+                if g is not None:
+                    self.set_map(im, g)
+
+    def close(self):
+        if self._h:
+            self.lib.rjb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(self.lib.rjb_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_bounding_box(self, min_x, min_y, max_x, max_y):
+        _check(self.lib.rjb_set_bounding_box(self._h, C.c_double(min_x), C.c_double(min_y),
+                                             C.c_double(max_x), C.c_double(max_y)))
+
+    def get_scaling(self):
+        s = Scaling()
+        _check(self.lib.rjb_get_scaling(self._h, C.byref(s)))
+        return s
+
+    def set_option(self, name, value):
+        _check(self.lib.rjb_set_option(self._h, name.encode(), C.c_int64(value)))
+
+    def set_map(self, map_id, g):
+        self.graphs[map_id] = g
+        _check(self.lib.rjb_set_map(self._h, C.c_int(map_id), _ptr(g.xy), C.c_uint64(g.n_points),
+                                    _ptr(g.row_index), _ptr(g.left), _ptr(g.right),
+                                    C.c_uint64(g.n_chains)))
+
+    def set_map_raw(self, map_id, xy_ptr, n_points, row_index_ptr, left_ptr, right_ptr, n_chains):
+        """Pointers to (pinned) host buffers, e.g. torch tensors' data_ptr()."""
+        _check(self.lib.rjb_set_map(self._h, C.c_int(map_id), C.c_void_p(xy_ptr),
+                                    C.c_uint64(n_points), C.c_void_p(row_index_ptr),
+                                    C.c_void_p(left_ptr), C.c_void_p(right_ptr),
+                                    C.c_uint64(n_chains)))
+
+    def map_info(self, map_id):
+        out = (C.c_uint64 * 3)()
+        _check(self.lib.rjb_map_info(self._h, C.c_int(map_id), out))
+        return {"points": out[0], "edges": out[1], "chains": out[2]}
+
+    def map_points(self, map_id):
+        """Scaled (internal) coordinates of the map's vertices, copied to the host."""
+        info = self.map_info(map_id)
+        d = C.c_void_p()
+        _check(self.lib.rjb_map_device_views(self._h, C.c_int(map_id), C.byref(d), None))
+        out = np.empty((info["points"], 2), np.int64)
+        self.copy_to_host(d.value, out)
+        return out
+
+    def map_points_device_ptr(self, map_id):
+        d = C.c_void_p()
+        _check(self.lib.rjb_map_device_views(self._h, C.c_int(map_id), C.byref(d), None))
+        return d.value
+
+    def build_index(self, map_id, mode, grid_size=2048):
+        ms = C.c_double(0)
+        _check(self.lib.rjb_build_index(self._h, C.c_int(map_id), C.c_int(MODES.get(mode, mode)),
+                                        C.c_uint32(grid_size), C.byref(ms)))
+        return ms.value
+
+    def index_info(self, map_id, mode):
+        out = (C.c_uint64 * 4)()
+        _check(self.lib.rjb_index_info(self._h, C.c_int(map_id), C.c_int(MODES.get(mode, mode)), out))
+        return {"units": out[0], "bytes": out[1], "param": out[2]}
+
+    def last_kernel_ms(self):
+        out = (C.c_double * 2)()
+        _check(self.lib.rjb_last_kernel_ms(self._h, out))
+        return out[0], out[1]
+
+    def copy_to_host(self, d_ptr, out):
+        if out.nbytes:
+            _check(self.lib.rjb_copy_to_host(self._h, C.c_void_p(d_ptr), _ptr(out),
+                                             C.c_uint64(out.nbytes)))
+        return out
+
+    def sync(self):
+        _check(self.lib.rjb_sync(self._h))
+
+    # -- raw queries (device-resident results) ---------------------------------
+    def lsi_device(self, query_map_id, mode, xsect_factor):
+        d = C.c_void_p()
+        n = C.c_uint64(0)
+        cand = C.c_uint64(0)
+        rc = self.lib.rjb_lsi(self._h, C.c_int(query_map_id), C.c_int(MODES.get(mode, mode)),
+                              C.c_double(xsect_factor), C.byref(d), C.byref(n), C.byref(cand))
+        if rc != 0:
+            err = RjbError(rc, self.lib.rjb_last_error().decode("utf-8", "replace"))
+            err.needed = n.value
+            raise err
+        return d.value, n.value, cand.value
+
+    def pip_device(self, query_map_id, mode, d_points_ptr=None, n_points=0):
+        de, df = C.c_void_p(), C.c_void_p()
+        cand = C.c_uint64(0)
+        _check(self.lib.rjb_pip(self._h, C.c_int(query_map_id), C.c_int(MODES.get(mode, mode)),
+                                C.c_void_p(d_points_ptr), C.c_uint64(n_points), C.byref(de),
+                                C.byref(df), C.byref(cand)))
+        return de.value, df.value, cand.value
+
+
+class LSI:
+    """LSI<CTX> (reference src/app/lsi.h:7-43): Init / Query / get_xsects."""
+
+    def __init__(self, ctx, mode="lbvh"):
+        self.ctx, self.mode = ctx, mode
+        self.xsect_factor = 0.2  # FLAGS_xsect_factor default, src/flags.cc:7
+        self._res = None
+        self.n_candidates = 0
+
+    def Init(self, xsect_factor):
+        self.xsect_factor = xsect_factor
+
+    def Query(self, query_map_id):
+        d, n, cand = self.ctx.lsi_device(query_map_id, self.mode, self.xsect_factor)
+        self._res = (d, n)
+        self.n_candidates = cand
+        return n
+
+    def get_xsects(self):
+        """Host copy of the result queue as a structured array (rjb_xsect)."""
+        d, n = self._res
+        out = np.empty(n, XSECT_DTYPE)
+        return self.ctx.copy_to_host(d, out)
+
+
+class PIP:
+    """PIP<CTX> (reference src/app/pip.h:8-38): Query / get_closest_eids."""
+
+    def __init__(self, ctx, mode="lbvh"):
+        self.ctx, self.mode = ctx, mode
+        self._res = None
+        self.n_candidates = 0
+
+    def Query(self, query_map_id, points_xy=None):
+        """points_xy: host int64 (n, 2) scaled points, or None for all vertices of the
+        query map (src/run_query.cu:346)."""
+        if points_xy is None:
+            n = self.ctx.map_info(query_map_id)["points"]
+            de, df, cand = self.ctx.pip_device(query_map_id, self.mode)
+        else:
+            import torch  # device memory plumbing only
+            pts = np.ascontiguousarray(points_xy, dtype=np.int64).reshape(-1, 2)
+            n = len(pts)
+            self._dev_pts = torch.from_numpy(pts).to("cuda:%d" % self.ctx.device)
+            torch.cuda.synchronize()
+            de, df, cand = self.ctx.pip_device(query_map_id, self.mode,
+                                               self._dev_pts.data_ptr(), n)
+        self._res = (de, df, n)
+        self.n_candidates = cand
+        return n
+
+    def get_closest_eids(self):
+        de, _, n = self._res
+        return self.ctx.copy_to_host(de, np.empty(n, np.uint32))
+
+    def get_face_ids(self):
+        _, df, n = self._res
+        return self.ctx.copy_to_host(df, np.empty(n, np.int32))
+
+
+class MapOverlay:
+    """MapOverlay<CTX> (reference src/app/map_overlay.h:9-56, driver order of
+    src/run_overlay.cu:196-226)."""
+
+    def __init__(self, ctx, mode="lbvh", grid_size=2048, xsect_factor=0.2):
+        self.ctx, self.mode, self.grid_size, self.xsect_factor = ctx, mode, grid_size, xsect_factor
+        self.phase_ms = None
+
+    def Run(self):
+        ms = (C.c_double * 6)()
+        _check(self.ctx.lib.rjb_overlay_run(self.ctx._h, C.c_int(MODES.get(self.mode, self.mode)),
+                                            C.c_uint32(self.grid_size),
+                                            C.c_double(self.xsect_factor), ms))
+        self.phase_ms = dict(zip(("build", "lsi", "pip0", "pip1", "polygons", "total"), ms))
+        return self.phase_ms
+
+    def _results(self, im):
+        dx, de, dp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_uint64(0)
+        _check(self.ctx.lib.rjb_overlay_results(self.ctx._h, C.c_int(im), C.byref(dx), C.byref(n),
+                                                C.byref(de), C.byref(dp)))
+        return dx.value, n.value, de.value, dp.value
+
+    def get_xsect_edges(self, im=0):
+        dx, n, _, _ = self._results(im)
+        return self.ctx.copy_to_host(dx, np.empty(n, XSECT_DTYPE))
+
+    def get_closet_eids(self, im):
+        _, _, de, _ = self._results(im)
+        return self.ctx.copy_to_host(de, np.empty(self.ctx.map_info(im)["points"], np.uint32))
+
+    def get_point_in_polygon(self, im):
+        _, _, _, dp = self._results(im)
+        return self.ctx.copy_to_host(dp, np.empty(self.ctx.map_info(im)["points"], np.int32))
+
+    def WriteResult(self, path):
+        _check(self.ctx.lib.rjb_overlay_write(self.ctx._h, path.encode()))

@@ -1,0 +1,648 @@
+// C ABI of librjb200 (see include/rjb200.h).  Host-side orchestration of the
+// CUDA kernels; no exceptions leave this file.
+#include <math.h>
+#include <string.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "rjb_grid.cuh"
+#include "rjb_lbvh.cuh"
+#include "rjb_lsi.cuh"
+#include "rjb_pip.cuh"
+
+namespace rjb {
+
+static thread_local std::string g_last_error;
+
+struct DeviceMap {
+  bool loaded = false;
+  uint32_t n_points = 0, n_edges = 0, n_chains = 0;
+  DBuf<double2> raw;
+  DBuf<longlong2> pts;
+  DBuf<uint32_t> edge_chain, row_index;
+  DBuf<int32_t> left, right;
+  std::vector<int32_t> h_left, h_right;
+  // host copy of the source graph kept for the overlay writer (points as
+  // given, chains) -- WriteOutputChain reads ctx.get_planar_graph(im)
+  std::vector<double> h_xy;
+  std::vector<uint32_t> h_row_index;
+  Bvh bvh;
+  Grid grid;
+  MapView view() const {
+    MapView v;
+    v.pts = pts.p;
+    v.edge_chain = edge_chain.p;
+    v.row_index = row_index.p;
+    v.left = left.p;
+    v.right = right.p;
+    v.n_points = n_points;
+    v.n_edges = n_edges;
+    v.n_chains = n_chains;
+    return v;
+  }
+};
+
+// results of the last overlay run (xsect_edges_sorted_[2], closest_eids_[2],
+// point_in_polygon_[2] of reference src/app/map_overlay.h:52-55)
+struct OverlayState {
+  bool done = false;
+  uint64_t n_xsects = 0;
+  uint32_t n_segs[2] = {0, 0};
+  DBuf<rjb_xsect> xsects_sorted[2];
+  DBuf<uint32_t> closest_eid[2];
+  DBuf<int32_t> point_in_polygon[2];
+  DBuf<uint32_t> seg_start[2];
+  DBuf<uint64_t> keys_a, keys_b;
+  DBuf<uint32_t> vals_a, vals_b, seg_flag, seg_scan;
+  DBuf<longlong2> mid_pts;
+  SortTemp sort_tmp;
+  ScanTemp scan_tmp;
+};
+
+}  // namespace rjb
+
+using namespace rjb;
+
+struct rjb_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  bool have_scaling = false;
+  rjb_scaling sc;
+  DeviceMap maps[2];
+  int leaf_size = 4;
+  int sort_queries = 0;
+  // LSI result queue
+  DBuf<uint2> pairs;
+  DBuf<rjb_xsect> xsects;
+  DBuf<unsigned long long> counters;  // [0] = queue counter (low 32 bits), [1] = candidates
+  // PIP results
+  DBuf<uint32_t> pip_eid;
+  DBuf<int32_t> pip_face;
+  DBuf<longlong2> pip_pts;
+  DBuf<double2> pip_raw;
+  // query ordering scratch
+  DBuf<uint64_t> ord_keys_a, ord_keys_b;
+  DBuf<uint32_t> ord_vals_a, ord_vals_b;
+  SortTemp ord_sort;
+  // overlay state
+  OverlayState ov;
+  // timing of the kernels of the last query call
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float last_ms[4] = {0, 0, 0, 0};
+};
+
+namespace rjb {
+
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return RJB_OK;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return RJB_ERR_INVALID;
+  }
+}
+
+// ---- kernels of the load path ---------------------------------------------
+// Scaling exactly like the reference's device kernel (src/map/map.h:171-180 ->
+// src/map/scaling.h:79-95): fma.rn.f64 then cvt.rzi.s64.f64.
+__global__ void k_scale_points(const double2* __restrict__ in, uint32_t n, double rx, double ry,
+                               double dx, double dy, longlong2* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double2 p = in[i];
+  longlong2 o;
+  o.x = (long long) fma(p.x, rx, dx);
+  o.y = (long long) fma(p.y, ry, dy);
+  out[i] = o;
+}
+
+// edge numbering of src/map/map.h:200-207: eid = p - chain
+__global__ void k_edge_chain(const uint32_t* __restrict__ row_index, uint32_t n_chains,
+                             uint32_t n_edges, uint32_t* __restrict__ edge_chain) {
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  // last chain c with first_eid(c) = row_index[c] - c <= e
+  uint32_t lo = 0, hi = n_chains;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (row_index[mid] - mid <= e) lo = mid; else hi = mid;
+  }
+  edge_chain[e] = lo;
+}
+
+__global__ void k_query_keys_edges(MapView Q, long long imin, uint64_t* __restrict__ key,
+                                   uint32_t* __restrict__ val) {
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Q.n_edges) return;
+  Seg s = load_seg(Q, e);
+  key[e] = morton64(s.x1 + ((s.x2 - s.x1) >> 1), s.y1 + ((s.y2 - s.y1) >> 1), imin);
+  val[e] = e;
+}
+
+__global__ void k_query_keys_points(const longlong2* __restrict__ pts, uint32_t n, long long imin,
+                                    uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  longlong2 p = pts[i];
+  key[i] = morton64(p.x, p.y, imin);
+  val[i] = i;
+}
+
+static void scaling_init(rjb_scaling& s, double bminx, double bminy, double bmaxx, double bmaxy) {
+  // src/map/scaling.h:43-46,56-71 (host arithmetic, no FMA contraction here:
+  // every product feeds exactly one rounding because of the volatile temps)
+  s.internal_max = INT64_MAX >> 17;
+  s.internal_min = INT64_MIN >> 17;
+  s.internal_range = s.internal_max - s.internal_min;
+  double max_x = bmaxx + 1, min_x = bminx - 1, max_y = bmaxy + 1, min_y = bminy - 1;
+  s.rx = (double) s.internal_range / (max_x - min_x);
+  s.ry = (double) s.internal_range / (max_y - min_y);
+  s.rrx = 1 / s.rx;
+  s.rry = 1 / s.ry;
+  int64_t isum = s.internal_max + s.internal_min;
+  volatile double tx = (max_x + min_x) * s.rx, ty = (max_y + min_y) * s.ry;
+  volatile double ux = isum * s.rrx, uy = isum * s.rry;
+  s.deltax = 0.5 * (isum - tx);
+  s.deltay = 0.5 * (isum - ty);
+  s.ddeltax = 0.5 * ((max_x + min_x) - ux);
+  s.ddeltay = 0.5 * ((max_y + min_y) - uy);
+}
+
+static void check_map_id(int id) { RJB_REQUIRE(id == 0 || id == 1, "map id must be 0 or 1"); }
+
+static const uint32_t* query_order_edges(rjb_ctx* c, const MapView& Q) {
+  if (!c->sort_queries || Q.n_edges == 0) return nullptr;
+  uint32_t n = Q.n_edges;
+  uint64_t* ka = c->ord_keys_a.ensure(n);
+  uint64_t* kb = c->ord_keys_b.ensure(n);
+  uint32_t* va = c->ord_vals_a.ensure(n);
+  uint32_t* vb = c->ord_vals_b.ensure(n);
+  k_query_keys_edges<<<div_up(n, 256), 256, 0, c->stream>>>(Q, c->sc.internal_min, ka, va);
+  sort_pairs_u64_u32(ka, kb, va, vb, n, 0, 64, c->ord_sort, c->stream);
+  return vb;
+}
+
+static const uint32_t* query_order_points(rjb_ctx* c, const longlong2* pts, uint32_t n) {
+  if (!c->sort_queries || n == 0) return nullptr;
+  uint64_t* ka = c->ord_keys_a.ensure(n);
+  uint64_t* kb = c->ord_keys_b.ensure(n);
+  uint32_t* va = c->ord_vals_a.ensure(n);
+  uint32_t* vb = c->ord_vals_b.ensure(n);
+  k_query_keys_points<<<div_up(n, 256), 256, 0, c->stream>>>(pts, n, c->sc.internal_min, ka, va);
+  sort_pairs_u64_u32(ka, kb, va, vb, n, 0, 64, c->ord_sort, c->stream);
+  return vb;
+}
+
+static void ensure_events(rjb_ctx* c) {
+  for (int i = 0; i < 4; i++)
+    if (!c->ev[i]) RJB_CUDA(cudaEventCreate(&c->ev[i]));
+}
+
+static void do_build_index(rjb_ctx* c, int map_id, int mode, uint32_t grid_size, double* build_ms) {
+  check_map_id(map_id);
+  DeviceMap& m = c->maps[map_id];
+  RJB_REQUIRE(m.loaded, "rjb_build_index: map not loaded");
+  ensure_events(c);
+  RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  if (mode == RJB_MODE_LBVH) {
+    build_lbvh(m.bvh, m.view(), c->leaf_size, c->sc.internal_min, c->stream);
+  } else if (mode == RJB_MODE_GRID) {
+    build_grid(m.grid, m.view(), grid_size, c->sc.internal_min, c->sc.internal_range, c->stream);
+  } else if (mode == RJB_MODE_BRUTE) {
+    // no index
+  } else {
+    throw Error(RJB_ERR_INVALID, "rjb_build_index: unknown mode");
+  }
+  RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  RJB_CUDA(cudaEventSynchronize(c->ev[1]));
+  float ms = 0;
+  RJB_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+  if (build_ms) *build_ms = ms;
+}
+
+// LSI into c->pairs / c->xsects.  Returns the number found.
+static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_t* n_candidates) {
+  check_map_id(q);
+  DeviceMap& Qm = c->maps[q];
+  DeviceMap& Bm = c->maps[1 - q];
+  RJB_REQUIRE(Qm.loaded && Bm.loaded, "rjb_lsi: both maps must be loaded");
+  // queue capacity as in src/run_query.cu:226-228 (float arithmetic)
+  float total_e = (float) ((size_t) Qm.n_edges + (size_t) Bm.n_edges);
+  uint64_t cap64 = (uint64_t) (total_e * (float) xsect_factor);
+  RJB_REQUIRE(cap64 < 0xFFFFFFFFull, "rjb_lsi: xsect queue exceeds 2^32 entries");
+  uint32_t cap = (uint32_t) cap64;
+  uint2* pairs = c->pairs.ensure(cap ? cap : 1);
+  rjb_xsect* xs = c->xsects.ensure(cap ? cap : 1);
+  unsigned long long* ctr = c->counters.ensure(2);
+  ensure_events(c);
+  MapView Q = Qm.view(), B = Bm.view();
+  RJB_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), c->stream));
+  const uint32_t* order = nullptr;
+  RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  if (Q.n_edges > 0 && B.n_edges > 0) {
+    if (mode == RJB_MODE_LBVH) {
+      if (!Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no LBVH on the base map");
+      order = query_order_edges(c, Q);
+      RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+      unsigned blocks = div_up(Q.n_edges, kLsiWarps * 32);
+      k_lsi_bvh<<<blocks, kLsiWarps * 32, 0, c->stream>>>(Q, B, Bm.bvh.view(), order, pairs, cap,
+                                                          (unsigned int*) ctr, ctr + 1);
+    } else if (mode == RJB_MODE_GRID) {
+      if (!Bm.grid.built) throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no grid on the base map");
+      lsi_grid(Bm.grid, Q, B, pairs, cap, (unsigned int*) ctr, ctr + 1, c->stream);
+    } else if (mode == RJB_MODE_BRUTE) {
+      dim3 g(div_up(Q.n_edges, 256), min(64u, div_up(B.n_edges, 256)));
+      k_lsi_brute<<<g, 256, 0, c->stream>>>(Q, B, pairs, cap, (unsigned int*) ctr, ctr + 1);
+    } else {
+      throw Error(RJB_ERR_INVALID, "rjb_lsi: unknown mode");
+    }
+  }
+  RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  // the point pass reads the count on the device: no host round trip between
+  // the two kernels
+  if (cap > 0)
+    k_xsect_points_dyn<<<div_up(cap, 128), 128, 0, c->stream>>>(Q, B, q, pairs,
+                                                               (const unsigned int*) ctr, cap, xs);
+  RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  RJB_CUDA(cudaGetLastError());
+  unsigned long long h[2];
+  RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  RJB_CUDA(cudaStreamSynchronize(c->stream));
+  RJB_CUDA(cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]));
+  RJB_CUDA(cudaEventElapsedTime(&c->last_ms[1], c->ev[1], c->ev[2]));
+  uint64_t n = (uint32_t) h[0];
+  if (n_candidates) *n_candidates = h[1];
+  if (n > cap) {
+    throw Error(RJB_ERR_QUEUE_OVERFLOW,
+                "rjb_lsi: " + std::to_string(n) + " intersections exceed the queue capacity " +
+                    std::to_string(cap) + " (raise -xsect_factor)");
+  }
+  return n;
+}
+
+static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t n,
+                   uint64_t* n_candidates) {
+  check_map_id(q);
+  DeviceMap& Bm = c->maps[1 - q];
+  RJB_REQUIRE(Bm.loaded, "rjb_pip: base map not loaded");
+  uint32_t* eid = c->pip_eid.ensure(n ? n : 1);
+  int32_t* face = c->pip_face.ensure(n ? n : 1);
+  unsigned long long* ctr = c->counters.ensure(2);
+  ensure_events(c);
+  RJB_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), c->stream));
+  MapView B = Bm.view();
+  RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  if (n > 0) {
+    if (mode == RJB_MODE_LBVH) {
+      if (!Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no LBVH on the base map");
+      const uint32_t* order = query_order_points(c, d_pts, n);
+      RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+      k_pip_bvh<<<div_up(n, kLsiWarps * 32), kLsiWarps * 32, 0, c->stream>>>(
+          d_pts, n, order, B, Bm.bvh.view(), q, eid, face, ctr + 1);
+    } else if (mode == RJB_MODE_GRID) {
+      if (!Bm.grid.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no grid on the base map");
+      pip_grid(Bm.grid, d_pts, n, B, q, eid, face, ctr + 1, c->stream);
+    } else if (mode == RJB_MODE_BRUTE) {
+      k_pip_brute<<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, B, q, eid, face);
+    } else {
+      throw Error(RJB_ERR_INVALID, "rjb_pip: unknown mode");
+    }
+  }
+  RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  RJB_CUDA(cudaGetLastError());
+  unsigned long long h[2];
+  RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  RJB_CUDA(cudaStreamSynchronize(c->stream));
+  RJB_CUDA(cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]));
+  c->last_ms[1] = 0;
+  if (n_candidates) *n_candidates = h[1];
+}
+
+}  // namespace rjb
+
+#include "rjb_overlay.cuh"
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char* rjb_last_error(void) { return g_last_error.c_str(); }
+void rjb__set_error(const char* msg) { g_last_error = msg ? msg : ""; }
+const char* rjb_version(void) { return "rjb200 0.1 (sm_100a)"; }
+
+int rjb_create(int device, rjb_ctx** out) {
+  return guarded([&] {
+    RJB_REQUIRE(out != nullptr, "rjb_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      throw Error(RJB_ERR_CUDA, std::string("rjb_create: no CUDA device (") +
+                                    cudaGetErrorString(e) + "); there is no CPU fallback");
+    RJB_REQUIRE(device >= 0 && device < n, "rjb_create: bad device ordinal");
+    RJB_CUDA(cudaSetDevice(device));
+    std::unique_ptr<rjb_ctx> c(new rjb_ctx());
+    c->device = device;
+    RJB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    *out = c.release();
+  });
+}
+
+void rjb_destroy(rjb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 4; i++)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int rjb_set_stream(rjb_ctx* c, void* s) {
+  return guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    RJB_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t) s : c->own_stream;
+  });
+}
+
+int rjb_set_bounding_box(rjb_ctx* c, double min_x, double min_y, double max_x, double max_y) {
+  return guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    RJB_REQUIRE(min_x <= max_x && min_y <= max_y, "rjb_set_bounding_box: empty box");
+    scaling_init(c->sc, min_x, min_y, max_x, max_y);
+    c->have_scaling = true;
+    // scaled coordinates of loaded maps are stale now
+    for (auto& m : c->maps) { m.loaded = false; m.bvh.built = false; m.grid.built = false; }
+  });
+}
+
+int rjb_get_scaling(const rjb_ctx* c, rjb_scaling* out) {
+  return guarded([&] {
+    RJB_REQUIRE(c && out, "NULL argument");
+    RJB_REQUIRE(c->have_scaling, "rjb_get_scaling: call rjb_set_bounding_box first");
+    *out = c->sc;
+  });
+}
+
+int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
+  return guarded([&] {
+    RJB_REQUIRE(c && name, "NULL argument");
+    std::string n(name);
+    if (n == "lbvh_leaf_size") {
+      RJB_REQUIRE(value >= 1 && value <= 8, "lbvh_leaf_size must be in 1..8");
+      c->leaf_size = (int) value;
+    } else if (n == "sort_queries") {
+      c->sort_queries = value != 0;
+    } else {
+      throw Error(RJB_ERR_INVALID, "rjb_set_option: unknown option " + n);
+    }
+  });
+}
+
+int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
+                const uint32_t* row_index, const int64_t* left, const int64_t* right,
+                uint64_t n_chains) {
+  return guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    check_map_id(map_id);
+    RJB_REQUIRE(c->have_scaling, "rjb_set_map: call rjb_set_bounding_box first");
+    RJB_REQUIRE(n_points < 0xFFFFFFF0ull, "rjb_set_map: index_t is 32-bit (src/config.h:12)");
+    RJB_REQUIRE(n_chains == 0 || (xy && row_index && left && right), "rjb_set_map: NULL array");
+    RJB_CUDA(cudaSetDevice(c->device));
+    DeviceMap& m = c->maps[map_id];
+    m.loaded = false;
+    m.bvh.built = false;
+    m.grid.built = false;
+    if (n_chains > 0) {
+      RJB_REQUIRE(row_index[0] == 0 && row_index[n_chains] == n_points,
+                  "rjb_set_map: row_index must span [0, n_points]");
+    } else {
+      RJB_REQUIRE(n_points == 0, "rjb_set_map: points without chains");
+    }
+    m.n_points = (uint32_t) n_points;
+    m.n_chains = (uint32_t) n_chains;
+    m.n_edges = (uint32_t) (n_points - n_chains);
+    m.h_left.resize(n_chains);
+    m.h_right.resize(n_chains);
+    for (uint64_t i = 0; i < n_chains; i++) {
+      RJB_REQUIRE(row_index[i + 1] >= row_index[i] + 2, "rjb_set_map: chain with < 2 points");
+      m.h_left[i] = (int32_t) left[i];
+      m.h_right[i] = (int32_t) right[i];
+    }
+    m.h_xy.assign(xy, xy + 2 * n_points);
+    m.h_row_index.assign(row_index, row_index + (n_chains ? n_chains + 1 : 0));
+    double2* raw = m.raw.ensure(n_points ? n_points : 1);
+    longlong2* pts = m.pts.ensure(n_points ? n_points + 1 : 1);
+    uint32_t* ri = m.row_index.ensure(n_chains + 1);
+    int32_t* l = m.left.ensure(n_chains ? n_chains : 1);
+    int32_t* r = m.right.ensure(n_chains ? n_chains : 1);
+    uint32_t* ec = m.edge_chain.ensure(m.n_edges ? m.n_edges : 1);
+    cudaStream_t st = c->stream;
+    if (n_points) {
+      RJB_CUDA(cudaMemcpyAsync(raw, xy, n_points * sizeof(double2), cudaMemcpyHostToDevice, st));
+      RJB_CUDA(cudaMemcpyAsync(ri, row_index, (n_chains + 1) * sizeof(uint32_t),
+                               cudaMemcpyHostToDevice, st));
+      RJB_CUDA(cudaMemcpyAsync(l, m.h_left.data(), n_chains * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, st));
+      RJB_CUDA(cudaMemcpyAsync(r, m.h_right.data(), n_chains * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, st));
+      k_scale_points<<<div_up(n_points, 256), 256, 0, st>>>(raw, m.n_points, c->sc.rx, c->sc.ry,
+                                                            c->sc.deltax, c->sc.deltay, pts);
+      k_edge_chain<<<div_up(m.n_edges, 256), 256, 0, st>>>(ri, m.n_chains, m.n_edges, ec);
+      RJB_CUDA(cudaGetLastError());
+    }
+    RJB_CUDA(cudaStreamSynchronize(st));
+    m.loaded = true;
+  });
+}
+
+int rjb_map_info(const rjb_ctx* c, int map_id, uint64_t out[3]) {
+  return guarded([&] {
+    RJB_REQUIRE(c && out, "NULL argument");
+    check_map_id(map_id);
+    const DeviceMap& m = c->maps[map_id];
+    RJB_REQUIRE(m.loaded, "rjb_map_info: map not loaded");
+    out[0] = m.n_points;
+    out[1] = m.n_edges;
+    out[2] = m.n_chains;
+  });
+}
+
+int rjb_map_device_views(const rjb_ctx* c, int map_id, const int64_t** d_points_xy,
+                         const uint32_t** d_edge_chain) {
+  return guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    check_map_id(map_id);
+    const DeviceMap& m = c->maps[map_id];
+    RJB_REQUIRE(m.loaded, "rjb_map_device_views: map not loaded");
+    if (d_points_xy) *d_points_xy = (const int64_t*) m.pts.p;
+    if (d_edge_chain) *d_edge_chain = m.edge_chain.p;
+  });
+}
+
+int rjb_build_index(rjb_ctx* c, int map_id, int mode, uint32_t grid_size, double* build_ms) {
+  return guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    RJB_CUDA(cudaSetDevice(c->device));
+    do_build_index(c, map_id, mode, grid_size, build_ms);
+  });
+}
+
+int rjb_lsi(rjb_ctx* c, int query_map_id, int mode, double xsect_factor,
+            const rjb_xsect** d_xsects, uint64_t* n_xsects, uint64_t* n_candidates) {
+  if (n_xsects) *n_xsects = 0;
+  if (d_xsects) *d_xsects = nullptr;
+  uint64_t needed = 0;
+  int rc = guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    RJB_CUDA(cudaSetDevice(c->device));
+    try {
+      needed = do_lsi(c, query_map_id, mode, xsect_factor, n_candidates);
+    } catch (const Error& e) {
+      if (e.code == RJB_ERR_QUEUE_OVERFLOW) {
+        // report how many were needed
+        unsigned long long h = 0;
+        cudaMemcpy(&h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost);
+        needed = (uint32_t) h;
+      }
+      throw;
+    }
+    if (d_xsects) *d_xsects = c->xsects.p;
+  });
+  if (n_xsects) *n_xsects = needed;
+  return rc;
+}
+
+int rjb_pip(rjb_ctx* c, int query_map_id, int mode, const int64_t* d_points_xy, uint64_t n_points,
+            const uint32_t** d_closest_eid, const int32_t** d_face_id, uint64_t* n_candidates) {
+  return guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    RJB_CUDA(cudaSetDevice(c->device));
+    check_map_id(query_map_id);
+    const longlong2* pts = (const longlong2*) d_points_xy;
+    if (!pts) {
+      const DeviceMap& Qm = c->maps[query_map_id];
+      RJB_REQUIRE(Qm.loaded, "rjb_pip: query map not loaded and no points given");
+      pts = Qm.pts.p;
+      n_points = Qm.n_points;
+    }
+    RJB_REQUIRE(n_points < 0xFFFFFFF0ull, "rjb_pip: too many points");
+    do_pip(c, query_map_id, mode, pts, (uint32_t) n_points, n_candidates);
+    if (d_closest_eid) *d_closest_eid = c->pip_eid.p;
+    if (d_face_id) *d_face_id = c->pip_face.p;
+  });
+}
+
+int rjb_pip_host(rjb_ctx* c, int query_map_id, int mode, const double* h_xy, uint64_t n_points,
+                 uint32_t* h_closest_eid, int32_t* h_face_id) {
+  return guarded([&] {
+    RJB_REQUIRE(c && (h_xy || n_points == 0), "NULL argument");
+    RJB_REQUIRE(c->have_scaling, "rjb_pip_host: call rjb_set_bounding_box first");
+    RJB_REQUIRE(n_points < 0xFFFFFFF0ull, "rjb_pip_host: too many points");
+    RJB_CUDA(cudaSetDevice(c->device));
+    uint32_t n = (uint32_t) n_points;
+    double2* raw = c->pip_raw.ensure(n ? n : 1);
+    longlong2* pts = c->pip_pts.ensure(n ? n : 1);
+    if (n) {
+      RJB_CUDA(cudaMemcpyAsync(raw, h_xy, (size_t) n * sizeof(double2), cudaMemcpyHostToDevice,
+                               c->stream));
+      k_scale_points<<<div_up(n, 256), 256, 0, c->stream>>>(raw, n, c->sc.rx, c->sc.ry,
+                                                            c->sc.deltax, c->sc.deltay, pts);
+    }
+    do_pip(c, query_map_id, mode, pts, n, nullptr);
+    if (n && h_closest_eid)
+      RJB_CUDA(cudaMemcpyAsync(h_closest_eid, c->pip_eid.p, (size_t) n * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, c->stream));
+    if (n && h_face_id)
+      RJB_CUDA(cudaMemcpyAsync(h_face_id, c->pip_face.p, (size_t) n * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, c->stream));
+    RJB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+/* device times (ms) of the kernels of the last rjb_lsi / rjb_pip call:
+ * out[0] = traversal / cell kernel, out[1] = intersection-point pass */
+int rjb_last_kernel_ms(const rjb_ctx* c, double out[2]) {
+  return guarded([&] {
+    RJB_REQUIRE(c && out, "NULL argument");
+    out[0] = c->last_ms[0];
+    out[1] = c->last_ms[1];
+  });
+}
+
+/* bytes of the index of map_id (for the roofline's algorithmic bytes) */
+int rjb_index_info(const rjb_ctx* c, int map_id, int mode, uint64_t out[4]) {
+  return guarded([&] {
+    RJB_REQUIRE(c && out, "NULL argument");
+    check_map_id(map_id);
+    const DeviceMap& m = c->maps[map_id];
+    memset(out, 0, 4 * sizeof(uint64_t));
+    if (mode == RJB_MODE_LBVH && m.bvh.built) {
+      out[0] = m.bvh.n_leaves;
+      out[1] = m.bvh.index_bytes();
+      out[2] = m.bvh.leaf_size;
+    } else if (mode == RJB_MODE_GRID && m.grid.built) {
+      out[0] = m.grid.n_items;
+      out[1] = m.grid.index_bytes();
+      out[2] = m.grid.gsize;
+    }
+  });
+}
+
+int rjb_overlay_run(rjb_ctx* c, int mode, uint32_t grid_size, double xsect_factor,
+                    double* phase_ms) {
+  return guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    RJB_CUDA(cudaSetDevice(c->device));
+    overlay_run(c, mode, grid_size, xsect_factor, phase_ms);
+  });
+}
+
+int rjb_overlay_results(const rjb_ctx* c, int im, const rjb_xsect** d_xsects, uint64_t* n_xsects,
+                        const uint32_t** d_closest_eid, const int32_t** d_point_in_polygon) {
+  return guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    check_map_id(im);
+    RJB_REQUIRE(c->ov.done, "rjb_overlay_results: run rjb_overlay_run first");
+    if (d_xsects) *d_xsects = c->ov.xsects_sorted[im].p;
+    if (n_xsects) *n_xsects = c->ov.n_xsects;
+    if (d_closest_eid) *d_closest_eid = c->ov.closest_eid[im].p;
+    if (d_point_in_polygon) *d_point_in_polygon = c->ov.point_in_polygon[im].p;
+  });
+}
+
+int rjb_overlay_write(rjb_ctx* c, const char* path) {
+  return guarded([&] {
+    RJB_REQUIRE(c && path, "NULL argument");
+    RJB_CUDA(cudaSetDevice(c->device));
+    overlay_write(c, path);
+  });
+}
+
+int rjb_copy_to_host(rjb_ctx* c, const void* d_src, void* h_dst, uint64_t bytes) {
+  return guarded([&] {
+    RJB_REQUIRE(c && (bytes == 0 || (d_src && h_dst)), "NULL argument");
+    if (bytes == 0) return;
+    RJB_CUDA(cudaSetDevice(c->device));
+    RJB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    RJB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int rjb_sync(rjb_ctx* c) {
+  return guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    RJB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// Shared declarations of the device side of librjb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "rjb200.h"
+
+namespace rjb {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define RJB_CUDA(call)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess)                                                   \
+      throw ::rjb::Error(RJB_ERR_CUDA, std::string(#call) + ": " +            \
+                                           cudaGetErrorString(e__) + " at " + \
+                                           __FILE__ + ":" +                   \
+                                           std::to_string(__LINE__));         \
+  } while (0)
+
+#define RJB_REQUIRE(cond, msg)                          \
+  do {                                                  \
+    if (!(cond)) throw ::rjb::Error(RJB_ERR_INVALID, msg); \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+constexpr int kQuantShift = 16;  // 47-bit coordinate -> 31-bit box coordinate
+
+// Device view of one loaded map.  Points are interleaved int64 (x, y) so one
+// 16-byte load fetches a vertex; an edge is (pts[eid + chain], pts[eid + chain + 1]).
+struct MapView {
+  const longlong2* pts;
+  const uint32_t* edge_chain;  // per edge
+  const uint32_t* row_index;   // per chain, CSR into pts
+  const int32_t* left;         // per chain
+  const int32_t* right;        // per chain
+  uint32_t n_points, n_edges, n_chains;
+};
+
+// BVH2 over leaves of <= leaf_size consecutive chain edges.  Internal node i
+// keeps the boxes of BOTH children (quantised int32: coord >> kQuantShift) so
+// one visit = 2 x 16 B + 8 B.  child < 0  ->  leaf ~child (sorted order).
+struct BvhView {
+  const int4* node_box;    // 2 per internal node: {xmin, ymin, xmax, ymax}
+  const int2* node_child;  // {left, right}
+  const uint2* leaf_rec;   // {first_eid, (count << 28) | chain}
+  int4 root_box;
+  uint32_t n_leaves;
+};
+
+static __device__ __forceinline__ int quant(long long v) {
+  return (int) (v >> kQuantShift);  // arithmetic shift = floor, monotone
+}
+
+static __device__ __forceinline__ bool box_overlap(const int4& a, const int4& b) {
+  // closed boxes {xmin, ymin, xmax, ymax}
+  return a.x <= b.z && b.x <= a.z && a.y <= b.w && b.y <= a.w;
+}
+
+static inline unsigned div_up(uint64_t a, uint64_t b) {
+  return (unsigned) ((a + b - 1) / b);
+}
+
+}  // namespace rjb

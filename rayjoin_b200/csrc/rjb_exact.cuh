@@ -1,0 +1,218 @@
+// Exact fixed-point predicates (device).  These reproduce RayJoin's results
+// bit for bit; they are written from the arithmetic definition, not from the
+// reference's AoS Edge{a,b,c} objects:
+//
+//   S(p, e) = a*p.x + b*p.y + c  with  c = -x1*a - y1*b   (src/map/map.h:216-226)
+//           = a*(p.x - x1) + b*(p.y - y1)                 (exact integers)
+//
+// so the edge equation never has to be stored: a, b come from the endpoints
+// (sign-normalised so that b >= 0, or a unchanged when b == 0) and the 2^95
+// constant term disappears.  All products are < 2^96 -> int128 is exact.
+#pragma once
+#include "rjb_common.cuh"
+
+namespace rjb {
+
+typedef __int128 i128;
+
+struct Seg {
+  long long x1, y1, x2, y2;
+};
+
+// (a, b) of the edge equation, normalised like src/map/map.h:222-226
+static __device__ __forceinline__ void edge_ab(const Seg& e, long long& a,
+                                               long long& b) {
+  a = e.y1 - e.y2;
+  b = e.x2 - e.x1;
+  if (b < 0) {
+    a = -a;
+    b = -b;
+  }
+}
+
+// sign of a*dx + b*dy (|a|,|b|,|dx|,|dy| < 2^48): -1, 0, +1
+static __device__ __forceinline__ int side_sign(long long a, long long b,
+                                                long long dx, long long dy) {
+  // 32-bit fast path: one IMAD.WIDE per product, the sum cannot overflow
+  const long long lim = 1ll << 31;
+  if ((unsigned long long) (a + lim) < (1ull << 32) &&
+      (unsigned long long) (b + lim) < (1ull << 32) &&
+      (unsigned long long) (dx + lim) < (1ull << 32) &&
+      (unsigned long long) (dy + lim) < (1ull << 32)) {
+    long long s = (long long) (int) a * (int) dx + (long long) (int) b * (int) dy;
+    return (s > 0) - (s < 0);
+  }
+  i128 s = (i128) a * dx + (i128) b * dy;
+  return (s > 0) - (s < 0);
+}
+
+static __device__ __forceinline__ int sgn(long long v) { return (v > 0) - (v < 0); }
+
+// intersect_test(e1, e2), src/algo/lsi.h:27-103.  e1 is the QUERY-side edge,
+// e2 the BASE-side edge (src/app/lsi_lbvh.h:71); the simulation-of-simplicity
+// perturbations are not symmetric in (e1, e2).
+static __device__ __forceinline__ bool lsi_intersect(const Seg& e1, const Seg& e2) {
+  long long a1, b1, a2, b2;
+  edge_ab(e1, a1, b1);
+  edge_ab(e2, a2, b2);
+  // endpoints of e1 against the line of e2 (lsi.h:42-67)
+  int s11 = side_sign(a2, b2, e1.x1 - e2.x1, e1.y1 - e2.y1);
+  if (s11 == 0) s11 = -sgn(a2);
+  if (s11 == 0) s11 = -sgn(b2);
+  if (s11 == 0) return false;
+  int s12 = side_sign(a2, b2, e1.x2 - e2.x1, e1.y2 - e2.y1);
+  if (s12 == 0) s12 = -sgn(a2);
+  if (s12 == 0) s12 = -sgn(b2);
+  if (s12 == 0) return false;
+  if (s11 == s12) return false;
+  // endpoints of e2 against the line of e1 (lsi.h:70-91)
+  int s21 = side_sign(a1, b1, e2.x1 - e1.x1, e2.y1 - e1.y1);
+  if (s21 == 0) s21 = sgn(a1);
+  if (s21 == 0) s21 = sgn(b1);
+  if (s21 == 0) return false;
+  int s22 = side_sign(a1, b1, e2.x2 - e1.x1, e2.y2 - e1.y1);
+  if (s22 == 0) s22 = sgn(a1);
+  if (s22 == 0) s22 = sgn(b1);
+  if (s22 == 0) return false;
+  if (s21 == s22) return false;
+  // identical edges (lsi.h:97-100)
+  if ((e1.x1 == e2.x1 && e1.y1 == e2.y1 && e1.x2 == e2.x2 && e1.y2 == e2.y2) ||
+      (e1.x1 == e2.x2 && e1.y1 == e2.y2 && e1.x2 == e2.x1 && e1.y2 == e2.y1))
+    return false;
+  return true;
+}
+
+// closed integer boxes of two segments overlap.  intersect_test() == true
+// implies this (the crossing point lies on both closed segments), so it is a
+// loss-free prefilter in exact arithmetic.
+static __device__ __forceinline__ bool seg_boxes_overlap(const Seg& p, const Seg& q) {
+  return min(p.x1, p.x2) <= max(q.x1, q.x2) && min(q.x1, q.x2) <= max(p.x1, p.x2) &&
+         min(p.y1, p.y2) <= max(q.y1, q.y2) && min(q.y1, q.y2) <= max(p.y1, p.y2);
+}
+
+// ---- intersection point ----------------------------------------------------
+// src/algo/lsi.h:117-141 + tcb::rational (src/util/rational.h): the point is
+// rational(num, den) gcd-reduced in int128 (wrapping like the device code of
+// the reference does for very long edges), clamped to the bbox of the four
+// endpoints, then converted with (int64)((double)num / (double)den).
+static __device__ __forceinline__ i128 iabs128(i128 v) { return v < 0 ? -v : v; }
+
+static __device__ i128 gcd128(i128 a, i128 b) {
+  // magnitude of Euclid's gcd; any algorithm gives the same value.  Work on
+  // unsigned magnitudes and drop to 64-bit as soon as both fit.
+  unsigned __int128 x = (unsigned __int128) iabs128(a);
+  unsigned __int128 y = (unsigned __int128) iabs128(b);
+  while (y != 0) {
+    if ((x >> 64) == 0 && (y >> 64) == 0) {
+      unsigned long long p = (unsigned long long) x, q = (unsigned long long) y;
+      while (q != 0) {
+        unsigned long long t = p % q;
+        p = q;
+        q = t;
+      }
+      return (i128) p;
+    }
+    unsigned __int128 t = x % y;
+    x = y;
+    y = t;
+  }
+  return (i128) x;
+}
+
+static __device__ __forceinline__ void rat_make(i128 num, i128 den, i128& on,
+                                                i128& od) {
+  i128 g = gcd128(num, den);  // den != 0 for a true intersection
+  i128 sn = den < 0 ? -num : num;
+  on = sn / g;
+  od = iabs128(den) / g;
+}
+
+static __device__ __forceinline__ long long min4ll(long long a, long long b,
+                                                   long long c, long long d) {
+  return min(min(a, b), min(c, d));
+}
+static __device__ __forceinline__ long long max4ll(long long a, long long b,
+                                                   long long c, long long d) {
+  return max(max(a, b), max(c, d));
+}
+
+static __device__ void lsi_point(const Seg& e1, const Seg& e2, long long& ox,
+                                 long long& oy) {
+  long long a1l, b1l, a2l, b2l;
+  edge_ab(e1, a1l, b1l);
+  edge_ab(e2, a2l, b2l);
+  // c with the SAME normalisation sign as (a, b): c = -x1*a - y1*b
+  i128 a1 = a1l, b1 = b1l, a2 = a2l, b2 = b2l;
+  i128 c1 = -(i128) e1.x1 * a1 - (i128) e1.y1 * b1;
+  i128 c2 = -(i128) e2.x1 * a2 - (i128) e2.y1 * b2;
+  // unsigned products: two's-complement wrap-around, no UB
+  typedef unsigned __int128 u128;
+  i128 denom = (i128) ((u128) a1 * (u128) b2 - (u128) a2 * (u128) b1);
+  i128 numx = (i128) ((u128) c2 * (u128) b1 - (u128) c1 * (u128) b2);
+  i128 numy = (i128) ((u128) a2 * (u128) c1 - (u128) a1 * (u128) c2);
+  i128 xn, xd, yn, yd;
+  rat_make(numx, denom, xn, xd);
+  rat_make(numy, denom, yn, yd);
+  long long t = min4ll(e1.x1, e1.x2, e2.x1, e2.x2);
+  if (xn < (i128) ((u128) (i128) t * (u128) xd)) { xn = t; xd = 1; }
+  t = max4ll(e1.x1, e1.x2, e2.x1, e2.x2);
+  if ((i128) ((u128) (i128) t * (u128) xd) < xn) { xn = t; xd = 1; }
+  t = min4ll(e1.y1, e1.y2, e2.y1, e2.y2);
+  if (yn < (i128) ((u128) (i128) t * (u128) yd)) { yn = t; yd = 1; }
+  t = max4ll(e1.y1, e1.y2, e2.y1, e2.y2);
+  if ((i128) ((u128) (i128) t * (u128) yd) < yn) { yn = t; yd = 1; }
+  ox = (long long) ((double) xn / (double) xd);
+  oy = (long long) ((double) yn / (double) yd);
+}
+
+// ---- PIP: closest edge above -----------------------------------------------
+// Update rule of src/algo/pip.h:27-96 == src/app/pip_lbvh.h:57-123.  Full ties
+// (same y*, same slope = coincident edges) are resolved like a scan in
+// increasing eid order: q == 1 keeps the smallest eid, q == 0 the largest.
+struct PipBest {
+  double y;        // best_y
+  long long a, b;  // equation of the best edge (|.| < 2^48)
+  uint32_t eid;
+};
+
+static __device__ __forceinline__ void pip_init(PipBest& st) {
+  st.y = __longlong_as_double(0x7ff0000000000000ll);  // +inf
+  st.a = 0;
+  st.b = 1;
+  st.eid = RJB_NO_HIT;
+}
+
+// returns true when st changed
+static __device__ __forceinline__ bool pip_update(PipBest& st, int q, long long px,
+                                                  long long py, const Seg& e,
+                                                  uint32_t eid) {
+  long long x_min = min(e.x1, e.x2), x_max = max(e.x1, e.x2);
+  if (px < x_min || px > x_max || px == (q == 0 ? x_min : x_max)) return false;
+  long long a, b;
+  edge_ab(e, a, b);
+  // -a*px - c = a*(x1 - px) + b*y1   (exact, < 2^97)
+  i128 num = (i128) a * (e.x1 - px) + (i128) b * e.y1;
+  double ys = (double) num / (double) b;
+  double diff = (double) py - ys;
+  if (diff == 0) diff = (double) (q == 0 ? -a : a);
+  if (diff == 0) diff = (double) (q == 0 ? -b : b);
+  if (diff > 0) return false;
+  if (ys > st.y) return false;
+  if (ys == st.y) {
+    double cur = (double) a / (double) b;
+    double best = (double) st.a / (double) st.b;
+    if (cur == best) {
+      if (q ? (eid > st.eid) : (eid < st.eid)) return false;
+    } else {
+      bool flag = cur > best;
+      if ((q && !flag) || (flag && !q)) return false;
+    }
+  }
+  st.y = ys;
+  st.a = a;
+  st.b = b;
+  st.eid = eid;
+  return true;
+}
+
+}  // namespace rjb

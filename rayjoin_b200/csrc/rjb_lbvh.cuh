@@ -1,0 +1,246 @@
+// LBVH over the edges of one map: leaves of <= G consecutive chain edges,
+// 64-bit 2-D Morton keys of the leaf-box centre, radix sort, Karras hierarchy,
+// bottom-up refit of quantised integer boxes.
+//
+// Replaces FillPrimitivesLBVH + lbvh::bvh::construct
+// (reference: src/tree/primtive.h:33-57, deps/lbvh/lbvh/bvh.cuh:277-481).
+// Differences that matter: boxes are conservative in the INTEGER domain
+// (coord >> 16, floor on both ends is monotone so exact overlap => quantised
+// overlap) instead of floats widened by 2 ulp; keys are 64-bit Morton codes
+// with an index tie-break, so no uniqueness pass is needed; a node stores the
+// boxes of both children so traversal reads one record per visit.
+#pragma once
+#include "rjb_prims.cuh"
+
+namespace rjb {
+
+struct Bvh {
+  DBuf<int4> node_box;
+  DBuf<int2> node_child;
+  DBuf<uint2> leaf_rec;
+  int4 root_box = {0, 0, -1, -1};
+  uint32_t n_leaves = 0;
+  int leaf_size = 0;
+  bool built = false;
+  // build scratch (kept for rebuilds)
+  DBuf<uint32_t> chain_cnt, leaf_base, vals_a, vals_b, parent, flags;
+  DBuf<uint64_t> keys_a, keys_b;
+  DBuf<int4> leaf_box_u, leaf_box_s;
+  DBuf<uint2> leaf_rec_u;
+  DBuf<int4> root_box_d;
+  ScanTemp scan_tmp;
+  SortTemp sort_tmp;
+
+  BvhView view() const {
+    BvhView v;
+    v.node_box = node_box.p;
+    v.node_child = node_child.p;
+    v.leaf_rec = leaf_rec.p;
+    v.root_box = root_box;
+    v.n_leaves = n_leaves;
+    return v;
+  }
+  size_t index_bytes() const {
+    uint32_t n_int = n_leaves > 1 ? n_leaves - 1 : 1;
+    return (size_t) n_int * (2 * sizeof(int4) + sizeof(int2)) + (size_t) n_leaves * sizeof(uint2);
+  }
+};
+
+__global__ void k_chain_leaf_counts(const uint32_t* __restrict__ row_index, uint32_t n_chains,
+                                    int G, uint32_t* __restrict__ cnt) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  uint32_t ne = row_index[c + 1] - row_index[c] - 1;
+  cnt[c] = (ne + G - 1) / G;
+}
+
+static __device__ __forceinline__ uint64_t spread32(uint32_t v) {
+  uint64_t x = v;
+  x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+  x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+  x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+  x = (x | (x << 2)) & 0x3333333333333333ull;
+  x = (x | (x << 1)) & 0x5555555555555555ull;
+  return x;
+}
+
+// 64-bit Morton code of a point in internal coordinates (47-bit range)
+static __device__ __forceinline__ uint64_t morton64(long long x, long long y, long long imin) {
+  uint32_t ux = (uint32_t) ((unsigned long long) (x - imin) >> 15);
+  uint32_t uy = (uint32_t) ((unsigned long long) (y - imin) >> 15);
+  return (spread32(uy) << 1) | spread32(ux);
+}
+
+// one thread per leaf: locate the chain, emit {record, quantised box, key}
+__global__ void k_leaf_fill(MapView m, const uint32_t* __restrict__ leaf_base, uint32_t n_leaves,
+                            int G, long long imin, uint2* __restrict__ rec,
+                            int4* __restrict__ box, uint64_t* __restrict__ key,
+                            uint32_t* __restrict__ val) {
+  uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_leaves) return;
+  // chain c with leaf_base[c] <= l < leaf_base[c+1]
+  uint32_t lo = 0, hi = m.n_chains;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (leaf_base[mid] <= l) lo = mid; else hi = mid;
+  }
+  uint32_t c = lo;
+  uint32_t p_begin = m.row_index[c], p_end = m.row_index[c + 1];
+  uint32_t k = l - leaf_base[c];
+  uint32_t p1 = p_begin + k * G;                   // first point of the leaf
+  uint32_t cnt = min((uint32_t) G, p_end - 1 - p1);  // edges in the leaf
+  long long xmin, xmax, ymin, ymax;
+  longlong2 p = m.pts[p1];
+  xmin = xmax = p.x;
+  ymin = ymax = p.y;
+  for (uint32_t i = 1; i <= cnt; i++) {
+    p = m.pts[p1 + i];
+    xmin = min(xmin, p.x); xmax = max(xmax, p.x);
+    ymin = min(ymin, p.y); ymax = max(ymax, p.y);
+  }
+  rec[l] = make_uint2(p1 - c, (cnt << 28) | c);
+  box[l] = make_int4(quant(xmin), quant(ymin), quant(xmax), quant(ymax));
+  key[l] = morton64(xmin + ((xmax - xmin) >> 1), ymin + ((ymax - ymin) >> 1), imin);
+  val[l] = l;
+}
+
+__global__ void k_leaf_gather(const uint32_t* __restrict__ order, uint32_t n,
+                              const uint2* __restrict__ rec_u, const int4* __restrict__ box_u,
+                              uint2* __restrict__ rec_s, int4* __restrict__ box_s) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t j = order[i];
+  rec_s[i] = rec_u[j];
+  box_s[i] = box_u[j];
+}
+
+// Karras 2012: common-prefix length of sorted keys i and j, index tie-break
+static __device__ __forceinline__ int delta(const uint64_t* __restrict__ key, uint32_t n, int i, int j) {
+  if (j < 0 || j >= (int) n) return -1;
+  uint64_t a = key[i], b = key[j];
+  if (a == b) return 64 + __clz((uint32_t) i ^ (uint32_t) j);
+  return __clzll((long long) (a ^ b));
+}
+
+// parent[] is indexed by node id: internal i -> i, leaf j -> (n - 1) + j
+__global__ void k_karras(const uint64_t* __restrict__ key, uint32_t n, int2* __restrict__ child,
+                         uint32_t* __restrict__ parent) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int) n - 1) return;
+  int d = (delta(key, n, i, i + 1) - delta(key, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = delta(key, n, i, i - d);
+  int lmax = 2;
+  while (delta(key, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta(key, n, i, i + (l + t) * d) > dmin) l += t;
+  int j = i + l * d;
+  int dnode = delta(key, n, i, j);
+  int s = 0;
+  for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+    if (delta(key, n, i, i + (s + t) * d) > dnode) s += t;
+    if (t == 1) break;
+  }
+  int gamma = i + s * d + min(d, 0);
+  int left, right;
+  if (min(i, j) == gamma) { left = ~gamma; parent[(n - 1) + gamma] = i; }
+  else { left = gamma; parent[gamma] = i; }
+  if (max(i, j) == gamma + 1) { right = ~(gamma + 1); parent[(n - 1) + gamma + 1] = i; }
+  else { right = gamma + 1; parent[gamma + 1] = i; }
+  child[i] = make_int2(left, right);
+  if (i == 0) parent[0] = 0xFFFFFFFFu;
+}
+
+static __device__ __forceinline__ int4 box_union(const int4& a, const int4& b) {
+  return make_int4(min(a.x, b.x), min(a.y, b.y), max(a.z, b.z), max(a.w, b.w));
+}
+
+// one thread per leaf climbs while it is the second arrival at a node
+__global__ void k_refit(const int4* __restrict__ leaf_box, uint32_t n, const int2* __restrict__ child,
+                        const uint32_t* __restrict__ parent, int4* node_box,
+                        uint32_t* flags, int4* root_box) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int4 box = leaf_box[j];
+  int me = ~(int) j;
+  uint32_t cur = parent[(n - 1) + j];
+  while (true) {
+    int2 ch = child[cur];
+    int slot = (ch.x == me) ? 0 : 1;
+    // plain store then fence: the second arrival reads it after its atomic
+    node_box[2 * cur + slot] = box;
+    __threadfence();
+    uint32_t old = atomicAdd(&flags[cur], 1u);
+    if (old == 0) return;
+    __threadfence();
+    int4 sib = __ldcg(&node_box[2 * cur + (1 - slot)]);
+    box = box_union(box, sib);
+    me = (int) cur;
+    uint32_t up = parent[cur];
+    if (up == 0xFFFFFFFFu) {
+      *root_box = box;
+      return;
+    }
+    cur = up;
+  }
+}
+
+__global__ void k_single_leaf_root(const int4* __restrict__ leaf_box, int4* node_box,
+                                   int2* child, int4* root_box) {
+  node_box[0] = leaf_box[0];
+  node_box[1] = make_int4(1, 1, 0, 0);  // empty: never overlaps
+  child[0] = make_int2(~0, ~0);
+  *root_box = leaf_box[0];
+}
+
+static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long imin,
+                              cudaStream_t st) {
+  RJB_REQUIRE(leaf_size >= 1 && leaf_size <= 8, "lbvh_leaf_size must be in 1..8");
+  RJB_REQUIRE(m.n_chains < (1u << 28), "too many chains for the leaf record (2^28)");
+  b.leaf_size = leaf_size;
+  b.built = true;
+  b.n_leaves = 0;
+  b.root_box = make_int4(1, 1, 0, 0);
+  if (m.n_edges == 0) return;
+  const int T = 256;
+  uint32_t* cnt = b.chain_cnt.ensure(m.n_chains + 1);
+  uint32_t* base = b.leaf_base.ensure(m.n_chains + 1);
+  k_chain_leaf_counts<<<div_up(m.n_chains, T), T, 0, st>>>(m.row_index, m.n_chains, leaf_size, cnt);
+  exclusive_scan_u32(cnt, base, m.n_chains, b.scan_tmp, st);
+  uint32_t n = 0;
+  RJB_CUDA(cudaMemcpyAsync(&n, base + m.n_chains, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  RJB_CUDA(cudaStreamSynchronize(st));
+  b.n_leaves = n;
+  uint32_t n_int = n > 1 ? n - 1 : 1;
+  uint2* rec_u = b.leaf_rec_u.ensure(n);
+  int4* box_u = b.leaf_box_u.ensure(n);
+  int4* box_s = b.leaf_box_s.ensure(n);
+  uint64_t* ka = b.keys_a.ensure(n);
+  uint64_t* kb = b.keys_b.ensure(n);
+  uint32_t* va = b.vals_a.ensure(n);
+  uint32_t* vb = b.vals_b.ensure(n);
+  uint2* rec_s = b.leaf_rec.ensure(n);
+  int4* nbox = b.node_box.ensure(2 * (size_t) n_int);
+  int2* nchild = b.node_child.ensure(n_int);
+  uint32_t* parent = b.parent.ensure(2 * (size_t) n);
+  uint32_t* flags = b.flags.ensure(n_int);
+  int4* root_d = b.root_box_d.ensure(1);
+
+  k_leaf_fill<<<div_up(n, T), T, 0, st>>>(m, base, n, leaf_size, imin, rec_u, box_u, ka, va);
+  // 2 x 32 bits of Morton code: the top bit pair is always 0 for a 47-bit
+  // range >> 15, so 62 key bits suffice
+  sort_pairs_u64_u32(ka, kb, va, vb, n, 0, 64, b.sort_tmp, st);
+  k_leaf_gather<<<div_up(n, T), T, 0, st>>>(vb, n, rec_u, box_u, rec_s, box_s);
+  if (n == 1) {
+    k_single_leaf_root<<<1, 1, 0, st>>>(box_s, nbox, nchild, root_d);
+  } else {
+    RJB_CUDA(cudaMemsetAsync(flags, 0, n_int * sizeof(uint32_t), st));
+    k_karras<<<div_up(n - 1, T), T, 0, st>>>(kb, n, nchild, parent);
+    k_refit<<<div_up(n, T), T, 0, st>>>(box_s, n, nchild, parent, nbox, flags, root_d);
+  }
+  RJB_CUDA(cudaGetLastError());
+  RJB_CUDA(cudaMemcpyAsync(&b.root_box, root_d, sizeof(int4), cudaMemcpyDeviceToHost, st));
+  RJB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace rjb

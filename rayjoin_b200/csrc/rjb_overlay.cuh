@@ -1,0 +1,309 @@
+// Polygon overlay: MapOverlay protocol on top of the LSI / PIP kernels, and the
+// host writer of the output chains.
+//
+// Replaces MapOverlay{LBVH,Grid}::{Init,BuildIndex,IntersectEdge,
+// LocateVerticesInOtherMap,ComputeOutputPolygons,WriteResult}
+// (reference: src/app/map_overlay_lbvh.h:25-270, src/run_overlay.cu:196-226)
+// and WriteOutputChain (src/app/output_chain.h:41-205).
+//
+// Included by rjb_api.cu after rjb_ctx and the do_* helpers are defined.
+#pragma once
+#include <stdio.h>
+
+#include <algorithm>
+#include <map>
+#include <unordered_map>
+#include <utility>
+
+namespace rjb {
+
+// key = eid[im] (high 32 bits) | queue position (low 32 bits)
+__global__ void k_ov_keys(const rjb_xsect* __restrict__ xs, uint32_t n, int im,
+                          uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  key[i] = ((uint64_t) xs[i].eid[im] << 32);
+  val[i] = i;
+}
+
+__global__ void k_ov_gather(const rjb_xsect* __restrict__ xs, const uint32_t* __restrict__ order,
+                            uint32_t n, int im, rjb_xsect* __restrict__ out,
+                            uint32_t* __restrict__ seg_flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rjb_xsect x = xs[order[i]];
+  out[i] = x;
+  uint32_t prev = i ? xs[order[i - 1]].eid[im] : 0xFFFFFFFFu;
+  seg_flag[i] = (i == 0 || prev != x.eid[im]) ? 1u : 0u;
+}
+
+__global__ void k_ov_seg_starts(const uint32_t* __restrict__ seg_flag,
+                                const uint32_t* __restrict__ seg_scan, uint32_t n,
+                                uint32_t* __restrict__ seg_start) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (seg_flag[i]) seg_start[seg_scan[i]] = i;
+  if (i == n - 1) seg_start[seg_scan[i] + seg_flag[i]] = n;
+}
+
+// per intersected edge of map im: order its intersections along the edge
+// (squared distance to p1 in exact integers, src/app/map_overlay_lbvh.h:204-214;
+// ties by the other map's eid for determinism) and emit the integer mid-points
+// of consecutive intersections (:216-228): trunc((x1 + x2) / 2).
+__global__ void k_ov_sort_segments(MapView M, int im, rjb_xsect* __restrict__ xs,
+                                   const uint32_t* __restrict__ seg_start, uint32_t n_segs,
+                                   longlong2* __restrict__ mid_pts) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_segs) return;
+  uint32_t b = seg_start[s], e = seg_start[s + 1];
+  uint32_t n = e - b;
+  if (n < 2) return;
+  uint32_t eid = xs[b].eid[im];
+  longlong2 p1 = M.pts[eid + M.edge_chain[eid]];
+  auto dist = [&](const rjb_xsect& x) {
+    i128 dx = (i128) x.x - p1.x, dy = (i128) x.y - p1.y;
+    return dx * dx + dy * dy;
+  };
+  // insertion sort (segments are short)
+  for (uint32_t i = b + 1; i < e; i++) {
+    rjb_xsect cur = xs[i];
+    i128 dc = dist(cur);
+    uint32_t j = i;
+    while (j > b) {
+      rjb_xsect pv = xs[j - 1];
+      i128 dp = dist(pv);
+      bool less = dc < dp || (dc == dp && cur.eid[1 - im] < pv.eid[1 - im]);
+      if (!less) break;
+      xs[j] = pv;
+      j--;
+    }
+    xs[j] = cur;
+  }
+  for (uint32_t k = 0; k + 1 < n; k++) {
+    const rjb_xsect& a = xs[b + k];
+    const rjb_xsect& c = xs[b + k + 1];
+    longlong2 m;
+    m.x = (a.x + c.x) / 2;  // C division truncates toward zero like the
+    m.y = (a.y + c.y) / 2;  // rational -> double -> int64 path of the reference
+    mid_pts[b + k - s] = m;
+  }
+}
+
+__global__ void k_ov_fill_mid_faces(rjb_xsect* __restrict__ xs, const uint32_t* __restrict__ seg_start,
+                                    uint32_t n_segs, const int32_t* __restrict__ mid_face) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_segs) return;
+  uint32_t b = seg_start[s], e = seg_start[s + 1];
+  for (uint32_t k = 0; b + k + 1 < e; k++) xs[b + k].mid_point_polygon_id = mid_face[b + k - s];
+}
+
+static void overlay_run(rjb_ctx* c, int mode, uint32_t grid_size, double xsect_factor,
+                        double* phase_ms) {
+  RJB_REQUIRE(c->maps[0].loaded && c->maps[1].loaded, "rjb_overlay_run: load both maps first");
+  RJB_REQUIRE(mode == RJB_MODE_LBVH || mode == RJB_MODE_GRID || mode == RJB_MODE_BRUTE,
+              "rjb_overlay_run: unknown mode");
+  OverlayState& ov = c->ov;
+  ov.done = false;
+  cudaStream_t st = c->stream;
+  cudaEvent_t ev[7];
+  for (auto& e : ev) RJB_CUDA(cudaEventCreate(&e));
+  auto mark = [&](int i) { RJB_CUDA(cudaEventRecord(ev[i], st)); };
+  mark(0);
+  // BuildIndex: one index per map, both directions are queried
+  for (int im = 0; im < 2; im++) do_build_index(c, im, mode, grid_size, nullptr);
+  mark(1);
+  // IntersectEdge(0): map 0 is the query side (src/run_overlay.cu:206)
+  uint64_t n = do_lsi(c, 0, mode, xsect_factor, nullptr);
+  ov.n_xsects = n;
+  mark(2);
+  // LocateVerticesInOtherMap(im)
+  for (int im = 0; im < 2; im++) {
+    DeviceMap& Qm = c->maps[im];
+    do_pip(c, im, mode, Qm.pts.p, Qm.n_points, nullptr);
+    uint32_t* ce = ov.closest_eid[im].ensure(Qm.n_points ? Qm.n_points : 1);
+    int32_t* pf = ov.point_in_polygon[im].ensure(Qm.n_points ? Qm.n_points : 1);
+    RJB_CUDA(cudaMemcpyAsync(ce, c->pip_eid.p, Qm.n_points * sizeof(uint32_t),
+                             cudaMemcpyDeviceToDevice, st));
+    RJB_CUDA(cudaMemcpyAsync(pf, c->pip_face.p, Qm.n_points * sizeof(int32_t),
+                             cudaMemcpyDeviceToDevice, st));
+    mark(3 + im);
+  }
+  // ComputeOutputPolygons
+  for (int im = 0; im < 2; im++) {
+    rjb_xsect* sorted = ov.xsects_sorted[im].ensure(n ? n : 1);
+    ov.n_segs[im] = 0;
+    if (n == 0) continue;
+    uint32_t n32 = (uint32_t) n;
+    uint64_t* ka = ov.keys_a.ensure(n);
+    uint64_t* kb = ov.keys_b.ensure(n);
+    uint32_t* va = ov.vals_a.ensure(n);
+    uint32_t* vb = ov.vals_b.ensure(n);
+    uint32_t* flag = ov.seg_flag.ensure(n + 1);
+    uint32_t* scan = ov.seg_scan.ensure(n + 1);
+    k_ov_keys<<<div_up(n, 256), 256, 0, st>>>(c->xsects.p, n32, im, ka, va);
+    sort_pairs_u64_u32(ka, kb, va, vb, n32, 32, 64, ov.sort_tmp, st);
+    k_ov_gather<<<div_up(n, 256), 256, 0, st>>>(c->xsects.p, vb, n32, im, sorted, flag);
+    exclusive_scan_u32(flag, scan, n32, ov.scan_tmp, st);
+    uint32_t n_segs = 0;
+    RJB_CUDA(cudaMemcpyAsync(&n_segs, scan + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    RJB_CUDA(cudaStreamSynchronize(st));
+    ov.n_segs[im] = n_segs;
+    uint32_t* seg_start = ov.seg_start[im].ensure(n_segs + 1);
+    k_ov_seg_starts<<<div_up(n, 256), 256, 0, st>>>(flag, scan, n32, seg_start);
+    uint32_t n_mid = n32 - n_segs;
+    longlong2* mid = ov.mid_pts.ensure(n_mid ? n_mid : 1);
+    k_ov_sort_segments<<<div_up(n_segs, 128), 128, 0, st>>>(c->maps[im].view(), im, sorted,
+                                                            seg_start, n_segs, mid);
+    RJB_CUDA(cudaGetLastError());
+    // mid-points are located in the OTHER map with query_map_id = im
+    // (src/app/map_overlay_lbvh.h:233-236)
+    do_pip(c, im, mode, mid, n_mid, nullptr);
+    k_ov_fill_mid_faces<<<div_up(n_segs, 128), 128, 0, st>>>(sorted, seg_start, n_segs,
+                                                             c->pip_face.p);
+    RJB_CUDA(cudaGetLastError());
+  }
+  mark(5);
+  RJB_CUDA(cudaStreamSynchronize(st));
+  if (phase_ms) {
+    float ms;
+    for (int i = 0; i < 5; i++) {
+      RJB_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      phase_ms[i] = ms;
+    }
+    RJB_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[5]));
+    phase_ms[5] = ms;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  ov.done = true;
+}
+
+// ---------------------------------------------------------------------------
+// host writer
+// ---------------------------------------------------------------------------
+struct P2 {
+  double x, y;
+  bool operator==(const P2& o) const { return x == o.x && y == o.y; }
+};
+struct P2Hash {
+  size_t operator()(const P2& p) const {
+    uint64_t a, b;
+    memcpy(&a, &p.x, 8);
+    memcpy(&b, &p.y, 8);
+    return (size_t) (a * 0x9E3779B97F4A7C15ull ^ (b + 0x7F4A7C15ull + (a << 6) + (a >> 2)));
+  }
+};
+
+struct OutChain {
+  std::vector<P2> pts;
+  int64_t left, right, other;
+  uint32_t first_pid, last_pid;
+};
+
+static void overlay_write(rjb_ctx* c, const char* path) {
+  OverlayState& ov = c->ov;
+  RJB_REQUIRE(ov.done, "rjb_overlay_write: run rjb_overlay_run first");
+  const rjb_scaling& sc = c->sc;
+  std::vector<OutChain> out;
+  OutChain cur;
+  // flush(): keep a piece iff one of its own faces and the other map's face
+  // are both non-exterior (src/app/output_chain.h:56-76)
+  auto flush = [&]() {
+    if (cur.pts.empty()) return;
+    if (cur.left * cur.other != 0 || cur.right * cur.other != 0) {
+      cur.pts.erase(std::unique(cur.pts.begin(), cur.pts.end()), cur.pts.end());
+      out.push_back(cur);
+    }
+    cur.pts.clear();
+  };
+  // host Unscale (src/map/scaling.h:100-106) without FMA contraction
+  auto unscale = [&](const rjb_xsect& x) {
+    volatile double tx = (double) x.x * sc.rrx, ty = (double) x.y * sc.rry;
+    P2 p = {tx + sc.ddeltax, ty + sc.ddeltay};
+    return p;
+  };
+  for (int im = 0; im < 2; im++) {
+    DeviceMap& m = c->maps[im];
+    uint64_t n = ov.n_xsects;
+    std::vector<rjb_xsect> xs(n);
+    std::vector<int32_t> pip(m.n_points);
+    if (n)
+      RJB_CUDA(cudaMemcpy(xs.data(), ov.xsects_sorted[im].p, n * sizeof(rjb_xsect),
+                          cudaMemcpyDeviceToHost));
+    if (m.n_points)
+      RJB_CUDA(cudaMemcpy(pip.data(), ov.point_in_polygon[im].p, m.n_points * sizeof(int32_t),
+                          cudaMemcpyDeviceToHost));
+    // xs is sorted by eid[im]: group = contiguous run
+    std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> groups;
+    for (uint64_t i = 0; i < n;) {
+      uint64_t j = i;
+      while (j < n && xs[j].eid[im] == xs[i].eid[im]) j++;
+      groups[xs[i].eid[im]] = std::make_pair((uint32_t) i, (uint32_t) j);
+      i = j;
+    }
+    for (uint32_t ic = 0; ic < m.n_chains; ic++) {
+      uint32_t pb = m.h_row_index[ic], pe = m.h_row_index[ic + 1];
+      cur.pts.clear();
+      cur.left = m.h_left[ic];
+      cur.right = m.h_right[ic];
+      for (uint32_t pid = pb; pid < pe; pid++) {
+        cur.other = pip[pid];
+        P2 p = {m.h_xy[2 * (size_t) pid], m.h_xy[2 * (size_t) pid + 1]};
+        cur.pts.push_back(p);
+        if (pid != pe - 1) {
+          auto it = groups.find(pid - ic);
+          if (it != groups.end()) {
+            uint32_t b = it->second.first, e = it->second.second;
+            cur.pts.push_back(unscale(xs[b]));
+            for (uint32_t k = b; k + 1 < e; k++) {
+              flush();
+              cur.other = xs[k].mid_point_polygon_id;
+              cur.pts.push_back(unscale(xs[k]));
+              cur.pts.push_back(unscale(xs[k + 1]));
+            }
+            flush();
+            cur.pts.push_back(unscale(xs[e - 1]));
+          }
+        }
+      }
+      flush();
+    }
+  }
+  // face pairs and point ids by first appearance (output_chain.h:141-182)
+  std::map<std::pair<int64_t, int64_t>, size_t> face_ids;
+  std::unordered_map<P2, uint32_t, P2Hash> point_ids;
+  uint32_t point_counter = 0;
+  auto create_polygon = [&](int64_t a, int64_t b) -> size_t {
+    if (a == 0 || b == 0) return 0;
+    auto k = std::make_pair(a, b);
+    auto it = face_ids.find(k);
+    if (it == face_ids.end()) {
+      size_t id = face_ids.size() + 1;
+      face_ids[k] = id;
+      return id;
+    }
+    return it->second;
+  };
+  for (auto& ch : out) {
+    ch.left = ch.left < ch.other ? (int64_t) create_polygon(ch.left, ch.other)
+                                 : (int64_t) create_polygon(ch.other, ch.left);
+    ch.right = ch.right < ch.other ? (int64_t) create_polygon(ch.right, ch.other)
+                                   : (int64_t) create_polygon(ch.other, ch.right);
+    for (const P2& p : ch.pts)
+      if (point_ids.find(p) == point_ids.end()) point_ids[p] = point_counter++;
+    ch.first_pid = point_ids[ch.pts.front()];
+    ch.last_pid = point_ids[ch.pts.back()];
+  }
+  FILE* f = fopen(path, "w");
+  if (!f) throw Error(RJB_ERR_IO, std::string("Cannot open ") + path);
+  std::vector<char> buf(1 << 20);
+  setvbuf(f, buf.data(), _IOFBF, buf.size());
+  for (size_t i = 0; i < out.size(); i++) {
+    const OutChain& ch = out[i];
+    fprintf(f, "%zu %zu %u %u %lld %lld\n", i + 1, ch.pts.size(), ch.first_pid, ch.last_pid,
+            (long long) ch.left, (long long) ch.right);
+    for (const P2& p : ch.pts) fprintf(f, "%.6f %.6f\n", p.x, p.y);
+  }
+  fclose(f);
+}
+
+}  // namespace rjb

@@ -1,0 +1,285 @@
+// CDB chain files: text parser, .bin cache, load_from.  Host C++ only.
+//
+// Behaviour-compatible with the reference loader
+// (src/map/planar_graph.h:41-126 read_pgraph, :128-167 serialize_pgraph,
+//  :169-220 deserialize_pgraph, :222-252 load_from):
+//   * lines that are empty or start with '#' or '%' are skipped (:58);
+//   * a chain header is `id np first last left right`, followed by np lines
+//     `x y`; np < 2 and two consecutive identical points are errors (:71,85);
+//   * row_index gets one entry per chain plus a final one unless the graph is
+//     empty (:102-104); the bounding box covers every point (:88-91);
+//   * <prefix>/<path with '/' -> '-'>.bin is read when readable, else the text
+//     is parsed and the .bin written when the prefix is writable (:222-252);
+//   * .bin layout: u64 0xabcdabcd, n_chains, n_row_index, n_points; per chain
+//     5 x i64; row_index as u32; points as double x,y; bbox min_x,min_y,max_x,
+//     max_y; u64 0xabcdabcd (:129-167).
+// The parser itself is new: one pass over a memory-mapped buffer with
+// strtod/strtoll instead of an istringstream per line.
+#include <errno.h>
+#include <fcntl.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "rjb200.h"
+
+namespace {
+
+struct GraphOwner {
+  std::vector<int64_t> chain_id, first_point, last_point, left, right;
+  std::vector<uint32_t> row_index;
+  std::vector<double> xy;
+  double min_x = std::numeric_limits<double>::max();
+  double min_y = std::numeric_limits<double>::max();
+  double max_x = -std::numeric_limits<double>::max();
+  double max_y = -std::numeric_limits<double>::max();
+};
+
+}  // namespace
+extern "C" void rjb__set_error(const char* msg);  // rjb_api.cu
+namespace {
+
+void publish(GraphOwner* o, rjb_graph* g) {
+  g->n_chains = o->chain_id.size();
+  g->n_points = o->xy.size() / 2;
+  g->chain_id = o->chain_id.data();
+  g->first_point = o->first_point.data();
+  g->last_point = o->last_point.data();
+  g->left = o->left.data();
+  g->right = o->right.data();
+  g->row_index = o->row_index.data();
+  g->xy = o->xy.data();
+  g->min_x = o->min_x;
+  g->min_y = o->min_y;
+  g->max_x = o->max_x;
+  g->max_y = o->max_y;
+  g->_owner = o;
+}
+
+int fail(const std::string& msg) {
+  rjb__set_error(msg.c_str());
+  return RJB_ERR_IO;
+}
+
+int read_text(const char* path, GraphOwner* o) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(std::string("Cannot open file ") + path);
+  struct stat sb;
+  if (fstat(fd, &sb) != 0) {
+    close(fd);
+    return fail(std::string("Cannot stat file ") + path);
+  }
+  size_t len = (size_t) sb.st_size;
+  std::vector<char> buf(len + 1);
+  size_t got = 0;
+  while (got < len) {
+    ssize_t r = read(fd, buf.data() + got, len - got);
+    if (r <= 0) break;
+    got += (size_t) r;
+  }
+  close(fd);
+  if (got != len) return fail(std::string("Short read on ") + path);
+  buf[len] = '\0';
+
+  int64_t np = 0;
+  bool have_last = false;
+  double last_x = 0, last_y = 0;
+  size_t lno = 0;
+  char* p = buf.data();
+  char* end = p + len;
+  while (p < end) {
+    char* eol = (char*) memchr(p, '\n', (size_t) (end - p));
+    if (!eol) eol = end;
+    lno++;
+    char saved = *eol;
+    *eol = '\0';
+    char* line = p;
+    p = eol + 1;
+    size_t ll = (size_t) (eol - line);
+    if (ll > 0 && line[ll - 1] == '\r') line[ll - 1] = '\0';
+    if (line[0] == '\0' || line[0] == '#' || line[0] == '%') {
+      *eol = saved;
+      continue;
+    }
+    bool bad = false;
+    char* q = line;
+    if (np == 0) {
+      long long v[6];
+      for (int i = 0; i < 6 && !bad; i++) {
+        char* e;
+        errno = 0;
+        v[i] = strtoll(q, &e, 10);
+        if (e == q) bad = true;
+        q = e;
+      }
+      if (!bad) {
+        np = v[1];
+        bad |= np < 2;
+        o->chain_id.push_back(v[0]);
+        o->first_point.push_back(v[2]);
+        o->last_point.push_back(v[3]);
+        o->left.push_back(v[4]);
+        o->right.push_back(v[5]);
+        o->row_index.push_back((uint32_t) (o->xy.size() / 2));
+        have_last = false;
+      }
+    } else {
+      char* e;
+      double x = strtod(q, &e);
+      if (e == q) bad = true;
+      q = e;
+      double y = strtod(q, &e);
+      if (e == q) bad = true;
+      if (!bad) {
+        if (have_last) bad |= (x == last_x && y == last_y);
+        if (x < o->min_x) o->min_x = x;
+        if (x > o->max_x) o->max_x = x;
+        if (y < o->min_y) o->min_y = y;
+        if (y > o->max_y) o->max_y = y;
+        o->xy.push_back(x);
+        o->xy.push_back(y);
+        last_x = x;
+        last_y = y;
+        have_last = true;
+        np--;
+      }
+    }
+    if (bad) {
+      std::string l(line);
+      return fail(std::string("Bad line. Check your dataset! ") + path + "[" + std::to_string(lno) +
+                  "]: " + l);
+    }
+    *eol = saved;
+  }
+  if (!o->xy.empty()) o->row_index.push_back((uint32_t) (o->xy.size() / 2));
+  if (np != 0) return fail(std::string("Truncated chain at end of ") + path);
+  return RJB_OK;
+}
+
+template <typename T>
+bool rd(FILE* f, T& v) {
+  return fread(&v, sizeof(T), 1, f) == 1;
+}
+
+int read_bin(const char* path, GraphOwner* o) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(std::string("Cannot open file ") + path);
+  uint64_t magic = 0, n_chains = 0, n_row = 0, n_points = 0;
+  bool ok = rd(f, magic) && magic == 0xabcdabcdull && rd(f, n_chains) && rd(f, n_row) &&
+            rd(f, n_points);
+  if (ok) {
+    o->chain_id.resize(n_chains);
+    o->first_point.resize(n_chains);
+    o->last_point.resize(n_chains);
+    o->left.resize(n_chains);
+    o->right.resize(n_chains);
+    o->row_index.resize(n_row);
+    o->xy.resize(2 * n_points);
+    for (uint64_t i = 0; i < n_chains && ok; i++)
+      ok = rd(f, o->chain_id[i]) && rd(f, o->first_point[i]) && rd(f, o->last_point[i]) &&
+           rd(f, o->left[i]) && rd(f, o->right[i]);
+    if (ok && n_row) ok = fread(o->row_index.data(), sizeof(uint32_t), n_row, f) == n_row;
+    if (ok && n_points) ok = fread(o->xy.data(), 2 * sizeof(double), n_points, f) == n_points;
+    ok = ok && rd(f, o->min_x) && rd(f, o->min_y) && rd(f, o->max_x) && rd(f, o->max_y);
+    ok = ok && rd(f, magic) && magic == 0xabcdabcdull;
+  }
+  fclose(f);
+  if (!ok) return fail(std::string("Corrupt .bin graph ") + path);
+  return RJB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rjb_graph_read_text(const char* path, rjb_graph* out) {
+  if (!path || !out) return RJB_ERR_INVALID;
+  GraphOwner* o = new GraphOwner();
+  int rc = read_text(path, o);
+  if (rc != RJB_OK) {
+    delete o;
+    return rc;
+  }
+  publish(o, out);
+  return RJB_OK;
+}
+
+int rjb_graph_read_bin(const char* path, rjb_graph* out) {
+  if (!path || !out) return RJB_ERR_INVALID;
+  GraphOwner* o = new GraphOwner();
+  int rc = read_bin(path, o);
+  if (rc != RJB_OK) {
+    delete o;
+    return rc;
+  }
+  publish(o, out);
+  return RJB_OK;
+}
+
+int rjb_graph_write_bin(const rjb_graph* g, const char* path) {
+  if (!g || !path) return RJB_ERR_INVALID;
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(std::string("Cannot open ") + path);
+  uint64_t magic = 0xabcdabcdull, n_chains = g->n_chains, n_points = g->n_points;
+  uint64_t n_row = n_points ? n_chains + 1 : 0;
+  fwrite(&magic, 8, 1, f);
+  fwrite(&n_chains, 8, 1, f);
+  fwrite(&n_row, 8, 1, f);
+  fwrite(&n_points, 8, 1, f);
+  for (uint64_t i = 0; i < n_chains; i++) {
+    fwrite(&g->chain_id[i], 8, 1, f);
+    fwrite(&g->first_point[i], 8, 1, f);
+    fwrite(&g->last_point[i], 8, 1, f);
+    fwrite(&g->left[i], 8, 1, f);
+    fwrite(&g->right[i], 8, 1, f);
+  }
+  if (n_row) fwrite(g->row_index, sizeof(uint32_t), n_row, f);
+  if (n_points) fwrite(g->xy, 2 * sizeof(double), n_points, f);
+  fwrite(&g->min_x, 8, 1, f);
+  fwrite(&g->min_y, 8, 1, f);
+  fwrite(&g->max_x, 8, 1, f);
+  fwrite(&g->max_y, 8, 1, f);
+  fwrite(&magic, 8, 1, f);
+  bool ok = ferror(f) == 0;
+  ok = (fclose(f) == 0) && ok;
+  return ok ? RJB_OK : fail(std::string("Write failed: ") + path);
+}
+
+int rjb_graph_load(const char* path, const char* serialize_prefix, rjb_graph* out) {
+  if (!path || !out) return RJB_ERR_INVALID;
+  std::string prefix = serialize_prefix ? serialize_prefix : "";
+  std::string escaped(path);
+  for (char& ch : escaped)
+    if (ch == '/') ch = '-';
+  if (!prefix.empty()) {
+    struct stat sb;
+    if (stat(prefix.c_str(), &sb) != 0) {
+      if (errno == ENOENT) {
+        if (mkdir(prefix.c_str(), 0755) != 0) return fail("Cannot create dir " + prefix);
+      } else {
+        return fail("Cannot open dir " + prefix);
+      }
+    }
+  }
+  std::string ser = prefix + "/" + escaped + ".bin";
+  if (access(ser.c_str(), R_OK) == 0) return rjb_graph_read_bin(ser.c_str(), out);
+  int rc = rjb_graph_read_text(path, out);
+  if (rc != RJB_OK) return rc;
+  if (!prefix.empty() && access(prefix.c_str(), W_OK) == 0) rjb_graph_write_bin(out, ser.c_str());
+  return RJB_OK;
+}
+
+void rjb_graph_free(rjb_graph* g) {
+  if (!g || !g->_owner) return;
+  delete (GraphOwner*) g->_owner;
+  memset(g, 0, sizeof(*g));
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+Bit-exact: pair sets, intersection coordinates, closest edges, face ids."""
+import numpy as np
+import pytest
+
+from helpers import DATASETS, OracleMaps, dataset, sort_xsects
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["brute", "lbvh", "grid"]
+
+
+@pytest.fixture(scope="module")
+def loaded(rjb, oracle):
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            R, S = dataset(name)
+            ctx = rjb.Context([R, S])
+            cache[name] = (ctx, OracleMaps(oracle, [R, S]))
+        return cache[name]
+    yield get
+    for ctx, _ in cache.values():
+        ctx.close()
+
+
+@pytest.mark.parametrize("name", DATASETS)
+def test_scaling_matches_oracle(loaded, name):
+    ctx, om = loaded(name)
+    s = ctx.get_scaling()
+    for f in ("rx", "ry", "rrx", "rry", "deltax", "deltay", "ddeltax", "ddeltay"):
+        assert getattr(s, f) == getattr(om.sc, f), f
+    for im in range(2):
+        assert np.array_equal(ctx.map_points(im), om.pts[im])
+
+
+@pytest.mark.parametrize("q", [1, 0])
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", DATASETS)
+def test_lsi_pair_set_and_points(rjb, loaded, name, mode, q):
+    ctx, om = loaded(name)
+    ctx.build_index(1 - q, mode, grid_size=64)
+    lsi = rjb.LSI(ctx, mode)
+    lsi.Init(4.0)
+    n = lsi.Query(q)
+    got = sort_xsects(lsi.get_xsects(), q)
+    want = om.lsi(q)
+    assert n == len(want[0])
+    for g, w, what in zip(got, want, ("eid_query", "eid_base", "x", "y")):
+        assert np.array_equal(g, w), what
+    assert lsi.n_candidates >= n
+
+
+@pytest.mark.parametrize("leaf", [1, 2, 8])
+def test_lsi_lbvh_leaf_sizes_and_sorted_queries(rjb, loaded, leaf):
+    ctx, om = loaded("shared")
+    ctx.set_option("lbvh_leaf_size", leaf)
+    ctx.set_option("sort_queries", leaf % 2)
+    try:
+        ctx.build_index(0, "lbvh")
+        lsi = rjb.LSI(ctx, "lbvh")
+        lsi.Init(4.0)
+        lsi.Query(1)
+        got = sort_xsects(lsi.get_xsects(), 1)
+        for g, w in zip(got, om.lsi(1)):
+            assert np.array_equal(g, w)
+    finally:
+        ctx.set_option("lbvh_leaf_size", 4)
+        ctx.set_option("sort_queries", 0)
+
+
+def test_lsi_queue_overflow_is_detected(rjb, loaded):
+    ctx, om = loaded("voronoi")
+    ctx.build_index(0, "lbvh")
+    want = len(om.lsi(1)[0])
+    lsi = rjb.LSI(ctx, "lbvh")
+    lsi.Init(1e-4)  # far too small
+    with pytest.raises(rjb.RjbError) as ei:
+        lsi.Query(1)
+    assert ei.value.code == 3
+    assert ei.value.needed == want
+
+
+@pytest.mark.parametrize("q", [1, 0])
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", DATASETS)
+def test_pip_vertices_of_other_map(rjb, loaded, name, mode, q):
+    """PIP of every vertex of map q in map 1-q (what overlay and query_exec -poly2 do)."""
+    ctx, om = loaded(name)
+    ctx.build_index(1 - q, mode, grid_size=64)
+    pip = rjb.PIP(ctx, mode)
+    pip.Query(q)
+    eids = pip.get_closest_eids()
+    want = om.pip(q, om.pts[q])
+    assert np.array_equal(eids, want)
+    assert np.array_equal(pip.get_face_ids(), om.faces(q, want))
+
+
+@pytest.mark.parametrize("mode", ["lbvh", "grid"])
+def test_pip_random_points_sorted(rjb, loaded, mode):
+    ctx, om = loaded("voronoi")
+    rng = np.random.default_rng(7)
+    s = om.sc
+    pts = rng.integers(s.imin // 2, s.imax // 2, size=(20000, 2))
+    ctx.set_option("sort_queries", 1)
+    try:
+        ctx.build_index(0, mode, grid_size=128)
+        pip = rjb.PIP(ctx, mode)
+        pip.Query(1, pts)
+        assert np.array_equal(pip.get_closest_eids(), om.pip(1, pts))
+    finally:
+        ctx.set_option("sort_queries", 0)
+
+
+def test_oracle_brute_equals_grid_filter(oracle):
+    """the oracle's own filter loses nothing (CPU only, but cheap enough to keep here)"""
+    for name in ("lattice", "shared"):
+        R, S = dataset(name)
+        om = OracleMaps(oracle, [R, S])
+        for q in (0, 1):
+            for a, b in zip(om.lsi(q, brute=True), om.lsi(q)):
+                assert np.array_equal(a, b)
+            assert np.array_equal(om.pip(q, om.pts[q], brute=True), om.pip(q, om.pts[q]))
+
+
+def test_empty_query_map(rjb, oracle):
+    R, _ = dataset("tiny")
+    from rayjoin_b200.capi import PlanarGraph
+    E = PlanarGraph(np.zeros((0, 2)), np.zeros(0, np.uint32), [], [], bbox=R.bbox)
+    ctx = rjb.Context([R, E], bbox=R.bbox)
+    ctx.build_index(0, "lbvh")
+    lsi = rjb.LSI(ctx, "lbvh")
+    lsi.Init(1.0)
+    assert lsi.Query(1) == 0
+    ctx.close()
+
+
+def test_query_without_index_fails(rjb):
+    R, S = dataset("tiny")
+    ctx = rjb.Context([R, S])
+    lsi = rjb.LSI(ctx, "lbvh")
+    with pytest.raises(rjb.RjbError) as ei:
+        lsi.Query(1)
+    assert ei.value.code == 5
+    ctx.close()
