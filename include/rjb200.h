@@ -126,7 +126,9 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
 
 /* tuning knobs that have no RayJoin flag (defaults are fine):
  *   "lbvh_leaf_size"  edges per LBVH leaf, 1..8 (default 4)
- *   "sort_queries"    1 = visit query edges / points in Morton order       */
+ *   "sort_queries"    1 = visit query edges / points in Morton order
+ *   "keep_host_graph" 0 = rjb_set_map keeps no host copy of the source graph
+ *                     (saves a memcpy; rjb_overlay_write then refuses)     */
 int rjb_set_option(rjb_ctx* ctx, const char* name, int64_t value);
 
 /* ---- LSI ------------------------------------------------------------------
@@ -185,6 +187,12 @@ int rjb_overlay_write(rjb_ctx* ctx, const char* path);
  * out[1] = intersection-point pass.  Replaces the reference's Stopwatch /
  * -profile sub-stage timers (src/util/stopwatch.h).                            */
 int rjb_last_kernel_ms(const rjb_ctx* ctx, double out[2]);
+/* raw counters of the last query: [0] results, [1] candidates; with option
+ * "stats" = 1 also traversal statistics ([2] node visits, [3] leaf visits,
+ * [4] single-child prefix visits, [5] lane-level leaf tests, [6] warps that
+ * reached a leaf, [7] deepest stack).  Replaces the reference's Debug-build
+ * "Total tests" / "Visited nodes" counters (src/app/lsi_lbvh.h:37-42,83-96).   */
+int rjb_last_stats(const rjb_ctx* ctx, uint64_t out[8]);
 /* index of map_id: out[0] = leaves (LBVH) / edge-cell incidences (grid),
  * out[1] = bytes of the index, out[2] = leaf size / grid size, out[3] = 0      */
 int rjb_index_info(const rjb_ctx* ctx, int map_id, int mode, uint64_t out[4]);

@@ -188,3 +188,19 @@ def face_ids(xyb, b_p1, b_chain, left, right, eids):
     lib().orc_face_ids(_p(xyb), _p(b_p1), _p(b_chain), _p(left), _p(right), _p(eids),
                        C.c_uint64(len(eids)), _p(out))
     return out
+
+
+def ref_scaling_apply(bbox, xy, ixy):
+    """Reference Scaling<double> on the host (no FMA): ScaleX/Y of xy, UnscaleX/Y of ixy."""
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(_REF_LSI)
+    bbox = np.ascontiguousarray(bbox, dtype=np.float64)
+    xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+    ixy = _i64(ixy).reshape(-1, 2)
+    scaled = np.empty(xy.shape, np.int64)
+    unscaled = np.empty(ixy.shape, np.float64)
+    limits = np.zeros(3, np.int64)
+    _ref.ref_scaling_apply(_p(bbox), _p(xy), C.c_uint64(len(xy)), _p(scaled), _p(ixy),
+                           C.c_uint64(len(ixy)), _p(unscaled), _p(limits))
+    return scaled, unscaled, limits

@@ -18,6 +18,7 @@
 
 #include "config.h"
 #include "algo/lsi.h"
+#include "map/scaling.h"
 
 namespace {
 struct Pt {
@@ -70,4 +71,31 @@ extern "C" void ref_intersect_batch(const int64_t* pts, uint64_t n,
       }
     }
   }
+}
+
+// Scaling<double> of the reference (src/map/scaling.h:32-136) evaluated on the
+// host: constants {rx, ry, rrx, rry, deltax, deltay, ddeltax, ddeltay} via
+// Unscale/Scale probes are not accessible (private), so the pin exposes the
+// observable behaviour: ScaleX/ScaleY (host arithmetic, no FMA) and
+// UnscaleX/UnscaleY of caller-provided values.
+extern "C" void ref_scaling_apply(const double* bbox, const double* xy, uint64_t n,
+                                  int64_t* scaled, const int64_t* ixy, uint64_t m,
+                                  double* unscaled, int64_t* limits) {
+  rayjoin::BoundingBox<double> bb;
+  bb.min_x = bbox[0];
+  bb.min_y = bbox[1];
+  bb.max_x = bbox[2];
+  bb.max_y = bbox[3];
+  rayjoin::Scaling<double> s(bb);
+  for (uint64_t i = 0; i < n; i++) {
+    scaled[2 * i] = s.ScaleX(xy[2 * i]);
+    scaled[2 * i + 1] = s.ScaleY(xy[2 * i + 1]);
+  }
+  for (uint64_t i = 0; i < m; i++) {
+    unscaled[2 * i] = s.UnscaleX(ixy[2 * i]);
+    unscaled[2 * i + 1] = s.UnscaleY(ixy[2 * i + 1]);
+  }
+  limits[0] = s.get_internal_min();
+  limits[1] = s.get_internal_max();
+  limits[2] = s.get_internal_range();
 }

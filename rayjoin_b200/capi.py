@@ -23,7 +23,7 @@ EXPORTS = [
     "rjb_set_bounding_box", "rjb_get_scaling", "rjb_set_map", "rjb_map_info",
     "rjb_map_device_views", "rjb_build_index", "rjb_set_option", "rjb_lsi", "rjb_pip",
     "rjb_pip_host", "rjb_overlay_run", "rjb_overlay_results", "rjb_overlay_write",
-    "rjb_last_kernel_ms", "rjb_index_info", "rjb_copy_to_host", "rjb_sync",
+    "rjb_last_kernel_ms", "rjb_last_stats", "rjb_index_info", "rjb_copy_to_host", "rjb_sync",
     "rjb_graph_load", "rjb_graph_read_text", "rjb_graph_read_bin", "rjb_graph_write_bin",
     "rjb_graph_free",
 ]
@@ -279,6 +279,11 @@ class Context:
         out = (C.c_double * 2)()
         _check(self.lib.rjb_last_kernel_ms(self._h, out))
         return out[0], out[1]
+
+    def last_stats(self):
+        out = (C.c_uint64 * 8)()
+        _check(self.lib.rjb_last_stats(self._h, out))
+        return list(out)
 
     def copy_to_host(self, d_ptr, out):
         if out.nbytes:

@@ -73,6 +73,9 @@ struct rjb_ctx {
   DeviceMap maps[2];
   int leaf_size = 4;
   int sort_queries = 0;
+  int stats = 0;  // collect traversal statistics (slower)
+  unsigned long long last_stats[8] = {0};
+  int keep_host_graph = 1;  // overlay writer needs the source coordinates
   // LSI result queue
   DBuf<uint2> pairs;
   DBuf<rjb_xsect> xsects;
@@ -240,10 +243,10 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
   uint32_t cap = (uint32_t) cap64;
   uint2* pairs = c->pairs.ensure(cap ? cap : 1);
   rjb_xsect* xs = c->xsects.ensure(cap ? cap : 1);
-  unsigned long long* ctr = c->counters.ensure(2);
+  unsigned long long* ctr = c->counters.ensure(8);
   ensure_events(c);
   MapView Q = Qm.view(), B = Bm.view();
-  RJB_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), c->stream));
+  RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
   const uint32_t* order = nullptr;
   RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
   if (Q.n_edges > 0 && B.n_edges > 0) {
@@ -252,8 +255,12 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
       order = query_order_edges(c, Q);
       RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
       unsigned blocks = div_up(Q.n_edges, kLsiWarps * 32);
-      k_lsi_bvh<<<blocks, kLsiWarps * 32, 0, c->stream>>>(Q, B, Bm.bvh.view(), order, pairs, cap,
-                                                          (unsigned int*) ctr, ctr + 1);
+      if (c->stats)
+        k_lsi_bvh<true><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
+            Q, B, Bm.bvh.view(), order, pairs, cap, (unsigned int*) ctr, ctr + 1);
+      else
+        k_lsi_bvh<false><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
+            Q, B, Bm.bvh.view(), order, pairs, cap, (unsigned int*) ctr, ctr + 1);
     } else if (mode == RJB_MODE_GRID) {
       if (!Bm.grid.built) throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no grid on the base map");
       lsi_grid(Bm.grid, Q, B, pairs, cap, (unsigned int*) ctr, ctr + 1, c->stream);
@@ -272,9 +279,10 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
                                                                (const unsigned int*) ctr, cap, xs);
   RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
   RJB_CUDA(cudaGetLastError());
-  unsigned long long h[2];
+  unsigned long long h[8];
   RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   RJB_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(c->last_stats, h, sizeof(h));
   RJB_CUDA(cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]));
   RJB_CUDA(cudaEventElapsedTime(&c->last_ms[1], c->ev[1], c->ev[2]));
   uint64_t n = (uint32_t) h[0];
@@ -294,9 +302,9 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
   RJB_REQUIRE(Bm.loaded, "rjb_pip: base map not loaded");
   uint32_t* eid = c->pip_eid.ensure(n ? n : 1);
   int32_t* face = c->pip_face.ensure(n ? n : 1);
-  unsigned long long* ctr = c->counters.ensure(2);
+  unsigned long long* ctr = c->counters.ensure(8);
   ensure_events(c);
-  RJB_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), c->stream));
+  RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
   MapView B = Bm.view();
   RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
   if (n > 0) {
@@ -402,6 +410,10 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
       c->leaf_size = (int) value;
     } else if (n == "sort_queries") {
       c->sort_queries = value != 0;
+    } else if (n == "stats") {
+      c->stats = value != 0;
+    } else if (n == "keep_host_graph") {
+      c->keep_host_graph = value != 0;
     } else {
       throw Error(RJB_ERR_INVALID, "rjb_set_option: unknown option " + n);
     }
@@ -438,8 +450,13 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
       m.h_left[i] = (int32_t) left[i];
       m.h_right[i] = (int32_t) right[i];
     }
-    m.h_xy.assign(xy, xy + 2 * n_points);
-    m.h_row_index.assign(row_index, row_index + (n_chains ? n_chains + 1 : 0));
+    if (c->keep_host_graph) {
+      m.h_xy.assign(xy, xy + 2 * n_points);
+      m.h_row_index.assign(row_index, row_index + (n_chains ? n_chains + 1 : 0));
+    } else {
+      m.h_xy.clear();
+      m.h_row_index.clear();
+    }
     double2* raw = m.raw.ensure(n_points ? n_points : 1);
     longlong2* pts = m.pts.ensure(n_points ? n_points + 1 : 1);
     uint32_t* ri = m.row_index.ensure(n_chains + 1);
@@ -576,6 +593,16 @@ int rjb_last_kernel_ms(const rjb_ctx* c, double out[2]) {
     RJB_REQUIRE(c && out, "NULL argument");
     out[0] = c->last_ms[0];
     out[1] = c->last_ms[1];
+  });
+}
+
+/* raw device counters of the last query: [0] results, [1] candidates, and with
+ * option "stats" = 1: [2] node visits, [3] leaf visits, [4] single-child prefix
+ * visits, [5] lane-level leaf tests, [6] warps that reached a leaf, [7] max stack */
+int rjb_last_stats(const rjb_ctx* c, uint64_t out[8]) {
+  return guarded([&] {
+    RJB_REQUIRE(c && out, "NULL argument");
+    for (int i = 0; i < 8; i++) out[i] = c->last_stats[i];
   });
 }
 

@@ -42,6 +42,7 @@ static __device__ __forceinline__ void emit_pair(bool found, uint32_t q, uint32_
 // ever diverges in the traversal loop and the stack is a single warp-shared
 // array in shared memory.  `order` (optional) maps slot -> query eid so that
 // the 32 edges of a warp are spatial neighbours.
+template <bool kStats>
 __global__ void __launch_bounds__(kLsiWarps * 32)
 k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
           uint2* __restrict__ out, uint32_t cap, unsigned int* counter,
@@ -61,6 +62,10 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
                    quant(max(q.x1, q.x2)), quant(max(q.y1, q.y2)));
   }
   unsigned long long cand = 0;
+  // traversal statistics (kStats only): node visits, leaf visits, length of the
+  // initial single-child descent, lane-level leaf tests, deepest stack
+  unsigned st_nodes = 0, st_leaves = 0, st_prefix = 0, st_lane_leaf = 0, st_maxsp = 0;
+  bool st_in_prefix = true;
   if (__ballot_sync(0xffffffffu, box_overlap(qb, bvh.root_box)) != 0) {
     int sp = 0;
     int node = 0;
@@ -71,6 +76,11 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
       const bool hl = box_overlap(qb, lb), hr = box_overlap(qb, rb);
       const unsigned ml = __ballot_sync(0xffffffffu, hl);
       const unsigned mr = __ballot_sync(0xffffffffu, hr);
+      if (kStats) {
+        st_nodes++;
+        bool single = ((ml != 0) != (mr != 0)) && ((ml ? ch.x : ch.y) >= 0);
+        if (st_in_prefix && single) st_prefix++; else st_in_prefix = false;
+      }
       int next = -1;
 #pragma unroll
       for (int side = 0; side < 2; side++) {
@@ -84,6 +94,7 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
         }
         // leaf: the hit lanes test their edge against its <= 8 base edges,
         // whose vertices are one contiguous run of points (uniform loads)
+        if (kStats) { st_leaves++; st_lane_leaf += __popc(m); }
         const uint2 rec = __ldg(&bvh.leaf_rec[~c]);
         const uint32_t first_eid = rec.x, cnt = rec.y >> 28, chain = rec.y & 0x0FFFFFFFu;
         const longlong2* bp = B.pts + (first_eid + chain);
@@ -100,6 +111,7 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
           p1 = p2;
         }
       }
+      if (kStats) st_maxsp = max(st_maxsp, (unsigned) sp);
       if (next >= 0) { node = next; continue; }
       if (sp == 0) break;
       node = stack[--sp];
@@ -109,6 +121,14 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
     if (lane == 0 && cand) atomicAdd(n_cand, cand);
+    if (kStats && lane == 0) {  // n_cand points at counters[1]; stats live at counters[2..7]
+      atomicAdd(n_cand + 1, (unsigned long long) st_nodes);
+      atomicAdd(n_cand + 2, (unsigned long long) st_leaves);
+      atomicAdd(n_cand + 3, (unsigned long long) st_prefix);
+      atomicAdd(n_cand + 4, (unsigned long long) st_lane_leaf);
+      atomicAdd(n_cand + 5, (unsigned long long) (st_leaves ? 1 : 0));
+      atomicMax(n_cand + 6, (unsigned long long) st_maxsp);
+    }
   }
 }
 

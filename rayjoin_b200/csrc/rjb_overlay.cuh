@@ -202,6 +202,9 @@ struct OutChain {
 static void overlay_write(rjb_ctx* c, const char* path) {
   OverlayState& ov = c->ov;
   RJB_REQUIRE(ov.done, "rjb_overlay_write: run rjb_overlay_run first");
+  for (int im = 0; im < 2; im++)
+    RJB_REQUIRE(c->maps[im].h_xy.size() == 2 * (size_t) c->maps[im].n_points,
+                "rjb_overlay_write: maps were loaded with keep_host_graph=0");
   const rjb_scaling& sc = c->sc;
   std::vector<OutChain> out;
   OutChain cur;
