@@ -163,6 +163,12 @@ int rjb_pip(rjb_ctx* ctx, int query_map_id, int mode, const int64_t* d_points_xy
 int rjb_pip_host(rjb_ctx* ctx, int query_map_id, int mode, const double* h_xy,
                  uint64_t n_points, uint32_t* h_closest_eid, int32_t* h_face_id);
 
+/* same, for points the caller already scaled on the HOST (GeneratePIPQueries,
+ * src/run_query.cu:146-167, scales -gen_n random points without FMA)        */
+int rjb_pip_host_scaled(rjb_ctx* ctx, int query_map_id, int mode,
+                        const int64_t* h_points_xy, uint64_t n_points,
+                        uint32_t* h_closest_eid, int32_t* h_face_id);
+
 /* ---- overlay ----------------------------------------------------------------
  * MapOverlay<CTX> protocol (src/app/map_overlay.h:20-30, call order of
  * src/run_overlay.cu:196-226).  rjb_overlay_run performs Init, BuildIndex (both

@@ -22,7 +22,7 @@ EXPORTS = [
     "rjb_last_error", "rjb_version", "rjb_create", "rjb_destroy", "rjb_set_stream",
     "rjb_set_bounding_box", "rjb_get_scaling", "rjb_set_map", "rjb_map_info",
     "rjb_map_device_views", "rjb_build_index", "rjb_set_option", "rjb_lsi", "rjb_pip",
-    "rjb_pip_host", "rjb_overlay_run", "rjb_overlay_results", "rjb_overlay_write",
+    "rjb_pip_host", "rjb_pip_host_scaled", "rjb_overlay_run", "rjb_overlay_results", "rjb_overlay_write",
     "rjb_last_kernel_ms", "rjb_last_stats", "rjb_index_info", "rjb_copy_to_host", "rjb_sync",
     "rjb_graph_load", "rjb_graph_read_text", "rjb_graph_read_bin", "rjb_graph_write_bin",
     "rjb_graph_free",

@@ -586,6 +586,28 @@ int rjb_pip_host(rjb_ctx* c, int query_map_id, int mode, const double* h_xy, uin
   });
 }
 
+int rjb_pip_host_scaled(rjb_ctx* c, int query_map_id, int mode, const int64_t* h_points_xy,
+                        uint64_t n_points, uint32_t* h_closest_eid, int32_t* h_face_id) {
+  return guarded([&] {
+    RJB_REQUIRE(c && (h_points_xy || n_points == 0), "NULL argument");
+    RJB_REQUIRE(n_points < 0xFFFFFFF0ull, "rjb_pip_host_scaled: too many points");
+    RJB_CUDA(cudaSetDevice(c->device));
+    uint32_t n = (uint32_t) n_points;
+    longlong2* pts = c->pip_pts.ensure(n ? n : 1);
+    if (n)
+      RJB_CUDA(cudaMemcpyAsync(pts, h_points_xy, (size_t) n * sizeof(longlong2),
+                               cudaMemcpyHostToDevice, c->stream));
+    do_pip(c, query_map_id, mode, pts, n, nullptr);
+    if (n && h_closest_eid)
+      RJB_CUDA(cudaMemcpyAsync(h_closest_eid, c->pip_eid.p, (size_t) n * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, c->stream));
+    if (n && h_face_id)
+      RJB_CUDA(cudaMemcpyAsync(h_face_id, c->pip_face.p, (size_t) n * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, c->stream));
+    RJB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
 /* device times (ms) of the kernels of the last rjb_lsi / rjb_pip call:
  * out[0] = traversal / cell kernel, out[1] = intersection-point pass */
 int rjb_last_kernel_ms(const rjb_ctx* c, double out[2]) {

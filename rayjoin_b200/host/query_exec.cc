@@ -1,0 +1,207 @@
+// query_exec: flag-compatible stand-in for RayJoin's query_exec
+// (reference src/query.cc:8-58 -> RunLSIQuery / RunPIPQuery, src/run_query.cu:169-463)
+// on top of the C ABI.  Phase names and timer output follow the reference.
+//
+//   query_exec -poly1 R.cdb -poly2 S.cdb -mode=lbvh|grid -query=lsi|pip
+//              [-xsect_factor f] [-grid_size n] [-warmup w] [-repeat r] [-serialize dir]
+//              [-check] [-output file] [-gen_n n -seed s]   (pip without -poly2)
+//
+// Additions over the reference: -output writes the result (LSI: sorted
+// "eid_map0 eid_map1 x y" lines; PIP: one closest eid per line), which the
+// reference parses but never uses (src/query.cc:27); -check also works for LSI
+// (pair set compared against -mode=grid).
+#include <algorithm>
+#include <random>
+
+#include "cli_common.h"
+
+using namespace cli;
+
+static std::vector<rjb_xsect> fetch_xsects(rjb_ctx* ctx, const rjb_xsect* d, uint64_t n) {
+  std::vector<rjb_xsect> h(n);
+  if (n) ok(rjb_copy_to_host(ctx, d, h.data(), n * sizeof(rjb_xsect)), "rjb_copy_to_host");
+  std::sort(h.begin(), h.end(), [](const rjb_xsect& a, const rjb_xsect& b) {
+    return a.eid[0] != b.eid[0] ? a.eid[0] < b.eid[0] : a.eid[1] < b.eid[1];
+  });
+  return h;
+}
+
+static int run_lsi(const Flags& f) {
+  Timer tm;
+  rjb_graph g0{}, g1{};
+  tm.next("Read map 0");
+  load_graph(f.s("poly1"), f.s("serialize"), &g0);
+  if (f.s("poly2").empty()) die("-query=lsi needs -poly2 (generated workloads: use -query=pip)");
+  tm.next("Read map 1");
+  load_graph(f.s("poly2"), f.s("serialize"), &g1);
+  tm.next("Create App");
+  int mode = parse_mode(f.s("mode"));
+  rjb_ctx* ctx = nullptr;
+  ok(rjb_create(f.i("device"), &ctx), "rjb_create");
+  ok(rjb_set_option(ctx, "lbvh_leaf_size", f.i("lbvh_leaf_size")), "rjb_set_option");
+  tm.next("Load Data");
+  set_maps(ctx, &g0, &g1);
+  tm.next("Init");
+  uint64_t ne = (g0.n_points - g0.n_chains) + (g1.n_points - g1.n_chains);
+  std::cerr << "Queue capacity: " << (uint64_t) ((float) ne * (float) f.d("xsect_factor")) << std::endl;
+  tm.next("Build Index");
+  double build_ms = 0;
+  ok(rjb_build_index(ctx, 0, mode, f.i("grid_size"), &build_ms), "rjb_build_index");
+  const rjb_xsect* d = nullptr;
+  uint64_t n = 0, cand = 0;
+  tm.next("Warmup");
+  for (int i = 0; i < f.i("warmup"); i++)
+    ok(rjb_lsi(ctx, 1, mode, f.d("xsect_factor"), &d, &n, &cand), "rjb_lsi");
+  tm.next("Query", std::max(1, f.i("repeat")));
+  for (int i = 0; i < f.i("repeat"); i++)
+    ok(rjb_lsi(ctx, 1, mode, f.d("xsect_factor"), &d, &n, &cand), "rjb_lsi");
+  uint64_t cap = (uint64_t) ((float) ne * (float) f.d("xsect_factor"));
+  std::cerr << "Intersections: " << n << " Queue Load Factor: " << (cap ? (double) n / cap : 0.0)
+            << std::endl;
+  if (f.b("profile")) std::cerr << "Total tests: " << cand << std::endl;
+  std::vector<rjb_xsect> res;
+  if (!f.s("output").empty() || (f.b("check") && mode != RJB_MODE_GRID)) res = fetch_xsects(ctx, d, n);
+  if (!f.s("output").empty()) {
+    tm.next("Write to file");
+    FILE* o = fopen(f.s("output").c_str(), "w");
+    if (!o) die("Cannot open " + f.s("output"));
+    for (auto& x : res)
+      fprintf(o, "%u %u %lld %lld\n", x.eid[0], x.eid[1], (long long) x.x, (long long) x.y);
+    fclose(o);
+  }
+  if (f.b("check") && mode != RJB_MODE_GRID) {
+    tm.next("Check");
+    std::cerr << "Checking LSI Results" << std::endl;
+    ok(rjb_build_index(ctx, 0, RJB_MODE_GRID, f.i("grid_size"), nullptr), "rjb_build_index(grid)");
+    ok(rjb_lsi(ctx, 1, RJB_MODE_GRID, f.d("xsect_factor"), &d, &n, nullptr), "rjb_lsi(grid)");
+    auto ans = fetch_xsects(ctx, d, n);
+    bool same = ans.size() == res.size();
+    for (size_t i = 0; same && i < ans.size(); i++)
+      same = ans[i].eid[0] == res[i].eid[0] && ans[i].eid[1] == res[i].eid[1] &&
+             ans[i].x == res[i].x && ans[i].y == res[i].y;
+    if (same) std::cerr << "LSI passed check" << std::endl;
+    else std::cerr << "LSI  xsects (Answer): " << ans.size() << " xsects (Result): " << res.size()
+                   << " MISMATCH" << std::endl;
+  }
+  tm.next("Cleanup");
+  rjb_destroy(ctx);
+  rjb_graph_free(&g0);
+  rjb_graph_free(&g1);
+  tm.end();
+  return 0;
+}
+
+static int run_pip(const Flags& f) {
+  Timer tm;
+  rjb_graph g0{}, g1{};
+  tm.next("Read map 0");
+  load_graph(f.s("poly1"), f.s("serialize"), &g0);
+  int mode = parse_mode(f.s("mode"));
+  rjb_ctx* ctx = nullptr;
+  ok(rjb_create(f.i("device"), &ctx), "rjb_create");
+  std::vector<uint32_t> eids;
+  std::vector<int64_t> gen_pts;
+  bool generated = f.s("poly2").empty();
+  uint64_t n_points = 0;
+  if (generated) {
+    tm.next("Generate Workloads");
+    set_maps(ctx, &g0, nullptr);
+    // GeneratePIPQueries, src/run_query.cu:146-167: mt19937 + uniform_real_distribution
+    // draws in the bounding box, scaled on the HOST (no FMA)
+    rjb_scaling sc;
+    ok(rjb_get_scaling(ctx, &sc), "rjb_get_scaling");
+    int seed = f.i("seed");
+    std::random_device rd;
+    std::mt19937 gen(seed == 0 ? rd() : seed);
+    std::uniform_real_distribution<> dist_x(g0.min_x, g0.max_x), dist_y(g0.min_y, g0.max_y);
+    n_points = (uint64_t) f.i("gen_n");
+    gen_pts.resize(2 * n_points);
+    for (uint64_t i = 0; i < n_points; i++) {
+      double x = dist_x(gen), y = dist_y(gen);
+      volatile double tx = x * sc.rx, ty = y * sc.ry;
+      gen_pts[2 * i] = (int64_t) (tx + sc.deltax);
+      gen_pts[2 * i + 1] = (int64_t) (ty + sc.deltay);
+    }
+    tm.next("Load Data");
+  } else {
+    tm.next("Read map 1");
+    load_graph(f.s("poly2"), f.s("serialize"), &g1);
+    tm.next("Load Data");
+    set_maps(ctx, &g0, &g1);
+    n_points = g1.n_points;
+  }
+  tm.next("Create App");
+  tm.next("Init");
+  tm.next("Build Index");
+  ok(rjb_build_index(ctx, 0, mode, f.i("grid_size"), nullptr), "rjb_build_index");
+  eids.resize(n_points);
+  auto query = [&](int m, std::vector<uint32_t>& out) {
+    if (generated) {
+      ok(rjb_pip_host_scaled(ctx, 1, m, gen_pts.data(), n_points, out.data(), nullptr), "rjb_pip");
+    } else {
+      const uint32_t* d = nullptr;
+      ok(rjb_pip(ctx, 1, m, nullptr, 0, &d, nullptr, nullptr), "rjb_pip");
+      if (n_points) ok(rjb_copy_to_host(ctx, d, out.data(), n_points * 4), "rjb_copy_to_host");
+    }
+  };
+  tm.next("Warmup");
+  for (int i = 0; i < f.i("warmup"); i++) query(mode, eids);
+  tm.next("Query", std::max(1, f.i("repeat")));
+  for (int i = 0; i < f.i("repeat"); i++) query(mode, eids);
+  if (f.b("check") && mode != RJB_MODE_GRID) {
+    tm.next("Check");
+    std::cerr << "Checking point in polygon" << std::endl;
+    std::vector<uint32_t> ans(n_points);
+    ok(rjb_build_index(ctx, 0, RJB_MODE_GRID, f.i("grid_size"), nullptr), "rjb_build_index(grid)");
+    query(RJB_MODE_GRID, ans);
+    // compare by scaled end points like src/run_query.cu:49-98
+    const int64_t* d_pts = nullptr;
+    const uint32_t* d_chain = nullptr;
+    ok(rjb_map_device_views(ctx, 0, &d_pts, &d_chain), "rjb_map_device_views");
+    uint64_t info[3];
+    ok(rjb_map_info(ctx, 0, info), "rjb_map_info");
+    std::vector<int64_t> pts(2 * info[0]);
+    std::vector<uint32_t> chain(info[1]);
+    ok(rjb_copy_to_host(ctx, d_pts, pts.data(), pts.size() * 8), "copy");
+    ok(rjb_copy_to_host(ctx, d_chain, chain.data(), chain.size() * 4), "copy");
+    size_t n_diff = 0;
+    for (uint64_t i = 0; i < n_points; i++) {
+      if (ans[i] == eids[i]) continue;
+      bool diff = ans[i] == RJB_NO_HIT || eids[i] == RJB_NO_HIT;
+      if (!diff) {
+        uint64_t pa = ans[i] + chain[ans[i]], pr = eids[i] + chain[eids[i]];
+        diff = memcmp(&pts[2 * pa], &pts[2 * pr], 32) != 0;
+      }
+      n_diff += diff;
+    }
+    if (n_diff) std::cerr << "Map: 0 Total points: " << n_points << " n diff: " << n_diff << std::endl;
+    else std::cerr << "Map: 0 passed check" << std::endl;
+  }
+  if (!f.s("output").empty()) {
+    tm.next("Write to file");
+    FILE* o = fopen(f.s("output").c_str(), "w");
+    if (!o) die("Cannot open " + f.s("output"));
+    for (uint32_t e : eids) fprintf(o, "%u\n", e);
+    fclose(o);
+  }
+  tm.next("Cleanup");
+  rjb_destroy(ctx);
+  rjb_graph_free(&g0);
+  rjb_graph_free(&g1);
+  tm.end();
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  Flags f;
+  std::string err;
+  if (argc == 1) {
+    std::cerr << "Usage: -poly1 <cdb> [-poly2 <cdb>] -mode=grid|lbvh -query=lsi|pip ..." << std::endl;
+    return 1;
+  }
+  if (!f.parse(argc, argv, &err)) die(err);
+  if (f.s("query") == "lsi") return run_lsi(f);
+  if (f.s("query") == "pip") return run_pip(f);
+  die("Invalid query: " + f.s("query"));
+  return 1;
+}
