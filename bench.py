@@ -63,36 +63,63 @@ def get_map(kind, seed, scale=1.0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML in-process,
+    ~1 ms per sample; nvidia-smi as a fallback)."""
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+           0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.sm, self.mx, self.reasons, self.stop_flag = index, [], [], set(), False
+        self.power = []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+            self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+            try:
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            try:
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.BAD.items():
+                if r & bit:
+                    self.reasons.add(name)
+        else:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index),
+                                  "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+            self.sm.append(float(out[0]))
+            self.mx.append(float(out[1]))
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.sample()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.002)
 
     def summary(self):
         self.stop_flag = True
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names)
-                   if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "power_w_max": max(self.power) if self.power else None,
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peak():
