@@ -194,8 +194,8 @@ int rjb_overlay_write(rjb_ctx* ctx, const char* path);
  * -profile sub-stage timers (src/util/stopwatch.h).                            */
 int rjb_last_kernel_ms(const rjb_ctx* ctx, double out[2]);
 /* raw counters of the last query: [0] results, [1] candidates; with option
- * "stats" = 1 also traversal statistics ([2] node visits, [3] leaf visits,
- * [4] single-child prefix visits, [5] lane-level leaf tests, [6] warps that
+ * "stats" = 1 also traversal statistics ([2] binary node visits, [3] leaf visits,
+ * [4] top-tree steps, [5] lane-level leaf tests, [6] warps that
  * reached a leaf, [7] deepest stack).  Replaces the reference's Debug-build
  * "Total tests" / "Visited nodes" counters (src/app/lsi_lbvh.h:37-42,83-96).   */
 int rjb_last_stats(const rjb_ctx* ctx, uint64_t out[8]);

@@ -78,6 +78,8 @@ struct rjb_ctx {
   int keep_host_graph = 1;  // overlay writer needs the source coordinates
   // LSI result queue
   DBuf<uint2> pairs;
+  DBuf<uint2> cands;      // LBVH traversal output: pairs whose exact boxes overlap
+  size_t cand_cap = 0;
   DBuf<rjb_xsect> xsects;
   DBuf<unsigned long long> counters;  // [0] = queue counter (low 32 bits), [1] = candidates
   // PIP results
@@ -243,45 +245,71 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
   uint32_t cap = (uint32_t) cap64;
   uint2* pairs = c->pairs.ensure(cap ? cap : 1);
   rjb_xsect* xs = c->xsects.ensure(cap ? cap : 1);
+  // counters: [0] results, [1] candidates (= exact-predicate evaluations),
+  // [2..7] traversal statistics
   unsigned long long* ctr = c->counters.ensure(8);
   ensure_events(c);
   MapView Q = Qm.view(), B = Bm.view();
-  RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
-  const uint32_t* order = nullptr;
-  RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
-  if (Q.n_edges > 0 && B.n_edges > 0) {
-    if (mode == RJB_MODE_LBVH) {
-      if (!Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no LBVH on the base map");
-      order = query_order_edges(c, Q);
+  unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (mode == RJB_MODE_LBVH && Q.n_edges > 0 && B.n_edges > 0) {
+    if (!Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no LBVH on the base map");
+    // traversal -> candidate pairs (exact integer boxes overlap) -> dense exact pass.
+    // The candidate buffer is internal: it grows and the query is repeated if it
+    // was too small (the needed size is known exactly after the first attempt).
+    if (c->cand_cap < (size_t) cap + 65536) c->cand_cap = 2 * (size_t) cap + 65536;
+    const uint32_t* order = query_order_edges(c, Q);
+    for (int attempt = 0;; attempt++) {
+      RJB_REQUIRE(c->cand_cap < 0xFFFFFFF0ull, "rjb_lsi: candidate queue exceeds 2^32 entries");
+      uint32_t ccap = (uint32_t) c->cand_cap;
+      uint2* cands = c->cands.ensure(ccap);
+      RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
       RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
       unsigned blocks = div_up(Q.n_edges, kLsiWarps * 32);
       if (c->stats)
         k_lsi_bvh<true><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-            Q, B, Bm.bvh.view(), order, pairs, cap, (unsigned int*) ctr, ctr + 1);
+            Q, B, Bm.bvh.view(), order, cands, ccap, (unsigned int*) (ctr + 1), ctr + 2);
       else
         k_lsi_bvh<false><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-            Q, B, Bm.bvh.view(), order, pairs, cap, (unsigned int*) ctr, ctr + 1);
-    } else if (mode == RJB_MODE_GRID) {
-      if (!Bm.grid.built) throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no grid on the base map");
-      lsi_grid(Bm.grid, Q, B, pairs, cap, (unsigned int*) ctr, ctr + 1, c->stream);
-    } else if (mode == RJB_MODE_BRUTE) {
-      dim3 g(div_up(Q.n_edges, 256), min(64u, div_up(B.n_edges, 256)));
-      k_lsi_brute<<<g, 256, 0, c->stream>>>(Q, B, pairs, cap, (unsigned int*) ctr, ctr + 1);
-    } else {
-      throw Error(RJB_ERR_INVALID, "rjb_lsi: unknown mode");
+            Q, B, Bm.bvh.view(), order, cands, ccap, (unsigned int*) (ctr + 1), ctr + 2);
+      RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+      k_lsi_exact<<<div_up(ccap, 128), 128, 0, c->stream>>>(
+          Q, B, q, cands, (const unsigned int*) (ctr + 1), ccap, xs, cap, (unsigned int*) ctr);
+      RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
+      RJB_CUDA(cudaGetLastError());
+      RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+      RJB_CUDA(cudaStreamSynchronize(c->stream));
+      if ((uint32_t) h[1] <= ccap) break;
+      RJB_REQUIRE(attempt == 0, "rjb_lsi: candidate queue overflowed twice");
+      c->cand_cap = (size_t) (uint32_t) h[1] + (uint32_t) h[1] / 8 + 65536;
     }
+    h[1] = (uint32_t) h[1];
+  } else {
+    RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
+    RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    if (Q.n_edges > 0 && B.n_edges > 0) {
+      if (mode == RJB_MODE_GRID) {
+        if (!Bm.grid.built) throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no grid on the base map");
+        lsi_grid(Bm.grid, Q, B, pairs, cap, (unsigned int*) ctr, ctr + 1, c->stream);
+      } else if (mode == RJB_MODE_BRUTE) {
+        dim3 g(div_up(Q.n_edges, 256), min(64u, div_up(B.n_edges, 256)));
+        k_lsi_brute<<<g, 256, 0, c->stream>>>(Q, B, pairs, cap, (unsigned int*) ctr, ctr + 1);
+      } else if (mode != RJB_MODE_LBVH) {
+        throw Error(RJB_ERR_INVALID, "rjb_lsi: unknown mode");
+      }
+    } else if (mode == RJB_MODE_LBVH && !Bm.bvh.built) {
+      throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no LBVH on the base map");
+    }
+    RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    // the point pass reads the count on the device: no host round trip between
+    // the two kernels
+    if (cap > 0)
+      k_xsect_points_dyn<<<div_up(cap, 128), 128, 0, c->stream>>>(
+          Q, B, q, pairs, (const unsigned int*) ctr, cap, xs);
+    RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    RJB_CUDA(cudaGetLastError());
+    RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    RJB_CUDA(cudaStreamSynchronize(c->stream));
   }
-  RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
-  // the point pass reads the count on the device: no host round trip between
-  // the two kernels
-  if (cap > 0)
-    k_xsect_points_dyn<<<div_up(cap, 128), 128, 0, c->stream>>>(Q, B, q, pairs,
-                                                               (const unsigned int*) ctr, cap, xs);
-  RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
-  RJB_CUDA(cudaGetLastError());
-  unsigned long long h[8];
-  RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  RJB_CUDA(cudaStreamSynchronize(c->stream));
   memcpy(c->last_stats, h, sizeof(h));
   RJB_CUDA(cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]));
   RJB_CUDA(cudaEventElapsedTime(&c->last_ms[1], c->ev[1], c->ev[2]));
@@ -527,9 +555,7 @@ int rjb_lsi(rjb_ctx* c, int query_map_id, int mode, double xsect_factor,
     } catch (const Error& e) {
       if (e.code == RJB_ERR_QUEUE_OVERFLOW) {
         // report how many were needed
-        unsigned long long h = 0;
-        cudaMemcpy(&h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost);
-        needed = (uint32_t) h;
+        needed = (uint32_t) c->last_stats[0];
       }
       throw;
     }

@@ -51,12 +51,26 @@ struct BvhView {
   const int4* node_box;    // 2 per internal node: {xmin, ymin, xmax, ymax}
   const int2* node_child;  // {left, right}
   const uint2* leaf_rec;   // {first_eid, (count << 28) | chain}
+  // 32-ary top tree: the binary nodes at depth 5, 10 and 15, addressed by their
+  // root path (bit string), so that a warp resolves 5 levels per step with one
+  // lane per slot.  Level k has 32^(k+1) slots; empty slots have an empty box.
+  const int4* top_box;     // [32 | 1024 | 32768]
+  const int* top_code;     // child code per slot (>= 0 internal node, < 0 ~leaf)
   int4 root_box;
   uint32_t n_leaves;
 };
 
+constexpr int kTopOff0 = 0, kTopOff1 = 32, kTopOff2 = 32 + 1024, kTopSlots = 32 + 1024 + 32768;
+
 static __device__ __forceinline__ int quant(long long v) {
   return (int) (v >> kQuantShift);  // arithmetic shift = floor, monotone
+}
+
+// A box that overlaps nothing: quantised coordinates are 31-bit, so no real box
+// reaches INT_MAX / INT_MIN.  (An "inverted" box such as {1,1,0,0} is NOT safe:
+// it passes the overlap test against any box that contains [0,1]^2.)
+static __host__ __device__ __forceinline__ int4 empty_box() {
+  return make_int4(0x7fffffff, 0x7fffffff, (int) 0x80000000, (int) 0x80000000);
 }
 
 static __device__ __forceinline__ bool box_overlap(const int4& a, const int4& b) {

@@ -97,34 +97,70 @@ static __device__ __forceinline__ bool seg_boxes_overlap(const Seg& p, const Seg
 // endpoints, then converted with (int64)((double)num / (double)den).
 static __device__ __forceinline__ i128 iabs128(i128 v) { return v < 0 ? -v : v; }
 
-static __device__ i128 gcd128(i128 a, i128 b) {
-  // magnitude of Euclid's gcd; any algorithm gives the same value.  Work on
-  // unsigned magnitudes and drop to 64-bit as soon as both fit.
-  unsigned __int128 x = (unsigned __int128) iabs128(a);
-  unsigned __int128 y = (unsigned __int128) iabs128(b);
-  while (y != 0) {
-    if ((x >> 64) == 0 && (y >> 64) == 0) {
-      unsigned long long p = (unsigned long long) x, q = (unsigned long long) y;
-      while (q != 0) {
-        unsigned long long t = p % q;
-        p = q;
-        q = t;
-      }
-      return (i128) p;
+typedef unsigned __int128 u128;
+
+static __device__ __forceinline__ int ctz64(unsigned long long v) { return __ffsll((long long) v) - 1; }
+
+// binary gcd of two 64-bit magnitudes (no hardware divide on the GPU: Euclid's
+// `%` would cost ~100 instructions per step)
+static __device__ __forceinline__ unsigned long long gcd64(unsigned long long a,
+                                                           unsigned long long b) {
+  if (a == 0) return b;
+  if (b == 0) return a;
+  int sh = ctz64(a | b);
+  a >>= ctz64(a);
+  do {
+    b >>= ctz64(b);
+    if (a > b) {
+      unsigned long long t = a;
+      a = b;
+      b = t;
     }
-    unsigned __int128 t = x % y;
-    x = y;
-    y = t;
+    b -= a;
+  } while (b != 0);
+  return a << sh;
+}
+
+static __device__ __forceinline__ int ctz128(u128 v) {
+  unsigned long long lo = (unsigned long long) v;
+  return lo ? ctz64(lo) : 64 + ctz64((unsigned long long) (v >> 64));
+}
+
+// magnitude of gcd(a, b); any algorithm gives the same value as the reference's
+// Euclid loop (src/util/rational.h:36-43).  Binary gcd in 128 bits until both
+// operands fit 64 bits (typically after a few dozen steps: |den| < 2^64).
+static __device__ i128 gcd128(i128 a, i128 b) {
+  u128 x = (u128) iabs128(a), y = (u128) iabs128(b);
+  if (x == 0) return (i128) y;
+  if (y == 0) return (i128) x;
+  int sh = ctz128(x | y);
+  x >>= ctz128(x);
+  while (true) {
+    y >>= ctz128(y);
+    if ((x >> 64) == 0 && (y >> 64) == 0)
+      return (i128) ((u128) gcd64((unsigned long long) x, (unsigned long long) y) << sh);
+    if (x > y) {
+      u128 t = x;
+      x = y;
+      y = t;
+    }
+    y -= x;
+    if (y == 0) return (i128) (x << sh);
   }
-  return (i128) x;
 }
 
 static __device__ __forceinline__ void rat_make(i128 num, i128 den, i128& on,
                                                 i128& od) {
   i128 g = gcd128(num, den);  // den != 0 for a true intersection
   i128 sn = den < 0 ? -num : num;
-  on = sn / g;
-  od = iabs128(den) / g;
+  i128 ad = iabs128(den);
+  if (g == 1) {  // the common case: skip two software 128-bit divisions
+    on = sn;
+    od = ad;
+  } else {
+    on = sn / g;
+    od = ad / g;
+  }
 }
 
 static __device__ __forceinline__ long long min4ll(long long a, long long b,
@@ -146,7 +182,6 @@ static __device__ void lsi_point(const Seg& e1, const Seg& e2, long long& ox,
   i128 c1 = -(i128) e1.x1 * a1 - (i128) e1.y1 * b1;
   i128 c2 = -(i128) e2.x1 * a2 - (i128) e2.y1 * b2;
   // unsigned products: two's-complement wrap-around, no UB
-  typedef unsigned __int128 u128;
   i128 denom = (i128) ((u128) a1 * (u128) b2 - (u128) a2 * (u128) b1);
   i128 numx = (i128) ((u128) c2 * (u128) b1 - (u128) c1 * (u128) b2);
   i128 numy = (i128) ((u128) a2 * (u128) c1 - (u128) a1 * (u128) c2);

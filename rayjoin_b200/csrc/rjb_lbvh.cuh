@@ -28,6 +28,8 @@ struct Bvh {
   DBuf<int4> leaf_box_u, leaf_box_s;
   DBuf<uint2> leaf_rec_u;
   DBuf<int4> root_box_d;
+  DBuf<int4> top_box;
+  DBuf<int> top_code;
   ScanTemp scan_tmp;
   SortTemp sort_tmp;
 
@@ -38,11 +40,14 @@ struct Bvh {
     v.leaf_rec = leaf_rec.p;
     v.root_box = root_box;
     v.n_leaves = n_leaves;
+    v.top_box = top_box.p;
+    v.top_code = top_code.p;
     return v;
   }
   size_t index_bytes() const {
     uint32_t n_int = n_leaves > 1 ? n_leaves - 1 : 1;
-    return (size_t) n_int * (2 * sizeof(int4) + sizeof(int2)) + (size_t) n_leaves * sizeof(uint2);
+    return (size_t) n_int * (2 * sizeof(int4) + sizeof(int2)) + (size_t) n_leaves * sizeof(uint2) +
+           (size_t) kTopSlots * (sizeof(int4) + sizeof(int));
   }
 };
 
@@ -188,9 +193,47 @@ __global__ void k_refit(const int4* __restrict__ leaf_box, uint32_t n, const int
 __global__ void k_single_leaf_root(const int4* __restrict__ leaf_box, int4* node_box,
                                    int2* child, int4* root_box) {
   node_box[0] = leaf_box[0];
-  node_box[1] = make_int4(1, 1, 0, 0);  // empty: never overlaps
+  node_box[1] = empty_box();  // empty: never overlaps
   child[0] = make_int2(~0, ~0);
   *root_box = leaf_box[0];
+}
+
+// 32-ary top tree: thread P (a 15-bit root path) walks 15 binary levels and
+// publishes the node it stands on after 5, 10 and 15 steps into the slot named
+// by the path prefix.  A leaf met early stays in the all-zero continuation of
+// its path; every other slot below it is empty.
+__global__ void k_top_tree(const int4* __restrict__ node_box, const int2* __restrict__ node_child,
+                           const int4* __restrict__ root_box, uint32_t n_leaves,
+                           int4* __restrict__ top_box, int* __restrict__ top_code) {
+  uint32_t P = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P >= 32768) return;
+  int code = 0;  // root = internal node 0
+  int4 box = *root_box;
+  bool alive = n_leaves > 0;
+  const int4 empty = empty_box();
+  for (int level = 0; level < 15; level++) {
+    int bit = (P >> (14 - level)) & 1;
+    if (alive) {
+      if (code < 0) {
+        if (bit) alive = false;  // a leaf lives only in the zero continuation
+      } else {
+        int2 ch = node_child[code];
+        box = node_box[2 * code + bit];
+        code = bit ? ch.y : ch.x;
+        if (box.x > box.z) alive = false;  // empty child of the single-leaf root (empty_box)
+      }
+    }
+    int depth = level + 1;
+    if (depth % 5 == 0) {
+      int rest = 15 - depth;  // lower path bits must be zero: one writer per slot
+      if ((P & ((1u << rest) - 1)) == 0) {
+        int off = depth == 5 ? kTopOff0 : (depth == 10 ? kTopOff1 : kTopOff2);
+        uint32_t slot = P >> rest;
+        top_box[off + slot] = alive ? box : empty;
+        top_code[off + slot] = code;
+      }
+    }
+  }
 }
 
 static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long imin,
@@ -200,7 +243,7 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
   b.leaf_size = leaf_size;
   b.built = true;
   b.n_leaves = 0;
-  b.root_box = make_int4(1, 1, 0, 0);
+  b.root_box = empty_box();
   if (m.n_edges == 0) return;
   const int T = 256;
   uint32_t* cnt = b.chain_cnt.ensure(m.n_chains + 1);
@@ -238,6 +281,9 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
     k_karras<<<div_up(n - 1, T), T, 0, st>>>(kb, n, nchild, parent);
     k_refit<<<div_up(n, T), T, 0, st>>>(box_s, n, nchild, parent, nbox, flags, root_d);
   }
+  int4* tbox = b.top_box.ensure(kTopSlots);
+  int* tcode = b.top_code.ensure(kTopSlots);
+  k_top_tree<<<32768 / 256, 256, 0, st>>>(nbox, nchild, root_d, n, tbox, tcode);
   RJB_CUDA(cudaGetLastError());
   RJB_CUDA(cudaMemcpyAsync(&b.root_box, root_d, sizeof(int4), cudaMemcpyDeviceToHost, st));
   RJB_CUDA(cudaStreamSynchronize(st));

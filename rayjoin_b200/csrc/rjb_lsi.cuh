@@ -1,5 +1,5 @@
-// LSI kernels: warp-cooperative BVH traversal, all-pairs reference kernel,
-// and the intersection-point post-pass.
+// LSI kernels: warp-cooperative BVH traversal (candidate generation), the dense
+// exact pass (predicate + intersection point), and an all-pairs kernel.
 //
 // Replaces LSILBVH::Query (reference: src/app/lsi_lbvh.h:27-98 +
 // deps/lbvh/lbvh/query.cuh:8-51, one thread per query edge with a 64-entry
@@ -9,8 +9,8 @@
 
 namespace rjb {
 
-constexpr int kLsiWarps = 8;    // warps per CTA
-constexpr int kStackDepth = 96; // >= max LBVH depth (64 key bits + 32 index bits)
+constexpr int kLsiWarps = 4;     // warps per CTA (small CTAs: a slow warp holds few others)
+constexpr int kStackDepth = 96;  // >= max LBVH depth (64 key bits + 32 index bits)
 
 static __device__ __forceinline__ Seg load_seg(const MapView& m, uint32_t eid) {
   uint32_t p = eid + m.edge_chain[eid];
@@ -19,7 +19,7 @@ static __device__ __forceinline__ Seg load_seg(const MapView& m, uint32_t eid) {
   return s;
 }
 
-// Warp-aggregated append of (query eid, base eid) to the result queue.
+// Warp-aggregated append of (query eid, base eid) to a queue: one atomic per warp.
 static __device__ __forceinline__ void emit_pair(bool found, uint32_t q, uint32_t b,
                                                  uint2* __restrict__ out, uint32_t cap,
                                                  unsigned int* counter, int lane) {
@@ -35,18 +35,95 @@ static __device__ __forceinline__ void emit_pair(bool found, uint32_t q, uint32_
   }
 }
 
-// One warp = 32 query edges.  The warp walks the BVH ONCE for all of them:
-// node records are loaded at a warp-uniform address (one transaction,
-// broadcast), every lane tests its own query box against both child boxes,
-// and __ballot_sync decides warp-uniformly which children to enter.  No lane
-// ever diverges in the traversal loop and the stack is a single warp-shared
-// array in shared memory.  `order` (optional) maps slot -> query eid so that
-// the 32 edges of a warp are spatial neighbours.
+static __device__ __forceinline__ int4 shfl_box(const int4& b, int src) {
+  return make_int4(__shfl_sync(0xffffffffu, b.x, src), __shfl_sync(0xffffffffu, b.y, src),
+                   __shfl_sync(0xffffffffu, b.z, src), __shfl_sync(0xffffffffu, b.w, src));
+}
+
+// union of the lanes' boxes (REDUX); lanes that do not take part pass the neutral box
+static __device__ __forceinline__ int4 warp_union(const int4& b) {
+  return make_int4(__reduce_min_sync(0xffffffffu, b.x), __reduce_min_sync(0xffffffffu, b.y),
+                   __reduce_max_sync(0xffffffffu, b.z), __reduce_max_sync(0xffffffffu, b.w));
+}
+
+// statistics of one warp's traversal (option "stats")
+struct TravStats {
+  unsigned nodes, leaves, top_steps, lane_leaf, maxsp;
+};
+
+// One leaf = <= 8 consecutive edges of one chain = one contiguous run of points,
+// read with warp-uniform (broadcast) loads.  Lanes in `h` test their own edge;
+// pairs whose exact integer boxes overlap become candidates.
+template <bool kStats>
+static __device__ __forceinline__ void lsi_leaf(const MapView& B, const BvhView& bvh, int leaf,
+                                                bool h, const Seg& q, uint32_t qe,
+                                                uint2* __restrict__ out, uint32_t cap,
+                                                unsigned int* counter, int lane, TravStats& st) {
+  const uint2 rec = __ldg(&bvh.leaf_rec[leaf]);
+  const uint32_t first_eid = rec.x, cnt = rec.y >> 28, chain = rec.y & 0x0FFFFFFFu;
+  const longlong2* bp = B.pts + (first_eid + chain);
+  longlong2 p1 = __ldg(bp);
+  if (kStats) st.leaves++;
+  for (uint32_t k = 0; k < cnt; k++) {
+    const longlong2 p2 = __ldg(bp + k + 1);
+    const Seg e2 = {p1.x, p1.y, p2.x, p2.y};
+    emit_pair(h && seg_boxes_overlap(q, e2), qe, first_eid + k, out, cap, counter, lane);
+    p1 = p2;
+  }
+}
+
+// Binary part of the traversal, below the 32-ary top tree: node records are read
+// at a warp-uniform address (one transaction), every lane tests ITS box against
+// both child boxes and __ballot_sync decides warp-uniformly where to go.
+template <bool kStats>
+static __device__ __forceinline__ void lsi_subtree(const MapView& B, const BvhView& bvh, int root,
+                                                   int* stack, const int4& qb, const Seg& q,
+                                                   uint32_t qe, uint2* __restrict__ out,
+                                                   uint32_t cap, unsigned int* counter, int lane,
+                                                   TravStats& st) {
+  int sp = 0;
+  int node = root;
+  while (true) {
+    const int4 lb = __ldg(&bvh.node_box[2 * node]);
+    const int4 rb = __ldg(&bvh.node_box[2 * node + 1]);
+    const int2 ch = __ldg(&bvh.node_child[node]);
+    const bool hl = box_overlap(qb, lb), hr = box_overlap(qb, rb);
+    const unsigned ml = __ballot_sync(0xffffffffu, hl);
+    const unsigned mr = __ballot_sync(0xffffffffu, hr);
+    if (kStats) st.nodes++;
+    int next = -1;
+    if (ml) {
+      if (ch.x >= 0) next = ch.x;
+      else {
+        if (kStats) st.lane_leaf += __popc(ml);
+        lsi_leaf<kStats>(B, bvh, ~ch.x, hl, q, qe, out, cap, counter, lane, st);
+      }
+    }
+    if (mr) {
+      if (ch.y >= 0) {
+        if (next < 0) next = ch.y; else stack[sp++] = ch.y;
+      } else {
+        if (kStats) st.lane_leaf += __popc(mr);
+        lsi_leaf<kStats>(B, bvh, ~ch.y, hr, q, qe, out, cap, counter, lane, st);
+      }
+    }
+    if (kStats) st.maxsp = max(st.maxsp, (unsigned) sp);
+    if (next >= 0) { node = next; continue; }
+    if (sp == 0) break;
+    node = stack[--sp];
+  }
+}
+
+// One warp = 32 query edges.  The warp first resolves the top 15 levels of the
+// tree in three steps of a 32-ary top tree (one LANE PER CHILD SLOT tests the
+// warp's union box; loads are coalesced and the 21 KB of the first two levels
+// stay L1-resident), then walks the remaining binary subtrees with per-lane
+// boxes.  Output: candidate pairs whose exact integer boxes overlap.
 template <bool kStats>
 __global__ void __launch_bounds__(kLsiWarps * 32)
 k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
           uint2* __restrict__ out, uint32_t cap, unsigned int* counter,
-          unsigned long long* n_cand) {
+          unsigned long long* stats) {
   __shared__ int s_stack[kLsiWarps][kStackDepth];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* stack = s_stack[warp];
@@ -54,80 +131,130 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
   const bool valid = slot < Q.n_edges;
   uint32_t qe = 0;
   Seg q = {0, 0, 0, 0};
-  int4 qb = make_int4(1, 1, 0, 0);  // empty box for idle lanes
+  int4 qb = empty_box();  // empty box for idle lanes
+  int4 ub = make_int4(0x7fffffff, 0x7fffffff, (int) 0x80000000, (int) 0x80000000);
   if (valid) {
     qe = order ? order[slot] : slot;
     q = load_seg(Q, qe);
     qb = make_int4(quant(min(q.x1, q.x2)), quant(min(q.y1, q.y2)),
                    quant(max(q.x1, q.x2)), quant(max(q.y1, q.y2)));
+    ub = qb;
   }
-  unsigned long long cand = 0;
-  // traversal statistics (kStats only): node visits, leaf visits, length of the
-  // initial single-child descent, lane-level leaf tests, deepest stack
-  unsigned st_nodes = 0, st_leaves = 0, st_prefix = 0, st_lane_leaf = 0, st_maxsp = 0;
-  bool st_in_prefix = true;
-  if (__ballot_sync(0xffffffffu, box_overlap(qb, bvh.root_box)) != 0) {
-    int sp = 0;
-    int node = 0;
-    while (true) {
-      const int4 lb = __ldg(&bvh.node_box[2 * node]);
-      const int4 rb = __ldg(&bvh.node_box[2 * node + 1]);
-      const int2 ch = __ldg(&bvh.node_child[node]);
-      const bool hl = box_overlap(qb, lb), hr = box_overlap(qb, rb);
-      const unsigned ml = __ballot_sync(0xffffffffu, hl);
-      const unsigned mr = __ballot_sync(0xffffffffu, hr);
-      if (kStats) {
-        st_nodes++;
-        bool single = ((ml != 0) != (mr != 0)) && ((ml ? ch.x : ch.y) >= 0);
-        if (st_in_prefix && single) st_prefix++; else st_in_prefix = false;
+  const int4 U = warp_union(ub);
+  TravStats st = {0, 0, 0, 0, 0};
+  const int4 kNeutral = make_int4(0x7fffffff, 0x7fffffff, (int) 0x80000000, (int) 0x80000000);
+  const int4 kEmpty = empty_box();
+  if (bvh.n_leaves > 0 && box_overlap(U, bvh.root_box)) {
+    // level 0: the 32 nodes at depth 5.  The union box only preselects slots; each
+    // preselected slot is confirmed with the lanes' own boxes (ballot) before the
+    // warp descends, and the union box is re-tightened to the confirming lanes, so
+    // a warp whose edges form several far-apart clusters follows each cluster
+    // separately instead of sweeping everything under a huge union box.
+    const int4 b0 = __ldg(&bvh.top_box[kTopOff0 + lane]);
+    const int c0 = __ldg(&bvh.top_code[kTopOff0 + lane]);
+    unsigned m0 = __ballot_sync(0xffffffffu, box_overlap(U, b0));
+    if (kStats) st.top_steps++;
+    while (m0) {
+      const int g = __ffs(m0) - 1;
+      m0 &= m0 - 1;
+      const int4 sb0 = shfl_box(b0, g);
+      const bool h0 = box_overlap(qb, sb0);
+      if (__ballot_sync(0xffffffffu, h0) == 0) continue;
+      const int code0 = __shfl_sync(0xffffffffu, c0, g);
+      if (code0 < 0) {
+        lsi_leaf<kStats>(B, bvh, ~code0, h0, q, qe, out, cap, counter, lane, st);
+        continue;
       }
-      int next = -1;
-#pragma unroll
-      for (int side = 0; side < 2; side++) {
-        const unsigned m = side ? mr : ml;
-        const int c = side ? ch.y : ch.x;
-        const bool h = side ? hr : hl;
-        if (m == 0) continue;
-        if (c >= 0) {  // internal child: enter now or later
-          if (next < 0) next = c; else stack[sp++] = c;
+      const int4 U1 = warp_union(h0 ? qb : kNeutral);
+      // level 1: the 32 depth-10 nodes below slot g
+      const int4 b1 = __ldg(&bvh.top_box[kTopOff1 + g * 32 + lane]);
+      const int c1 = __ldg(&bvh.top_code[kTopOff1 + g * 32 + lane]);
+      unsigned m1 = __ballot_sync(0xffffffffu, box_overlap(U1, b1));
+      if (kStats) st.top_steps++;
+      while (m1) {
+        const int h = __ffs(m1) - 1;
+        m1 &= m1 - 1;
+        const int4 sb1 = shfl_box(b1, h);
+        const bool h1 = h0 && box_overlap(qb, sb1);
+        if (__ballot_sync(0xffffffffu, h1) == 0) continue;
+        const int code1 = __shfl_sync(0xffffffffu, c1, h);
+        if (code1 < 0) {
+          lsi_leaf<kStats>(B, bvh, ~code1, h1, q, qe, out, cap, counter, lane, st);
           continue;
         }
-        // leaf: the hit lanes test their edge against its <= 8 base edges,
-        // whose vertices are one contiguous run of points (uniform loads)
-        if (kStats) { st_leaves++; st_lane_leaf += __popc(m); }
-        const uint2 rec = __ldg(&bvh.leaf_rec[~c]);
-        const uint32_t first_eid = rec.x, cnt = rec.y >> 28, chain = rec.y & 0x0FFFFFFFu;
-        const longlong2* bp = B.pts + (first_eid + chain);
-        longlong2 p1 = __ldg(bp);
-        for (uint32_t k = 0; k < cnt; k++) {
-          const longlong2 p2 = __ldg(bp + k + 1);
-          const Seg e2 = {p1.x, p1.y, p2.x, p2.y};
-          bool found = false;
-          if (h && seg_boxes_overlap(q, e2)) {
-            cand++;
-            found = lsi_intersect(q, e2);
-          }
-          emit_pair(found, qe, first_eid + k, out, cap, counter, lane);
-          p1 = p2;
+        const int4 U2 = warp_union(h1 ? qb : kNeutral);
+        // level 2: the 32 depth-15 nodes below slot (g, h)
+        const int4 b2 = __ldg(&bvh.top_box[kTopOff2 + (g * 32 + h) * 32 + lane]);
+        const int c2 = __ldg(&bvh.top_code[kTopOff2 + (g * 32 + h) * 32 + lane]);
+        unsigned m2 = __ballot_sync(0xffffffffu, box_overlap(U2, b2));
+        if (kStats) st.top_steps++;
+        while (m2) {
+          const int i = __ffs(m2) - 1;
+          m2 &= m2 - 1;
+          const int4 sb2 = shfl_box(b2, i);
+          const bool h2 = h1 && box_overlap(qb, sb2);
+          if (__ballot_sync(0xffffffffu, h2) == 0) continue;
+          const int code2 = __shfl_sync(0xffffffffu, c2, i);
+          if (code2 < 0)
+            lsi_leaf<kStats>(B, bvh, ~code2, h2, q, qe, out, cap, counter, lane, st);
+          else
+            lsi_subtree<kStats>(B, bvh, code2, stack, h2 ? qb : kEmpty, q, qe, out, cap, counter,
+                                lane, st);
         }
       }
-      if (kStats) st_maxsp = max(st_maxsp, (unsigned) sp);
-      if (next >= 0) { node = next; continue; }
-      if (sp == 0) break;
-      node = stack[--sp];
     }
   }
-  if (n_cand) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
-    if (lane == 0 && cand) atomicAdd(n_cand, cand);
-    if (kStats && lane == 0) {  // n_cand points at counters[1]; stats live at counters[2..7]
-      atomicAdd(n_cand + 1, (unsigned long long) st_nodes);
-      atomicAdd(n_cand + 2, (unsigned long long) st_leaves);
-      atomicAdd(n_cand + 3, (unsigned long long) st_prefix);
-      atomicAdd(n_cand + 4, (unsigned long long) st_lane_leaf);
-      atomicAdd(n_cand + 5, (unsigned long long) (st_leaves ? 1 : 0));
-      atomicMax(n_cand + 6, (unsigned long long) st_maxsp);
+  if (kStats && lane == 0) {
+    atomicAdd(stats + 0, (unsigned long long) st.nodes);
+    atomicAdd(stats + 1, (unsigned long long) st.leaves);
+    atomicAdd(stats + 2, (unsigned long long) st.top_steps);
+    atomicAdd(stats + 3, (unsigned long long) st.lane_leaf);
+    atomicAdd(stats + 4, (unsigned long long) (st.leaves ? 1 : 0));
+    atomicMax(stats + 5, (unsigned long long) st.maxsp);
+  }
+}
+
+// Dense exact pass over the candidate list: intersect_test, and for the hits the
+// rational intersection point -> rjb_xsect (reference computes both inside the
+// traversal callback, lsi_lbvh.h:69-78; the RT backend has the same post-pass
+// structure, src/app/lsi_rt.h:66-112).  The candidate count is read on the
+// device, so no host round trip separates the two kernels.
+__global__ void __launch_bounds__(128)
+k_lsi_exact(MapView Q, MapView B, int query_map_id, const uint2* __restrict__ cand,
+            const unsigned int* __restrict__ n_cand_dev, uint32_t cand_cap,
+            rjb_xsect* __restrict__ out, uint32_t cap, unsigned int* counter) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = min(*n_cand_dev, cand_cap);
+  const int lane = threadIdx.x & 31;
+  if (i - lane >= n) return;  // whole warp idle
+  bool found = false;
+  uint2 pr = make_uint2(0, 0);
+  Seg e1 = {0, 0, 0, 0}, e2 = {0, 0, 0, 0};
+  if (i < n) {
+    pr = cand[i];
+    e1 = load_seg(Q, pr.x);
+    e2 = load_seg(B, pr.y);
+    found = lsi_intersect(e1, e2);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, found);
+  if (m == 0) return;
+  unsigned base = 0;
+  const int leader = __ffs(m) - 1;
+  if (lane == leader) base = atomicAdd(counter, (unsigned) __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (found) {
+    const unsigned pos = base + __popc(m & ((1u << lane) - 1));
+    if (pos < cap) {
+      long long x, y;
+      lsi_point(e1, e2, x, y);
+      rjb_xsect r;
+      r.x = x;
+      r.y = y;
+      r.eid[0] = query_map_id == 0 ? pr.x : pr.y;
+      r.eid[1] = query_map_id == 0 ? pr.y : pr.x;
+      r.mid_point_polygon_id = RJB_DONTKNOW;
+      r._pad = 0;
+      out[pos] = r;
     }
   }
 }
@@ -166,11 +293,8 @@ k_lsi_brute(MapView Q, MapView B, uint2* __restrict__ out, uint32_t cap,
   }
 }
 
-// Intersection points of the found pairs -> rjb_xsect records
-// (reference: src/app/lsi_rt.h:66-112 does the same as a post-pass; the LBVH
-// backend computes it inside the traversal callback, lsi_lbvh.h:69-78).
-// The pair count is read from the device counter so that no host round trip
-// separates the traversal from this pass (grid is sized by the capacity).
+// Intersection points of already verified pairs -> rjb_xsect records (grid and
+// brute modes).  The pair count is read from the device counter.
 __global__ void __launch_bounds__(128)
 k_xsect_points_dyn(MapView Q, MapView B, int query_map_id, const uint2* __restrict__ pairs,
                    const unsigned int* __restrict__ counter, uint32_t cap,

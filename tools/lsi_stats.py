@@ -20,6 +20,6 @@ for leaf in (4,):
         lsi.Query(1); lsi.Query(1)
         st = ctx.last_stats()
         warps = (S.n_edges + 31) // 32
-        print("leaf %d sort %d: warps %d results %d cand %d | node visits/warp %.1f leaf visits/warp %.2f prefix/warp %.1f lane-leaf tests/warp %.2f warps with leaf %.1f%% max stack %d kernel ms %.3f"
-              % (leaf, sortq, warps, st[0], st[1], st[2] / warps, st[3] / warps, st[4] / warps, st[5] / warps, 100.0 * st[6] / warps, st[7], ctx.last_kernel_ms()[0]))
+        print("leaf %d sort %d: warps %d results %d cand %d | binary node visits/warp %.2f leaf visits/warp %.2f top steps/warp %.2f lane-leaf tests/warp %.2f warps with leaf %.1f%% max stack %d kernel ms %.3f + %.3f"
+              % (leaf, sortq, warps, st[0], st[1], st[2] / warps, st[3] / warps, st[4] / warps, st[5] / warps, 100.0 * st[6] / warps, st[7], *ctx.last_kernel_ms()))
         ctx.close()
