@@ -21,7 +21,7 @@ struct DeviceMap {
   uint32_t n_points = 0, n_edges = 0, n_chains = 0;
   DBuf<double2> raw;
   DBuf<longlong2> pts;
-  DBuf<uint32_t> edge_chain, row_index;
+  DBuf<uint32_t> edge_chain, row_index, last_bits;
   DBuf<int32_t> left, right;
   std::vector<int32_t> h_left, h_right;
   // host copy of the source graph kept for the overlay writer (points as
@@ -35,6 +35,7 @@ struct DeviceMap {
     v.pts = pts.p;
     v.edge_chain = edge_chain.p;
     v.row_index = row_index.p;
+    v.last_bits = last_bits.p;
     v.left = left.p;
     v.right = right.p;
     v.n_points = n_points;
@@ -142,13 +143,22 @@ __global__ void k_edge_chain(const uint32_t* __restrict__ row_index, uint32_t n_
   edge_chain[e] = lo;
 }
 
+// bit p set <=> p is the last point of its chain (the slot owns no edge)
+__global__ void k_chain_last_bits(const uint32_t* __restrict__ row_index, uint32_t n_chains,
+                                  uint32_t* __restrict__ bits) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  uint32_t p = row_index[c + 1] - 1;
+  atomicOr(&bits[p >> 5], 1u << (p & 31));
+}
+
 __global__ void k_query_keys_edges(MapView Q, long long imin, uint64_t* __restrict__ key,
                                    uint32_t* __restrict__ val) {
   uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= Q.n_edges) return;
   Seg s = load_seg(Q, e);
   key[e] = morton64(s.x1 + ((s.x2 - s.x1) >> 1), s.y1 + ((s.y2 - s.y1) >> 1), imin);
-  val[e] = e;
+  val[e] = e + Q.edge_chain[e];  // the edge's start point: what the traversal consumes
 }
 
 __global__ void k_query_keys_points(const longlong2* __restrict__ pts, uint32_t n, long long imin,
@@ -264,16 +274,20 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
       uint2* cands = c->cands.ensure(ccap);
       RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
       RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
-      unsigned blocks = div_up(Q.n_edges, kLsiWarps * 32);
+      // query slots: point indices (edge = slot, slot + 1), or the sorted edge list
+      uint32_t n_slots = order ? Q.n_edges : Q.n_points;
+      unsigned tiles = div_up(n_slots, 32);
+      unsigned blocks = div_up(tiles, kLsiWarps);
       if (c->stats)
         k_lsi_bvh<true><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-            Q, B, Bm.bvh.view(), order, cands, ccap, (unsigned int*) (ctr + 1), ctr + 2);
+            Q, B, Bm.bvh.view(), order, n_slots, cands, ccap, (unsigned int*) (ctr + 1), ctr + 2);
       else
         k_lsi_bvh<false><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-            Q, B, Bm.bvh.view(), order, cands, ccap, (unsigned int*) (ctr + 1), ctr + 2);
+            Q, B, Bm.bvh.view(), order, n_slots, cands, ccap, (unsigned int*) (ctr + 1), ctr + 2);
       RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
-      k_lsi_exact<<<div_up(ccap, 128), 128, 0, c->stream>>>(
-          Q, B, q, cands, (const unsigned int*) (ctr + 1), ccap, xs, cap, (unsigned int*) ctr);
+      k_lsi_exact<<<kNumSMs * 8, 256, 0, c->stream>>>(Q, B, cands, (const unsigned int*) (ctr + 1),
+                                                    ccap, xs, cap, (unsigned int*) ctr);
+      k_lsi_points<<<kNumSMs * 16, 128, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs);
       RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
       RJB_CUDA(cudaGetLastError());
       RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -491,6 +505,8 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
     int32_t* l = m.left.ensure(n_chains ? n_chains : 1);
     int32_t* r = m.right.ensure(n_chains ? n_chains : 1);
     uint32_t* ec = m.edge_chain.ensure(m.n_edges ? m.n_edges : 1);
+    uint32_t n_words = (uint32_t) (n_points / 32 + 2);
+    uint32_t* lb = m.last_bits.ensure(n_words);
     cudaStream_t st = c->stream;
     if (n_points) {
       RJB_CUDA(cudaMemcpyAsync(raw, xy, n_points * sizeof(double2), cudaMemcpyHostToDevice, st));
@@ -503,6 +519,8 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
       k_scale_points<<<div_up(n_points, 256), 256, 0, st>>>(raw, m.n_points, c->sc.rx, c->sc.ry,
                                                             c->sc.deltax, c->sc.deltay, pts);
       k_edge_chain<<<div_up(m.n_edges, 256), 256, 0, st>>>(ri, m.n_chains, m.n_edges, ec);
+      RJB_CUDA(cudaMemsetAsync(lb, 0, n_words * sizeof(uint32_t), st));
+      k_chain_last_bits<<<div_up(m.n_chains, 256), 256, 0, st>>>(ri, m.n_chains, lb);
       RJB_CUDA(cudaGetLastError());
     }
     RJB_CUDA(cudaStreamSynchronize(st));

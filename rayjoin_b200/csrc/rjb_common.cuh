@@ -39,6 +39,7 @@ struct MapView {
   const longlong2* pts;
   const uint32_t* edge_chain;  // per edge
   const uint32_t* row_index;   // per chain, CSR into pts
+  const uint32_t* last_bits;   // bit p set <=> point p is the last of its chain (no edge starts there)
   const int32_t* left;         // per chain
   const int32_t* right;        // per chain
   uint32_t n_points, n_edges, n_chains;

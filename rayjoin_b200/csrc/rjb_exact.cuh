@@ -186,8 +186,33 @@ static __device__ void lsi_point(const Seg& e1, const Seg& e2, long long& ox,
   i128 numx = (i128) ((u128) c2 * (u128) b1 - (u128) c1 * (u128) b2);
   i128 numy = (i128) ((u128) a2 * (u128) c1 - (u128) a1 * (u128) c2);
   i128 xn, xd, yn, yd;
-  rat_make(numx, denom, xn, xd);
-  rat_make(numy, denom, yn, yd);
+  const long long lim = 1ll << 38;
+  if (a1l > -lim && a1l < lim && b1l < lim && a2l > -lim && a2l < lim && b2l < lim) {
+    // Edges spanning < 2^38 internal units (1/512 of the coordinate range): nothing
+    // wraps (|num| < 2^126) and the gcd inputs can be shrunk first.
+    // gcd(num, den) = gcd(num - t*den, den) for any integer t; with t = e1.p1 the
+    // shifted numerators are (x - x1)*den = c2'*b1 and (y - y1)*den = -a1*c2', where
+    // c2' is e2's constant term in coordinates relative to e1.p1.  (x - x1) and
+    // (y - y1) are bounded by e1's span (< 2^38), so one double division yields the
+    // quotient to +-1 and the remainder is < 2*|den|: the binary gcd then starts
+    // from ~2k-bit operands instead of a ~110-bit numerator.
+    const i128 aden = iabs128(denom);
+    const i128 c2p = -((i128) (e2.x1 - e1.x1) * a2l + (i128) (e2.y1 - e1.y1) * b2l);
+    const i128 nxp = c2p * b1l, nyp = -c2p * a1l;
+    const double dden = (double) denom;
+    const long long qx = (long long) rint((double) nxp / dden);
+    const long long qy = (long long) rint((double) nyp / dden);
+    const i128 rx = nxp - (i128) qx * denom, ry = nyp - (i128) qy * denom;  // |r| < 2*|den|
+    const i128 gx = gcd128(rx, denom), gy = gcd128(ry, denom);
+    const i128 sx = denom < 0 ? -numx : numx, sy = denom < 0 ? -numy : numy;
+    xn = gx == 1 ? sx : sx / gx;
+    xd = gx == 1 ? aden : aden / gx;
+    yn = gy == 1 ? sy : sy / gy;
+    yd = gy == 1 ? aden : aden / gy;
+  } else {
+    rat_make(numx, denom, xn, xd);
+    rat_make(numy, denom, yn, yd);
+  }
   long long t = min4ll(e1.x1, e1.x2, e2.x1, e2.x2);
   if (xn < (i128) ((u128) (i128) t * (u128) xd)) { xn = t; xd = 1; }
   t = max4ll(e1.x1, e1.x2, e2.x1, e2.x2);

@@ -53,7 +53,9 @@ struct TravStats {
 
 // One leaf = <= 8 consecutive edges of one chain = one contiguous run of points,
 // read with warp-uniform (broadcast) loads.  Lanes in `h` test their own edge;
-// pairs whose exact integer boxes overlap become candidates.
+// pairs whose exact integer boxes overlap become candidates, recorded as the
+// START POINT indices (query point, base point) of the two edges: the exact pass
+// then needs no eid -> chain lookup at all.
 template <bool kStats>
 static __device__ __forceinline__ void lsi_leaf(const MapView& B, const BvhView& bvh, int leaf,
                                                 bool h, const Seg& q, uint32_t qe,
@@ -67,7 +69,7 @@ static __device__ __forceinline__ void lsi_leaf(const MapView& B, const BvhView&
   for (uint32_t k = 0; k < cnt; k++) {
     const longlong2 p2 = __ldg(bp + k + 1);
     const Seg e2 = {p1.x, p1.y, p2.x, p2.y};
-    emit_pair(h && seg_boxes_overlap(q, e2), qe, first_eid + k, out, cap, counter, lane);
+    emit_pair(h && seg_boxes_overlap(q, e2), qe, first_eid + chain + k, out, cap, counter, lane);
     p1 = p2;
   }
 }
@@ -119,31 +121,67 @@ static __device__ __forceinline__ void lsi_subtree(const MapView& B, const BvhVi
 // warp's union box; loads are coalesced and the 21 KB of the first two levels
 // stay L1-resident), then walks the remaining binary subtrees with per-lane
 // boxes.  Output: candidate pairs whose exact integer boxes overlap.
+//
+// Query slots are POINT indices: lane p owns the edge (pts[p], pts[p+1]) unless p
+// is the last point of a chain (one bit per point), so a tile is two coalesced
+// 16-byte loads per lane plus one 32-bit word per warp -- no dependent
+// eid -> chain -> point chain.  One tile per warp: the hardware CTA scheduler
+// balances the load (a persistent, software-pipelined variant measured slower).
+// With `order` (Morton-sorted queries) a slot is order[slot] instead.
+struct QTile {
+  longlong2 a, b;
+  uint32_t p;
+  bool valid;
+};
+
+static __device__ __forceinline__ QTile load_tile(const MapView& Q, const uint32_t* __restrict__ order,
+                                                  uint32_t n_slots, uint32_t tile, int lane) {
+  QTile t;
+  t.a = make_longlong2(0, 0);
+  t.b = make_longlong2(0, 0);
+  const uint32_t slot = tile * 32 + lane;
+  t.valid = slot < n_slots;
+  t.p = 0;
+  if (order) {
+    if (t.valid) t.p = order[slot];
+  } else {
+    t.p = slot;
+    if (tile * 32 < n_slots) {
+      const uint32_t w = __ldg(&Q.last_bits[tile]);  // warp-uniform
+      t.valid = t.valid && !((w >> lane) & 1u);
+    }
+  }
+  if (t.valid) {
+    t.a = __ldg(&Q.pts[t.p]);
+    t.b = __ldg(&Q.pts[t.p + 1]);
+  }
+  return t;
+}
+
 template <bool kStats>
 __global__ void __launch_bounds__(kLsiWarps * 32)
-k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
+k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order, uint32_t n_slots,
           uint2* __restrict__ out, uint32_t cap, unsigned int* counter,
           unsigned long long* stats) {
   __shared__ int s_stack[kLsiWarps][kStackDepth];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* stack = s_stack[warp];
-  const uint32_t slot = (blockIdx.x * kLsiWarps + warp) * 32 + lane;
-  const bool valid = slot < Q.n_edges;
-  uint32_t qe = 0;
-  Seg q = {0, 0, 0, 0};
+  const uint32_t n_tiles = (n_slots + 31) / 32;
+  const uint32_t tile = blockIdx.x * kLsiWarps + warp;
+  TravStats st = {0, 0, 0, 0, 0};
+  const int4 kNeutral = empty_box();
+  const int4 kEmpty = empty_box();
+  if (tile >= n_tiles) return;
+  const QTile cur = load_tile(Q, order, n_slots, tile, lane);
+  const bool valid = cur.valid;
+  const uint32_t qe = cur.p;
+  const Seg q = {cur.a.x, cur.a.y, cur.b.x, cur.b.y};
   int4 qb = empty_box();  // empty box for idle lanes
-  int4 ub = make_int4(0x7fffffff, 0x7fffffff, (int) 0x80000000, (int) 0x80000000);
-  if (valid) {
-    qe = order ? order[slot] : slot;
-    q = load_seg(Q, qe);
+  if (valid)
     qb = make_int4(quant(min(q.x1, q.x2)), quant(min(q.y1, q.y2)),
                    quant(max(q.x1, q.x2)), quant(max(q.y1, q.y2)));
-    ub = qb;
-  }
+  const int4 ub = qb;
   const int4 U = warp_union(ub);
-  TravStats st = {0, 0, 0, 0, 0};
-  const int4 kNeutral = make_int4(0x7fffffff, 0x7fffffff, (int) 0x80000000, (int) 0x80000000);
-  const int4 kEmpty = empty_box();
   if (bvh.n_leaves > 0 && box_overlap(U, bvh.root_box)) {
     // level 0: the 32 nodes at depth 5.  The union box only preselects slots; each
     // preselected slot is confirmed with the lanes' own boxes (ballot) before the
@@ -214,48 +252,75 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
   }
 }
 
-// Dense exact pass over the candidate list: intersect_test, and for the hits the
-// rational intersection point -> rjb_xsect (reference computes both inside the
-// traversal callback, lsi_lbvh.h:69-78; the RT backend has the same post-pass
-// structure, src/app/lsi_rt.h:66-112).  The candidate count is read on the
-// device, so no host round trip separates the two kernels.
-__global__ void __launch_bounds__(128)
-k_lsi_exact(MapView Q, MapView B, int query_map_id, const uint2* __restrict__ cand,
+// chain of point p: last c with row_index[c] <= p
+static __device__ __forceinline__ uint32_t chain_of_point(const MapView& m, uint32_t p) {
+  uint32_t lo = 0, hi = m.n_chains;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&m.row_index[mid]) <= p) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// Exact pass 1: intersect_test on every candidate (start-point pairs); the hits
+// are compacted into the result queue (one atomic per warp) as point-index pairs.
+// The candidate count is read on the device: no host round trip between kernels.
+__global__ void __launch_bounds__(256)
+k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ cand,
             const unsigned int* __restrict__ n_cand_dev, uint32_t cand_cap,
             rjb_xsect* __restrict__ out, uint32_t cap, unsigned int* counter) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n = min(*n_cand_dev, cand_cap);
   const int lane = threadIdx.x & 31;
-  if (i - lane >= n) return;  // whole warp idle
-  bool found = false;
-  uint2 pr = make_uint2(0, 0);
-  Seg e1 = {0, 0, 0, 0}, e2 = {0, 0, 0, 0};
-  if (i < n) {
-    pr = cand[i];
-    e1 = load_seg(Q, pr.x);
-    e2 = load_seg(B, pr.y);
-    found = lsi_intersect(e1, e2);
-  }
-  const unsigned m = __ballot_sync(0xffffffffu, found);
-  if (m == 0) return;
-  unsigned base = 0;
-  const int leader = __ffs(m) - 1;
-  if (lane == leader) base = atomicAdd(counter, (unsigned) __popc(m));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (found) {
-    const unsigned pos = base + __popc(m & ((1u << lane) - 1));
-    if (pos < cap) {
-      long long x, y;
-      lsi_point(e1, e2, x, y);
-      rjb_xsect r;
-      r.x = x;
-      r.y = y;
-      r.eid[0] = query_map_id == 0 ? pr.x : pr.y;
-      r.eid[1] = query_map_id == 0 ? pr.y : pr.x;
-      r.mid_point_polygon_id = RJB_DONTKNOW;
-      r._pad = 0;
-      out[pos] = r;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i - lane < n;
+       i += gridDim.x * blockDim.x) {
+    bool found = false;
+    uint2 pr = make_uint2(0, 0);
+    if (i < n) {
+      pr = cand[i];
+      const longlong2 a = __ldg(&Q.pts[pr.x]), b = __ldg(&Q.pts[pr.x + 1]);
+      const longlong2 c = __ldg(&B.pts[pr.y]), d = __ldg(&B.pts[pr.y + 1]);
+      const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
+      found = lsi_intersect(e1, e2);
     }
+    const unsigned m = __ballot_sync(0xffffffffu, found);
+    if (m == 0) continue;
+    unsigned base = 0;
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) base = atomicAdd(counter, (unsigned) __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (found) {
+      const unsigned pos = base + __popc(m & ((1u << lane) - 1));
+      if (pos < cap) {
+        out[pos].eid[0] = pr.x;  // point indices for now; pass 2 turns them into eids
+        out[pos].eid[1] = pr.y;
+      }
+    }
+  }
+}
+
+// Exact pass 2, dense over the hits: rational intersection point and the final
+// edge ids -> rjb_xsect (reference computes it inside the traversal callback,
+// lsi_lbvh.h:69-78; its RT backend has the same post-pass, src/app/lsi_rt.h:66-112).
+__global__ void __launch_bounds__(128)
+k_lsi_points(MapView Q, MapView B, int query_map_id, const unsigned int* __restrict__ counter,
+             uint32_t cap, rjb_xsect* __restrict__ out) {
+  const uint32_t n = min(*counter, cap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t pq = out[i].eid[0], pb = out[i].eid[1];
+    const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
+    const longlong2 c = __ldg(&B.pts[pb]), d = __ldg(&B.pts[pb + 1]);
+    const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
+    long long x, y;
+    lsi_point(e1, e2, x, y);
+    const uint32_t eq = pq - chain_of_point(Q, pq), eb = pb - chain_of_point(B, pb);
+    rjb_xsect r;
+    r.x = x;
+    r.y = y;
+    r.eid[0] = query_map_id == 0 ? eq : eb;
+    r.eid[1] = query_map_id == 0 ? eb : eq;
+    r.mid_point_polygon_id = RJB_DONTKNOW;
+    r._pad = 0;
+    out[i] = r;
   }
 }
 
