@@ -200,7 +200,7 @@ static const uint32_t* query_order_edges(rjb_ctx* c, const MapView& Q) {
   uint32_t* va = c->ord_vals_a.ensure(n);
   uint32_t* vb = c->ord_vals_b.ensure(n);
   k_query_keys_edges<<<div_up(n, 256), 256, 0, c->stream>>>(Q, c->sc.internal_min, ka, va);
-  sort_pairs_u64_u32(ka, kb, va, vb, n, 0, 64, c->ord_sort, c->stream);
+  sort_pairs_u64_u32(ka, kb, va, vb, n, 24, 64, c->ord_sort, c->stream);
   return vb;
 }
 
@@ -211,7 +211,9 @@ static const uint32_t* query_order_points(rjb_ctx* c, const longlong2* pts, uint
   uint32_t* va = c->ord_vals_a.ensure(n);
   uint32_t* vb = c->ord_vals_b.ensure(n);
   k_query_keys_points<<<div_up(n, 256), 256, 0, c->stream>>>(pts, n, c->sc.internal_min, ka, va);
-  sort_pairs_u64_u32(ka, kb, va, vb, n, 0, 64, c->ord_sort, c->stream);
+  // only coherence is needed, not a total order: 40 of the 62 Morton bits
+  // (cells of 2^-20 of the range per axis) = 5 radix passes instead of 8
+  sort_pairs_u64_u32(ka, kb, va, vb, n, 24, 64, c->ord_sort, c->stream);
   return vb;
 }
 
@@ -354,8 +356,12 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
       if (!Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no LBVH on the base map");
       const uint32_t* order = query_order_points(c, d_pts, n);
       RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
-      k_pip_bvh<<<div_up(n, kLsiWarps * 32), kLsiWarps * 32, 0, c->stream>>>(
-          d_pts, n, order, B, Bm.bvh.view(), q, eid, face, ctr + 1);
+      if (c->stats)
+        k_pip_bvh<true><<<div_up(n, kLsiWarps * 32), kLsiWarps * 32, 0, c->stream>>>(
+            d_pts, n, order, B, Bm.bvh.view(), q, eid, face, ctr);
+      else
+        k_pip_bvh<false><<<div_up(n, kLsiWarps * 32), kLsiWarps * 32, 0, c->stream>>>(
+            d_pts, n, order, B, Bm.bvh.view(), q, eid, face, ctr);
     } else if (mode == RJB_MODE_GRID) {
       if (!Bm.grid.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no grid on the base map");
       pip_grid(Bm.grid, d_pts, n, B, q, eid, face, ctr + 1, c->stream);
@@ -367,9 +373,10 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
   }
   RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
   RJB_CUDA(cudaGetLastError());
-  unsigned long long h[2];
+  unsigned long long h[8];
   RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   RJB_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(c->last_stats, h, sizeof(h));
   RJB_CUDA(cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]));
   c->last_ms[1] = 0;
   if (n_candidates) *n_candidates = h[1];

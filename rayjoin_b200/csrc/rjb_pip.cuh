@@ -19,98 +19,195 @@ static __device__ __forceinline__ int pip_y_bound(double best_y) {
   return quant((long long) floor(best_y) + 2);
 }
 
-__global__ void __launch_bounds__(kLsiWarps * 32)
+// per-lane query state of the PIP traversal
+struct PipLane {
+  long long px, py;
+  int qx, qy_lo, y_hi;  // quantised: x, lower y bound (py - 1), pruning bound
+  bool valid;
+  PipBest best;
+};
+
+// lane wants a box: its x range contains px, it reaches up to py, and it starts
+// below the lane's current best hit
+static __device__ __forceinline__ bool pip_wants(const PipLane& L, const int4& b) {
+  return L.valid && b.x <= L.qx && L.qx <= b.z && b.w >= L.qy_lo && b.y <= L.y_hi;
+}
+
+template <bool kStats>
+static __device__ __forceinline__ void pip_leaf(const MapView& B, const BvhView& bvh, int leaf, bool h,
+                                                PipLane& L, int q, unsigned long long& cand,
+                                                TravStats& st) {
+  const uint2 rec = __ldg(&bvh.leaf_rec[leaf]);
+  const uint32_t first_eid = rec.x, cnt = rec.y >> 28, chain = rec.y & 0x0FFFFFFFu;
+  const longlong2* bp = B.pts + (first_eid + chain);
+  longlong2 p1 = __ldg(bp);
+  if (kStats) st.leaves++;
+  for (uint32_t k = 0; k < cnt; k++) {
+    const longlong2 p2 = __ldg(bp + k + 1);
+    // cheap integer rejections before the int128 / double arithmetic: the edge must
+    // span px in x, reach up to py - 1, and start below the best crossing so far
+    // (same +-1 margins as the box test, exact in the integer domain)
+    if (h && min(p1.x, p2.x) <= L.px && L.px <= max(p1.x, p2.x) && max(p1.y, p2.y) >= L.py - 1 &&
+        quant(min(p1.y, p2.y)) <= L.y_hi) {
+      const Seg e = {p1.x, p1.y, p2.x, p2.y};
+      cand++;
+      if (pip_update(L.best, q, L.px, L.py, e, first_eid + k)) L.y_hi = pip_y_bound(L.best.y);
+    }
+    p1 = p2;
+  }
+}
+
+// binary subtree, near child (lower ymin) first; boxes are re-tested when a node
+// is reached because the pruning bounds shrink while the warp works
+template <bool kStats>
+static __device__ __forceinline__ void pip_subtree(const MapView& B, const BvhView& bvh, int root,
+                                                   int* stack, PipLane& L, int q,
+                                                   unsigned long long& cand, TravStats& st) {
+  int sp = 0;
+  int node = root;
+  while (true) {
+    const int4 lb = __ldg(&bvh.node_box[2 * node]);
+    const int4 rb = __ldg(&bvh.node_box[2 * node + 1]);
+    const int2 ch = __ldg(&bvh.node_child[node]);
+    const bool swap = rb.y < lb.y;
+    const int4 b0 = swap ? rb : lb, b1 = swap ? lb : rb;
+    const int c0 = swap ? ch.y : ch.x, c1 = swap ? ch.x : ch.y;
+    if (kStats) st.nodes++;
+    int next = -1;
+    {
+      const bool h = pip_wants(L, b0);
+      const unsigned m = __ballot_sync(0xffffffffu, h);
+      if (m) {
+        if (c0 >= 0) next = c0;
+        else {
+          if (kStats) st.lane_leaf += __popc(m);
+          pip_leaf<kStats>(B, bvh, ~c0, h, L, q, cand, st);
+        }
+      }
+    }
+    {
+      const bool h = pip_wants(L, b1);  // after the near child: bounds may have shrunk
+      const unsigned m = __ballot_sync(0xffffffffu, h);
+      if (m) {
+        if (c1 >= 0) {
+          if (next < 0) next = c1; else stack[sp++] = c1;
+        } else {
+          if (kStats) st.lane_leaf += __popc(m);
+          pip_leaf<kStats>(B, bvh, ~c1, h, L, q, cand, st);
+        }
+      }
+    }
+    if (kStats) st.maxsp = max(st.maxsp, (unsigned) sp);
+    if (next >= 0) { node = next; continue; }
+    if (sp == 0) break;
+    node = stack[--sp];
+  }
+}
+
+// the slot of a 32-ary top level that starts lowest among the candidates in m
+static __device__ __forceinline__ int lowest_slot(unsigned m, int ymin, int lane) {
+  const int key = ((m >> lane) & 1u) ? ymin : 0x7fffffff;
+  const int best = __reduce_min_sync(0xffffffffu, key);
+  return __ffs(__ballot_sync(0xffffffffu, key == best && ((m >> lane) & 1u))) - 1;
+}
+
+template <bool kStats>
+__global__ void __launch_bounds__(kLsiWarps * 32, 8)
 k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __restrict__ order,
           MapView B, BvhView bvh, int query_map_id, uint32_t* __restrict__ out_eid,
-          int32_t* __restrict__ out_face, unsigned long long* n_cand) {
+          int32_t* __restrict__ out_face, unsigned long long* counters) {
   __shared__ int s_stack[kLsiWarps][kStackDepth];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* stack = s_stack[warp];
   const uint32_t slot = (blockIdx.x * kLsiWarps + warp) * 32 + lane;
-  const bool valid = slot < n_pts;
+  PipLane L;
+  L.valid = slot < n_pts;
+  L.px = L.py = 0;
+  L.qx = L.qy_lo = 0;
+  L.y_hi = 0x7fffffff;
   uint32_t pi = 0;
-  long long px = 0, py = 0;
-  int qx = 1, qy_lo = 1;
-  if (valid) {
+  if (L.valid) {
     pi = order ? order[slot] : slot;
-    longlong2 p = pts[pi];
-    px = p.x;
-    py = p.y;
-    qx = quant(px);
-    qy_lo = quant(py - 1);
+    const longlong2 p = pts[pi];
+    L.px = p.x;
+    L.py = p.y;
+    L.qx = quant(p.x);
+    L.qy_lo = quant(p.y - 1);
   }
-  PipBest best;
-  pip_init(best);
-  int y_hi = 0x7fffffff;  // quantised pruning bound, shrinks as best improves
+  pip_init(L.best);
   unsigned long long cand = 0;
-  // lane wants a node box: x range contains px, box reaches up to py, and box
-  // starts below the current best hit
-  auto wants = [&](const int4& b) {
-    return valid && b.x <= qx && qx <= b.z && b.w >= qy_lo && b.y <= y_hi;
-  };
-  if (bvh.n_leaves > 0 && __ballot_sync(0xffffffffu, wants(bvh.root_box)) != 0) {
-    int sp = 0;
-    int node = 0;
-    while (true) {
-      const int4 lb = __ldg(&bvh.node_box[2 * node]);
-      const int4 rb = __ldg(&bvh.node_box[2 * node + 1]);
-      const int2 ch = __ldg(&bvh.node_child[node]);
-      // near child first: the one that starts lower in y (warp-uniform choice)
-      const bool swap = rb.y < lb.y;
-      const int4 b0 = swap ? rb : lb, b1 = swap ? lb : rb;
-      const int c0 = swap ? ch.y : ch.x, c1 = swap ? ch.x : ch.y;
-      int next = -1;
-#pragma unroll
-      for (int side = 0; side < 2; side++) {
-        const int4 bb = side ? b1 : b0;
-        const int c = side ? c1 : c0;
-        const bool h = wants(bb);  // re-evaluated: y_hi may have shrunk
-        const unsigned m = __ballot_sync(0xffffffffu, h);
-        if (m == 0) continue;
-        if (c >= 0) {
-          // far child goes to the stack and is re-tested when popped
-          if (next < 0) next = c; else stack[sp++] = c;
-          continue;
-        }
-        const uint2 rec = __ldg(&bvh.leaf_rec[~c]);
-        const uint32_t first_eid = rec.x, cnt = rec.y >> 28, chain = rec.y & 0x0FFFFFFFu;
-        const longlong2* bp = B.pts + (first_eid + chain);
-        longlong2 p1 = __ldg(bp);
-        for (uint32_t k = 0; k < cnt; k++) {
-          const longlong2 p2 = __ldg(bp + k + 1);
-          if (h) {
-            const Seg e = {p1.x, p1.y, p2.x, p2.y};
-            cand++;
-            if (pip_update(best, query_map_id, px, py, e, first_eid + k))
-              y_hi = pip_y_bound(best.y);
-          }
-          p1 = p2;
+  TravStats st = {0, 0, 0, 0, 0};
+  // the union of the lanes' rays: x range of the points, from the lowest point up
+  const int ux0 = __reduce_min_sync(0xffffffffu, L.valid ? L.qx : 0x7fffffff);
+  const int ux1 = __reduce_max_sync(0xffffffffu, L.valid ? L.qx : (int) 0x80000000);
+  const int uy0 = __reduce_min_sync(0xffffffffu, L.valid ? L.qy_lo : 0x7fffffff);
+  auto pre = [&](const int4& b) { return b.x <= ux1 && ux0 <= b.z && b.w >= uy0; };
+  if (bvh.n_leaves > 0 && pre(bvh.root_box)) {
+    // three levels of the 32-ary top tree (one lane per slot); slots are taken in
+    // order of their lower y bound so that near hits prune far slots
+    const int4 b0 = __ldg(&bvh.top_box[kTopOff0 + lane]);
+    const int c0 = __ldg(&bvh.top_code[kTopOff0 + lane]);
+    unsigned m0 = __ballot_sync(0xffffffffu, pre(b0));
+    if (kStats) st.top_steps++;
+    while (m0) {
+      const int g = lowest_slot(m0, b0.y, lane);
+      m0 &= ~(1u << g);
+      const bool h0 = pip_wants(L, shfl_box(b0, g));
+      if (__ballot_sync(0xffffffffu, h0) == 0) continue;
+      const int code0 = __shfl_sync(0xffffffffu, c0, g);
+      if (code0 < 0) { pip_leaf<kStats>(B, bvh, ~code0, h0, L, query_map_id, cand, st); continue; }
+      const int4 b1 = __ldg(&bvh.top_box[kTopOff1 + g * 32 + lane]);
+      const int c1 = __ldg(&bvh.top_code[kTopOff1 + g * 32 + lane]);
+      unsigned m1 = __ballot_sync(0xffffffffu, pre(b1));
+      if (kStats) st.top_steps++;
+      while (m1) {
+        const int h = lowest_slot(m1, b1.y, lane);
+        m1 &= ~(1u << h);
+        const bool h1 = pip_wants(L, shfl_box(b1, h));
+        if (__ballot_sync(0xffffffffu, h1) == 0) continue;
+        const int code1 = __shfl_sync(0xffffffffu, c1, h);
+        if (code1 < 0) { pip_leaf<kStats>(B, bvh, ~code1, h1, L, query_map_id, cand, st); continue; }
+        const int4 b2 = __ldg(&bvh.top_box[kTopOff2 + (g * 32 + h) * 32 + lane]);
+        const int c2 = __ldg(&bvh.top_code[kTopOff2 + (g * 32 + h) * 32 + lane]);
+        unsigned m2 = __ballot_sync(0xffffffffu, pre(b2));
+        if (kStats) st.top_steps++;
+        while (m2) {
+          const int i = lowest_slot(m2, b2.y, lane);
+          m2 &= ~(1u << i);
+          const bool h2 = pip_wants(L, shfl_box(b2, i));
+          if (__ballot_sync(0xffffffffu, h2) == 0) continue;
+          const int code2 = __shfl_sync(0xffffffffu, c2, i);
+          if (code2 < 0) pip_leaf<kStats>(B, bvh, ~code2, h2, L, query_map_id, cand, st);
+          else pip_subtree<kStats>(B, bvh, code2, stack, L, query_map_id, cand, st);
         }
       }
-      if (next >= 0) { node = next; continue; }
-      // pop until a node some lane still wants (its box is in the parent record,
-      // so the test happens after loading; cheap because loads are broadcast)
-      if (sp == 0) break;
-      node = stack[--sp];
     }
   }
-  if (valid) {
-    out_eid[pi] = best.eid;
+  if (L.valid) {
+    out_eid[pi] = L.best.eid;
     if (out_face) {
       int32_t face = RJB_EXTERIOR_FACE;
-      if (best.eid != RJB_NO_HIT) {
+      if (L.best.eid != RJB_NO_HIT) {
         // get_face_id, src/map/map.h:79-87
-        uint32_t c = B.edge_chain[best.eid];
-        longlong2 a = B.pts[best.eid + c], b = B.pts[best.eid + c + 1];
+        uint32_t c = B.edge_chain[L.best.eid];
+        longlong2 a = B.pts[L.best.eid + c], b = B.pts[L.best.eid + c + 1];
         face = a.x < b.x ? B.right[c] : B.left[c];
       }
       out_face[pi] = face;
     }
   }
-  if (n_cand) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
-    if (lane == 0 && cand) atomicAdd(n_cand, cand);
+  for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
+  if (lane == 0) {
+    if (cand) atomicAdd(counters + 1, cand);
+    if (kStats) {
+      atomicAdd(counters + 2, (unsigned long long) st.nodes);
+      atomicAdd(counters + 3, (unsigned long long) st.leaves);
+      atomicAdd(counters + 4, (unsigned long long) st.top_steps);
+      atomicAdd(counters + 5, (unsigned long long) st.lane_leaf);
+      atomicAdd(counters + 6, (unsigned long long) (st.leaves ? 1 : 0));
+      atomicMax(counters + 7, (unsigned long long) st.maxsp);
+    }
   }
 }
 
