@@ -130,6 +130,16 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the
+    committed `ncu --set full` capture of this workload (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
 def cpu_oracle_lsi(R, S, bbox, repeats=1):
     """The multithreaded host exact-predicate oracle on the same workload."""
     from oracle import oracle as O
@@ -208,6 +218,7 @@ def main():
     ap.add_argument("--grid-size", type=int, default=8192)
     ap.add_argument("--leaf-size", type=int, default=4)
     ap.add_argument("--sort-queries", type=int, default=0)
+    ap.add_argument("--filter", type=int, default=-1, help="occupancy pre-filter: -1 auto, 0 off, 1 on")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
@@ -246,6 +257,7 @@ def main():
     ctx.set_option("keep_host_graph", 0)
     ctx.set_option("lbvh_leaf_size", args.leaf_size)
     ctx.set_option("sort_queries", args.sort_queries)
+    ctx.set_option("lsi_filter", args.filter)
     ctx.set_bounding_box(*bbox)
     ctx.set_map(0, R)
     # pinned host copies of the S batch for the end-to-end leg
@@ -262,19 +274,27 @@ def main():
     lsi.Init(XSECT_FACTOR)
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    counts = torch.zeros(2, dtype=torch.int64, device=dev)
-    gathered = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    pending = []  # outstanding count all-gathers (NCCL runs them on its own stream)
 
     def step():
         n = lsi.Query(1)
-        if world > 1:  # the only data-path collective: per-rank result / candidate counts
-            with torch.cuda.stream(stream):
-                counts[0], counts[1] = n, lsi.n_candidates
-                dist.all_gather(gathered, counts)
+        if world > 1:
+            # the only data-path collective: per-rank {result, candidate} counts.  It is
+            # issued asynchronously (nothing in the next query depends on it) and waited
+            # for before the step's closing event, see wait_counts()
+            counts = torch.tensor([n, lsi.n_candidates], dtype=torch.int64).to(dev, non_blocking=True)
+            out = torch.empty(2 * world, dtype=torch.int64, device=dev)
+            pending.append((dist.all_gather_into_tensor(out, counts, async_op=True), out))
         return n
+
+    def wait_counts():
+        for w, _ in pending:
+            w.wait()
+        pending.clear()
 
     for _ in range(args.warmup):
         step()
+    wait_counts()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -290,6 +310,8 @@ def main():
             flush_buf.zero_()  # evict L2 between timed iterations (outside the events)
             ev[i][0].record(stream)
             n_pairs = step()
+            if i == args.steps - 1:
+                wait_counts()  # every count exchange has landed inside the timed region
             ev[i][1].record(stream)
         a, b = ctx.last_kernel_ms()
         k_ms.append(a)
@@ -361,14 +383,15 @@ def main():
             "candidate_pairs_per_s": all_cand / (ms_per_step / 1e3),
             "index_build_ms": float(np.min(build_ms)), "index_bytes": int(idx["bytes"]),
             "index_units": int(idx["units"]),
-            "kernel_ms": {kname: k_avg, "k_xsect_points_dyn": float(np.mean(p_ms))},
+            "kernel_ms": {kname: k_avg, "exact_pass(k_lsi_exact+k_lsi_points)" if args.mode == "lbvh"
+                          else "k_xsect_points_dyn": float(np.mean(p_ms))},
             "e2e": {"value": all_edges / (e2e_ms / 1e3 / args.steps), "unit": "query_edges/s",
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": (2 + (6 if args.sort_queries else 0)) * args.steps,
+            "gpu_launches": ((3 if args.mode == "lbvh" else 2) + (7 if args.sort_queries else 0)) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(kname),
                          "algorithmic_bytes": int(alg), "peak_source": peak_src},
         }
         # check the last result against the host oracle, and time it: the CPU baseline

@@ -127,6 +127,9 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
 /* tuning knobs that have no RayJoin flag (defaults are fine):
  *   "lbvh_leaf_size"  edges per LBVH leaf, 1..8 (default 4)
  *   "sort_queries"    1 = visit query edges / points in Morton order
+ *   "lsi_filter"      LBVH LSI occupancy pre-filter: -1 auto (default: on when the
+ *                     base map occupies < 25 % of a 4096^2 bitmap), 0 off, 1 on
+ *   "stats"           1 = collect traversal statistics (rjb_last_stats; slower)
  *   "keep_host_graph" 0 = rjb_set_map keeps no host copy of the source graph
  *                     (saves a memcpy; rjb_overlay_write then refuses)     */
 int rjb_set_option(rjb_ctx* ctx, const char* name, int64_t value);

@@ -80,6 +80,10 @@ struct rjb_ctx {
   // LSI result queue
   DBuf<uint2> pairs;
   DBuf<uint2> cands;      // LBVH traversal output: pairs whose exact boxes overlap
+  DBuf<uint32_t> survivors;  // occupancy pre-filter output (query start points)
+  DBuf<unsigned int> survivor_count;
+  int use_filter = -1;    // -1 auto (by occupancy), 0 off, 1 on
+  uint32_t last_survivors = 0;
   size_t cand_cap = 0;
   DBuf<rjb_xsect> xsects;
   DBuf<unsigned long long> counters;  // [0] = queue counter (low 32 bits), [1] = candidates
@@ -270,35 +274,56 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
     // was too small (the needed size is known exactly after the first attempt).
     if (c->cand_cap < (size_t) cap + 65536) c->cand_cap = 2 * (size_t) cap + 65536;
     const uint32_t* order = query_order_edges(c, Q);
+    // occupancy pre-filter: worthwhile when the base map covers a small part of the
+    // plane; it replaces the Morton order (survivors come out in map order)
+    bool filter = !order && (c->use_filter == 1 || (c->use_filter < 0 && Bm.bvh.occ_fraction < 0.25));
+    uint32_t* surv = filter ? c->survivors.ensure(Q.n_points) : nullptr;
+    unsigned int* surv_n = c->survivor_count.ensure(2);  // [0] survivors, [1] (query, leaf) pairs
     for (int attempt = 0;; attempt++) {
       RJB_REQUIRE(c->cand_cap < 0xFFFFFFF0ull, "rjb_lsi: candidate queue exceeds 2^32 entries");
       uint32_t ccap = (uint32_t) c->cand_cap;
       uint2* cands = c->cands.ensure(ccap);
       RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
       RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
-      // query slots: point indices (edge = slot, slot + 1), or the sorted edge list
+      // query slots: point indices (edge = slot, slot + 1), or a list of start points
+      // (Morton-sorted edges, or the survivors of the occupancy filter, whose count
+      // stays on the device)
       uint32_t n_slots = order ? Q.n_edges : Q.n_points;
+      const uint32_t* slots = order;
+      const unsigned int* n_slots_dev = nullptr;
+      RJB_CUDA(cudaMemsetAsync(surv_n, 0, 2 * sizeof(unsigned int), c->stream));
+      if (filter) {
+        k_lsi_filter<<<div_up(Q.n_points, 256), 256, 0, c->stream>>>(Q, Bm.bvh.occ.p, surv, surv_n);
+        slots = surv;
+        n_slots_dev = surv_n;
+        // grid for the worst case; warps beyond the survivor count exit at once
+        n_slots = c->last_survivors ? min(Q.n_points, c->last_survivors * 2 + 4096) : Q.n_points;
+      }
       unsigned tiles = div_up(n_slots, 32);
       unsigned blocks = div_up(tiles, kLsiWarps);
       if (c->stats)
         k_lsi_bvh<true><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-            Q, B, Bm.bvh.view(), order, n_slots, cands, ccap, (unsigned int*) (ctr + 1), ctr + 2);
+            Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, cands, ccap, surv_n + 1, ctr + 2);
       else
         k_lsi_bvh<false><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-            Q, B, Bm.bvh.view(), order, n_slots, cands, ccap, (unsigned int*) (ctr + 1), ctr + 2);
+            Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, cands, ccap, surv_n + 1, ctr + 2);
       RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
-      k_lsi_exact<<<kNumSMs * 8, 256, 0, c->stream>>>(Q, B, cands, (const unsigned int*) (ctr + 1),
-                                                    ccap, xs, cap, (unsigned int*) ctr);
+      k_lsi_exact<<<kNumSMs * 8, 256, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
+                                                    xs, cap, (unsigned int*) ctr, ctr + 1);
       k_lsi_points<<<kNumSMs * 16, 128, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs);
       RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
       RJB_CUDA(cudaGetLastError());
+      unsigned int hs[2] = {0, 0};
       RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+      RJB_CUDA(cudaMemcpyAsync(hs, surv_n, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
       RJB_CUDA(cudaStreamSynchronize(c->stream));
-      if ((uint32_t) h[1] <= ccap) break;
-      RJB_REQUIRE(attempt == 0, "rjb_lsi: candidate queue overflowed twice");
-      c->cand_cap = (size_t) (uint32_t) h[1] + (uint32_t) h[1] / 8 + 65536;
+      bool grid_too_small = filter && hs[0] > n_slots;  // launch was sized from the last query
+      if (filter) c->last_survivors = hs[0];
+      if (hs[1] <= ccap && !grid_too_small) break;
+      RJB_REQUIRE(attempt < 2, "rjb_lsi: internal queues overflowed repeatedly");
+      if (hs[1] > ccap) c->cand_cap = (size_t) hs[1] + hs[1] / 8 + 65536;
     }
-    h[1] = (uint32_t) h[1];
+    if (filter) h[7] = c->last_survivors;
   } else {
     RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
     RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
@@ -459,6 +484,8 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
       c->leaf_size = (int) value;
     } else if (n == "sort_queries") {
       c->sort_queries = value != 0;
+    } else if (n == "lsi_filter") {
+      c->use_filter = (int) value;
     } else if (n == "stats") {
       c->stats = value != 0;
     } else if (n == "keep_host_graph") {

@@ -57,9 +57,22 @@ struct BvhView {
   // lane per slot.  Level k has 32^(k+1) slots; empty slots have an empty box.
   const int4* top_box;     // [32 | 1024 | 32768]
   const int* top_code;     // child code per slot (>= 0 internal node, < 0 ~leaf)
+  // occupancy bitmap: kOccDim x kOccDim cells over the whole coordinate range, bit
+  // set <=> some base edge's box touches the cell.  2 MB, cache resident: a query
+  // edge whose box touches no occupied cell cannot intersect anything.
+  const uint32_t* occ;
   int4 root_box;
   uint32_t n_leaves;
 };
+
+constexpr int kOccBits = 12;             // 4096 x 4096 cells
+constexpr int kOccDim = 1 << kOccBits;
+constexpr int kOccShift = 31 - kOccBits;  // quantised coordinates span 31 bits
+
+// occupancy cell of a quantised coordinate (monotone, in [0, kOccDim))
+static __host__ __device__ __forceinline__ int occ_cell(int q) {
+  return (int) (((unsigned) q + (1u << 30)) >> kOccShift) & (kOccDim - 1);
+}
 
 constexpr int kTopOff0 = 0, kTopOff1 = 32, kTopOff2 = 32 + 1024, kTopSlots = 32 + 1024 + 32768;
 

@@ -30,6 +30,9 @@ struct Bvh {
   DBuf<int4> root_box_d;
   DBuf<int4> top_box;
   DBuf<int> top_code;
+  DBuf<uint32_t> occ;
+  DBuf<unsigned int> occ_count_d;
+  double occ_fraction = 1.0;  // share of occupied cells (the filter pays off when it is small)
   ScanTemp scan_tmp;
   SortTemp sort_tmp;
 
@@ -42,12 +45,13 @@ struct Bvh {
     v.n_leaves = n_leaves;
     v.top_box = top_box.p;
     v.top_code = top_code.p;
+    v.occ = occ.p;
     return v;
   }
   size_t index_bytes() const {
     uint32_t n_int = n_leaves > 1 ? n_leaves - 1 : 1;
     return (size_t) n_int * (2 * sizeof(int4) + sizeof(int2)) + (size_t) n_leaves * sizeof(uint2) +
-           (size_t) kTopSlots * (sizeof(int4) + sizeof(int));
+           (size_t) kTopSlots * (sizeof(int4) + sizeof(int)) + (size_t) kOccDim * kOccDim / 8;
   }
 };
 
@@ -236,6 +240,28 @@ __global__ void k_top_tree(const int4* __restrict__ node_box, const int2* __rest
   }
 }
 
+// occupancy bitmap: every cell the (quantised) box of a leaf touches.  Leaves, not
+// edges: 4x fewer boxes, and the leaf box is what the traversal would test anyway.
+__global__ void k_occ_mark(const int4* __restrict__ leaf_box, uint32_t n, uint32_t* __restrict__ occ) {
+  uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n) return;
+  const int4 b = leaf_box[l];
+  const int x0 = occ_cell(b.x), x1 = occ_cell(b.z), y0 = occ_cell(b.y), y1 = occ_cell(b.w);
+  for (int y = y0; y <= y1; y++)
+    for (int x = x0; x <= x1; x++) {
+      const uint32_t bit = (uint32_t) y * kOccDim + x;
+      atomicOr(&occ[bit >> 5], 1u << (bit & 31));
+    }
+}
+
+__global__ void k_occ_count(const uint32_t* __restrict__ occ, uint32_t n_words, unsigned int* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned c = i < n_words ? __popc(occ[i]) : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long imin,
                               cudaStream_t st) {
   RJB_REQUIRE(leaf_size >= 1 && leaf_size <= 8, "lbvh_leaf_size must be in 1..8");
@@ -284,9 +310,19 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
   int4* tbox = b.top_box.ensure(kTopSlots);
   int* tcode = b.top_code.ensure(kTopSlots);
   k_top_tree<<<32768 / 256, 256, 0, st>>>(nbox, nchild, root_d, n, tbox, tcode);
+  const uint32_t occ_words = (uint32_t) kOccDim * kOccDim / 32;
+  uint32_t* occ = b.occ.ensure(occ_words);
+  unsigned int* occ_cnt = b.occ_count_d.ensure(1);
+  RJB_CUDA(cudaMemsetAsync(occ, 0, occ_words * sizeof(uint32_t), st));
+  RJB_CUDA(cudaMemsetAsync(occ_cnt, 0, sizeof(unsigned int), st));
+  k_occ_mark<<<div_up(n, T), T, 0, st>>>(box_s, n, occ);
+  k_occ_count<<<div_up(occ_words, T), T, 0, st>>>(occ, occ_words, occ_cnt);
   RJB_CUDA(cudaGetLastError());
+  unsigned int occ_set = 0;
   RJB_CUDA(cudaMemcpyAsync(&b.root_box, root_d, sizeof(int4), cudaMemcpyDeviceToHost, st));
+  RJB_CUDA(cudaMemcpyAsync(&occ_set, occ_cnt, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
   RJB_CUDA(cudaStreamSynchronize(st));
+  b.occ_fraction = (double) occ_set / ((double) kOccDim * kOccDim);
 }
 
 }  // namespace rjb

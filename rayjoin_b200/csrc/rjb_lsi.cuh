@@ -51,27 +51,18 @@ struct TravStats {
   unsigned nodes, leaves, top_steps, lane_leaf, maxsp;
 };
 
-// One leaf = <= 8 consecutive edges of one chain = one contiguous run of points,
-// read with warp-uniform (broadcast) loads.  Lanes in `h` test their own edge;
-// pairs whose exact integer boxes overlap become candidates, recorded as the
-// START POINT indices (query point, base point) of the two edges: the exact pass
-// then needs no eid -> chain lookup at all.
+// A leaf that some lanes' boxes overlap is NOT opened by the traversing warp: the
+// (query start point, leaf) pairs are appended to a queue (one atomic per warp)
+// and resolved later by a dense kernel in which every thread is independent.
+// Keeping the leaf's dependent loads and its divergent edge tests out of the
+// warp-synchronous walk roughly halves the traversal time.
 template <bool kStats>
-static __device__ __forceinline__ void lsi_leaf(const MapView& B, const BvhView& bvh, int leaf,
-                                                bool h, const Seg& q, uint32_t qe,
-                                                uint2* __restrict__ out, uint32_t cap,
-                                                unsigned int* counter, int lane, TravStats& st) {
-  const uint2 rec = __ldg(&bvh.leaf_rec[leaf]);
-  const uint32_t first_eid = rec.x, cnt = rec.y >> 28, chain = rec.y & 0x0FFFFFFFu;
-  const longlong2* bp = B.pts + (first_eid + chain);
-  longlong2 p1 = __ldg(bp);
+static __device__ __forceinline__ void lsi_leaf(const MapView&, const BvhView&, int leaf, bool h,
+                                                const Seg&, uint32_t qe, uint2* __restrict__ out,
+                                                uint32_t cap, unsigned int* counter, int lane,
+                                                TravStats& st) {
   if (kStats) st.leaves++;
-  for (uint32_t k = 0; k < cnt; k++) {
-    const longlong2 p2 = __ldg(bp + k + 1);
-    const Seg e2 = {p1.x, p1.y, p2.x, p2.y};
-    emit_pair(h && seg_boxes_overlap(q, e2), qe, first_eid + chain + k, out, cap, counter, lane);
-    p1 = p2;
-  }
+  emit_pair(h, qe, (uint32_t) leaf, out, cap, counter, lane);
 }
 
 // Binary part of the traversal, below the 32-ary top tree: node records are read
@@ -158,14 +149,46 @@ static __device__ __forceinline__ QTile load_tile(const MapView& Q, const uint32
   return t;
 }
 
+// Occupancy pre-filter: streams every query edge once, keeps the start-point index
+// of those whose (quantised) box touches an occupied cell of the base map's
+// bitmap.  For a sparse base map (county boundaries: ~1 % of the cells) a few per
+// cent of the query edges survive, and only those are traversed.
+__global__ void __launch_bounds__(256)
+k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__ survivors,
+             unsigned int* counter) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (tile * 32 >= Q.n_points) return;
+  const QTile t = load_tile(Q, nullptr, Q.n_points, tile, lane);
+  bool keep = false;
+  if (t.valid) {
+    const int x0 = occ_cell(quant(min(t.a.x, t.b.x))), x1 = occ_cell(quant(max(t.a.x, t.b.x)));
+    const int y0 = occ_cell(quant(min(t.a.y, t.b.y))), y1 = occ_cell(quant(max(t.a.y, t.b.y)));
+    for (int y = y0; y <= y1 && !keep; y++)
+      for (int x = x0; x <= x1; x++) {
+        const uint32_t bit = (uint32_t) y * kOccDim + x;
+        if ((__ldg(&occ[bit >> 5]) >> (bit & 31)) & 1u) { keep = true; break; }
+      }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (m == 0) return;
+  unsigned base = 0;
+  const int leader = __ffs(m) - 1;
+  if (lane == leader) base = atomicAdd(counter, (unsigned) __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (keep) survivors[base + __popc(m & ((1u << lane) - 1))] = t.p;
+}
+
 template <bool kStats>
 __global__ void __launch_bounds__(kLsiWarps * 32)
 k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order, uint32_t n_slots,
+          const unsigned int* __restrict__ n_slots_dev,
           uint2* __restrict__ out, uint32_t cap, unsigned int* counter,
           unsigned long long* stats) {
   __shared__ int s_stack[kLsiWarps][kStackDepth];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* stack = s_stack[warp];
+  if (n_slots_dev) n_slots = *n_slots_dev;  // survivor count of the pre-filter
   const uint32_t n_tiles = (n_slots + 31) / 32;
   const uint32_t tile = blockIdx.x * kLsiWarps + warp;
   TravStats st = {0, 0, 0, 0, 0};
@@ -262,40 +285,66 @@ static __device__ __forceinline__ uint32_t chain_of_point(const MapView& m, uint
   return lo;
 }
 
-// Exact pass 1: intersect_test on every candidate (start-point pairs); the hits
-// are compacted into the result queue (one atomic per warp) as point-index pairs.
-// The candidate count is read on the device: no host round trip between kernels.
+// Exact pass 1, dense over the (query start point, leaf) pairs of the traversal:
+// each thread tests its query edge against the <= 8 consecutive base edges of the
+// leaf (one contiguous run of points): exact integer box test, then
+// intersect_test.  Hits are compacted into the result queue (one atomic per warp
+// and edge slot) as start-point index pairs.  The pair count is read on the
+// device: no host round trip between the kernels.
 __global__ void __launch_bounds__(256)
-k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ cand,
-            const unsigned int* __restrict__ n_cand_dev, uint32_t cand_cap,
-            rjb_xsect* __restrict__ out, uint32_t cap, unsigned int* counter) {
-  const uint32_t n = min(*n_cand_dev, cand_cap);
+k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ pairs, const uint2* __restrict__ leaf_rec,
+            const unsigned int* __restrict__ n_pairs_dev, uint32_t pair_cap,
+            rjb_xsect* __restrict__ out, uint32_t cap, unsigned int* counter,
+            unsigned long long* n_cand) {
+  const uint32_t n = min(*n_pairs_dev, pair_cap);
   const int lane = threadIdx.x & 31;
+  unsigned long long cand = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i - lane < n;
        i += gridDim.x * blockDim.x) {
-    bool found = false;
-    uint2 pr = make_uint2(0, 0);
-    if (i < n) {
-      pr = cand[i];
-      const longlong2 a = __ldg(&Q.pts[pr.x]), b = __ldg(&Q.pts[pr.x + 1]);
-      const longlong2 c = __ldg(&B.pts[pr.y]), d = __ldg(&B.pts[pr.y + 1]);
-      const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
-      found = lsi_intersect(e1, e2);
+    const bool act = i < n;
+    uint32_t pq = 0, pb0 = 0, cnt = 0;
+    Seg e1 = {0, 0, 0, 0};
+    longlong2 p1 = make_longlong2(0, 0);
+    if (act) {
+      const uint2 pr = pairs[i];
+      pq = pr.x;
+      const uint2 rec = __ldg(&leaf_rec[pr.y]);
+      cnt = rec.y >> 28;
+      pb0 = rec.x + (rec.y & 0x0FFFFFFFu);
+      const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
+      e1 = {a.x, a.y, b.x, b.y};
+      p1 = __ldg(&B.pts[pb0]);
     }
-    const unsigned m = __ballot_sync(0xffffffffu, found);
-    if (m == 0) continue;
-    unsigned base = 0;
-    const int leader = __ffs(m) - 1;
-    if (lane == leader) base = atomicAdd(counter, (unsigned) __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (found) {
-      const unsigned pos = base + __popc(m & ((1u << lane) - 1));
-      if (pos < cap) {
-        out[pos].eid[0] = pr.x;  // point indices for now; pass 2 turns them into eids
-        out[pos].eid[1] = pr.y;
+    const uint32_t cmax = __reduce_max_sync(0xffffffffu, cnt);
+    for (uint32_t k = 0; k < cmax; k++) {
+      bool found = false;
+      if (k < cnt) {
+        const longlong2 p2 = __ldg(&B.pts[pb0 + k + 1]);
+        const Seg e2 = {p1.x, p1.y, p2.x, p2.y};
+        if (seg_boxes_overlap(e1, e2)) {
+          cand++;
+          found = lsi_intersect(e1, e2);
+        }
+        p1 = p2;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, found);
+      if (m == 0) continue;
+      unsigned base = 0;
+      const int leader = __ffs(m) - 1;
+      if (lane == leader) base = atomicAdd(counter, (unsigned) __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (found) {
+        const unsigned pos = base + __popc(m & ((1u << lane) - 1));
+        if (pos < cap) {
+          out[pos].eid[0] = pq;  // point indices for now; pass 2 turns them into eids
+          out[pos].eid[1] = pb0 + k;
+        }
       }
     }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
+  if (lane == 0 && cand) atomicAdd(n_cand, cand);
 }
 
 // Exact pass 2, dense over the hits: rational intersection point and the final
