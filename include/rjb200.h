@@ -206,6 +206,11 @@ int rjb_last_stats(const rjb_ctx* ctx, uint64_t out[8]);
  * out[1] = bytes of the index, out[2] = leaf size / grid size, out[3] = 0      */
 int rjb_index_info(const rjb_ctx* ctx, int map_id, int mode, uint64_t out[4]);
 
+/* test hook: the engine's onesweep radix sort on host (key, value) pairs, key
+ * bits [begin_bit, end_bit), stable; arrays are sorted in place                 */
+int rjb_debug_sort_pairs(rjb_ctx* ctx, uint64_t* h_keys, uint32_t* h_vals,
+                         uint64_t n, int begin_bit, int end_bit);
+
 /* ---- transfers --------------------------------------------------------------- */
 int rjb_copy_to_host(rjb_ctx* ctx, const void* d_src, void* h_dst,
                      uint64_t bytes);

@@ -23,7 +23,7 @@ EXPORTS = [
     "rjb_set_bounding_box", "rjb_get_scaling", "rjb_set_map", "rjb_map_info",
     "rjb_map_device_views", "rjb_build_index", "rjb_set_option", "rjb_lsi", "rjb_pip",
     "rjb_pip_host", "rjb_pip_host_scaled", "rjb_overlay_run", "rjb_overlay_results", "rjb_overlay_write",
-    "rjb_last_kernel_ms", "rjb_last_stats", "rjb_index_info", "rjb_copy_to_host", "rjb_sync",
+    "rjb_debug_sort_pairs", "rjb_last_kernel_ms", "rjb_last_stats", "rjb_index_info", "rjb_copy_to_host", "rjb_sync",
     "rjb_graph_load", "rjb_graph_read_text", "rjb_graph_read_bin", "rjb_graph_write_bin",
     "rjb_graph_free",
 ]
@@ -279,6 +279,13 @@ class Context:
         out = (C.c_double * 2)()
         _check(self.lib.rjb_last_kernel_ms(self._h, out))
         return out[0], out[1]
+
+    def debug_sort_pairs(self, keys, vals, begin_bit=0, end_bit=64):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+        vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+        _check(self.lib.rjb_debug_sort_pairs(self._h, _ptr(keys), _ptr(vals), C.c_uint64(len(keys)),
+                                             C.c_int(begin_bit), C.c_int(end_bit)))
+        return keys, vals
 
     def last_stats(self):
         out = (C.c_uint64 * 8)()

@@ -725,6 +725,28 @@ int rjb_index_info(const rjb_ctx* c, int map_id, int mode, uint64_t out[4]) {
   });
 }
 
+/* debug hook for the test-suite: sorts host (key, value) pairs on the device with
+ * the engine's radix sort over key bits [begin_bit, end_bit) (stable) */
+int rjb_debug_sort_pairs(rjb_ctx* c, uint64_t* h_keys, uint32_t* h_vals, uint64_t n, int begin_bit,
+                         int end_bit) {
+  return guarded([&] {
+    RJB_REQUIRE(c && (n == 0 || (h_keys && h_vals)), "NULL argument");
+    RJB_REQUIRE(n < (1u << 30), "too many pairs");
+    RJB_CUDA(cudaSetDevice(c->device));
+    if (n == 0) return;
+    uint64_t* ka = c->ord_keys_a.ensure(n);
+    uint64_t* kb = c->ord_keys_b.ensure(n);
+    uint32_t* va = c->ord_vals_a.ensure(n);
+    uint32_t* vb = c->ord_vals_b.ensure(n);
+    RJB_CUDA(cudaMemcpyAsync(ka, h_keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+    RJB_CUDA(cudaMemcpyAsync(va, h_vals, n * 4, cudaMemcpyHostToDevice, c->stream));
+    sort_pairs_u64_u32(ka, kb, va, vb, (uint32_t) n, begin_bit, end_bit, c->ord_sort, c->stream);
+    RJB_CUDA(cudaMemcpyAsync(h_keys, kb, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    RJB_CUDA(cudaMemcpyAsync(h_vals, vb, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    RJB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
 int rjb_overlay_run(rjb_ctx* c, int mode, uint32_t grid_size, double xsect_factor,
                     double* phase_ms) {
   return guarded([&] {

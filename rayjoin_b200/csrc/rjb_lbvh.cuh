@@ -14,6 +14,8 @@
 
 namespace rjb {
 
+constexpr int kMortonDrop = 24;  // Morton bits ignored by the leaf order
+
 struct Bvh {
   DBuf<int4> node_box;
   DBuf<int2> node_child;
@@ -109,7 +111,9 @@ __global__ void k_leaf_fill(MapView m, const uint32_t* __restrict__ leaf_base, u
   }
   rec[l] = make_uint2(p1 - c, (cnt << 28) | c);
   box[l] = make_int4(quant(xmin), quant(ymin), quant(xmax), quant(ymax));
-  key[l] = morton64(xmin + ((xmax - xmin) >> 1), ymin + ((ymax - ymin) >> 1), imin);
+  // 40 significant key bits (cells of 2^-20 of the range per axis) = 5 radix passes;
+  // the low bits are cleared so that the sorted keys stay monotone for Karras' delta()
+  key[l] = morton64(xmin + ((xmax - xmin) >> 1), ymin + ((ymax - ymin) >> 1), imin) & ~((1ull << kMortonDrop) - 1);
   val[l] = l;
 }
 
@@ -296,9 +300,7 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
   int4* root_d = b.root_box_d.ensure(1);
 
   k_leaf_fill<<<div_up(n, T), T, 0, st>>>(m, base, n, leaf_size, imin, rec_u, box_u, ka, va);
-  // 2 x 32 bits of Morton code: the top bit pair is always 0 for a 47-bit
-  // range >> 15, so 62 key bits suffice
-  sort_pairs_u64_u32(ka, kb, va, vb, n, 0, 64, b.sort_tmp, st);
+  sort_pairs_u64_u32(ka, kb, va, vb, n, kMortonDrop, 64, b.sort_tmp, st);
   k_leaf_gather<<<div_up(n, T), T, 0, st>>>(vb, n, rec_u, box_u, rec_s, box_s);
   if (n == 1) {
     k_single_leaf_root<<<1, 1, 0, st>>>(box_s, nbox, nchild, root_d);

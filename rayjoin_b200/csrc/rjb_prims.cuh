@@ -1,8 +1,6 @@
 // Device primitives: RAII buffers, a hand-written exclusive scan, and the
 // radix sort used by the LBVH / grid builders and the overlay.
 #pragma once
-#include <cub/device/device_radix_sort.cuh>
-
 #include "rjb_common.cuh"
 
 namespace rjb {
@@ -142,24 +140,6 @@ static inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_
   RJB_CUDA(cudaGetLastError());
 }
 
-// ---------------------------------------------------------------------------
-// radix sort of (u64 key, u32 value) pairs over key bits [begin_bit, end_bit)
-// ---------------------------------------------------------------------------
-struct SortTemp {
-  DBuf<uint8_t> cub_tmp;
-};
-
-static inline void sort_pairs_u64_u32(const uint64_t* k_in, uint64_t* k_out,
-                                      const uint32_t* v_in, uint32_t* v_out, uint32_t n,
-                                      int begin_bit, int end_bit, SortTemp& tmp,
-                                      cudaStream_t st) {
-  if (n == 0) return;
-  size_t bytes = 0;
-  RJB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k_in, k_out, v_in, v_out, (int) n,
-                                           begin_bit, end_bit, st));
-  void* t = tmp.cub_tmp.ensure(bytes);
-  RJB_CUDA(cub::DeviceRadixSort::SortPairs(t, bytes, k_in, k_out, v_in, v_out, (int) n,
-                                           begin_bit, end_bit, st));
-}
-
 }  // namespace rjb
+
+#include "rjb_sort.cuh"
