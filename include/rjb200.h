@@ -181,6 +181,16 @@ int rjb_pip_host_scaled(rjb_ctx* ctx, int query_map_id, int mode,
  * WriteOutputChain (src/app/output_chain.h:41-205), same text format.       */
 int rjb_overlay_run(rjb_ctx* ctx, int mode, uint32_t grid_size,
                     double xsect_factor, double* phase_ms);
+/* Multi-GPU overlay, final step on one rank: IntersectEdge and
+ * LocateVerticesInOtherMap were run on shards (rjb_lsi / rjb_pip per rank) and
+ * gathered; this call builds the indexes, imports the gathered host arrays
+ * (edge / point ids of the UNSHARDED maps) and runs ComputeOutputPolygons, after
+ * which rjb_overlay_results / rjb_overlay_write behave as after rjb_overlay_run. */
+int rjb_overlay_finish(rjb_ctx* ctx, int mode, uint32_t grid_size,
+                       const rjb_xsect* h_xsects, uint64_t n_xsects,
+                       const uint32_t* h_closest_eid0, const int32_t* h_point_in_polygon0,
+                       const uint32_t* h_closest_eid1, const int32_t* h_point_in_polygon1,
+                       double* phase_ms);
 /* results of the last rjb_overlay_run, device pointers:
  *  xsects sorted by eid[im] and along the edge, with mid_point_polygon_id
  *  (xsect_edges_sorted_[im]); closest_eid / point_in_polygon per vertex of

@@ -22,7 +22,7 @@ EXPORTS = [
     "rjb_last_error", "rjb_version", "rjb_create", "rjb_destroy", "rjb_set_stream",
     "rjb_set_bounding_box", "rjb_get_scaling", "rjb_set_map", "rjb_map_info",
     "rjb_map_device_views", "rjb_build_index", "rjb_set_option", "rjb_lsi", "rjb_pip",
-    "rjb_pip_host", "rjb_pip_host_scaled", "rjb_overlay_run", "rjb_overlay_results", "rjb_overlay_write",
+    "rjb_pip_host", "rjb_pip_host_scaled", "rjb_overlay_run", "rjb_overlay_finish", "rjb_overlay_results", "rjb_overlay_write",
     "rjb_debug_sort_pairs", "rjb_last_kernel_ms", "rjb_last_stats", "rjb_index_info", "rjb_copy_to_host", "rjb_sync",
     "rjb_graph_load", "rjb_graph_read_text", "rjb_graph_read_bin", "rjb_graph_write_bin",
     "rjb_graph_free",
@@ -396,6 +396,20 @@ class MapOverlay:
         _check(self.ctx.lib.rjb_overlay_run(self.ctx._h, C.c_int(MODES.get(self.mode, self.mode)),
                                             C.c_uint32(self.grid_size),
                                             C.c_double(self.xsect_factor), ms))
+        self.phase_ms = dict(zip(("build", "lsi", "pip0", "pip1", "polygons", "total"), ms))
+        return self.phase_ms
+
+    def Finish(self, xsects, closest_eids, point_in_polygon):
+        """Final step of the multi-GPU overlay on one rank (rjb_overlay_finish): the
+        gathered results of the sharded LSI / vertex-location phases go in,
+        ComputeOutputPolygons runs here."""
+        xs = np.ascontiguousarray(xsects, dtype=XSECT_DTYPE)
+        ce = [np.ascontiguousarray(a, dtype=np.uint32) for a in closest_eids]
+        pf = [np.ascontiguousarray(a, dtype=np.int32) for a in point_in_polygon]
+        ms = (C.c_double * 6)()
+        _check(self.ctx.lib.rjb_overlay_finish(
+            self.ctx._h, C.c_int(MODES.get(self.mode, self.mode)), C.c_uint32(self.grid_size),
+            _ptr(xs), C.c_uint64(len(xs)), _ptr(ce[0]), _ptr(pf[0]), _ptr(ce[1]), _ptr(pf[1]), ms))
         self.phase_ms = dict(zip(("build", "lsi", "pip0", "pip1", "polygons", "total"), ms))
         return self.phase_ms
 

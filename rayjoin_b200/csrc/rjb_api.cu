@@ -756,6 +756,27 @@ int rjb_overlay_run(rjb_ctx* c, int mode, uint32_t grid_size, double xsect_facto
   });
 }
 
+int rjb_overlay_finish(rjb_ctx* c, int mode, uint32_t grid_size, const rjb_xsect* h_xsects,
+                       uint64_t n_xsects, const uint32_t* h_closest_eid0,
+                       const int32_t* h_point_in_polygon0, const uint32_t* h_closest_eid1,
+                       const int32_t* h_point_in_polygon1, double* phase_ms) {
+  return guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    RJB_REQUIRE(n_xsects == 0 || h_xsects, "rjb_overlay_finish: NULL xsects");
+    RJB_REQUIRE(h_closest_eid0 && h_point_in_polygon0 && h_closest_eid1 && h_point_in_polygon1,
+                "rjb_overlay_finish: NULL vertex-location arrays");
+    RJB_CUDA(cudaSetDevice(c->device));
+    OverlayImport imp;
+    imp.h_xsects = h_xsects;
+    imp.n_xsects = n_xsects;
+    imp.h_closest_eid[0] = h_closest_eid0;
+    imp.h_closest_eid[1] = h_closest_eid1;
+    imp.h_point_in_polygon[0] = h_point_in_polygon0;
+    imp.h_point_in_polygon[1] = h_point_in_polygon1;
+    overlay_run(c, mode, grid_size, 0.0, phase_ms, &imp);
+  });
+}
+
 int rjb_overlay_results(const rjb_ctx* c, int im, const rjb_xsect** d_xsects, uint64_t* n_xsects,
                         const uint32_t** d_closest_eid, const int32_t** d_point_in_polygon) {
   return guarded([&] {

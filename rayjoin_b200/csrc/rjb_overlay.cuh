@@ -97,8 +97,18 @@ __global__ void k_ov_fill_mid_faces(rjb_xsect* __restrict__ xs, const uint32_t* 
   for (uint32_t k = 0; b + k + 1 < e; k++) xs[b + k].mid_point_polygon_id = mid_face[b + k - s];
 }
 
+// Results computed elsewhere (the multi-GPU driver: LSI and vertex location are
+// sharded over the ranks and gathered on one) handed to overlay_run instead of
+// running IntersectEdge / LocateVerticesInOtherMap here.
+struct OverlayImport {
+  const rjb_xsect* h_xsects = nullptr;
+  uint64_t n_xsects = 0;
+  const uint32_t* h_closest_eid[2] = {nullptr, nullptr};
+  const int32_t* h_point_in_polygon[2] = {nullptr, nullptr};
+};
+
 static void overlay_run(rjb_ctx* c, int mode, uint32_t grid_size, double xsect_factor,
-                        double* phase_ms) {
+                        double* phase_ms, const OverlayImport* imp = nullptr) {
   RJB_REQUIRE(c->maps[0].loaded && c->maps[1].loaded, "rjb_overlay_run: load both maps first");
   RJB_REQUIRE(mode == RJB_MODE_LBVH || mode == RJB_MODE_GRID || mode == RJB_MODE_BRUTE,
               "rjb_overlay_run: unknown mode");
@@ -112,22 +122,42 @@ static void overlay_run(rjb_ctx* c, int mode, uint32_t grid_size, double xsect_f
   // BuildIndex: one index per map, both directions are queried
   for (int im = 0; im < 2; im++) do_build_index(c, im, mode, grid_size, nullptr);
   mark(1);
-  // IntersectEdge(0): map 0 is the query side (src/run_overlay.cu:206)
-  uint64_t n = do_lsi(c, 0, mode, xsect_factor, nullptr);
-  ov.n_xsects = n;
-  mark(2);
-  // LocateVerticesInOtherMap(im)
-  for (int im = 0; im < 2; im++) {
-    DeviceMap& Qm = c->maps[im];
-    do_pip(c, im, mode, Qm.pts.p, Qm.n_points, nullptr);
-    uint32_t* ce = ov.closest_eid[im].ensure(Qm.n_points ? Qm.n_points : 1);
-    int32_t* pf = ov.point_in_polygon[im].ensure(Qm.n_points ? Qm.n_points : 1);
-    RJB_CUDA(cudaMemcpyAsync(ce, c->pip_eid.p, Qm.n_points * sizeof(uint32_t),
-                             cudaMemcpyDeviceToDevice, st));
-    RJB_CUDA(cudaMemcpyAsync(pf, c->pip_face.p, Qm.n_points * sizeof(int32_t),
-                             cudaMemcpyDeviceToDevice, st));
-    mark(3 + im);
+  uint64_t n = 0;
+  if (imp) {
+    // gathered results of the sharded phases
+    n = imp->n_xsects;
+    rjb_xsect* xs = c->xsects.ensure(n ? n : 1);
+    if (n)
+      RJB_CUDA(cudaMemcpyAsync(xs, imp->h_xsects, n * sizeof(rjb_xsect), cudaMemcpyHostToDevice, st));
+    mark(2);
+    for (int im = 0; im < 2; im++) {
+      DeviceMap& Qm = c->maps[im];
+      uint32_t* ce = ov.closest_eid[im].ensure(Qm.n_points ? Qm.n_points : 1);
+      int32_t* pf = ov.point_in_polygon[im].ensure(Qm.n_points ? Qm.n_points : 1);
+      RJB_CUDA(cudaMemcpyAsync(ce, imp->h_closest_eid[im], Qm.n_points * sizeof(uint32_t),
+                               cudaMemcpyHostToDevice, st));
+      RJB_CUDA(cudaMemcpyAsync(pf, imp->h_point_in_polygon[im], Qm.n_points * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, st));
+      mark(3 + im);
+    }
+  } else {
+    // IntersectEdge(0): map 0 is the query side (src/run_overlay.cu:206)
+    n = do_lsi(c, 0, mode, xsect_factor, nullptr);
+    mark(2);
+    // LocateVerticesInOtherMap(im)
+    for (int im = 0; im < 2; im++) {
+      DeviceMap& Qm = c->maps[im];
+      do_pip(c, im, mode, Qm.pts.p, Qm.n_points, nullptr);
+      uint32_t* ce = ov.closest_eid[im].ensure(Qm.n_points ? Qm.n_points : 1);
+      int32_t* pf = ov.point_in_polygon[im].ensure(Qm.n_points ? Qm.n_points : 1);
+      RJB_CUDA(cudaMemcpyAsync(ce, c->pip_eid.p, Qm.n_points * sizeof(uint32_t),
+                               cudaMemcpyDeviceToDevice, st));
+      RJB_CUDA(cudaMemcpyAsync(pf, c->pip_face.p, Qm.n_points * sizeof(int32_t),
+                               cudaMemcpyDeviceToDevice, st));
+      mark(3 + im);
+    }
   }
+  ov.n_xsects = n;
   // ComputeOutputPolygons
   for (int im = 0; im < 2; im++) {
     rjb_xsect* sorted = ov.xsects_sorted[im].ensure(n ? n : 1);

@@ -86,3 +86,61 @@ def gather_array(dist, local, counts, device, dst=0):
         return None
     return np.concatenate([recv[r].cpu().numpy().view(local.dtype)[:int(counts[r])]
                            for r in range(world)])
+
+
+def distributed_overlay(dist, graphs, mode="lbvh", grid_size=2048, xsect_factor=0.5, device=0,
+                        torch_device=None, output=None, bbox=None):
+    """Polygon overlay of graphs[0] x graphs[1] over all ranks of `dist` (one process
+    per GPU).  Every rank holds two contexts -- (shard of map 0, full map 1) for
+    IntersectEdge(0) and the location of map 0's vertices, (full map 0, shard of map 1)
+    for the location of map 1's vertices -- so the base side and its index are always
+    complete and replicated while the query side is sharded by whole chains.  Counts go
+    through an all-gather, the results through padded gathers to rank 0, which imports
+    them (rjb_overlay_finish), runs ComputeOutputPolygons and writes the chains.
+    Returns (MapOverlay on rank 0 | None, phase dict)."""
+    import time
+    import torch
+    from . import capi, synth
+    world, rank = dist.get_world_size(), dist.get_rank()
+    tdev = torch_device if torch_device is not None else torch.device("cuda", device)
+    bbox = bbox or synth.union_bbox(*graphs)
+    t0 = time.perf_counter()
+    sh0, eoff0, poff0 = shard_graph(graphs[0], rank, world)
+    sh1, eoff1, poff1 = shard_graph(graphs[1], rank, world)
+    ctx_a = capi.Context([sh0, graphs[1]], device=device, bbox=bbox)
+    ctx_b = capi.Context([graphs[0], sh1], device=device, bbox=bbox)
+    ctx_a.build_index(1, mode, grid_size)
+    ctx_b.build_index(0, mode, grid_size)
+    t1 = time.perf_counter()
+    lsi = capi.LSI(ctx_a, mode)
+    lsi.Init(xsect_factor)
+    n = lsi.Query(0)
+    xs = lsi.get_xsects()
+    pip_a = capi.PIP(ctx_a, mode)
+    pip_a.Query(0)
+    e0, f0 = pip_a.get_closest_eids(), pip_a.get_face_ids()
+    pip_b = capi.PIP(ctx_b, mode)
+    pip_b.Query(1)
+    e1, f1 = pip_b.get_closest_eids(), pip_b.get_face_ids()
+    t2 = time.perf_counter()
+    counts = allgather_counts(dist, [n, sh0.n_points, sh1.n_points], tdev)
+    all_xs = gather_xsects(dist, xs, counts[:, 0], eoff0, 0, tdev)
+    g_e0 = gather_array(dist, e0, counts[:, 1], tdev)
+    g_f0 = gather_array(dist, f0, counts[:, 1], tdev)
+    g_e1 = gather_array(dist, e1, counts[:, 2], tdev)
+    g_f1 = gather_array(dist, f1, counts[:, 2], tdev)
+    t3 = time.perf_counter()
+    ctx_a.close()
+    ctx_b.close()
+    phases = {"load_build_s": t1 - t0, "sharded_queries_s": t2 - t1, "gather_s": t3 - t2,
+              "n_xsects_local": int(n)}
+    if rank != 0:
+        return None, phases
+    ctx = capi.Context(list(graphs), device=device, bbox=bbox)
+    ov = capi.MapOverlay(ctx, mode, grid_size, xsect_factor)
+    ov.Finish(all_xs, [g_e0, g_e1], [g_f0, g_f1])
+    if output:
+        ov.WriteResult(output)
+    phases["finish_s"] = time.perf_counter() - t3
+    phases["n_xsects"] = int(len(all_xs))
+    return ov, phases
