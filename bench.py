@@ -135,7 +135,8 @@ def ncu_traffic(kernel):
     committed `ncu --set full` capture of this workload (profiles/traffic.json)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(kernel)
+            t = json.load(f)
+        return sum(t[k] for k in kernel.split("+"))
     except Exception:
         return None
 
@@ -363,7 +364,7 @@ def main():
         # R vertices once, 8 B per result pair
         if args.mode == "lbvh":
             alg = 16 * S.n_points + 4 * S.n_edges + idx["bytes"] + 16 * R.n_points + 8 * n_pairs
-            kname = "k_lsi_bvh"
+            kname = "k_lsi_filter+k_lsi_bvh" if ctx.last_stats()[7] else "k_lsi_bvh"
         else:
             alg = 16 * S.n_points + 4 * S.n_edges + idx["bytes"] + 16 * R.n_points + 4 * R.n_edges + 8 * n_pairs
             kname = "k_lsi_grid"
@@ -388,7 +389,8 @@ def main():
             "e2e": {"value": all_edges / (e2e_ms / 1e3 / args.steps), "unit": "query_edges/s",
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": ((3 if args.mode == "lbvh" else 2) + (7 if args.sort_queries else 0)) * args.steps,
+            "gpu_launches": ((4 if kname.startswith("k_lsi_filter") else 3 if args.mode == "lbvh" else 2)
+                             + (8 if args.sort_queries else 0)) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(kname),
