@@ -218,7 +218,7 @@ def main():
     ap.add_argument("--mode", default="lbvh", choices=["lbvh", "grid"])
     ap.add_argument("--grid-size", type=int, default=8192)
     ap.add_argument("--leaf-size", type=int, default=4)
-    ap.add_argument("--sort-queries", type=int, default=0)
+    ap.add_argument("--sort-queries", type=int, default=-1)
     ap.add_argument("--filter", type=int, default=-1, help="occupancy pre-filter: -1 auto, 0 off, 1 on")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -368,6 +368,7 @@ def main():
         else:
             alg = 16 * S.n_points + 4 * S.n_edges + idx["bytes"] + 16 * R.n_points + 4 * R.n_edges + 8 * n_pairs
             kname = "k_lsi_grid"
+        sorted_queries = args.sort_queries > 0 or (args.sort_queries < 0 and S.n_edges / max(1, S.n_chains) < 32)
         k_avg = float(np.mean(k_ms))
         achieved = alg / (k_avg / 1e3) / 1e9
         line = {
@@ -390,7 +391,7 @@ def main():
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": ((4 if kname.startswith("k_lsi_filter") else 3 if args.mode == "lbvh" else 2)
-                             + (8 if args.sort_queries else 0)) * args.steps,
+                             + (6 if sorted_queries else 0)) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(kname),

@@ -126,7 +126,9 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
 
 /* tuning knobs that have no RayJoin flag (defaults are fine):
  *   "lbvh_leaf_size"  edges per LBVH leaf, 1..8 (default 4)
- *   "sort_queries"    1 = visit query edges / points in Morton order
+ *   "sort_queries"    visit queries in Morton order: 1 on, 0 off, -1 auto (default:
+ *                     LSI query edges are ordered when the query map averages
+ *                     < 32 edges per chain; points only on request)
  *   "lsi_filter"      LBVH LSI occupancy pre-filter: -1 auto (default: on when the
  *                     base map occupies < 25 % of a 4096^2 bitmap), 0 off, 1 on
  *   "stats"           1 = collect traversal statistics (rjb_last_stats; slower)

@@ -73,7 +73,8 @@ struct rjb_ctx {
   rjb_scaling sc;
   DeviceMap maps[2];
   int leaf_size = 4;
-  int sort_queries = 0;
+  int sort_queries = -1;  // -1 auto: Morton-order query EDGES when the chains are short
+  bool filter_useless = false;  // the occupancy filter kept > 50 % last time: skip it
   int stats = 0;  // collect traversal statistics (slower)
   unsigned long long last_stats[8] = {0};
   int keep_host_graph = 1;  // overlay writer needs the source coordinates
@@ -197,27 +198,32 @@ static void scaling_init(rjb_scaling& s, double bminx, double bminy, double bmax
 static void check_map_id(int id) { RJB_REQUIRE(id == 0 || id == 1, "map id must be 0 or 1"); }
 
 static const uint32_t* query_order_edges(rjb_ctx* c, const MapView& Q) {
-  if (!c->sort_queries || Q.n_edges == 0) return nullptr;
+  // Consecutive edges of a long chain are spatial neighbours already; maps made of
+  // short chains in arbitrary order (polygon soups: ~7 edges per chain) are not, and a
+  // warp would walk one cluster after the other.  auto = sort below 32 edges per chain.
+  bool want = c->sort_queries > 0 ||
+              (c->sort_queries < 0 && Q.n_chains > 0 && Q.n_edges / Q.n_chains < 32);
+  if (!want || Q.n_edges == 0) return nullptr;
   uint32_t n = Q.n_edges;
   uint64_t* ka = c->ord_keys_a.ensure(n);
   uint64_t* kb = c->ord_keys_b.ensure(n);
   uint32_t* va = c->ord_vals_a.ensure(n);
   uint32_t* vb = c->ord_vals_b.ensure(n);
   k_query_keys_edges<<<div_up(n, 256), 256, 0, c->stream>>>(Q, c->sc.internal_min, ka, va);
-  sort_pairs_u64_u32(ka, kb, va, vb, n, 24, 64, c->ord_sort, c->stream);
+  sort_pairs_u64_u32(ka, kb, va, vb, n, 40, 64, c->ord_sort, c->stream);
   return vb;
 }
 
 static const uint32_t* query_order_points(rjb_ctx* c, const longlong2* pts, uint32_t n) {
-  if (!c->sort_queries || n == 0) return nullptr;
+  if (c->sort_queries <= 0 || n == 0) return nullptr;  // points: only on request
   uint64_t* ka = c->ord_keys_a.ensure(n);
   uint64_t* kb = c->ord_keys_b.ensure(n);
   uint32_t* va = c->ord_vals_a.ensure(n);
   uint32_t* vb = c->ord_vals_b.ensure(n);
   k_query_keys_points<<<div_up(n, 256), 256, 0, c->stream>>>(pts, n, c->sc.internal_min, ka, va);
-  // only coherence is needed, not a total order: 40 of the 62 Morton bits
-  // (cells of 2^-20 of the range per axis) = 5 radix passes instead of 8
-  sort_pairs_u64_u32(ka, kb, va, vb, n, 24, 64, c->ord_sort, c->stream);
+  // only coherence is needed, not a total order: the top 24 Morton bits (4096 x 4096
+  // cells) = 3 radix passes instead of 8
+  sort_pairs_u64_u32(ka, kb, va, vb, n, 40, 64, c->ord_sort, c->stream);
   return vb;
 }
 
@@ -276,7 +282,8 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
     const uint32_t* order = query_order_edges(c, Q);
     // occupancy pre-filter: worthwhile when the base map covers a small part of the
     // plane; it replaces the Morton order (survivors come out in map order)
-    bool filter = !order && (c->use_filter == 1 || (c->use_filter < 0 && Bm.bvh.occ_fraction < 0.25));
+    bool filter = !order && (c->use_filter == 1 || (c->use_filter < 0 && Bm.bvh.occ_fraction < 0.25 &&
+                                                   !c->filter_useless));
     uint32_t* surv = filter ? c->survivors.ensure(Q.n_points) : nullptr;
     unsigned int* surv_n = c->survivor_count.ensure(2);  // [0] survivors, [1] (query, leaf) pairs
     for (int attempt = 0;; attempt++) {
@@ -318,7 +325,10 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
       RJB_CUDA(cudaMemcpyAsync(hs, surv_n, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
       RJB_CUDA(cudaStreamSynchronize(c->stream));
       bool grid_too_small = filter && hs[0] > n_slots;  // launch was sized from the last query
-      if (filter) c->last_survivors = hs[0];
+      if (filter) {
+        c->last_survivors = hs[0];
+        c->filter_useless = hs[0] > Q.n_edges / 2;  // adaptive: not worth a pass over S
+      }
       if (hs[1] <= ccap && !grid_too_small) break;
       RJB_REQUIRE(attempt < 2, "rjb_lsi: internal queues overflowed repeatedly");
       if (hs[1] > ccap) c->cand_cap = (size_t) hs[1] + hs[1] / 8 + 65536;
@@ -483,7 +493,7 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
       RJB_REQUIRE(value >= 1 && value <= 8, "lbvh_leaf_size must be in 1..8");
       c->leaf_size = (int) value;
     } else if (n == "sort_queries") {
-      c->sort_queries = value != 0;
+      c->sort_queries = (int) value;
     } else if (n == "lsi_filter") {
       c->use_filter = (int) value;
     } else if (n == "stats") {
@@ -510,6 +520,8 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
     m.loaded = false;
     m.bvh.built = false;
     m.grid.built = false;
+    c->filter_useless = false;  // new data: let the occupancy filter prove itself again
+    c->last_survivors = 0;
     if (n_chains > 0) {
       RJB_REQUIRE(row_index[0] == 0 && row_index[n_chains] == n_points,
                   "rjb_set_map: row_index must span [0, n_points]");

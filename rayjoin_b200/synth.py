@@ -89,7 +89,10 @@ def voronoi_map(n_faces, n_edges, bbox=US_BBOX, seed=1, wiggle=0.03, face_id_bas
 def polygon_soup(n_polys, dist="uniform", seed=1, polysize=0.001, maxseg=10,
                  affine=(50.0, 0.0, -119.0, 0.0, 30.0, 35.0)):
     """Independent small polygons like `generator.py distribution=<dist>
-    geometry=polygon polysize=0.001 maxseg=10 affinematrix=50,0,-119,0,30,35`."""
+    geometry=polygon polysize=0.001 maxseg=10 affinematrix=50,0,-119,0,30,35`
+    (reference misc/gen_polys.sh:4-22, misc/generator.py:174-199): the affine map
+    moves the CENTRE, the polygon is then built around it with vertices on a circle
+    of radius `polysize` at sorted uniform angles, 4..maxseg segments, closed ring."""
     rng = np.random.default_rng(seed)
     if dist == "uniform":
         c = rng.random((n_polys, 2))
@@ -97,24 +100,29 @@ def polygon_soup(n_polys, dist="uniform", seed=1, polysize=0.001, maxseg=10,
         c = np.clip(rng.normal(0.5, 0.1, size=(n_polys, 2)), 0.0, 1.0)
     else:
         raise ValueError(dist)
-    nseg = rng.integers(3, maxseg + 1, size=n_polys)
+    ax, bx, cx, ay, by, cy = affine
+    c = np.column_stack([ax * c[:, 0] + bx * c[:, 1] + cx, ay * c[:, 0] + by * c[:, 1] + cy])
+    nseg = rng.integers(4, maxseg + 1, size=n_polys)
     npts = nseg + 1  # closed ring: first point repeated
     row_index = np.zeros(n_polys + 1, np.int64)
     np.cumsum(npts, out=row_index[1:])
     total = int(row_index[-1])
     poly = np.repeat(np.arange(n_polys), npts)
-    j = np.arange(total) - row_index[poly]
-    # vertex j sits at angle 2*pi*(j + 0.8*u)/nseg, u ~ U[0,1): angles increase
-    # with j, so every polygon is simple (star-shaped around its centre)
-    theta = 2 * np.pi * (j + 0.8 * rng.random(total)) / nseg[poly]
-    rad = polysize * (0.5 + 0.5 * rng.random(n_polys))[poly]
-    xy = c[poly] + np.column_stack([np.cos(theta), np.sin(theta)]) * rad[:, None]
+    ang = rng.random(total) * (2 * np.pi)
+    ang[row_index[1:] - 1] = 7.0  # closing slot sorts last; overwritten below
+    order = np.lexsort((ang, poly))
+    theta = ang[order]
+    xy = c[poly] + polysize * np.column_stack([np.cos(theta), np.sin(theta)])
     xy[row_index[1:] - 1] = xy[row_index[:-1]]
-    ax, bx, cx, ay, by, cy = affine
-    out = np.column_stack([ax * xy[:, 0] + bx * xy[:, 1] + cx, ay * xy[:, 0] + by * xy[:, 1] + cy])
-    out[row_index[1:] - 1] = out[row_index[:-1]]
+    # the reference loader rejects consecutive duplicate points (equal random angles)
+    d = np.zeros(total, bool)
+    d[1:] = (xy[1:] == xy[:-1]).all(axis=1)
+    d[row_index[:-1]] = False
+    if d.any():
+        xy[d] += 1e-9
+        xy[row_index[1:] - 1] = xy[row_index[:-1]]
     ids = np.arange(1, n_polys + 1, dtype=np.int64)
-    return PlanarGraph(out, row_index.astype(np.uint32), np.zeros(n_polys, np.int64), ids)
+    return PlanarGraph(xy, row_index.astype(np.uint32), np.zeros(n_polys, np.int64), ids)
 
 
 def share_chains(base, other, frac=0.05, seed=3, stride=2):

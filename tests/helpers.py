@@ -37,8 +37,8 @@ def dataset(name):
         R = synth.voronoi_map(40, 2500, synth.BRAZIL_BBOX, seed=3)
         S = synth.share_chains(R, synth.voronoi_map(150, 3000, synth.BRAZIL_BBOX, seed=4), frac=0.3)
     elif name == "soup":
-        R = synth.polygon_soup(3000, "gaussian", seed=1, polysize=0.004)
-        S = synth.polygon_soup(2500, "gaussian", seed=2, polysize=0.004)
+        R = synth.polygon_soup(3000, "gaussian", seed=1, polysize=0.2)
+        S = synth.polygon_soup(2500, "gaussian", seed=2, polysize=0.2)
     elif name == "lattice":
         R = lattice_map(150, 11)
         S = lattice_map(170, 12, face_base=10)

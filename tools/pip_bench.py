@@ -17,7 +17,7 @@ ap.add_argument("--faces", type=int, default=220_000)
 ap.add_argument("--edges", type=int, default=28_000_000)
 ap.add_argument("--modes", default="lbvh,grid")
 ap.add_argument("--grid-size", type=int, default=8192)
-ap.add_argument("--sort", default="0,1")
+ap.add_argument("--sort", default="0,1")  # PIP: points are ordered only on request
 ap.add_argument("--repeat", type=int, default=3)
 ap.add_argument("--check", type=int, default=200_000)
 ap.add_argument("--stats", type=int, default=0)
