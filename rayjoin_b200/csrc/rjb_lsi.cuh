@@ -159,16 +159,37 @@ k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__
   const int lane = threadIdx.x & 31;
   const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (tile * 32 >= Q.n_points) return;
-  const QTile t = load_tile(Q, nullptr, Q.n_points, tile, lane);
+  // one 16-byte load per lane; the edge's second vertex is the next lane's point
+  const uint32_t p = tile * 32 + lane;
+  const bool in = p < Q.n_points;
+  const longlong2 a = in ? __ldg(&Q.pts[p]) : make_longlong2(0, 0);
+  // occupancy cell straight from the 47-bit coordinate: (v + 2^46) >> 35 equals
+  // occ_cell(quant(v)); packed as (cy << 12 | cx)
+  const uint32_t cx = (uint32_t) ((unsigned long long) (a.x + (1ll << 46)) >> (kQuantShift + kOccShift)) & (kOccDim - 1);
+  const uint32_t cy = (uint32_t) ((unsigned long long) (a.y + (1ll << 46)) >> (kQuantShift + kOccShift)) & (kOccDim - 1);
+  const uint32_t code = (cy << kOccBits) | cx;
+  uint32_t code2 = __shfl_down_sync(0xffffffffu, code, 1);
+  if (lane == 31 && p + 1 < Q.n_points) {
+    const longlong2 b = __ldg(&Q.pts[p + 1]);
+    code2 = ((uint32_t) ((unsigned long long) (b.y + (1ll << 46)) >> (kQuantShift + kOccShift)) & (kOccDim - 1)) << kOccBits |
+            ((uint32_t) ((unsigned long long) (b.x + (1ll << 46)) >> (kQuantShift + kOccShift)) & (kOccDim - 1));
+  }
+  const uint32_t w = __ldg(&Q.last_bits[tile]);  // warp-uniform: bit set = no edge starts here
+  const bool valid = in && !((w >> lane) & 1u);
   bool keep = false;
-  if (t.valid) {
-    const int x0 = occ_cell(quant(min(t.a.x, t.b.x))), x1 = occ_cell(quant(max(t.a.x, t.b.x)));
-    const int y0 = occ_cell(quant(min(t.a.y, t.b.y))), y1 = occ_cell(quant(max(t.a.y, t.b.y)));
-    for (int y = y0; y <= y1 && !keep; y++)
-      for (int x = x0; x <= x1; x++) {
-        const uint32_t bit = (uint32_t) y * kOccDim + x;
-        if ((__ldg(&occ[bit >> 5]) >> (bit & 31)) & 1u) { keep = true; break; }
-      }
+  if (valid) {
+    if (code == code2) {  // the usual case: both vertices in one cell
+      keep = (__ldg(&occ[code >> 5]) >> (code & 31)) & 1u;
+    } else {
+      const uint32_t x0 = min(code & (kOccDim - 1), code2 & (kOccDim - 1));
+      const uint32_t x1 = max(code & (kOccDim - 1), code2 & (kOccDim - 1));
+      const uint32_t y0 = min(code >> kOccBits, code2 >> kOccBits), y1 = max(code >> kOccBits, code2 >> kOccBits);
+      for (uint32_t y = y0; y <= y1 && !keep; y++)
+        for (uint32_t x = x0; x <= x1; x++) {
+          const uint32_t bit = y * kOccDim + x;
+          if ((__ldg(&occ[bit >> 5]) >> (bit & 31)) & 1u) { keep = true; break; }
+        }
+    }
   }
   const unsigned m = __ballot_sync(0xffffffffu, keep);
   if (m == 0) return;
@@ -176,7 +197,7 @@ k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__
   const int leader = __ffs(m) - 1;
   if (lane == leader) base = atomicAdd(counter, (unsigned) __popc(m));
   base = __shfl_sync(0xffffffffu, base, leader);
-  if (keep) survivors[base + __popc(m & ((1u << lane) - 1))] = t.p;
+  if (keep) survivors[base + __popc(m & ((1u << lane) - 1))] = p;
 }
 
 template <bool kStats>
