@@ -172,20 +172,22 @@ static __device__ __forceinline__ long long max4ll(long long a, long long b,
   return max(max(a, b), max(c, d));
 }
 
-static __device__ void lsi_point(const Seg& e1, const Seg& e2, long long& ox,
-                                 long long& oy) {
+// One coordinate (axis 0 = x, 1 = y) of the intersection point.  The two axes are
+// independent chains of ~10^3 dependent integer instructions each (gcd, division),
+// so callers that are latency bound give each axis its own thread.
+static __device__ long long lsi_point_axis(const Seg& e1, const Seg& e2, int axis) {
   long long a1l, b1l, a2l, b2l;
   edge_ab(e1, a1l, b1l);
   edge_ab(e2, a2l, b2l);
   // c with the SAME normalisation sign as (a, b): c = -x1*a - y1*b
-  i128 a1 = a1l, b1 = b1l, a2 = a2l, b2 = b2l;
-  i128 c1 = -(i128) e1.x1 * a1 - (i128) e1.y1 * b1;
-  i128 c2 = -(i128) e2.x1 * a2 - (i128) e2.y1 * b2;
+  const i128 a1 = a1l, b1 = b1l, a2 = a2l, b2 = b2l;
+  const i128 c1 = -(i128) e1.x1 * a1 - (i128) e1.y1 * b1;
+  const i128 c2 = -(i128) e2.x1 * a2 - (i128) e2.y1 * b2;
   // unsigned products: two's-complement wrap-around, no UB
-  i128 denom = (i128) ((u128) a1 * (u128) b2 - (u128) a2 * (u128) b1);
-  i128 numx = (i128) ((u128) c2 * (u128) b1 - (u128) c1 * (u128) b2);
-  i128 numy = (i128) ((u128) a2 * (u128) c1 - (u128) a1 * (u128) c2);
-  i128 xn, xd, yn, yd;
+  const i128 denom = (i128) ((u128) a1 * (u128) b2 - (u128) a2 * (u128) b1);
+  const i128 num = axis == 0 ? (i128) ((u128) c2 * (u128) b1 - (u128) c1 * (u128) b2)
+                             : (i128) ((u128) a2 * (u128) c1 - (u128) a1 * (u128) c2);
+  i128 rn, rd;
   const long long lim = 1ll << 38;
   if (a1l > -lim && a1l < lim && b1l < lim && a2l > -lim && a2l < lim && b2l < lim) {
     // Edges spanning < 2^38 internal units (1/512 of the coordinate range): nothing
@@ -198,31 +200,26 @@ static __device__ void lsi_point(const Seg& e1, const Seg& e2, long long& ox,
     // from ~2k-bit operands instead of a ~110-bit numerator.
     const i128 aden = iabs128(denom);
     const i128 c2p = -((i128) (e2.x1 - e1.x1) * a2l + (i128) (e2.y1 - e1.y1) * b2l);
-    const i128 nxp = c2p * b1l, nyp = -c2p * a1l;
-    const double dden = (double) denom;
-    const long long qx = (long long) rint((double) nxp / dden);
-    const long long qy = (long long) rint((double) nyp / dden);
-    const i128 rx = nxp - (i128) qx * denom, ry = nyp - (i128) qy * denom;  // |r| < 2*|den|
-    const i128 gx = gcd128(rx, denom), gy = gcd128(ry, denom);
-    const i128 sx = denom < 0 ? -numx : numx, sy = denom < 0 ? -numy : numy;
-    xn = gx == 1 ? sx : sx / gx;
-    xd = gx == 1 ? aden : aden / gx;
-    yn = gy == 1 ? sy : sy / gy;
-    yd = gy == 1 ? aden : aden / gy;
+    const i128 np = axis == 0 ? c2p * b1l : -c2p * a1l;
+    const long long q = (long long) rint((double) np / (double) denom);
+    const i128 r = np - (i128) q * denom;  // |r| < 2*|den|
+    const i128 g = gcd128(r, denom);
+    const i128 sn = denom < 0 ? -num : num;
+    rn = g == 1 ? sn : sn / g;
+    rd = g == 1 ? aden : aden / g;
   } else {
-    rat_make(numx, denom, xn, xd);
-    rat_make(numy, denom, yn, yd);
+    rat_make(num, denom, rn, rd);
   }
-  long long t = min4ll(e1.x1, e1.x2, e2.x1, e2.x2);
-  if (xn < (i128) ((u128) (i128) t * (u128) xd)) { xn = t; xd = 1; }
-  t = max4ll(e1.x1, e1.x2, e2.x1, e2.x2);
-  if ((i128) ((u128) (i128) t * (u128) xd) < xn) { xn = t; xd = 1; }
-  t = min4ll(e1.y1, e1.y2, e2.y1, e2.y2);
-  if (yn < (i128) ((u128) (i128) t * (u128) yd)) { yn = t; yd = 1; }
-  t = max4ll(e1.y1, e1.y2, e2.y1, e2.y2);
-  if ((i128) ((u128) (i128) t * (u128) yd) < yn) { yn = t; yd = 1; }
-  ox = (long long) ((double) xn / (double) xd);
-  oy = (long long) ((double) yn / (double) yd);
+  long long t = axis == 0 ? min4ll(e1.x1, e1.x2, e2.x1, e2.x2) : min4ll(e1.y1, e1.y2, e2.y1, e2.y2);
+  if (rn < (i128) ((u128) (i128) t * (u128) rd)) { rn = t; rd = 1; }
+  t = axis == 0 ? max4ll(e1.x1, e1.x2, e2.x1, e2.x2) : max4ll(e1.y1, e1.y2, e2.y1, e2.y2);
+  if ((i128) ((u128) (i128) t * (u128) rd) < rn) { rn = t; rd = 1; }
+  return (long long) ((double) rn / (double) rd);
+}
+
+static __device__ void lsi_point(const Seg& e1, const Seg& e2, long long& ox, long long& oy) {
+  ox = lsi_point_axis(e1, e2, 0);
+  oy = lsi_point_axis(e1, e2, 1);
 }
 
 // ---- PIP: closest edge above -----------------------------------------------

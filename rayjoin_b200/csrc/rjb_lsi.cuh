@@ -374,23 +374,38 @@ k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ pairs, const uint2* 
 __global__ void __launch_bounds__(128)
 k_lsi_points(MapView Q, MapView B, int query_map_id, const unsigned int* __restrict__ counter,
              uint32_t cap, rjb_xsect* __restrict__ out) {
+  // two threads per hit: the even lane computes x, the odd lane y (each axis is a
+  // long dependent chain: gcd + division), then the pair assembles the record
   const uint32_t n = min(*counter, cap);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t pq = out[i].eid[0], pb = out[i].eid[1];
-    const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
-    const longlong2 c = __ldg(&B.pts[pb]), d = __ldg(&B.pts[pb + 1]);
-    const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
-    long long x, y;
-    lsi_point(e1, e2, x, y);
-    const uint32_t eq = pq - chain_of_point(Q, pq), eb = pb - chain_of_point(B, pb);
-    rjb_xsect r;
-    r.x = x;
-    r.y = y;
-    r.eid[0] = query_map_id == 0 ? eq : eb;
-    r.eid[1] = query_map_id == 0 ? eb : eq;
-    r.mid_point_polygon_id = RJB_DONTKNOW;
-    r._pad = 0;
-    out[i] = r;
+  const uint32_t stride = (gridDim.x * blockDim.x) >> 1;
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 1; i - ((threadIdx.x & 31) >> 1) < n;
+       i += stride) {
+    const int axis = threadIdx.x & 1;
+    long long v = 0;
+    uint32_t pq = 0, pb = 0;
+    if (i < n) {
+      pq = out[i].eid[0];
+      pb = out[i].eid[1];
+      const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
+      const longlong2 c = __ldg(&B.pts[pb]), d = __ldg(&B.pts[pb + 1]);
+      const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
+      v = lsi_point_axis(e1, e2, axis);
+    }
+    // every lane of the warp takes part in the exchange (the loop bound is warp-uniform)
+    const long long other = __shfl_xor_sync(0xffffffffu, v, 1);
+    // the point-index fields are overwritten below: both lanes must have read them
+    __syncwarp();
+    if (i < n && axis == 0) {
+      const uint32_t eq = pq - chain_of_point(Q, pq), eb = pb - chain_of_point(B, pb);
+      rjb_xsect r;
+      r.x = v;
+      r.y = other;
+      r.eid[0] = query_map_id == 0 ? eq : eb;
+      r.eid[1] = query_map_id == 0 ? eb : eq;
+      r.mid_point_polygon_id = RJB_DONTKNOW;
+      r._pad = 0;
+      out[i] = r;
+    }
   }
 }
 
