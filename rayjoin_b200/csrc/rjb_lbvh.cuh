@@ -14,7 +14,7 @@
 
 namespace rjb {
 
-constexpr int kMortonDrop = 24;  // Morton bits ignored by the leaf order
+constexpr int kMortonDrop = 32;  // Morton bits ignored by the leaf order (keys: 16 bits per axis)
 
 struct Bvh {
   DBuf<int4> node_box;
@@ -110,7 +110,8 @@ __global__ void k_leaf_fill(MapView m, const uint32_t* __restrict__ leaf_base, u
   }
   rec[l] = make_uint2(p1 - c, (cnt << 28) | c);
   box[l] = make_int4(quant(xmin), quant(ymin), quant(xmax), quant(ymax));
-  // 40 significant key bits (cells of 2^-20 of the range per axis) = 5 radix passes;
+  // 32 significant key bits (cells of 2^-16 of the range per axis, about one edge
+  // length on a 10 M-edge map) = 4 radix passes;
   // the low bits are cleared so that the sorted keys stay monotone for Karras' delta()
   key[l] = morton64(xmin + ((xmax - xmin) >> 1), ymin + ((ymax - ymin) >> 1), imin) & ~((1ull << kMortonDrop) - 1);
   val[l] = l;
