@@ -110,7 +110,7 @@ class ClockSampler(threading.Thread):
                 self.sample()
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.005)
 
     def summary(self):
         self.stop_flag = True
@@ -157,7 +157,7 @@ def cpu_oracle_lsi(R, S, bbox, repeats=1):
     return best, len(res[0]), res[4], O.num_threads(), res
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, json_out):
     """Reference arm.  RayJoin has no CPU implementation of this path; its only
     code that can run on a B200 box are the -mode=lbvh / -mode=grid CUDA
     backends, built unmodified from /root/reference with stub OptiX/glog headers
@@ -205,7 +205,7 @@ def run_reference(args, rank, world):
                                                 % (R.n_edges, S.n_edges, max(1, min(args.steps, 3)))}})
     line["e2e"] = {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
                    "d2h_bytes_per_step": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
 
 
 def main():
@@ -229,9 +229,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: everything libraries print there (NCCL's
+    # version banner, ...) is sent to stderr, the line goes to the saved descriptor
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, json_out)
         return
 
     import torch
@@ -240,6 +244,7 @@ def main():
     from rayjoin_b200 import synth
 
     RJ.load_library()  # fail loudly when the CUDA extension is missing
+    torch.set_num_threads(1)  # N ranks share the host cores; the host side is launch-bound
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -301,7 +306,8 @@ def main():
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:  # one sampler per job: NVML calls from N processes serialise in the driver
+        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     k_ms, p_ms = [], []
@@ -414,7 +420,7 @@ def main():
                 line["parity_vs_oracle"] = "bit-exact" if ok else "MISMATCH"
                 if not ok:
                     log("PARITY MISMATCH against the oracle: %d vs %d pairs" % (n_pairs, n_ref))
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
