@@ -32,7 +32,7 @@ def _sources():
 def build(force=False, verbose=False):
     deps = _sources()
     if force or _newer(LIB, deps):
-        cmd = [NVCC] + ARCH + COMMON + ["-Xcompiler", "-fPIC", "-shared", "-o", LIB,
+        cmd = [NVCC] + ARCH + COMMON + ["-Xcompiler", "-fPIC,-pthread", "-shared", "-o", LIB,
                                         os.path.join(HERE, "csrc", "rjb_api.cu"),
                                         os.path.join(HERE, "host", "cdb.cc")]
         if verbose:

@@ -108,3 +108,28 @@ def test_synthetic_maps_are_well_formed():
     s = synth.polygon_soup(100, "gaussian", seed=4)
     first, last = s.row_index[:-1].astype(np.int64), s.row_index[1:].astype(np.int64) - 1
     assert np.array_equal(s.xy[first], s.xy[last])  # closed rings
+
+
+def test_parallel_cdb_parser_equals_sequential(rjb, tmp_path, monkeypatch):
+    """Files > 1 MiB take the multi-threaded from_chars path; it must give the same graph
+    as the sequential strtod path (and fall back to it on anything unusual)."""
+    from rayjoin_b200 import synth
+    g = synth.voronoi_map(300, 60000, synth.US_BBOX, seed=13)
+    p = str(tmp_path / "big.cdb")
+    synth.write_cdb(g, p)
+    assert os.path.getsize(p) > (1 << 20)
+    a = rjb.read_pgraph(p)
+    monkeypatch.setenv("RJB_CDB_SEQUENTIAL", "1")
+    b = rjb.read_pgraph(p)
+    monkeypatch.delenv("RJB_CDB_SEQUENTIAL")
+    for x in (a, b):
+        assert np.array_equal(x.xy, g.xy) and np.array_equal(x.row_index, g.row_index)
+        assert np.array_equal(x.left, g.left) and np.array_equal(x.right, g.right)
+    assert a.bbox == b.bbox
+    # an error in the middle of a big file is still reported with file and line number
+    lines = open(p).read().split("\n")
+    lines[40000] = "not a number"
+    open(p, "w").write("\n".join(lines))
+    with pytest.raises(rjb.RjbError) as ei:
+        rjb.read_pgraph(p)
+    assert ei.value.code == 4 and "[40001]" in str(ei.value)
