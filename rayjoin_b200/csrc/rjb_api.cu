@@ -300,7 +300,8 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
       const unsigned int* n_slots_dev = nullptr;
       RJB_CUDA(cudaMemsetAsync(surv_n, 0, 2 * sizeof(unsigned int), c->stream));
       if (filter) {
-        k_lsi_filter<<<div_up(Q.n_points, 256), 256, 0, c->stream>>>(Q, Bm.bvh.occ.p, surv, surv_n);
+        k_lsi_filter<<<div_up(Q.n_points, 32 * 8 * kFilterTilesPerWarp), 256, 0, c->stream>>>(
+            Q, Bm.bvh.occ.p, surv, surv_n);
         slots = surv;
         n_slots_dev = surv_n;
         // grid for the worst case; warps beyond the survivor count exit at once

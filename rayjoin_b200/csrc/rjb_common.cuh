@@ -65,7 +65,7 @@ struct BvhView {
   uint32_t n_leaves;
 };
 
-constexpr int kOccBits = 12;             // 4096 x 4096 cells
+constexpr int kOccBits = 12;             // 4096 x 4096 cells (8192^2 measured no better)
 constexpr int kOccDim = 1 << kOccBits;
 constexpr int kOccShift = 31 - kOccBits;  // quantised coordinates span 31 bits
 

@@ -153,26 +153,27 @@ static __device__ __forceinline__ QTile load_tile(const MapView& Q, const uint32
 // of those whose (quantised) box touches an occupied cell of the base map's
 // bitmap.  For a sparse base map (county boundaries: ~1 % of the cells) a few per
 // cent of the query edges survive, and only those are traversed.
-__global__ void __launch_bounds__(256)
-k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__ survivors,
-             unsigned int* counter) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (tile * 32 >= Q.n_points) return;
+constexpr int kFilterTilesPerWarp = 16;  // a CTA of 8 warps covers 128 consecutive tiles
+
+// keep-mask of one tile of 32 consecutive query points (bit = edge starting there
+// touches an occupied cell)
+static __device__ __forceinline__ unsigned filter_tile(const MapView& Q, const uint32_t* __restrict__ occ,
+                                                       uint32_t tile, int lane) {
   // one 16-byte load per lane; the edge's second vertex is the next lane's point
   const uint32_t p = tile * 32 + lane;
   const bool in = p < Q.n_points;
   const longlong2 a = in ? __ldg(&Q.pts[p]) : make_longlong2(0, 0);
   // occupancy cell straight from the 47-bit coordinate: (v + 2^46) >> 35 equals
-  // occ_cell(quant(v)); packed as (cy << 12 | cx)
-  const uint32_t cx = (uint32_t) ((unsigned long long) (a.x + (1ll << 46)) >> (kQuantShift + kOccShift)) & (kOccDim - 1);
-  const uint32_t cy = (uint32_t) ((unsigned long long) (a.y + (1ll << 46)) >> (kQuantShift + kOccShift)) & (kOccDim - 1);
+  // occ_cell(quant(v)); packed as (cy << kOccBits | cx)
+  const int sh = kQuantShift + kOccShift;
+  const uint32_t cx = (uint32_t) ((unsigned long long) (a.x + (1ll << 46)) >> sh) & (kOccDim - 1);
+  const uint32_t cy = (uint32_t) ((unsigned long long) (a.y + (1ll << 46)) >> sh) & (kOccDim - 1);
   const uint32_t code = (cy << kOccBits) | cx;
   uint32_t code2 = __shfl_down_sync(0xffffffffu, code, 1);
   if (lane == 31 && p + 1 < Q.n_points) {
     const longlong2 b = __ldg(&Q.pts[p + 1]);
-    code2 = ((uint32_t) ((unsigned long long) (b.y + (1ll << 46)) >> (kQuantShift + kOccShift)) & (kOccDim - 1)) << kOccBits |
-            ((uint32_t) ((unsigned long long) (b.x + (1ll << 46)) >> (kQuantShift + kOccShift)) & (kOccDim - 1));
+    code2 = ((uint32_t) ((unsigned long long) (b.y + (1ll << 46)) >> sh) & (kOccDim - 1)) << kOccBits |
+            ((uint32_t) ((unsigned long long) (b.x + (1ll << 46)) >> sh) & (kOccDim - 1));
   }
   const uint32_t w = __ldg(&Q.last_bits[tile]);  // warp-uniform: bit set = no edge starts here
   const bool valid = in && !((w >> lane) & 1u);
@@ -191,13 +192,56 @@ k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__
         }
     }
   }
-  const unsigned m = __ballot_sync(0xffffffffu, keep);
-  if (m == 0) return;
-  unsigned base = 0;
-  const int leader = __ffs(m) - 1;
-  if (lane == leader) base = atomicAdd(counter, (unsigned) __popc(m));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (keep) survivors[base + __popc(m & ((1u << lane) - 1))] = p;
+  return __ballot_sync(0xffffffffu, keep);
+}
+
+// A CTA filters 128 consecutive tiles (4096 points) and appends its survivors as ONE
+// contiguous, map-ordered run (block scan of the tile counts, one atomic per CTA):
+// the 32 survivors a traversal warp picks up are then neighbours on the map.  (With
+// one atomic per warp the runs of concurrently running warps from all over the map
+// interleave, and every traversal warp has to follow up to 32 separate clusters.)
+__global__ void __launch_bounds__(256)
+k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__ survivors,
+             unsigned int* counter) {
+  constexpr int kTiles = 8 * kFilterTilesPerWarp;
+  __shared__ unsigned s_mask[kTiles];
+  __shared__ unsigned s_off[kTiles];
+  __shared__ unsigned s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_tiles = (Q.n_points + 31) / 32;
+  const uint32_t tile0 = blockIdx.x * kTiles + warp * kFilterTilesPerWarp;
+#pragma unroll 4
+  for (int t = 0; t < kFilterTilesPerWarp; t++) {
+    const uint32_t tile = tile0 + t;
+    unsigned m = 0;
+    if (tile < n_tiles) m = filter_tile(Q, occ, tile, lane);
+    if (lane == 0) s_mask[warp * kFilterTilesPerWarp + t] = m;
+  }
+  __syncthreads();
+  // exclusive scan of the 128 tile counts by warp 0 (4 per lane)
+  if (warp == 0) {
+    unsigned c[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { c[k] = __popc(s_mask[lane * 4 + k]); sum += c[k]; }
+    unsigned inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    unsigned ex = inc - sum;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { s_off[lane * 4 + k] = ex; ex += c[k]; }
+    if (lane == 31) s_base = inc ? atomicAdd(counter, inc) : 0u;
+  }
+  __syncthreads();
+  const unsigned base = s_base;
+  for (int t = 0; t < kFilterTilesPerWarp; t++) {
+    const int i = warp * kFilterTilesPerWarp + t;
+    const unsigned m = s_mask[i];
+    if ((m >> lane) & 1u)
+      survivors[base + s_off[i] + __popc(m & ((1u << lane) - 1))] = (blockIdx.x * kTiles + i) * 32 + lane;
+  }
 }
 
 template <bool kStats>
