@@ -55,12 +55,13 @@ struct BvhView {
   // 32-ary top tree: the binary nodes at depth 5, 10 and 15, addressed by their
   // root path (bit string), so that a warp resolves 5 levels per step with one
   // lane per slot.  Level k has 32^(k+1) slots; empty slots have an empty box.
-  const int4* top_box;     // [32 | 1024 | 32768]
+  const int4* top_box;     // [32 | 1024 | 32768 | 1048576 (only when top_levels == 4)]
   const int* top_code;     // child code per slot (>= 0 internal node, < 0 ~leaf)
   // occupancy bitmap: kOccDim x kOccDim cells over the whole coordinate range, bit
   // set <=> some base edge's box touches the cell.  2 MB, cache resident: a query
   // edge whose box touches no occupied cell cannot intersect anything.
   const uint32_t* occ;
+  int top_levels;          // 3, or 4 for big trees (>= 2^18 leaves): depth 20 resolved in 4 steps
   int4 root_box;
   uint32_t n_leaves;
 };
@@ -74,7 +75,8 @@ static __host__ __device__ __forceinline__ int occ_cell(int q) {
   return (int) (((unsigned) q + (1u << 30)) >> kOccShift) & (kOccDim - 1);
 }
 
-constexpr int kTopOff0 = 0, kTopOff1 = 32, kTopOff2 = 32 + 1024, kTopSlots = 32 + 1024 + 32768;
+constexpr int kTopOff0 = 0, kTopOff1 = 32, kTopOff2 = 32 + 1024, kTopOff3 = 32 + 1024 + 32768;
+constexpr int kTopSlots3 = kTopOff3, kTopSlots4 = kTopOff3 + 32 * 32768;
 
 static __device__ __forceinline__ int quant(long long v) {
   return (int) (v >> kQuantShift);  // arithmetic shift = floor, monotone

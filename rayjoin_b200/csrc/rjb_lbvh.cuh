@@ -33,6 +33,7 @@ struct Bvh {
   DBuf<int4> top_box;
   DBuf<int> top_code;
   DBuf<uint32_t> occ;
+  int top_levels = 3;
   double occ_fraction = 1.0;  // share of occupied cells (the filter pays off when it is small)
   ScanTemp scan_tmp;
   SortTemp sort_tmp;
@@ -47,12 +48,14 @@ struct Bvh {
     v.top_box = top_box.p;
     v.top_code = top_code.p;
     v.occ = occ.p;
+    v.top_levels = top_levels;
     return v;
   }
   size_t index_bytes() const {
     uint32_t n_int = n_leaves > 1 ? n_leaves - 1 : 1;
     return (size_t) n_int * (2 * sizeof(int4) + sizeof(int2)) + (size_t) n_leaves * sizeof(uint2) +
-           (size_t) kTopSlots * (sizeof(int4) + sizeof(int)) + (size_t) kOccDim * kOccDim / 8;
+           (size_t) (top_levels == 4 ? kTopSlots4 : kTopSlots3) * (sizeof(int4) + sizeof(int)) +
+           (size_t) kOccDim * kOccDim / 8;
   }
 };
 
@@ -229,21 +232,21 @@ __global__ void k_single_leaf_root(const int4* __restrict__ leaf_box, int4* node
   *root_box = leaf_box[0];
 }
 
-// 32-ary top tree: thread P (a 15-bit root path) walks 15 binary levels and
-// publishes the node it stands on after 5, 10 and 15 steps into the slot named
-// by the path prefix.  A leaf met early stays in the all-zero continuation of
+// 32-ary top tree: thread P (a 15- or 20-bit root path) walks that many binary levels
+// and publishes the node it stands on after 5, 10, 15 (and 20) steps into the slot
+// named by the path prefix.  A leaf met early stays in the all-zero continuation of
 // its path; every other slot below it is empty.
 __global__ void k_top_tree(const int4* __restrict__ node_box, const int2* __restrict__ node_child,
-                           const int4* __restrict__ root_box, uint32_t n_leaves,
+                           const int4* __restrict__ root_box, uint32_t n_leaves, int depth_max,
                            int4* __restrict__ top_box, int* __restrict__ top_code) {
   uint32_t P = blockIdx.x * blockDim.x + threadIdx.x;
-  if (P >= 32768) return;
+  if (P >= (1u << depth_max)) return;
   int code = 0;  // root = internal node 0
   int4 box = *root_box;
   bool alive = n_leaves > 0;
   const int4 empty = empty_box();
-  for (int level = 0; level < 15; level++) {
-    int bit = (P >> (14 - level)) & 1;
+  for (int level = 0; level < depth_max; level++) {
+    int bit = (P >> (depth_max - 1 - level)) & 1;
     if (alive) {
       if (code < 0) {
         if (bit) alive = false;  // a leaf lives only in the zero continuation
@@ -256,9 +259,9 @@ __global__ void k_top_tree(const int4* __restrict__ node_box, const int2* __rest
     }
     int depth = level + 1;
     if (depth % 5 == 0) {
-      int rest = 15 - depth;  // lower path bits must be zero: one writer per slot
+      int rest = depth_max - depth;  // lower path bits must be zero: one writer per slot
       if ((P & ((1u << rest) - 1)) == 0) {
-        int off = depth == 5 ? kTopOff0 : (depth == 10 ? kTopOff1 : kTopOff2);
+        int off = depth == 5 ? kTopOff0 : (depth == 10 ? kTopOff1 : (depth == 15 ? kTopOff2 : kTopOff3));
         uint32_t slot = P >> rest;
         top_box[off + slot] = alive ? box : empty;
         top_code[off + slot] = code;
@@ -326,9 +329,12 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
     k_karras<<<div_up(n - 1, T), T, 0, st>>>(kb, n, nchild, parent);
     k_refit<<<div_up(n, T), T, 0, st>>>(box_s, n, nchild, parent, nbox, root_d);
   }
-  int4* tbox = b.top_box.ensure(kTopSlots);
-  int* tcode = b.top_code.ensure(kTopSlots);
-  k_top_tree<<<32768 / 256, 256, 0, st>>>(nbox, nchild, root_d, n, tbox, tcode);
+  b.top_levels = n >= (1u << 18) ? 4 : 3;
+  const int top_slots = b.top_levels == 4 ? kTopSlots4 : kTopSlots3;
+  int4* tbox = b.top_box.ensure(top_slots);
+  int* tcode = b.top_code.ensure(top_slots);
+  k_top_tree<<<(1u << (5 * b.top_levels)) / 256, 256, 0, st>>>(nbox, nchild, root_d, n,
+                                                              5 * b.top_levels, tbox, tcode);
   const uint32_t occ_words = (uint32_t) kOccDim * kOccDim / 32;
   uint32_t* occ = b.occ.ensure(occ_words);
   RJB_CUDA(cudaMemsetAsync(occ, 0, occ_words * sizeof(uint32_t), st));

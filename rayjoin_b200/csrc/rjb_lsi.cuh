@@ -321,11 +321,35 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
           const bool h2 = h1 && box_overlap(qb, sb2);
           if (__ballot_sync(0xffffffffu, h2) == 0) continue;
           const int code2 = __shfl_sync(0xffffffffu, c2, i);
-          if (code2 < 0)
+          if (code2 < 0) {
             lsi_leaf<kStats>(B, bvh, ~code2, h2, q, qe, out, cap, counter, lane, st);
-          else
+            continue;
+          }
+          if (bvh.top_levels < 4) {
             lsi_subtree<kStats>(B, bvh, code2, stack, h2 ? qb : kEmpty, q, qe, out, cap, counter,
                                 lane, st);
+            continue;
+          }
+          // level 3 (big trees only): the 32 depth-20 nodes below slot (g, h, i)
+          const int4 U3 = warp_union(h2 ? qb : kNeutral);
+          const uint32_t s3 = kTopOff3 + ((uint32_t) ((g * 32 + h) * 32 + i)) * 32 + lane;
+          const int4 b3 = __ldg(&bvh.top_box[s3]);
+          const int c3 = __ldg(&bvh.top_code[s3]);
+          unsigned m3 = __ballot_sync(0xffffffffu, box_overlap(U3, b3));
+          if (kStats) st.top_steps++;
+          while (m3) {
+            const int j = __ffs(m3) - 1;
+            m3 &= m3 - 1;
+            const int4 sb3 = shfl_box(b3, j);
+            const bool h3 = h2 && box_overlap(qb, sb3);
+            if (__ballot_sync(0xffffffffu, h3) == 0) continue;
+            const int code3 = __shfl_sync(0xffffffffu, c3, j);
+            if (code3 < 0)
+              lsi_leaf<kStats>(B, bvh, ~code3, h3, q, qe, out, cap, counter, lane, st);
+            else
+              lsi_subtree<kStats>(B, bvh, code3, stack, h3 ? qb : kEmpty, q, qe, out, cap, counter,
+                                  lane, st);
+          }
         }
       }
     }

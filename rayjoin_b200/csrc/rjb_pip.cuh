@@ -177,8 +177,26 @@ k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __r
           const bool h2 = pip_wants(L, shfl_box(b2, i));
           if (__ballot_sync(0xffffffffu, h2) == 0) continue;
           const int code2 = __shfl_sync(0xffffffffu, c2, i);
-          if (code2 < 0) pip_leaf<kStats>(B, bvh, ~code2, h2, L, query_map_id, cand, st);
-          else pip_subtree<kStats>(B, bvh, code2, stack, L, query_map_id, cand, st);
+          if (code2 < 0) { pip_leaf<kStats>(B, bvh, ~code2, h2, L, query_map_id, cand, st); continue; }
+          if (bvh.top_levels < 4) {
+            pip_subtree<kStats>(B, bvh, code2, stack, L, query_map_id, cand, st);
+            continue;
+          }
+          // level 3 (big trees only): the 32 depth-20 nodes below slot (g, h, i)
+          const uint32_t s3 = kTopOff3 + ((uint32_t) ((g * 32 + h) * 32 + i)) * 32 + lane;
+          const int4 b3 = __ldg(&bvh.top_box[s3]);
+          const int c3 = __ldg(&bvh.top_code[s3]);
+          unsigned m3 = __ballot_sync(0xffffffffu, pre(b3));
+          if (kStats) st.top_steps++;
+          while (m3) {
+            const int j = lowest_slot(m3, b3.y, lane);
+            m3 &= ~(1u << j);
+            const bool h3 = pip_wants(L, shfl_box(b3, j));
+            if (__ballot_sync(0xffffffffu, h3) == 0) continue;
+            const int code3 = __shfl_sync(0xffffffffu, c3, j);
+            if (code3 < 0) pip_leaf<kStats>(B, bvh, ~code3, h3, L, query_map_id, cand, st);
+            else pip_subtree<kStats>(B, bvh, code3, stack, L, query_map_id, cand, st);
+          }
         }
       }
     }
