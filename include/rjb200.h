@@ -131,6 +131,8 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
  *                     < 32 edges per chain; points only on request)
  *   "lsi_filter"      LBVH LSI occupancy pre-filter: -1 auto (default: on when the
  *                     base map occupies < 25 % of a 4096^2 bitmap), 0 off, 1 on
+ *   "pip_park"        LBVH PIP: 1 (default) = lanes park the leaf their ray meets and the
+ *                     warp opens the parked leaves together; 0 = open a leaf when reached
  *   "stats"           1 = collect traversal statistics (rjb_last_stats; slower)
  *   "keep_host_graph" 0 = rjb_set_map keeps no host copy of the source graph
  *                     (saves a memcpy; rjb_overlay_write then refuses)     */

@@ -21,7 +21,7 @@ struct DeviceMap {
   uint32_t n_points = 0, n_edges = 0, n_chains = 0;
   DBuf<double2> raw;
   DBuf<longlong2> pts;
-  DBuf<uint32_t> edge_chain, row_index, last_bits;
+  DBuf<uint32_t> edge_chain, point_chain, edge_desc, row_index, last_bits;
   DBuf<int32_t> left, right;
   std::vector<int32_t> h_left, h_right;
   // host copy of the source graph kept for the overlay writer (points as
@@ -34,6 +34,8 @@ struct DeviceMap {
     MapView v;
     v.pts = pts.p;
     v.edge_chain = edge_chain.p;
+    v.point_chain = point_chain.p;
+    v.edge_desc = edge_desc.p;
     v.row_index = row_index.p;
     v.last_bits = last_bits.p;
     v.left = left.p;
@@ -66,9 +68,16 @@ struct OverlayState {
 
 using namespace rjb;
 
+constexpr int kLoadChunksMax = 16;
+constexpr uint32_t kLoadChunkPoints = 1u << 20;  // 16 MB of double2 per chunk
+
 struct rjb_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // map upload pipeline: the copy runs on `stream`, the per-chunk load kernel on `aux`
+  cudaStream_t aux = nullptr;
+  cudaEvent_t chunk_ev[kLoadChunksMax + 1] = {};
+  unsigned long long* h_counters = nullptr;  // pinned: the counts a query reads back
   bool have_scaling = false;
   rjb_scaling sc;
   DeviceMap maps[2];
@@ -76,13 +85,13 @@ struct rjb_ctx {
   int sort_queries = -1;  // -1 auto: Morton-order query EDGES when the chains are short
   bool filter_useless = false;  // the occupancy filter kept > 50 % last time: skip it
   int stats = 0;  // collect traversal statistics (slower)
+  bool pip_park = true;  // PIP: park leaves per lane and open them together (rjb_pip.cuh)
   unsigned long long last_stats[8] = {0};
   int keep_host_graph = 1;  // overlay writer needs the source coordinates
   // LSI result queue
   DBuf<uint2> pairs;
   DBuf<uint2> cands;      // LBVH traversal output: pairs whose exact boxes overlap
   DBuf<uint32_t> survivors;  // occupancy pre-filter output (query start points)
-  DBuf<unsigned int> survivor_count;
   int use_filter = -1;    // -1 auto (by occupancy), 0 off, 1 on
   uint32_t last_survivors = 0;
   size_t cand_cap = 0;
@@ -120,9 +129,64 @@ static int guarded(F&& f) {
   }
 }
 
-// ---- kernels of the load path ---------------------------------------------
-// Scaling exactly like the reference's device kernel (src/map/map.h:171-180 ->
-// src/map/scaling.h:79-95): fma.rn.f64 then cvt.rzi.s64.f64.
+// ---- kernel of the load path -----------------------------------------------
+// One thread per point of [p_begin, p_end):
+//  * scaling exactly like the reference's device kernel (src/map/map.h:171-180 ->
+//    src/map/scaling.h:79-95): fma.rn.f64 then cvt.rzi.s64.f64;
+//  * the chain of the point and the edge numbering of src/map/map.h:200-207
+//    (eid = p - chain), both directions;
+//  * bit p of last_bits <=> p is the last point of its chain (the slot owns no edge);
+//  * the occupancy descriptor of the edge ENDING at p (edge_desc[p - 1], what
+//    k_lsi_filter streams): the previous vertex comes from the neighbour lane, or is
+//    re-scaled from the raw array -- uploaded already, chunks arrive in order.
+// p_begin is a multiple of 32, so a warp owns whole last_bits words.
+__global__ void __launch_bounds__(256)
+k_load_points(const double2* __restrict__ in, uint32_t p_begin, uint32_t p_end, uint32_t n_points,
+              double rx, double ry, double dx, double dy, const uint32_t* __restrict__ row_index,
+              uint32_t n_chains, longlong2* __restrict__ out, uint32_t* __restrict__ edge_desc,
+              uint32_t* __restrict__ point_chain, uint32_t* __restrict__ edge_chain,
+              uint32_t* __restrict__ last_bits) {
+  const uint32_t p = p_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool last = false, first = false;
+  longlong2 o = make_longlong2(0, 0);
+  if (p < p_end) {
+    const double2 v = in[p];
+    o.x = (long long) fma(v.x, rx, dx);
+    o.y = (long long) fma(v.y, ry, dy);
+    out[p] = o;
+    // last chain c with row_index[c] <= p
+    uint32_t lo = 0, hi = n_chains;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(&row_index[mid]) <= p) lo = mid; else hi = mid;
+    }
+    point_chain[p] = lo;
+    first = __ldg(&row_index[lo]) == p;
+    last = __ldg(&row_index[lo + 1]) - 1 == p;
+    if (!last) edge_chain[p - lo] = lo;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, last);
+  if (lane == 0 && p < p_end) last_bits[p >> 5] = m;
+  longlong2 q;  // vertex p - 1
+  q.x = __shfl_up_sync(0xffffffffu, o.x, 1);
+  q.y = __shfl_up_sync(0xffffffffu, o.y, 1);
+  if (p < p_end && p > 0) {
+    uint32_t d = kDescNone << 24;
+    if (!first) {
+      if (lane == 0) {
+        const double2 v = in[p - 1];
+        q.x = (long long) fma(v.x, rx, dx);
+        q.y = (long long) fma(v.y, ry, dy);
+      }
+      d = edge_desc_of(occ_code(q.x, q.y), occ_code(o.x, o.y));
+    }
+    edge_desc[p - 1] = d;
+  }
+  if (p == n_points - 1) edge_desc[p] = kDescNone << 24;
+}
+
+// scaling alone (query points of rjb_pip_host): fma.rn.f64 then cvt.rzi.s64.f64
 __global__ void k_scale_points(const double2* __restrict__ in, uint32_t n, double rx, double ry,
                                double dx, double dy, longlong2* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,29 +196,6 @@ __global__ void k_scale_points(const double2* __restrict__ in, uint32_t n, doubl
   o.x = (long long) fma(p.x, rx, dx);
   o.y = (long long) fma(p.y, ry, dy);
   out[i] = o;
-}
-
-// edge numbering of src/map/map.h:200-207: eid = p - chain
-__global__ void k_edge_chain(const uint32_t* __restrict__ row_index, uint32_t n_chains,
-                             uint32_t n_edges, uint32_t* __restrict__ edge_chain) {
-  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_edges) return;
-  // last chain c with first_eid(c) = row_index[c] - c <= e
-  uint32_t lo = 0, hi = n_chains;
-  while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (row_index[mid] - mid <= e) lo = mid; else hi = mid;
-  }
-  edge_chain[e] = lo;
-}
-
-// bit p set <=> p is the last point of its chain (the slot owns no edge)
-__global__ void k_chain_last_bits(const uint32_t* __restrict__ row_index, uint32_t n_chains,
-                                  uint32_t* __restrict__ bits) {
-  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_chains) return;
-  uint32_t p = row_index[c + 1] - 1;
-  atomicOr(&bits[p >> 5], 1u << (p & 31));
 }
 
 __global__ void k_query_keys_edges(MapView Q, long long imin, uint64_t* __restrict__ key,
@@ -227,7 +268,14 @@ static const uint32_t* query_order_points(rjb_ctx* c, const longlong2* pts, uint
   return vb;
 }
 
+static void ensure_load_pipeline(rjb_ctx* c) {
+  if (!c->aux) RJB_CUDA(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+  for (int i = 0; i <= kLoadChunksMax; i++)
+    if (!c->chunk_ev[i]) RJB_CUDA(cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming));
+}
+
 static void ensure_events(rjb_ctx* c) {
+  if (!c->h_counters) RJB_CUDA(cudaHostAlloc((void**) &c->h_counters, 16 * sizeof(unsigned long long), cudaHostAllocDefault));
   for (int i = 0; i < 4; i++)
     if (!c->ev[i]) RJB_CUDA(cudaEventCreate(&c->ev[i]));
 }
@@ -269,7 +317,8 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
   rjb_xsect* xs = c->xsects.ensure(cap ? cap : 1);
   // counters: [0] results, [1] candidates (= exact-predicate evaluations),
   // [2..7] traversal statistics
-  unsigned long long* ctr = c->counters.ensure(8);
+  // [8], [9]: {filter survivors, (query, leaf) pairs} as 32-bit counters
+  unsigned long long* ctr = c->counters.ensure(10);
   ensure_events(c);
   MapView Q = Qm.view(), B = Bm.view();
   unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -285,12 +334,12 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
     bool filter = !order && (c->use_filter == 1 || (c->use_filter < 0 && Bm.bvh.occ_fraction < 0.25 &&
                                                    !c->filter_useless));
     uint32_t* surv = filter ? c->survivors.ensure(Q.n_points) : nullptr;
-    unsigned int* surv_n = c->survivor_count.ensure(2);  // [0] survivors, [1] (query, leaf) pairs
+    unsigned int* surv_n = (unsigned int*) (ctr + 8);  // [0] survivors, [1] (query, leaf) pairs
     for (int attempt = 0;; attempt++) {
       RJB_REQUIRE(c->cand_cap < 0xFFFFFFF0ull, "rjb_lsi: candidate queue exceeds 2^32 entries");
       uint32_t ccap = (uint32_t) c->cand_cap;
       uint2* cands = c->cands.ensure(ccap);
-      RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
+      RJB_CUDA(cudaMemsetAsync(ctr, 0, 10 * sizeof(unsigned long long), c->stream));
       RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
       // query slots: point indices (edge = slot, slot + 1), or a list of start points
       // (Morton-sorted edges, or the survivors of the occupancy filter, whose count
@@ -298,14 +347,13 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
       uint32_t n_slots = order ? Q.n_edges : Q.n_points;
       const uint32_t* slots = order;
       const unsigned int* n_slots_dev = nullptr;
-      RJB_CUDA(cudaMemsetAsync(surv_n, 0, 2 * sizeof(unsigned int), c->stream));
       if (filter) {
-        k_lsi_filter<<<div_up(Q.n_points, 32 * 8 * kFilterTilesPerWarp), 256, 0, c->stream>>>(
+        k_lsi_filter<<<div_up(Q.n_points, kFilterCtaPoints), kFilterThreads, 0, c->stream>>>(
             Q, Bm.bvh.occ.p, surv, surv_n);
         slots = surv;
         n_slots_dev = surv_n;
         // grid for the worst case; warps beyond the survivor count exit at once
-        n_slots = c->last_survivors ? min(Q.n_points, c->last_survivors * 2 + 4096) : Q.n_points;
+        n_slots = c->last_survivors ? min(Q.n_points, c->last_survivors + c->last_survivors / 4 + 4096) : Q.n_points;
       }
       unsigned tiles = div_up(n_slots, 32);
       unsigned blocks = div_up(tiles, kLsiWarps);
@@ -316,15 +364,18 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
         k_lsi_bvh<false><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
             Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, cands, ccap, surv_n + 1, ctr + 2);
       RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
-      k_lsi_exact<<<kNumSMs * 8, 256, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
-                                                    xs, cap, (unsigned int*) ctr, ctr + 1);
-      k_lsi_points<<<kNumSMs * 16, 128, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs);
+      k_lsi_exact<<<kNumSMs * 8, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
+                                                     xs, cap, (unsigned int*) ctr, ctr + 1);
+      k_lsi_points<<<kNumSMs * 4, kPointsThreads, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs);
       RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
       RJB_CUDA(cudaGetLastError());
-      unsigned int hs[2] = {0, 0};
-      RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-      RJB_CUDA(cudaMemcpyAsync(hs, surv_n, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+      // one read-back into pinned memory: the only host round trip of the query
+      RJB_CUDA(cudaMemcpyAsync(c->h_counters, ctr, 10 * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, c->stream));
       RJB_CUDA(cudaStreamSynchronize(c->stream));
+      memcpy(h, c->h_counters, sizeof(h));
+      unsigned int hs[2];
+      memcpy(hs, c->h_counters + 8, sizeof(hs));
       bool grid_too_small = filter && hs[0] > n_slots;  // launch was sized from the last query
       if (filter) {
         c->last_survivors = hs[0];
@@ -382,7 +433,8 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
   RJB_REQUIRE(Bm.loaded, "rjb_pip: base map not loaded");
   uint32_t* eid = c->pip_eid.ensure(n ? n : 1);
   int32_t* face = c->pip_face.ensure(n ? n : 1);
-  unsigned long long* ctr = c->counters.ensure(8);
+  // [8], [9]: {filter survivors, (query, leaf) pairs} as 32-bit counters
+  unsigned long long* ctr = c->counters.ensure(10);
   ensure_events(c);
   RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
   MapView B = Bm.view();
@@ -392,12 +444,13 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
       if (!Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no LBVH on the base map");
       const uint32_t* order = query_order_points(c, d_pts, n);
       RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+      const unsigned pb = div_up(n, kLsiWarps * 32), pt = kLsiWarps * 32;
       if (c->stats)
-        k_pip_bvh<true><<<div_up(n, kLsiWarps * 32), kLsiWarps * 32, 0, c->stream>>>(
-            d_pts, n, order, B, Bm.bvh.view(), q, eid, face, ctr);
+        k_pip_bvh<true, false><<<pb, pt, 0, c->stream>>>(d_pts, n, order, B, Bm.bvh.view(), q, eid, face, ctr);
+      else if (c->pip_park)
+        k_pip_bvh<false, true><<<pb, pt, 0, c->stream>>>(d_pts, n, order, B, Bm.bvh.view(), q, eid, face, ctr);
       else
-        k_pip_bvh<false><<<div_up(n, kLsiWarps * 32), kLsiWarps * 32, 0, c->stream>>>(
-            d_pts, n, order, B, Bm.bvh.view(), q, eid, face, ctr);
+        k_pip_bvh<false, false><<<pb, pt, 0, c->stream>>>(d_pts, n, order, B, Bm.bvh.view(), q, eid, face, ctr);
     } else if (mode == RJB_MODE_GRID) {
       if (!Bm.grid.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no grid on the base map");
       pip_grid(Bm.grid, d_pts, n, B, q, eid, face, ctr + 1, c->stream);
@@ -455,6 +508,10 @@ void rjb_destroy(rjb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (int i = 0; i < 4; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i <= kLoadChunksMax; i++)
+    if (c->chunk_ev[i]) cudaEventDestroy(c->chunk_ev[i]);
+  if (c->aux) cudaStreamDestroy(c->aux);
+  if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -497,6 +554,8 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
       c->sort_queries = (int) value;
     } else if (n == "lsi_filter") {
       c->use_filter = (int) value;
+    } else if (n == "pip_park") {
+      c->pip_park = value != 0;
     } else if (n == "stats") {
       c->stats = value != 0;
     } else if (n == "keep_host_graph") {
@@ -522,7 +581,6 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
     m.bvh.built = false;
     m.grid.built = false;
     c->filter_useless = false;  // new data: let the occupancy filter prove itself again
-    c->last_survivors = 0;
     if (n_chains > 0) {
       RJB_REQUIRE(row_index[0] == 0 && row_index[n_chains] == n_points,
                   "rjb_set_map: row_index must span [0, n_points]");
@@ -552,23 +610,42 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
     int32_t* l = m.left.ensure(n_chains ? n_chains : 1);
     int32_t* r = m.right.ensure(n_chains ? n_chains : 1);
     uint32_t* ec = m.edge_chain.ensure(m.n_edges ? m.n_edges : 1);
+    uint32_t* pc = m.point_chain.ensure(n_points ? n_points : 1);
+    // padded with "no edge" (0xFF bytes: class bits = kDescNone): the filter reads 16 per thread
+    uint32_t* cc = m.edge_desc.ensure(n_points + 16);
     uint32_t n_words = (uint32_t) (n_points / 32 + 2);
     uint32_t* lb = m.last_bits.ensure(n_words);
     cudaStream_t st = c->stream;
     if (n_points) {
-      RJB_CUDA(cudaMemcpyAsync(raw, xy, n_points * sizeof(double2), cudaMemcpyHostToDevice, st));
+      // Small arrays first, then the vertices in chunks: the copy engine streams chunk
+      // k+1 on `stream` while the load kernel works on chunk k on `aux`, so scaling and
+      // edge numbering hide behind the PCIe transfer (which bounds the whole upload).
       RJB_CUDA(cudaMemcpyAsync(ri, row_index, (n_chains + 1) * sizeof(uint32_t),
                                cudaMemcpyHostToDevice, st));
       RJB_CUDA(cudaMemcpyAsync(l, m.h_left.data(), n_chains * sizeof(int32_t),
                                cudaMemcpyHostToDevice, st));
       RJB_CUDA(cudaMemcpyAsync(r, m.h_right.data(), n_chains * sizeof(int32_t),
                                cudaMemcpyHostToDevice, st));
-      k_scale_points<<<div_up(n_points, 256), 256, 0, st>>>(raw, m.n_points, c->sc.rx, c->sc.ry,
-                                                            c->sc.deltax, c->sc.deltay, pts);
-      k_edge_chain<<<div_up(m.n_edges, 256), 256, 0, st>>>(ri, m.n_chains, m.n_edges, ec);
-      RJB_CUDA(cudaMemsetAsync(lb, 0, n_words * sizeof(uint32_t), st));
-      k_chain_last_bits<<<div_up(m.n_chains, 256), 256, 0, st>>>(ri, m.n_chains, lb);
+      RJB_CUDA(cudaMemsetAsync(lb + (n_words - 2), 0, 2 * sizeof(uint32_t), st));
+      RJB_CUDA(cudaMemsetAsync(cc + n_points, 0xFF, 16 * sizeof(uint32_t), st));
+      ensure_load_pipeline(c);
+      uint32_t chunk = kLoadChunkPoints;
+      if (div_up(n_points, chunk) > (unsigned) kLoadChunksMax)
+        chunk = (div_up(n_points, kLoadChunksMax) + 1023u) & ~1023u;
+      int k = 0;
+      for (uint64_t p0 = 0; p0 < n_points; p0 += chunk, k++) {
+        const uint32_t p1 = (uint32_t) std::min<uint64_t>(n_points, p0 + chunk);
+        RJB_CUDA(cudaMemcpyAsync(raw + p0, xy + 2 * p0, (size_t) (p1 - p0) * sizeof(double2),
+                                 cudaMemcpyHostToDevice, st));
+        RJB_CUDA(cudaEventRecord(c->chunk_ev[k], st));
+        RJB_CUDA(cudaStreamWaitEvent(c->aux, c->chunk_ev[k], 0));
+        k_load_points<<<div_up(p1 - p0, 256), 256, 0, c->aux>>>(
+            raw, (uint32_t) p0, p1, m.n_points, c->sc.rx, c->sc.ry, c->sc.deltax, c->sc.deltay, ri,
+            m.n_chains, pts, cc, pc, ec, lb);
+      }
       RJB_CUDA(cudaGetLastError());
+      RJB_CUDA(cudaEventRecord(c->chunk_ev[kLoadChunksMax], c->aux));
+      RJB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[kLoadChunksMax], 0));
     }
     RJB_CUDA(cudaStreamSynchronize(st));
     m.loaded = true;

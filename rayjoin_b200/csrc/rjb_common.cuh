@@ -30,6 +30,8 @@ struct Error : std::runtime_error {
     if (!(cond)) throw ::rjb::Error(RJB_ERR_INVALID, msg); \
   } while (0)
 
+#define RJB_HD __host__ __device__ __forceinline__
+
 constexpr int kNumSMs = 148;  // B200
 constexpr int kQuantShift = 16;  // 47-bit coordinate -> 31-bit box coordinate
 
@@ -37,7 +39,9 @@ constexpr int kQuantShift = 16;  // 47-bit coordinate -> 31-bit box coordinate
 // 16-byte load fetches a vertex; an edge is (pts[eid + chain], pts[eid + chain + 1]).
 struct MapView {
   const longlong2* pts;
-  const uint32_t* edge_chain;  // per edge
+  const uint32_t* edge_chain;  // per edge: eid -> chain (start point = eid + chain)
+  const uint32_t* point_chain; // per point: p -> chain (eid of the edge starting at p = p - chain)
+  const uint32_t* edge_desc;   // per point: occupancy descriptor of the edge starting there (edge_desc_of)
   const uint32_t* row_index;   // per chain, CSR into pts
   const uint32_t* last_bits;   // bit p set <=> point p is the last of its chain (no edge starts there)
   const int32_t* left;         // per chain
@@ -59,7 +63,8 @@ struct BvhView {
   const int* top_code;     // child code per slot (>= 0 internal node, < 0 ~leaf)
   // occupancy bitmap: kOccDim x kOccDim cells over the whole coordinate range, bit
   // set <=> some base edge's box touches the cell.  2 MB, cache resident: a query
-  // edge whose box touches no occupied cell cannot intersect anything.
+  // edge whose box touches no occupied cell cannot intersect anything.  Followed by the
+  // dilated bitmap occ2 (bit (x, y) = OR of occ over {x, x+1} x {y, y+1}), see edge_desc_of.
   const uint32_t* occ;
   int top_levels;          // 3, or 4 for big trees (>= 2^18 leaves): depth 20 resolved in 4 steps
   int4 root_box;
@@ -73,6 +78,35 @@ constexpr int kOccShift = 31 - kOccBits;  // quantised coordinates span 31 bits
 // occupancy cell of a quantised coordinate (monotone, in [0, kOccDim))
 static __host__ __device__ __forceinline__ int occ_cell(int q) {
   return (int) (((unsigned) q + (1u << 30)) >> kOccShift) & (kOccDim - 1);
+}
+
+// occupancy cell code of a vertex straight from its 47-bit coordinates:
+// (v + 2^46) >> 35 equals occ_cell(quant(v)); packed as (cy << kOccBits | cx)
+static __host__ __device__ __forceinline__ uint32_t occ_code(long long x, long long y) {
+  const int sh = kQuantShift + kOccShift;
+  const uint32_t cx = (uint32_t) ((unsigned long long) (x + (1ll << 46)) >> sh) & (kOccDim - 1);
+  const uint32_t cy = (uint32_t) ((unsigned long long) (y + (1ll << 46)) >> sh) & (kOccDim - 1);
+  return (cy << kOccBits) | cx;
+}
+
+// Occupancy descriptor of an edge, computed once when the map is loaded and streamed
+// by k_lsi_filter (4 bytes per edge instead of two 16-byte vertices):
+//   bits 0..23  code of the min corner cell of the edge's box
+//   bits 24..25 class: kDescSame  both vertices in that cell -> test bitmap `occ`
+//                      kDescSmall box within the 2 x 2 cells at the min corner -> test the
+//                                 dilated bitmap `occ2` (bit = OR of those 2 x 2 cells)
+//                      kDescBig   anything longer (rare) -> rectangle loop over `occ`
+//                      kDescNone  no edge starts at this point (last point of a chain)
+// Both bitmaps are one array: occ2 starts kOccWords words after occ.
+constexpr uint32_t kDescSame = 0, kDescSmall = 1, kDescBig = 2, kDescNone = 3;
+constexpr uint32_t kOccWords = (uint32_t) kOccDim * kOccDim / 32;
+
+static __host__ __device__ __forceinline__ uint32_t edge_desc_of(uint32_t c1, uint32_t c2) {
+  const uint32_t x1 = c1 & (kOccDim - 1), x2 = c2 & (kOccDim - 1), y1 = c1 >> kOccBits, y2 = c2 >> kOccBits;
+  const uint32_t xm = x1 < x2 ? x1 : x2, ym = y1 < y2 ? y1 : y2;
+  const uint32_t ex = (x1 < x2 ? x2 : x1) - xm, ey = (y1 < y2 ? y2 : y1) - ym;
+  const uint32_t cls = (ex | ey) == 0 ? kDescSame : (ex <= 1 && ey <= 1) ? kDescSmall : kDescBig;
+  return (cls << 24) | (ym << kOccBits) | xm;
 }
 
 constexpr int kTopOff0 = 0, kTopOff1 = 32, kTopOff2 = 32 + 1024, kTopOff3 = 32 + 1024 + 32768;

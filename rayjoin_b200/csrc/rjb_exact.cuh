@@ -20,7 +20,7 @@ struct Seg {
 };
 
 // (a, b) of the edge equation, normalised like src/map/map.h:222-226
-static __device__ __forceinline__ void edge_ab(const Seg& e, long long& a,
+static RJB_HD void edge_ab(const Seg& e, long long& a,
                                                long long& b) {
   a = e.y1 - e.y2;
   b = e.x2 - e.x1;
@@ -31,7 +31,7 @@ static __device__ __forceinline__ void edge_ab(const Seg& e, long long& a,
 }
 
 // sign of a*dx + b*dy (|a|,|b|,|dx|,|dy| < 2^48): -1, 0, +1
-static __device__ __forceinline__ int side_sign(long long a, long long b,
+static RJB_HD int side_sign(long long a, long long b,
                                                 long long dx, long long dy) {
   // 32-bit fast path: one IMAD.WIDE per product, the sum cannot overflow
   const long long lim = 1ll << 31;
@@ -46,12 +46,12 @@ static __device__ __forceinline__ int side_sign(long long a, long long b,
   return (s > 0) - (s < 0);
 }
 
-static __device__ __forceinline__ int sgn(long long v) { return (v > 0) - (v < 0); }
+static RJB_HD int sgn(long long v) { return (v > 0) - (v < 0); }
 
 // intersect_test(e1, e2), src/algo/lsi.h:27-103.  e1 is the QUERY-side edge,
 // e2 the BASE-side edge (src/app/lsi_lbvh.h:71); the simulation-of-simplicity
 // perturbations are not symmetric in (e1, e2).
-static __device__ __forceinline__ bool lsi_intersect(const Seg& e1, const Seg& e2) {
+static RJB_HD bool lsi_intersect(const Seg& e1, const Seg& e2) {
   long long a1, b1, a2, b2;
   edge_ab(e1, a1, b1);
   edge_ab(e2, a2, b2);
@@ -85,7 +85,7 @@ static __device__ __forceinline__ bool lsi_intersect(const Seg& e1, const Seg& e
 // closed integer boxes of two segments overlap.  intersect_test() == true
 // implies this (the crossing point lies on both closed segments), so it is a
 // loss-free prefilter in exact arithmetic.
-static __device__ __forceinline__ bool seg_boxes_overlap(const Seg& p, const Seg& q) {
+static RJB_HD bool seg_boxes_overlap(const Seg& p, const Seg& q) {
   return min(p.x1, p.x2) <= max(q.x1, q.x2) && min(q.x1, q.x2) <= max(p.x1, p.x2) &&
          min(p.y1, p.y2) <= max(q.y1, q.y2) && min(q.y1, q.y2) <= max(p.y1, p.y2);
 }
@@ -95,15 +95,21 @@ static __device__ __forceinline__ bool seg_boxes_overlap(const Seg& p, const Seg
 // rational(num, den) gcd-reduced in int128 (wrapping like the device code of
 // the reference does for very long edges), clamped to the bbox of the four
 // endpoints, then converted with (int64)((double)num / (double)den).
-static __device__ __forceinline__ i128 iabs128(i128 v) { return v < 0 ? -v : v; }
+static RJB_HD i128 iabs128(i128 v) { return v < 0 ? -v : v; }
 
 typedef unsigned __int128 u128;
 
-static __device__ __forceinline__ int ctz64(unsigned long long v) { return __ffsll((long long) v) - 1; }
+static RJB_HD int ctz64(unsigned long long v) {
+#ifdef __CUDA_ARCH__
+  return __ffsll((long long) v) - 1;
+#else
+  return __builtin_ctzll(v);
+#endif
+}
 
 // binary gcd of two 64-bit magnitudes (no hardware divide on the GPU: Euclid's
 // `%` would cost ~100 instructions per step)
-static __device__ __forceinline__ unsigned long long gcd64(unsigned long long a,
+static RJB_HD unsigned long long gcd64(unsigned long long a,
                                                            unsigned long long b) {
   if (a == 0) return b;
   if (b == 0) return a;
@@ -121,7 +127,7 @@ static __device__ __forceinline__ unsigned long long gcd64(unsigned long long a,
   return a << sh;
 }
 
-static __device__ __forceinline__ int ctz128(u128 v) {
+static RJB_HD int ctz128(u128 v) {
   unsigned long long lo = (unsigned long long) v;
   return lo ? ctz64(lo) : 64 + ctz64((unsigned long long) (v >> 64));
 }
@@ -129,7 +135,7 @@ static __device__ __forceinline__ int ctz128(u128 v) {
 // magnitude of gcd(a, b); any algorithm gives the same value as the reference's
 // Euclid loop (src/util/rational.h:36-43).  Binary gcd in 128 bits until both
 // operands fit 64 bits (typically after a few dozen steps: |den| < 2^64).
-static __device__ i128 gcd128(i128 a, i128 b) {
+static __host__ __device__ i128 gcd128(i128 a, i128 b) {
   u128 x = (u128) iabs128(a), y = (u128) iabs128(b);
   if (x == 0) return (i128) y;
   if (y == 0) return (i128) x;
@@ -149,7 +155,7 @@ static __device__ i128 gcd128(i128 a, i128 b) {
   }
 }
 
-static __device__ __forceinline__ void rat_make(i128 num, i128 den, i128& on,
+static RJB_HD void rat_make(i128 num, i128 den, i128& on,
                                                 i128& od) {
   i128 g = gcd128(num, den);  // den != 0 for a true intersection
   i128 sn = den < 0 ? -num : num;
@@ -163,61 +169,102 @@ static __device__ __forceinline__ void rat_make(i128 num, i128 den, i128& on,
   }
 }
 
-static __device__ __forceinline__ long long min4ll(long long a, long long b,
+static RJB_HD long long min4ll(long long a, long long b,
                                                    long long c, long long d) {
   return min(min(a, b), min(c, d));
 }
-static __device__ __forceinline__ long long max4ll(long long a, long long b,
+static RJB_HD long long max4ll(long long a, long long b,
                                                    long long c, long long d) {
   return max(max(a, b), max(c, d));
 }
 
-// One coordinate (axis 0 = x, 1 = y) of the intersection point.  The two axes are
-// independent chains of ~10^3 dependent integer instructions each (gcd, division),
-// so callers that are latency bound give each axis its own thread.
-static __device__ long long lsi_point_axis(const Seg& e1, const Seg& e2, int axis) {
+// One coordinate (axis 0 = x, 1 = y) of the intersection point.
+//
+// kDefer == false: always returns the reference's value.
+// kDefer == true : returns it when the gcd-free path decides (*deferred = false);
+//                  otherwise sets *deferred and returns 0 -- the caller re-runs the
+//                  item with kDefer == false in a dense pass of its own.
+//
+// Why most points need no gcd.  The reference reduces num/den by their gcd g, clamps to
+// the bbox [lo, hi] of the four endpoints and stores trunc(fl(fl(num/g) / fl(den/g)))
+// (rational.h:190-203, lsi.h:124-141).  g only changes WHICH doubles are divided, never
+// the rational: three roundings of <= 2^-53 relative error each on a value of magnitude
+// <= 2^46 move the quotient by < 0.0235.  So when the exact value x = X0 + rs/D
+// (X0 integer, 0 <= rs < D) has its fraction in [1/32, 31/32], every g gives
+// trunc(x); when rs == 0 the reduced rational is X0/1 and the division is exact; the
+// clamp compares exact rationals with integers and needs no g either.  Only fractions
+// within 1/32 of an integer (6 % of the points) go through the gcd.
+template <bool kDefer>
+static __host__ __device__ long long lsi_point_axis(const Seg& e1, const Seg& e2, int axis,
+                                                    bool* deferred) {
   long long a1l, b1l, a2l, b2l;
   edge_ab(e1, a1l, b1l);
   edge_ab(e2, a2l, b2l);
-  // c with the SAME normalisation sign as (a, b): c = -x1*a - y1*b
+  const long long lo = axis == 0 ? min4ll(e1.x1, e1.x2, e2.x1, e2.x2) : min4ll(e1.y1, e1.y2, e2.y1, e2.y2);
+  const long long hi = axis == 0 ? max4ll(e1.x1, e1.x2, e2.x1, e2.x2) : max4ll(e1.y1, e1.y2, e2.y1, e2.y2);
   const i128 a1 = a1l, b1 = b1l, a2 = a2l, b2 = b2l;
-  const i128 c1 = -(i128) e1.x1 * a1 - (i128) e1.y1 * b1;
-  const i128 c2 = -(i128) e2.x1 * a2 - (i128) e2.y1 * b2;
   // unsigned products: two's-complement wrap-around, no UB
   const i128 denom = (i128) ((u128) a1 * (u128) b2 - (u128) a2 * (u128) b1);
-  const i128 num = axis == 0 ? (i128) ((u128) c2 * (u128) b1 - (u128) c1 * (u128) b2)
-                             : (i128) ((u128) a2 * (u128) c1 - (u128) a1 * (u128) c2);
   i128 rn, rd;
   const long long lim = 1ll << 38;
   if (a1l > -lim && a1l < lim && b1l < lim && a2l > -lim && a2l < lim && b2l < lim) {
     // Edges spanning < 2^38 internal units (1/512 of the coordinate range): nothing
-    // wraps (|num| < 2^126) and the gcd inputs can be shrunk first.
-    // gcd(num, den) = gcd(num - t*den, den) for any integer t; with t = e1.p1 the
-    // shifted numerators are (x - x1)*den = c2'*b1 and (y - y1)*den = -a1*c2', where
-    // c2' is e2's constant term in coordinates relative to e1.p1.  (x - x1) and
-    // (y - y1) are bounded by e1's span (< 2^38), so one double division yields the
-    // quotient to +-1 and the remainder is < 2*|den|: the binary gcd then starts
-    // from ~2k-bit operands instead of a ~110-bit numerator.
+    // wraps.  With t = e1.p1 the shifted numerators are (x - x1)*den = c2'*b1 and
+    // (y - y1)*den = -a1*c2', where c2' is e2's constant term in coordinates relative
+    // to e1.p1.  (x - x1) and (y - y1) are bounded by e1's span (< 2^38), so one double
+    // division yields the quotient to +-1.
     const i128 aden = iabs128(denom);
     const i128 c2p = -((i128) (e2.x1 - e1.x1) * a2l + (i128) (e2.y1 - e1.y1) * b2l);
     const i128 np = axis == 0 ? c2p * b1l : -c2p * a1l;
     const long long q = (long long) rint((double) np / (double) denom);
-    const i128 r = np - (i128) q * denom;  // |r| < 2*|den|
+    const i128 r = np - (i128) q * denom;  // |r| <= (1/2 + eps)*|den|
+    // exact value = X0 + rs/aden with 0 <= rs < aden
+    long long X0 = (axis == 0 ? e1.x1 : e1.y1) + q;
+    i128 rs = denom < 0 ? -r : r;
+    while (rs < 0) { rs += aden; X0--; }
+    while (rs >= aden) { rs -= aden; X0++; }
+    if (X0 < lo) return lo;                          // x < lo  <=>  floor(x) < lo
+    if (X0 > hi || (X0 == hi && rs != 0)) return hi; // x > hi
+    if (rs == 0) return X0;                          // the reduced rational is X0 / 1
+    // (the error bound above assumes |x| <= 2^46, the range Scaling produces)
+    if (32 * rs >= aden && 32 * (aden - rs) >= aden && lo >= -(1ll << 46) && hi <= (1ll << 46))
+      return X0 >= 0 ? X0 : X0 + 1;  // trunc(x)
+    if (kDefer) {
+      *deferred = true;
+      return 0;
+    }
+    // gcd(num, den) = gcd(num - t*den, den) for any integer t: the binary gcd starts
+    // from ~2k-bit operands instead of a ~110-bit numerator
+    const i128 c1 = -(i128) e1.x1 * a1 - (i128) e1.y1 * b1;
+    const i128 c2 = -(i128) e2.x1 * a2 - (i128) e2.y1 * b2;
+    const i128 num = axis == 0 ? (i128) ((u128) c2 * (u128) b1 - (u128) c1 * (u128) b2)
+                               : (i128) ((u128) a2 * (u128) c1 - (u128) a1 * (u128) c2);
     const i128 g = gcd128(r, denom);
     const i128 sn = denom < 0 ? -num : num;
     rn = g == 1 ? sn : sn / g;
     rd = g == 1 ? aden : aden / g;
   } else {
+    if (kDefer) {
+      *deferred = true;
+      return 0;
+    }
+    // c with the SAME normalisation sign as (a, b): c = -x1*a - y1*b
+    const i128 c1 = -(i128) e1.x1 * a1 - (i128) e1.y1 * b1;
+    const i128 c2 = -(i128) e2.x1 * a2 - (i128) e2.y1 * b2;
+    const i128 num = axis == 0 ? (i128) ((u128) c2 * (u128) b1 - (u128) c1 * (u128) b2)
+                               : (i128) ((u128) a2 * (u128) c1 - (u128) a1 * (u128) c2);
     rat_make(num, denom, rn, rd);
   }
-  long long t = axis == 0 ? min4ll(e1.x1, e1.x2, e2.x1, e2.x2) : min4ll(e1.y1, e1.y2, e2.y1, e2.y2);
-  if (rn < (i128) ((u128) (i128) t * (u128) rd)) { rn = t; rd = 1; }
-  t = axis == 0 ? max4ll(e1.x1, e1.x2, e2.x1, e2.x2) : max4ll(e1.y1, e1.y2, e2.y1, e2.y2);
-  if ((i128) ((u128) (i128) t * (u128) rd) < rn) { rn = t; rd = 1; }
+  if (rn < (i128) ((u128) (i128) lo * (u128) rd)) { rn = lo; rd = 1; }
+  if ((i128) ((u128) (i128) hi * (u128) rd) < rn) { rn = hi; rd = 1; }
   return (long long) ((double) rn / (double) rd);
 }
 
-static __device__ void lsi_point(const Seg& e1, const Seg& e2, long long& ox, long long& oy) {
+static __host__ __device__ long long lsi_point_axis(const Seg& e1, const Seg& e2, int axis) {
+  return lsi_point_axis<false>(e1, e2, axis, nullptr);
+}
+
+static __host__ __device__ void lsi_point(const Seg& e1, const Seg& e2, long long& ox, long long& oy) {
   ox = lsi_point_axis(e1, e2, 0);
   oy = lsi_point_axis(e1, e2, 1);
 }
@@ -232,15 +279,15 @@ struct PipBest {
   uint32_t eid;
 };
 
-static __device__ __forceinline__ void pip_init(PipBest& st) {
-  st.y = __longlong_as_double(0x7ff0000000000000ll);  // +inf
+static RJB_HD void pip_init(PipBest& st) {
+  st.y = __builtin_huge_val();  // +inf
   st.a = 0;
   st.b = 1;
   st.eid = RJB_NO_HIT;
 }
 
 // returns true when st changed
-static __device__ __forceinline__ bool pip_update(PipBest& st, int q, long long px,
+static RJB_HD bool pip_update(PipBest& st, int q, long long px,
                                                   long long py, const Seg& e,
                                                   uint32_t eid) {
   long long x_min = min(e.x1, e.x2), x_max = max(e.x1, e.x2);

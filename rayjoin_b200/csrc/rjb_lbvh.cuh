@@ -55,7 +55,7 @@ struct Bvh {
     uint32_t n_int = n_leaves > 1 ? n_leaves - 1 : 1;
     return (size_t) n_int * (2 * sizeof(int4) + sizeof(int2)) + (size_t) n_leaves * sizeof(uint2) +
            (size_t) (top_levels == 4 ? kTopSlots4 : kTopSlots3) * (sizeof(int4) + sizeof(int)) +
-           (size_t) kOccDim * kOccDim / 8;
+           2 * (size_t) kOccDim * kOccDim / 8;
   }
 };
 
@@ -287,6 +287,18 @@ __global__ void k_occ_mark(const int4* __restrict__ leaf_box, uint32_t n, uint32
     }
 }
 
+// occ2(x, y) = occ(x, y) | occ(x+1, y) | occ(x, y+1) | occ(x+1, y+1), one word per thread
+__global__ void k_occ_dilate(const uint32_t* __restrict__ occ, uint32_t* __restrict__ occ2) {
+  constexpr uint32_t kRowWords = kOccDim / 32;
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= kOccWords) return;
+  const uint32_t y = w / kRowWords, wx = w % kRowWords;
+  const bool has_row = y + 1 < (uint32_t) kOccDim, has_col = wx + 1 < kRowWords;
+  const uint32_t a = occ[w] | (has_row ? occ[w + kRowWords] : 0u);
+  const uint32_t an = has_col ? (occ[w + 1] | (has_row ? occ[w + 1 + kRowWords] : 0u)) : 0u;
+  occ2[w] = a | (a >> 1) | (an << 31);
+}
+
 static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long imin,
                               cudaStream_t st) {
   RJB_REQUIRE(leaf_size >= 1 && leaf_size <= 8, "lbvh_leaf_size must be in 1..8");
@@ -335,10 +347,11 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
   int* tcode = b.top_code.ensure(top_slots);
   k_top_tree<<<(1u << (5 * b.top_levels)) / 256, 256, 0, st>>>(nbox, nchild, root_d, n,
                                                               5 * b.top_levels, tbox, tcode);
-  const uint32_t occ_words = (uint32_t) kOccDim * kOccDim / 32;
-  uint32_t* occ = b.occ.ensure(occ_words);
+  const uint32_t occ_words = kOccWords;
+  uint32_t* occ = b.occ.ensure(2 * occ_words);  // occ, then the dilated occ2
   RJB_CUDA(cudaMemsetAsync(occ, 0, occ_words * sizeof(uint32_t), st));
   k_occ_mark<<<div_up(n, T), T, 0, st>>>(box_s, n, occ);
+  k_occ_dilate<<<div_up(occ_words, T), T, 0, st>>>(occ, occ + occ_words);
   RJB_CUDA(cudaGetLastError());
   RJB_CUDA(cudaMemcpyAsync(&b.root_box, root_d, sizeof(int4), cudaMemcpyDeviceToHost, st));
   RJB_CUDA(cudaStreamSynchronize(st));

@@ -52,27 +52,53 @@ struct TravStats {
 };
 
 // A leaf that some lanes' boxes overlap is NOT opened by the traversing warp: the
-// (query start point, leaf) pairs are appended to a queue (one atomic per warp)
-// and resolved later by a dense kernel in which every thread is independent.
-// Keeping the leaf's dependent loads and its divergent edge tests out of the
-// warp-synchronous walk roughly halves the traversal time.
+// (query start point, leaf) pairs are resolved later by a dense kernel in which every
+// thread is independent.  Keeping the leaf's dependent loads and its divergent edge
+// tests out of the warp-synchronous walk roughly halves the traversal time.
+//
+// The pairs are staged in a per-warp shared-memory buffer and appended to the global
+// queue kEmitFlush at a time: ONE atomic per flush instead of one per leaf, and its
+// round trip to L2 (the walk cannot proceed past it) is paid once per warp, not once
+// per leaf; the queue is written in full 256-byte runs.
+constexpr int kEmitFlush = 64;              // flush at >= this many staged pairs
+constexpr int kEmitBuf = kEmitFlush + 32;   // one more leaf always fits
+
+struct Emit {
+  uint2* buf;              // this warp's staging area (shared memory)
+  unsigned n;              // staged pairs (warp-uniform)
+  uint2* __restrict__ out;
+  uint32_t cap;
+  unsigned int* counter;
+};
+
+static __device__ __forceinline__ void emit_flush(Emit& E, int lane) {
+  if (E.n == 0) return;
+  unsigned base = 0;
+  if (lane == 0) base = atomicAdd(E.counter, E.n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  __syncwarp();
+  for (unsigned t = lane; t < E.n; t += 32)
+    if (base + t < E.cap) E.out[base + t] = E.buf[t];
+  __syncwarp();
+  E.n = 0;
+}
+
 template <bool kStats>
-static __device__ __forceinline__ void lsi_leaf(const MapView&, const BvhView&, int leaf, bool h,
-                                                const Seg&, uint32_t qe, uint2* __restrict__ out,
-                                                uint32_t cap, unsigned int* counter, int lane,
+static __device__ __forceinline__ void lsi_leaf(int leaf, bool h, uint32_t qe, Emit& E, int lane,
                                                 TravStats& st) {
   if (kStats) st.leaves++;
-  emit_pair(h, qe, (uint32_t) leaf, out, cap, counter, lane);
+  const unsigned m = __ballot_sync(0xffffffffu, h);
+  if (h) E.buf[E.n + __popc(m & ((1u << lane) - 1))] = make_uint2(qe, (uint32_t) leaf);
+  E.n += __popc(m);
+  if (E.n >= kEmitFlush) emit_flush(E, lane);
 }
 
 // Binary part of the traversal, below the 32-ary top tree: node records are read
 // at a warp-uniform address (one transaction), every lane tests ITS box against
 // both child boxes and __ballot_sync decides warp-uniformly where to go.
 template <bool kStats>
-static __device__ __forceinline__ void lsi_subtree(const MapView& B, const BvhView& bvh, int root,
-                                                   int* stack, const int4& qb, const Seg& q,
-                                                   uint32_t qe, uint2* __restrict__ out,
-                                                   uint32_t cap, unsigned int* counter, int lane,
+static __device__ __forceinline__ void lsi_subtree(const BvhView& bvh, int root, int* stack,
+                                                   const int4& qb, uint32_t qe, Emit& E, int lane,
                                                    TravStats& st) {
   int sp = 0;
   int node = root;
@@ -89,7 +115,7 @@ static __device__ __forceinline__ void lsi_subtree(const MapView& B, const BvhVi
       if (ch.x >= 0) next = ch.x;
       else {
         if (kStats) st.lane_leaf += __popc(ml);
-        lsi_leaf<kStats>(B, bvh, ~ch.x, hl, q, qe, out, cap, counter, lane, st);
+        lsi_leaf<kStats>(~ch.x, hl, qe, E, lane, st);
       }
     }
     if (mr) {
@@ -97,7 +123,7 @@ static __device__ __forceinline__ void lsi_subtree(const MapView& B, const BvhVi
         if (next < 0) next = ch.y; else stack[sp++] = ch.y;
       } else {
         if (kStats) st.lane_leaf += __popc(mr);
-        lsi_leaf<kStats>(B, bvh, ~ch.y, hr, q, qe, out, cap, counter, lane, st);
+        lsi_leaf<kStats>(~ch.y, hr, qe, E, lane, st);
       }
     }
     if (kStats) st.maxsp = max(st.maxsp, (unsigned) sp);
@@ -149,98 +175,112 @@ static __device__ __forceinline__ QTile load_tile(const MapView& Q, const uint32
   return t;
 }
 
-// Occupancy pre-filter: streams every query edge once, keeps the start-point index
-// of those whose (quantised) box touches an occupied cell of the base map's
-// bitmap.  For a sparse base map (county boundaries: ~1 % of the cells) a few per
-// cent of the query edges survive, and only those are traversed.
-constexpr int kFilterTilesPerWarp = 16;  // a CTA of 8 warps covers 128 consecutive tiles
+// Occupancy pre-filter: streams the query map once and keeps the start-point index of
+// the edges whose (quantised) box touches an occupied cell of the base map's bitmap.
+// For a sparse base map (county boundaries: ~1 % of the cells) a few per cent of the
+// query edges survive, and only those are traversed.
+//
+// The kernel reads the 4-byte occupancy DESCRIPTOR of every edge (edge_desc_of, written
+// once by the load kernel), not two 16-byte vertices: a quarter of the traffic, and the
+// decision is one bitmap look-up per edge -- in `occ` for an edge inside one cell, in the
+// 2 x 2-dilated `occ2` for an edge that crosses into a neighbour cell (conservative).  A
+// thread owns 16 consecutive edges: four 16-byte loads, then 16 independent look-ups,
+// all in flight together; a CTA owns 4096 consecutive points.
+constexpr int kFilterThreads = 256;
+constexpr int kFilterPerThread = 16;
+constexpr int kFilterCtaPoints = kFilterThreads * kFilterPerThread;
 
-// keep-mask of one tile of 32 consecutive query points (bit = edge starting there
-// touches an occupied cell)
-static __device__ __forceinline__ unsigned filter_tile(const MapView& Q, const uint32_t* __restrict__ occ,
-                                                       uint32_t tile, int lane) {
-  // one 16-byte load per lane; the edge's second vertex is the next lane's point
-  const uint32_t p = tile * 32 + lane;
-  const bool in = p < Q.n_points;
-  const longlong2 a = in ? __ldg(&Q.pts[p]) : make_longlong2(0, 0);
-  // occupancy cell straight from the 47-bit coordinate: (v + 2^46) >> 35 equals
-  // occ_cell(quant(v)); packed as (cy << kOccBits | cx)
-  const int sh = kQuantShift + kOccShift;
-  const uint32_t cx = (uint32_t) ((unsigned long long) (a.x + (1ll << 46)) >> sh) & (kOccDim - 1);
-  const uint32_t cy = (uint32_t) ((unsigned long long) (a.y + (1ll << 46)) >> sh) & (kOccDim - 1);
-  const uint32_t code = (cy << kOccBits) | cx;
-  uint32_t code2 = __shfl_down_sync(0xffffffffu, code, 1);
-  if (lane == 31 && p + 1 < Q.n_points) {
-    const longlong2 b = __ldg(&Q.pts[p + 1]);
-    code2 = ((uint32_t) ((unsigned long long) (b.y + (1ll << 46)) >> sh) & (kOccDim - 1)) << kOccBits |
-            ((uint32_t) ((unsigned long long) (b.x + (1ll << 46)) >> sh) & (kOccDim - 1));
-  }
-  const uint32_t w = __ldg(&Q.last_bits[tile]);  // warp-uniform: bit set = no edge starts here
-  const bool valid = in && !((w >> lane) & 1u);
-  bool keep = false;
-  if (valid) {
-    if (code == code2) {  // the usual case: both vertices in one cell
-      keep = (__ldg(&occ[code >> 5]) >> (code & 31)) & 1u;
-    } else {
-      const uint32_t x0 = min(code & (kOccDim - 1), code2 & (kOccDim - 1));
-      const uint32_t x1 = max(code & (kOccDim - 1), code2 & (kOccDim - 1));
-      const uint32_t y0 = min(code >> kOccBits, code2 >> kOccBits), y1 = max(code >> kOccBits, code2 >> kOccBits);
-      for (uint32_t y = y0; y <= y1 && !keep; y++)
-        for (uint32_t x = x0; x <= x1; x++) {
-          const uint32_t bit = y * kOccDim + x;
-          if ((__ldg(&occ[bit >> 5]) >> (bit & 31)) & 1u) { keep = true; break; }
-        }
+// edge longer than a cell (rare): every cell of its box
+static __device__ __noinline__ bool occ_rect(const MapView& Q, const uint32_t* __restrict__ occ, uint32_t p) {
+  const longlong2 a = __ldg(&Q.pts[p]), b = __ldg(&Q.pts[p + 1]);
+  const uint32_t c1 = occ_code(a.x, a.y), c2 = occ_code(b.x, b.y);
+  const uint32_t x0 = min(c1 & (kOccDim - 1), c2 & (kOccDim - 1));
+  const uint32_t x1 = max(c1 & (kOccDim - 1), c2 & (kOccDim - 1));
+  const uint32_t y0 = min(c1 >> kOccBits, c2 >> kOccBits), y1 = max(c1 >> kOccBits, c2 >> kOccBits);
+  for (uint32_t y = y0; y <= y1; y++)
+    for (uint32_t x = x0; x <= x1; x++) {
+      const uint32_t bit = y * kOccDim + x;
+      if ((__ldg(&occ[bit >> 5]) >> (bit & 31)) & 1u) return true;
     }
-  }
-  return __ballot_sync(0xffffffffu, keep);
+  return false;
 }
 
-// A CTA filters 128 consecutive tiles (4096 points) and appends its survivors as ONE
-// contiguous, map-ordered run (block scan of the tile counts, one atomic per CTA):
-// the 32 survivors a traversal warp picks up are then neighbours on the map.  (With
-// one atomic per warp the runs of concurrently running warps from all over the map
+// A CTA filters 4096 consecutive points and appends its survivors as ONE contiguous,
+// map-ordered run (block scan of the per-thread counts, one atomic per CTA): the 32
+// survivors a traversal warp picks up are then neighbours on the map.  (With one
+// atomic per warp the runs of concurrently running warps from all over the map
 // interleave, and every traversal warp has to follow up to 32 separate clusters.)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFilterThreads)
 k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__ survivors,
              unsigned int* counter) {
-  constexpr int kTiles = 8 * kFilterTilesPerWarp;
-  __shared__ unsigned s_mask[kTiles];
-  __shared__ unsigned s_off[kTiles];
+  constexpr int kWarps = kFilterThreads / 32;
+  __shared__ unsigned s_wsum[kWarps];
   __shared__ unsigned s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t n_tiles = (Q.n_points + 31) / 32;
-  const uint32_t tile0 = blockIdx.x * kTiles + warp * kFilterTilesPerWarp;
-#pragma unroll 4
-  for (int t = 0; t < kFilterTilesPerWarp; t++) {
-    const uint32_t tile = tile0 + t;
-    unsigned m = 0;
-    if (tile < n_tiles) m = filter_tile(Q, occ, tile, lane);
-    if (lane == 0) s_mask[warp * kFilterTilesPerWarp + t] = m;
-  }
-  __syncthreads();
-  // exclusive scan of the 128 tile counts by warp 0 (4 per lane)
-  if (warp == 0) {
-    unsigned c[4], sum = 0;
+  const uint32_t p0 = blockIdx.x * kFilterCtaPoints + threadIdx.x * kFilterPerThread;
+  // stage 1: the descriptors (edge_desc is padded with "no edge": whole groups are in bounds)
+  uint32_t d[kFilterPerThread];
+  {
+    // one predicate for the whole thread (p0 is a multiple of 16, the padding covers the
+    // rest), so the four loads issue back to back
+    uint4 v[kFilterPerThread / 4];
+    const uint4* src = reinterpret_cast<const uint4*>(Q.edge_desc + min(p0, Q.n_points & ~15u));
 #pragma unroll
-    for (int k = 0; k < 4; k++) { c[k] = __popc(s_mask[lane * 4 + k]); sum += c[k]; }
-    unsigned inc = sum;
+    for (int j = 0; j < kFilterPerThread / 4; j++) v[j] = __ldg(src + j);
+    const bool in = p0 < Q.n_points;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += v;
+    for (int j = 0; j < kFilterPerThread / 4; j++) {
+      d[4 * j] = in ? v[j].x : (kDescNone << 24);
+      d[4 * j + 1] = in ? v[j].y : (kDescNone << 24);
+      d[4 * j + 2] = in ? v[j].z : (kDescNone << 24);
+      d[4 * j + 3] = in ? v[j].w : (kDescNone << 24);
     }
-    unsigned ex = inc - sum;
+  }
+  // stage 2: one look-up per edge; class bit 0 selects occ2 (kDescNone / kDescBig read a
+  // valid word too and ignore it)
+  uint32_t w[kFilterPerThread];
 #pragma unroll
-    for (int k = 0; k < 4; k++) { s_off[lane * 4 + k] = ex; ex += c[k]; }
-    if (lane == 31) s_base = inc ? atomicAdd(counter, inc) : 0u;
+  for (int e = 0; e < kFilterPerThread; e++)
+    w[e] = __ldg(&occ[((d[e] & 0xFFFFFFu) >> 5) + ((d[e] >> 24) & 1u) * kOccWords]);
+  unsigned keep = 0, big = 0;
+#pragma unroll
+  for (int e = 0; e < kFilterPerThread; e++) {
+    const uint32_t cls = d[e] >> 24;
+    if (cls < kDescBig && ((w[e] >> (d[e] & 31u)) & 1u)) keep |= 1u << e;
+    if (cls == kDescBig) big |= 1u << e;
+  }
+  while (big) {
+    const int e = __ffs(big) - 1;
+    big &= big - 1;
+    if (occ_rect(Q, occ, p0 + e)) keep |= 1u << e;
+  }
+  // block-wide exclusive scan of the per-thread counts (thread order = point order)
+  const unsigned cnt = __popc(keep);
+  unsigned inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned sum = lane < kWarps ? s_wsum[lane] : 0u;
+    unsigned winc = sum;
+#pragma unroll
+    for (int o = 1; o < kWarps; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += v;
+    }
+    if (lane < kWarps) s_wsum[lane] = winc - sum;
+    if (lane == kWarps - 1) s_base = winc ? atomicAdd(counter, winc) : 0u;
   }
   __syncthreads();
-  const unsigned base = s_base;
-  for (int t = 0; t < kFilterTilesPerWarp; t++) {
-    const int i = warp * kFilterTilesPerWarp + t;
-    const unsigned m = s_mask[i];
-    if ((m >> lane) & 1u)
-      survivors[base + s_off[i] + __popc(m & ((1u << lane) - 1))] = (blockIdx.x * kTiles + i) * 32 + lane;
+  unsigned pos = s_base + s_wsum[warp] + inc - cnt;
+  while (keep) {
+    const int e = __ffs(keep) - 1;
+    keep &= keep - 1;
+    survivors[pos++] = p0 + e;
   }
 }
 
@@ -251,8 +291,10 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
           uint2* __restrict__ out, uint32_t cap, unsigned int* counter,
           unsigned long long* stats) {
   __shared__ int s_stack[kLsiWarps][kStackDepth];
+  __shared__ uint2 s_emit[kLsiWarps][kEmitBuf];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* stack = s_stack[warp];
+  Emit E = {s_emit[warp], 0u, out, cap, counter};
   if (n_slots_dev) n_slots = *n_slots_dev;  // survivor count of the pre-filter
   const uint32_t n_tiles = (n_slots + 31) / 32;
   const uint32_t tile = blockIdx.x * kLsiWarps + warp;
@@ -288,7 +330,7 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
       if (__ballot_sync(0xffffffffu, h0) == 0) continue;
       const int code0 = __shfl_sync(0xffffffffu, c0, g);
       if (code0 < 0) {
-        lsi_leaf<kStats>(B, bvh, ~code0, h0, q, qe, out, cap, counter, lane, st);
+        lsi_leaf<kStats>(~code0, h0, qe, E, lane, st);
         continue;
       }
       const int4 U1 = warp_union(h0 ? qb : kNeutral);
@@ -305,7 +347,7 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
         if (__ballot_sync(0xffffffffu, h1) == 0) continue;
         const int code1 = __shfl_sync(0xffffffffu, c1, h);
         if (code1 < 0) {
-          lsi_leaf<kStats>(B, bvh, ~code1, h1, q, qe, out, cap, counter, lane, st);
+          lsi_leaf<kStats>(~code1, h1, qe, E, lane, st);
           continue;
         }
         const int4 U2 = warp_union(h1 ? qb : kNeutral);
@@ -322,12 +364,11 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
           if (__ballot_sync(0xffffffffu, h2) == 0) continue;
           const int code2 = __shfl_sync(0xffffffffu, c2, i);
           if (code2 < 0) {
-            lsi_leaf<kStats>(B, bvh, ~code2, h2, q, qe, out, cap, counter, lane, st);
+            lsi_leaf<kStats>(~code2, h2, qe, E, lane, st);
             continue;
           }
           if (bvh.top_levels < 4) {
-            lsi_subtree<kStats>(B, bvh, code2, stack, h2 ? qb : kEmpty, q, qe, out, cap, counter,
-                                lane, st);
+            lsi_subtree<kStats>(bvh, code2, stack, h2 ? qb : kEmpty, qe, E, lane, st);
             continue;
           }
           // level 3 (big trees only): the 32 depth-20 nodes below slot (g, h, i)
@@ -345,15 +386,15 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
             if (__ballot_sync(0xffffffffu, h3) == 0) continue;
             const int code3 = __shfl_sync(0xffffffffu, c3, j);
             if (code3 < 0)
-              lsi_leaf<kStats>(B, bvh, ~code3, h3, q, qe, out, cap, counter, lane, st);
+              lsi_leaf<kStats>(~code3, h3, qe, E, lane, st);
             else
-              lsi_subtree<kStats>(B, bvh, code3, stack, h3 ? qb : kEmpty, q, qe, out, cap, counter,
-                                  lane, st);
+              lsi_subtree<kStats>(bvh, code3, stack, h3 ? qb : kEmpty, qe, E, lane, st);
           }
         }
       }
     }
   }
+  emit_flush(E, lane);
   if (kStats && lane == 0) {
     atomicAdd(stats + 0, (unsigned long long) st.nodes);
     atomicAdd(stats + 1, (unsigned long long) st.leaves);
@@ -364,37 +405,72 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
   }
 }
 
-// chain of point p: last c with row_index[c] <= p
-static __device__ __forceinline__ uint32_t chain_of_point(const MapView& m, uint32_t p) {
-  uint32_t lo = 0, hi = m.n_chains;
-  while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(&m.row_index[mid]) <= p) lo = mid; else hi = mid;
+// Exact pass 1 over the (query start point, leaf) pairs of the traversal, in two dense
+// steps per CTA:
+//  (1) FOUR LANES PER PAIR: lane k of a quad tests the exact integer boxes of the query
+//      edge and base edge k (and k + 4 for leaves of > 4 edges) of the leaf -- one
+//      contiguous run of points, so a quad's loads are five consecutive 16-byte
+//      vertices.  The ~1 in 8 that overlap go to a shared-memory list;
+//  (2) whenever the list holds a CTA's worth, intersect_test runs over it with every
+//      lane busy, and the hits are compacted into the result queue (one atomic per
+//      warp) as start-point index pairs.
+// (Running intersect_test where the box test passes kept 3 of 32 lanes busy: ncu showed
+// the int128 predicate executed by nearly every warp for one or two lanes.)
+// The pair count is read on the device: no host round trip between the kernels.
+constexpr int kExactThreads = 256;
+constexpr int kExactList = 3 * kExactThreads;  // < kExactThreads before a round, <= 2 per thread added
+
+static __device__ __forceinline__ void exact_drain(const MapView& Q, const MapView& B, const uint2* list,
+                                                   unsigned n_list, rjb_xsect* __restrict__ out,
+                                                   uint32_t cap, unsigned int* counter) {
+  const int lane = threadIdx.x & 31;
+  for (unsigned t0 = threadIdx.x - lane; t0 < n_list; t0 += kExactThreads) {
+    const unsigned t = t0 + lane;
+    bool found = false;
+    uint2 it = make_uint2(0, 0);
+    if (t < n_list) {
+      it = list[t];
+      const longlong2 a = __ldg(&Q.pts[it.x]), b = __ldg(&Q.pts[it.x + 1]);
+      const longlong2 c = __ldg(&B.pts[it.y]), d = __ldg(&B.pts[it.y + 1]);
+      const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
+      found = lsi_intersect(e1, e2);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, found);
+    if (m == 0) continue;
+    unsigned base = 0;
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) base = atomicAdd(counter, (unsigned) __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (found) {
+      const unsigned pos = base + __popc(m & ((1u << lane) - 1));
+      if (pos < cap) {
+        out[pos].eid[0] = it.x;  // point indices for now; pass 2 turns them into eids
+        out[pos].eid[1] = it.y;
+      }
+    }
   }
-  return lo;
 }
 
-// Exact pass 1, dense over the (query start point, leaf) pairs of the traversal:
-// each thread tests its query edge against the <= 8 consecutive base edges of the
-// leaf (one contiguous run of points): exact integer box test, then
-// intersect_test.  Hits are compacted into the result queue (one atomic per warp
-// and edge slot) as start-point index pairs.  The pair count is read on the
-// device: no host round trip between the kernels.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kExactThreads)
 k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ pairs, const uint2* __restrict__ leaf_rec,
             const unsigned int* __restrict__ n_pairs_dev, uint32_t pair_cap,
             rjb_xsect* __restrict__ out, uint32_t cap, unsigned int* counter,
             unsigned long long* n_cand) {
+  __shared__ uint2 s_list[kExactList];
+  __shared__ unsigned s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
   const uint32_t n = min(*n_pairs_dev, pair_cap);
   const int lane = threadIdx.x & 31;
-  unsigned long long cand = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i - lane < n;
-       i += gridDim.x * blockDim.x) {
-    const bool act = i < n;
+  const uint32_t sub = lane & 3;
+  unsigned cand = 0;
+  constexpr uint32_t kPairsPerRound = kExactThreads / 4;
+  // block-uniform trip count: every thread reaches the barriers
+  for (uint64_t i0 = (uint64_t) blockIdx.x * kPairsPerRound; i0 < n; i0 += (uint64_t) gridDim.x * kPairsPerRound) {
+    const uint64_t i = i0 + (threadIdx.x >> 2);
     uint32_t pq = 0, pb0 = 0, cnt = 0;
     Seg e1 = {0, 0, 0, 0};
-    longlong2 p1 = make_longlong2(0, 0);
-    if (act) {
+    if (i < n) {
       const uint2 pr = pairs[i];
       pq = pr.x;
       const uint2 rec = __ldg(&leaf_rec[pr.y]);
@@ -402,69 +478,102 @@ k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ pairs, const uint2* 
       pb0 = rec.x + (rec.y & 0x0FFFFFFFu);
       const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
       e1 = {a.x, a.y, b.x, b.y};
-      p1 = __ldg(&B.pts[pb0]);
     }
-    const uint32_t cmax = __reduce_max_sync(0xffffffffu, cnt);
-    for (uint32_t k = 0; k < cmax; k++) {
-      bool found = false;
+#pragma unroll
+    for (uint32_t r = 0; r < 2; r++) {
+      const uint32_t k = sub + 4 * r;
+      bool pass = false;
       if (k < cnt) {
-        const longlong2 p2 = __ldg(&B.pts[pb0 + k + 1]);
+        const longlong2 p1 = __ldg(&B.pts[pb0 + k]), p2 = __ldg(&B.pts[pb0 + k + 1]);
         const Seg e2 = {p1.x, p1.y, p2.x, p2.y};
-        if (seg_boxes_overlap(e1, e2)) {
-          cand++;
-          found = lsi_intersect(e1, e2);
-        }
-        p1 = p2;
+        pass = seg_boxes_overlap(e1, e2);
       }
-      const unsigned m = __ballot_sync(0xffffffffu, found);
-      if (m == 0) continue;
-      unsigned base = 0;
-      const int leader = __ffs(m) - 1;
-      if (lane == leader) base = atomicAdd(counter, (unsigned) __popc(m));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (found) {
-        const unsigned pos = base + __popc(m & ((1u << lane) - 1));
-        if (pos < cap) {
-          out[pos].eid[0] = pq;  // point indices for now; pass 2 turns them into eids
-          out[pos].eid[1] = pb0 + k;
-        }
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (m) {
+        unsigned base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(&s_n, (unsigned) __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pass) s_list[base + __popc(m & ((1u << lane) - 1))] = make_uint2(pq, pb0 + k);
+        cand += __popc(m);  // counted by every lane alike
       }
+    }
+    __syncthreads();
+    const unsigned n_list = s_n;
+    if (n_list >= kExactThreads) {
+      exact_drain(Q, B, s_list, n_list, out, cap, counter);
+      __syncthreads();
+      if (threadIdx.x == 0) s_n = 0;
+      __syncthreads();
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
-  if (lane == 0 && cand) atomicAdd(n_cand, cand);
+  __syncthreads();
+  exact_drain(Q, B, s_list, s_n, out, cap, counter);
+  if (lane == 0 && cand) atomicAdd(n_cand, (unsigned long long) cand);
 }
 
 // Exact pass 2, dense over the hits: rational intersection point and the final
 // edge ids -> rjb_xsect (reference computes it inside the traversal callback,
 // lsi_lbvh.h:69-78; its RT backend has the same post-pass, src/app/lsi_rt.h:66-112).
-__global__ void __launch_bounds__(128)
+//
+// Two threads per hit: the even lane computes x, the odd lane y.  94 % of the
+// coordinates are decided without the 128-bit gcd (lsi_point_axis<true>); the rest
+// would keep every warp waiting for one or two lanes' ~10^3-instruction gcd chains,
+// so they are parked in a shared-memory list and worked off densely -- 32 deferred
+// coordinates per warp -- when the list fills up and at the end.
+constexpr int kPointsThreads = 256;
+constexpr int kDeferCap = 2 * kPointsThreads;
+
+struct DeferItem {
+  uint32_t i, pq, pb, axis;
+};
+
+static __device__ __forceinline__ void points_flush(const MapView& Q, const MapView& B,
+                                                    const DeferItem* list, unsigned n_list,
+                                                    rjb_xsect* __restrict__ out) {
+  for (unsigned t = threadIdx.x; t < n_list; t += kPointsThreads) {
+    const DeferItem it = list[t];
+    const longlong2 a = __ldg(&Q.pts[it.pq]), b = __ldg(&Q.pts[it.pq + 1]);
+    const longlong2 c = __ldg(&B.pts[it.pb]), d = __ldg(&B.pts[it.pb + 1]);
+    const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
+    const long long v = lsi_point_axis<false>(e1, e2, (int) it.axis, nullptr);
+    if (it.axis == 0) out[it.i].x = v; else out[it.i].y = v;
+  }
+}
+
+__global__ void __launch_bounds__(kPointsThreads)
 k_lsi_points(MapView Q, MapView B, int query_map_id, const unsigned int* __restrict__ counter,
              uint32_t cap, rjb_xsect* __restrict__ out) {
-  // two threads per hit: the even lane computes x, the odd lane y (each axis is a
-  // long dependent chain: gcd + division), then the pair assembles the record
+  __shared__ DeferItem s_list[kDeferCap];
+  __shared__ unsigned s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
   const uint32_t n = min(*counter, cap);
-  const uint32_t stride = (gridDim.x * blockDim.x) >> 1;
-  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 1; i - ((threadIdx.x & 31) >> 1) < n;
-       i += stride) {
+  const uint32_t stride = (gridDim.x * kPointsThreads) >> 1;
+  // block-uniform trip count: every thread reaches the barriers
+  for (uint64_t i0 = (blockIdx.x * kPointsThreads) >> 1; i0 < n; i0 += stride) {
+    const uint32_t i = (uint32_t) min(i0 + (threadIdx.x >> 1), (uint64_t) 0xFFFFFFFFu);
     const int axis = threadIdx.x & 1;
     long long v = 0;
     uint32_t pq = 0, pb = 0;
+    bool deferred = false;
     if (i < n) {
       pq = out[i].eid[0];
       pb = out[i].eid[1];
       const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
       const longlong2 c = __ldg(&B.pts[pb]), d = __ldg(&B.pts[pb + 1]);
       const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
-      v = lsi_point_axis(e1, e2, axis);
+      v = lsi_point_axis<true>(e1, e2, axis, &deferred);
     }
-    // every lane of the warp takes part in the exchange (the loop bound is warp-uniform)
+    if (deferred) {
+      const unsigned slot = atomicAdd(&s_n, 1u);  // < kDeferCap: flushed below kPointsThreads
+      s_list[slot] = {i, pq, pb, (uint32_t) axis};
+    }
     const long long other = __shfl_xor_sync(0xffffffffu, v, 1);
     // the point-index fields are overwritten below: both lanes must have read them
     __syncwarp();
     if (i < n && axis == 0) {
-      const uint32_t eq = pq - chain_of_point(Q, pq), eb = pb - chain_of_point(B, pb);
+      const uint32_t eq = pq - __ldg(&Q.point_chain[pq]), eb = pb - __ldg(&B.point_chain[pb]);
       rjb_xsect r;
       r.x = v;
       r.y = other;
@@ -474,7 +583,17 @@ k_lsi_points(MapView Q, MapView B, int query_map_id, const unsigned int* __restr
       r._pad = 0;
       out[i] = r;
     }
+    __syncthreads();  // records written, list complete for this round
+    const unsigned n_list = s_n;
+    if (n_list > kDeferCap - kPointsThreads) {
+      points_flush(Q, B, s_list, n_list, out);
+      __syncthreads();
+      if (threadIdx.x == 0) s_n = 0;
+      __syncthreads();
+    }
   }
+  __syncthreads();
+  points_flush(Q, B, s_list, s_n, out);
 }
 
 // All |Q| x |B| pairs, no index: pins the exact arithmetic (RJB_MODE_BRUTE).

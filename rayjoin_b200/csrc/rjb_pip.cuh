@@ -25,6 +25,8 @@ struct PipLane {
   int qx, qy_lo, y_hi;  // quantised: x, lower y bound (py - 1), pruning bound
   bool valid;
   PipBest best;
+  // one leaf whose box the lane's ray meets, parked for pip_flush (or RJB_NO_HIT)
+  uint32_t pend_leaf;
 };
 
 // lane wants a box: its x range contains px, it reaches up to py, and it starts
@@ -33,33 +35,92 @@ static __device__ __forceinline__ bool pip_wants(const PipLane& L, const int4& b
   return L.valid && b.x <= L.qx && L.qx <= b.z && b.w >= L.qy_lo && b.y <= L.y_hi;
 }
 
-template <bool kStats>
+// Opens the parked leaf of every lane that has one -- all lanes in parallel, each on
+// ITS OWN leaf (per-lane gathers of <= 9 consecutive points).  Stage 1 screens the
+// leaf's edges with integer tests (x range contains px, reaches up to py - 1, starts
+// below the pruning bound) into a bit mask; stage 2 runs the exact update rule on the
+// pending edges, every lane on its own, until no lane has one left.
+static __device__ __forceinline__ void pip_flush(const MapView& B, const BvhView& bvh, PipLane& L,
+                                                 int q, unsigned long long& cand) {
+  unsigned mask = 0;
+  uint32_t first_eid = 0;
+  const longlong2* bp = B.pts;
+  if (L.pend_leaf != RJB_NO_HIT) {
+    const uint2 rec = __ldg(&bvh.leaf_rec[L.pend_leaf]);
+    first_eid = rec.x;
+    const uint32_t cnt = rec.y >> 28;
+    bp = B.pts + (first_eid + (rec.y & 0x0FFFFFFFu));
+    longlong2 p1 = __ldg(bp);
+    for (uint32_t k = 0; k < cnt; k++) {
+      const longlong2 p2 = __ldg(bp + k + 1);
+      if (min(p1.x, p2.x) <= L.px && L.px <= max(p1.x, p2.x) && max(p1.y, p2.y) >= L.py - 1 &&
+          quant(min(p1.y, p2.y)) <= L.y_hi)
+        mask |= 1u << k;
+      p1 = p2;
+    }
+    L.pend_leaf = RJB_NO_HIT;
+  }
+  while (__ballot_sync(0xffffffffu, mask != 0)) {
+    if (mask) {
+      const uint32_t k = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const longlong2 a = __ldg(bp + k), b = __ldg(bp + k + 1);
+      if (quant(min(a.y, b.y)) <= L.y_hi) {  // the bound may have shrunk meanwhile
+        const Seg e = {a.x, a.y, b.x, b.y};
+        cand++;
+        if (pip_update(L.best, q, L.px, L.py, e, first_eid + k)) L.y_hi = pip_y_bound(L.best.y);
+      }
+    }
+  }
+}
+
+// A leaf is <= 8 consecutive edges of one chain.  kPark (option "pip_park"): ncu showed
+// this kernel to be instruction bound (13 k warp-instructions per warp, 15 of 32
+// threads active): on the 100 M-point workload the 32 points of a warp need ~30
+// DIFFERENT leaves, so opening a leaf when the walk reaches it runs the screening and
+// the int128/double update rule with one or two active lanes, 30 times over.  Now the
+// walk only PARKS the leaf in the slot of every lane whose ray meets its box; parked
+// leaves are opened together (pip_flush) when a lane needs its slot again, when most
+// lanes hold one, and at the end.  A parked lane keeps its stale (larger) pruning
+// bound in the meantime, which only makes the warp visit more, never less.
+template <bool kStats, bool kPark>
 static __device__ __forceinline__ void pip_leaf(const MapView& B, const BvhView& bvh, int leaf, bool h,
                                                 PipLane& L, int q, unsigned long long& cand,
                                                 TravStats& st) {
-  const uint2 rec = __ldg(&bvh.leaf_rec[leaf]);
-  const uint32_t first_eid = rec.x, cnt = rec.y >> 28, chain = rec.y & 0x0FFFFFFFu;
-  const longlong2* bp = B.pts + (first_eid + chain);
-  longlong2 p1 = __ldg(bp);
   if (kStats) st.leaves++;
-  for (uint32_t k = 0; k < cnt; k++) {
-    const longlong2 p2 = __ldg(bp + k + 1);
-    // cheap integer rejections before the int128 / double arithmetic: the edge must
-    // span px in x, reach up to py - 1, and start below the best crossing so far
-    // (same +-1 margins as the box test, exact in the integer domain)
-    if (h && min(p1.x, p2.x) <= L.px && L.px <= max(p1.x, p2.x) && max(p1.y, p2.y) >= L.py - 1 &&
-        quant(min(p1.y, p2.y)) <= L.y_hi) {
-      const Seg e = {p1.x, p1.y, p2.x, p2.y};
-      cand++;
-      if (pip_update(L.best, q, L.px, L.py, e, first_eid + k)) L.y_hi = pip_y_bound(L.best.y);
+  if (!kPark) {
+    // open the leaf at once: every lane whose ray meets the box scans its edges
+    const uint2 rec = __ldg(&bvh.leaf_rec[leaf]);
+    const uint32_t first_eid = rec.x, cnt = rec.y >> 28, chain = rec.y & 0x0FFFFFFFu;
+    const longlong2* bp = B.pts + (first_eid + chain);
+    longlong2 p1 = __ldg(bp);
+    for (uint32_t k = 0; k < cnt; k++) {
+      const longlong2 p2 = __ldg(bp + k + 1);
+      // cheap integer rejections before the int128 / double arithmetic: the edge must
+      // span px in x, reach up to py - 1, and start below the best crossing so far
+      // (same +-1 margins as the box test, exact in the integer domain)
+      if (h && min(p1.x, p2.x) <= L.px && L.px <= max(p1.x, p2.x) && max(p1.y, p2.y) >= L.py - 1 &&
+          quant(min(p1.y, p2.y)) <= L.y_hi) {
+        const Seg e = {p1.x, p1.y, p2.x, p2.y};
+        cand++;
+        if (pip_update(L.best, q, L.px, L.py, e, first_eid + k)) L.y_hi = pip_y_bound(L.best.y);
+      }
+      p1 = p2;
     }
-    p1 = p2;
+    return;
   }
+  const unsigned mh = __ballot_sync(0xffffffffu, h);
+  if (__ballot_sync(0xffffffffu, h && L.pend_leaf != RJB_NO_HIT)) pip_flush(B, bvh, L, q, cand);
+  if (h) L.pend_leaf = (uint32_t) leaf;
+  // open at once when the leaf is shared by many lanes (coherent queries such as the
+  // vertices of a chain: fresh bounds prune better) or when most lanes hold a leaf
+  if (__popc(mh) >= 12 || __popc(__ballot_sync(0xffffffffu, L.pend_leaf != RJB_NO_HIT)) >= 24)
+    pip_flush(B, bvh, L, q, cand);
 }
 
 // binary subtree, near child (lower ymin) first; boxes are re-tested when a node
 // is reached because the pruning bounds shrink while the warp works
-template <bool kStats>
+template <bool kStats, bool kPark>
 static __device__ __forceinline__ void pip_subtree(const MapView& B, const BvhView& bvh, int root,
                                                    int* stack, PipLane& L, int q,
                                                    unsigned long long& cand, TravStats& st) {
@@ -81,7 +142,7 @@ static __device__ __forceinline__ void pip_subtree(const MapView& B, const BvhVi
         if (c0 >= 0) next = c0;
         else {
           if (kStats) st.lane_leaf += __popc(m);
-          pip_leaf<kStats>(B, bvh, ~c0, h, L, q, cand, st);
+          pip_leaf<kStats, kPark>(B, bvh, ~c0, h, L, q, cand, st);
         }
       }
     }
@@ -93,7 +154,7 @@ static __device__ __forceinline__ void pip_subtree(const MapView& B, const BvhVi
           if (next < 0) next = c1; else stack[sp++] = c1;
         } else {
           if (kStats) st.lane_leaf += __popc(m);
-          pip_leaf<kStats>(B, bvh, ~c1, h, L, q, cand, st);
+          pip_leaf<kStats, kPark>(B, bvh, ~c1, h, L, q, cand, st);
         }
       }
     }
@@ -111,8 +172,8 @@ static __device__ __forceinline__ int lowest_slot(unsigned m, int ymin, int lane
   return __ffs(__ballot_sync(0xffffffffu, key == best && ((m >> lane) & 1u))) - 1;
 }
 
-template <bool kStats>
-__global__ void __launch_bounds__(kLsiWarps * 32, 8)
+template <bool kStats, bool kPark>
+__global__ void __launch_bounds__(kLsiWarps * 32, kPark ? 6 : 8)
 k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __restrict__ order,
           MapView B, BvhView bvh, int query_map_id, uint32_t* __restrict__ out_eid,
           int32_t* __restrict__ out_face, unsigned long long* counters) {
@@ -135,6 +196,7 @@ k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __r
     L.qy_lo = quant(p.y - 1);
   }
   pip_init(L.best);
+  L.pend_leaf = RJB_NO_HIT;
   unsigned long long cand = 0;
   TravStats st = {0, 0, 0, 0, 0};
   // the union of the lanes' rays: x range of the points, from the lowest point up
@@ -155,7 +217,7 @@ k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __r
       const bool h0 = pip_wants(L, shfl_box(b0, g));
       if (__ballot_sync(0xffffffffu, h0) == 0) continue;
       const int code0 = __shfl_sync(0xffffffffu, c0, g);
-      if (code0 < 0) { pip_leaf<kStats>(B, bvh, ~code0, h0, L, query_map_id, cand, st); continue; }
+      if (code0 < 0) { pip_leaf<kStats, kPark>(B, bvh, ~code0, h0, L, query_map_id, cand, st); continue; }
       const int4 b1 = __ldg(&bvh.top_box[kTopOff1 + g * 32 + lane]);
       const int c1 = __ldg(&bvh.top_code[kTopOff1 + g * 32 + lane]);
       unsigned m1 = __ballot_sync(0xffffffffu, pre(b1));
@@ -166,7 +228,7 @@ k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __r
         const bool h1 = pip_wants(L, shfl_box(b1, h));
         if (__ballot_sync(0xffffffffu, h1) == 0) continue;
         const int code1 = __shfl_sync(0xffffffffu, c1, h);
-        if (code1 < 0) { pip_leaf<kStats>(B, bvh, ~code1, h1, L, query_map_id, cand, st); continue; }
+        if (code1 < 0) { pip_leaf<kStats, kPark>(B, bvh, ~code1, h1, L, query_map_id, cand, st); continue; }
         const int4 b2 = __ldg(&bvh.top_box[kTopOff2 + (g * 32 + h) * 32 + lane]);
         const int c2 = __ldg(&bvh.top_code[kTopOff2 + (g * 32 + h) * 32 + lane]);
         unsigned m2 = __ballot_sync(0xffffffffu, pre(b2));
@@ -177,9 +239,9 @@ k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __r
           const bool h2 = pip_wants(L, shfl_box(b2, i));
           if (__ballot_sync(0xffffffffu, h2) == 0) continue;
           const int code2 = __shfl_sync(0xffffffffu, c2, i);
-          if (code2 < 0) { pip_leaf<kStats>(B, bvh, ~code2, h2, L, query_map_id, cand, st); continue; }
+          if (code2 < 0) { pip_leaf<kStats, kPark>(B, bvh, ~code2, h2, L, query_map_id, cand, st); continue; }
           if (bvh.top_levels < 4) {
-            pip_subtree<kStats>(B, bvh, code2, stack, L, query_map_id, cand, st);
+            pip_subtree<kStats, kPark>(B, bvh, code2, stack, L, query_map_id, cand, st);
             continue;
           }
           // level 3 (big trees only): the 32 depth-20 nodes below slot (g, h, i)
@@ -194,13 +256,14 @@ k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __r
             const bool h3 = pip_wants(L, shfl_box(b3, j));
             if (__ballot_sync(0xffffffffu, h3) == 0) continue;
             const int code3 = __shfl_sync(0xffffffffu, c3, j);
-            if (code3 < 0) pip_leaf<kStats>(B, bvh, ~code3, h3, L, query_map_id, cand, st);
-            else pip_subtree<kStats>(B, bvh, code3, stack, L, query_map_id, cand, st);
+            if (code3 < 0) pip_leaf<kStats, kPark>(B, bvh, ~code3, h3, L, query_map_id, cand, st);
+            else pip_subtree<kStats, kPark>(B, bvh, code3, stack, L, query_map_id, cand, st);
           }
         }
       }
     }
   }
+  if (kPark) pip_flush(B, bvh, L, query_map_id, cand);  // whatever is still parked
   if (L.valid) {
     out_eid[pi] = L.best.eid;
     if (out_face) {

@@ -1,0 +1,49 @@
+// Test-only: compiles the product's exact arithmetic (rayjoin_b200/csrc/rjb_exact.cuh,
+// the SAME source the kernels use) for the HOST, so the CPU test-suite can pin it
+// against the oracle on millions of cases without a GPU.  Not part of librjb200.
+#include "rjb_exact.cuh"
+
+using namespace rjb;
+
+extern "C" {
+
+// pts: n x 8 int64 {e1.x1, e1.y1, e1.x2, e1.y2, e2.x1, e2.y1, e2.x2, e2.y2}
+// mode 0: always-exact path; 1: kDefer path, deferred items re-run like the kernel does
+void hx_intersect_batch(const long long* pts, unsigned long long n, int mode, unsigned char* hit,
+                        long long* ox, long long* oy, unsigned long long* n_deferred) {
+  unsigned long long nd = 0;
+  for (unsigned long long i = 0; i < n; i++) {
+    const long long* p = pts + 8 * i;
+    const Seg e1 = {p[0], p[1], p[2], p[3]}, e2 = {p[4], p[5], p[6], p[7]};
+    hit[i] = lsi_intersect(e1, e2) ? 1 : 0;
+    ox[i] = oy[i] = 0;
+    if (!hit[i]) continue;
+    for (int axis = 0; axis < 2; axis++) {
+      long long v;
+      if (mode == 0) {
+        v = lsi_point_axis(e1, e2, axis);
+      } else {
+        bool def = false;
+        v = lsi_point_axis<true>(e1, e2, axis, &def);
+        if (def) {
+          nd++;
+          v = lsi_point_axis<false>(e1, e2, axis, nullptr);
+        }
+      }
+      (axis == 0 ? ox : oy)[i] = v;
+    }
+  }
+  if (n_deferred) *n_deferred = nd;
+}
+
+// PIP update rule over a list of edges for one point (returns the chosen index or -1)
+int hx_pip_scan(const long long* edges, unsigned long long n, int q, long long px, long long py) {
+  PipBest st;
+  pip_init(st);
+  for (unsigned long long i = 0; i < n; i++) {
+    const Seg e = {edges[4 * i], edges[4 * i + 1], edges[4 * i + 2], edges[4 * i + 3]};
+    pip_update(st, q, px, py, e, (uint32_t) i);
+  }
+  return st.eid == RJB_NO_HIT ? -1 : (int) st.eid;
+}
+}

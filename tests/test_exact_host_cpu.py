@@ -1,0 +1,106 @@
+"""CPU suite: the PRODUCT's exact arithmetic (rayjoin_b200/csrc/rjb_exact.cuh -- the
+same source the kernels compile) built for the host by tests/native/host_exact.cu and
+pinned against the golden vectors of the reference's lsi.h / rational.h and against the
+oracle on random crossings.  In particular the gcd-free intersection-point path
+(lsi_point_axis<true>, used by k_lsi_points) must agree bit for bit with the always-gcd
+path, and defer only the coordinates whose fraction lies within 1/32 of an integer."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden")
+SRC = os.path.join(HERE, "native", "host_exact.cu")
+OUT = os.path.join(HERE, "native", "libhost_exact.so")
+
+
+@pytest.fixture(scope="module")
+def hx():
+    nvcc = os.environ.get("RJB_NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = shutil.which("nvcc")
+    deps = [SRC, os.path.join(ROOT, "rayjoin_b200", "csrc", "rjb_exact.cuh"),
+            os.path.join(ROOT, "rayjoin_b200", "csrc", "rjb_common.cuh")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        assert nvcc, "nvcc is needed to build the host view of rjb_exact.cuh"
+        subprocess.run([nvcc, "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets",
+                        "-I" + os.path.join(ROOT, "include"),
+                        "-I" + os.path.join(ROOT, "rayjoin_b200", "csrc"), "-Xcompiler", "-fPIC",
+                        "-shared", "-o", OUT, SRC], check=True)
+    return C.CDLL(OUT)
+
+
+def run(hx, pts, mode):
+    pts = np.ascontiguousarray(pts, np.int64)
+    n = len(pts)
+    hit = np.zeros(n, np.uint8)
+    ox = np.zeros(n, np.int64)
+    oy = np.zeros(n, np.int64)
+    nd = C.c_uint64(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    hx.hx_intersect_batch(p(pts), C.c_uint64(n), C.c_int(mode), p(hit), p(ox), p(oy), C.byref(nd))
+    return hit, ox, oy, nd.value
+
+
+def crossing(rng, n, span_bits, off_bits=46):
+    """pairs of edges of span ~2^span_bits around a common random centre: most cross"""
+    c = rng.integers(-2**off_bits + 2**(span_bits + 1), 2**off_bits - 2**(span_bits + 1), size=(n, 1, 2))
+    d = rng.integers(-2**span_bits, 2**span_bits, size=(n, 2, 2))
+    jb = max(1, span_bits - 3)
+    j = rng.integers(-2**jb, 2**jb, size=(n, 2, 2))
+    e = np.concatenate([c + j[:, :1] - d[:, :1], c + j[:, :1] + d[:, :1],
+                        c + j[:, 1:] - d[:, 1:], c + j[:, 1:] + d[:, 1:]], axis=1)
+    return e.reshape(n, 8)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_product_arithmetic_matches_reference_golden(hx, mode):
+    z = np.load(os.path.join(GOLD, "lsi_kat.npz"))
+    hit, x, y, _ = run(hx, z["pts"], mode)
+    assert np.array_equal(hit, z["hit"])
+    m = z["hit"] == 1
+    assert np.array_equal(x[m], z["x"][m]) and np.array_equal(y[m], z["y"][m])
+
+
+@pytest.mark.parametrize("span_bits", [3, 8, 16, 24, 30, 37, 38, 40])
+def test_gcd_free_point_path_is_bit_exact(hx, oracle, span_bits):
+    rng = np.random.default_rng(1000 + span_bits)
+    pts = crossing(rng, 60000, span_bits)
+    hit, x, y = oracle.intersect_batch(pts)
+    m = hit == 1
+    assert m.sum() > 30000
+    for mode in (0, 1):
+        h2, x2, y2, nd = run(hx, pts, mode)
+        assert np.array_equal(hit, h2)
+        assert np.array_equal(x[m], x2[m]) and np.array_equal(y[m], y2[m])
+        if mode == 1 and 8 <= span_bits < 38:
+            # 2 * 1/32 of the fractions, nothing else, take the gcd path
+            assert 0.05 < nd / (2.0 * m.sum()) < 0.075
+        if mode == 1 and span_bits >= 38 + 1:
+            assert nd > 1.9 * m.sum()  # long edges: always the general path
+
+
+def test_gcd_free_point_path_special_cases(hx, oracle):
+    rng = np.random.default_rng(5)
+    sets = [crossing(rng, 50000, 4, off_bits=7), crossing(rng, 50000, 10, off_bits=13)]  # around 0: negative x
+    p = crossing(rng, 50000, 10)
+    p[:, 1] = p[:, 3]  # horizontal e1: y is an exact integer (rs == 0)
+    sets.append(p)
+    p = crossing(rng, 50000, 10)
+    p[:, 4] = p[:, 6]  # vertical e2
+    sets.append(p)
+    p = crossing(rng, 50000, 12)
+    p[:, 4:6] = p[:, 0:2]  # shared end point: the clamp decides
+    sets.append(p)
+    for pts in sets:
+        hit, x, y = oracle.intersect_batch(pts)
+        m = hit == 1
+        for mode in (0, 1):
+            h2, x2, y2, _ = run(hx, pts, mode)
+            assert np.array_equal(hit, h2)
+            assert np.array_equal(x[m], x2[m]) and np.array_equal(y[m], y2[m])

@@ -21,6 +21,7 @@ ap.add_argument("--sort", default="0,1")  # PIP: points are ordered only on requ
 ap.add_argument("--repeat", type=int, default=3)
 ap.add_argument("--check", type=int, default=200_000)
 ap.add_argument("--stats", type=int, default=0)
+ap.add_argument("--park", default="0", help="option pip_park values to run (A/B), e.g. 0,1")
 args = ap.parse_args()
 
 t0 = time.time()
@@ -50,15 +51,16 @@ torch.cuda.synchronize()
 om_pts = None
 for mode in args.modes.split(","):
     build = min(ctx.build_index(0, mode, args.grid_size) for _ in range(2))
-    for sq in [int(x) for x in args.sort.split(",")]:
+    for sq, park in [(int(x), int(y)) for x in args.sort.split(",") for y in args.park.split(",")]:
         ctx.set_option("sort_queries", sq)
+        ctx.set_option("pip_park", park if mode == "lbvh" else 0)
         times, kms = [], []
         for it in range(args.repeat + 1):
             torch.cuda.synchronize(); t = time.perf_counter()
             de, df, cand = ctx.pip_device(1, mode, pts.data_ptr(), args.points)
             dt = time.perf_counter() - t
             if it: times.append(dt * 1e3); kms.append(ctx.last_kernel_ms()[0])
-        out = {"query": "pip", "mode": mode, "sort_queries": sq, "points": args.points,
+        out = {"query": "pip", "mode": mode, "sort_queries": sq, "pip_park": park, "points": args.points,
                "edges": R.n_edges, "build_ms": build, "query_ms": float(np.min(times)),
                "kernel_ms": float(np.min(kms)), "points_per_s": args.points / (np.min(times) / 1e3),
                "candidates": cand}
