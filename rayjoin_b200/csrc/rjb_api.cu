@@ -366,7 +366,7 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
       RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
       k_lsi_exact<<<kNumSMs * 8, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
                                                      xs, cap, (unsigned int*) ctr, ctr + 1);
-      k_lsi_points<<<kNumSMs * 4, kPointsThreads, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs);
+      k_lsi_points<<<kNumSMs * 3, kPointsThreads, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs);
       RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
       RJB_CUDA(cudaGetLastError());
       // one read-back into pinned memory: the only host round trip of the query

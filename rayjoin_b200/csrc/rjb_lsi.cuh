@@ -183,9 +183,13 @@ static __device__ __forceinline__ QTile load_tile(const MapView& Q, const uint32
 // The kernel reads the 4-byte occupancy DESCRIPTOR of every edge (edge_desc_of, written
 // once by the load kernel), not two 16-byte vertices: a quarter of the traffic, and the
 // decision is one bitmap look-up per edge -- in `occ` for an edge inside one cell, in the
-// 2 x 2-dilated `occ2` for an edge that crosses into a neighbour cell (conservative).  A
-// thread owns 16 consecutive edges: four 16-byte loads, then 16 independent look-ups,
-// all in flight together; a CTA owns 4096 consecutive points.
+// 2 x 2-dilated `occ2` for an edge that crosses into a neighbour cell (conservative).
+// A warp owns 512 consecutive points and works on them 32 at a time, lane = point:
+// consecutive points lie in the same or neighbouring cells, so the 32 look-ups of one
+// instruction fall into one or two 32-byte sectors.  (With 16 consecutive points per
+// LANE every look-up instruction touched ~30 sectors and the kernel was bound by the L1
+// tag stage at 88 %.)  All 16 descriptor loads and then all 16 look-ups of a thread are
+// independent and in flight together.
 constexpr int kFilterThreads = 256;
 constexpr int kFilterPerThread = 16;
 constexpr int kFilterCtaPoints = kFilterThreads * kFilterPerThread;
@@ -217,24 +221,16 @@ k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__
   __shared__ unsigned s_wsum[kWarps];
   __shared__ unsigned s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t p0 = blockIdx.x * kFilterCtaPoints + threadIdx.x * kFilterPerThread;
-  // stage 1: the descriptors (edge_desc is padded with "no edge": whole groups are in bounds)
+  // point of (round e, lane) = w0 + 32 * e + lane
+  const uint32_t w0 = blockIdx.x * kFilterCtaPoints + warp * (32 * kFilterPerThread);
+  // stage 1: the descriptors (edge_desc is padded with "no edge" up to a multiple of 16;
+  // beyond that the index is clamped and the value ignored)
   uint32_t d[kFilterPerThread];
-  {
-    // one predicate for the whole thread (p0 is a multiple of 16, the padding covers the
-    // rest), so the four loads issue back to back
-    uint4 v[kFilterPerThread / 4];
-    const uint4* src = reinterpret_cast<const uint4*>(Q.edge_desc + min(p0, Q.n_points & ~15u));
 #pragma unroll
-    for (int j = 0; j < kFilterPerThread / 4; j++) v[j] = __ldg(src + j);
-    const bool in = p0 < Q.n_points;
-#pragma unroll
-    for (int j = 0; j < kFilterPerThread / 4; j++) {
-      d[4 * j] = in ? v[j].x : (kDescNone << 24);
-      d[4 * j + 1] = in ? v[j].y : (kDescNone << 24);
-      d[4 * j + 2] = in ? v[j].z : (kDescNone << 24);
-      d[4 * j + 3] = in ? v[j].w : (kDescNone << 24);
-    }
+  for (int e = 0; e < kFilterPerThread; e++) {
+    const uint32_t p = w0 + 32 * e + lane;
+    d[e] = __ldg(&Q.edge_desc[min(p, Q.n_points)]);
+    if (p >= Q.n_points) d[e] = kDescNone << 24;
   }
   // stage 2: one look-up per edge; class bit 0 selects occ2 (kDescNone / kDescBig read a
   // valid word too and ignore it)
@@ -242,27 +238,20 @@ k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__
 #pragma unroll
   for (int e = 0; e < kFilterPerThread; e++)
     w[e] = __ldg(&occ[((d[e] & 0xFFFFFFu) >> 5) + ((d[e] >> 24) & 1u) * kOccWords]);
-  unsigned keep = 0, big = 0;
+  // stage 3: keep masks per round (bit = lane), positions from the ballots alone
+  unsigned m[kFilterPerThread];
+  unsigned cnt = 0;
 #pragma unroll
   for (int e = 0; e < kFilterPerThread; e++) {
     const uint32_t cls = d[e] >> 24;
-    if (cls < kDescBig && ((w[e] >> (d[e] & 31u)) & 1u)) keep |= 1u << e;
-    if (cls == kDescBig) big |= 1u << e;
+    bool keep = cls < kDescBig && ((w[e] >> (d[e] & 31u)) & 1u);
+    if (__any_sync(0xffffffffu, cls == kDescBig)) {
+      if (cls == kDescBig) keep = occ_rect(Q, occ, w0 + 32 * e + lane);
+    }
+    m[e] = __ballot_sync(0xffffffffu, keep);
+    cnt += __popc(m[e]);
   }
-  while (big) {
-    const int e = __ffs(big) - 1;
-    big &= big - 1;
-    if (occ_rect(Q, occ, p0 + e)) keep |= 1u << e;
-  }
-  // block-wide exclusive scan of the per-thread counts (thread order = point order)
-  const unsigned cnt = __popc(keep);
-  unsigned inc = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += v;
-  }
-  if (lane == 31) s_wsum[warp] = inc;
+  if (lane == 0) s_wsum[warp] = cnt;
   __syncthreads();
   if (warp == 0) {
     const unsigned sum = lane < kWarps ? s_wsum[lane] : 0u;
@@ -276,12 +265,35 @@ k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__
     if (lane == kWarps - 1) s_base = winc ? atomicAdd(counter, winc) : 0u;
   }
   __syncthreads();
-  unsigned pos = s_base + s_wsum[warp] + inc - cnt;
-  while (keep) {
-    const int e = __ffs(keep) - 1;
-    keep &= keep - 1;
-    survivors[pos++] = p0 + e;
+  unsigned pos = s_base + s_wsum[warp];
+  const unsigned lt = (1u << lane) - 1;
+#pragma unroll
+  for (int e = 0; e < kFilterPerThread; e++) {
+    if ((m[e] >> lane) & 1u) survivors[pos + __popc(m[e] & lt)] = w0 + 32 * e + lane;
+    pos += __popc(m[e]);
   }
+}
+
+// The walk is a chain of dependent loads (row of level k+1 after the ballots of level k).
+// When a row has SEVERAL candidate slots, their child rows are requested at once -- one
+// lane per candidate -- so that the second, third ... descent finds its row in L2
+// instead of paying a DRAM round trip each.
+static __device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+static __device__ __forceinline__ void prefetch_row(const BvhView& bvh, uint32_t first_slot) {
+  const char* b = reinterpret_cast<const char*>(bvh.top_box + first_slot);  // 32 x 16 B
+  prefetch_l2(b);
+  prefetch_l2(b + 128);
+  prefetch_l2(b + 256);
+  prefetch_l2(b + 384);
+  prefetch_l2(bvh.top_code + first_slot);  // 32 x 4 B
+}
+
+static __device__ __forceinline__ void prefetch_node(const BvhView& bvh, int node) {
+  prefetch_l2(bvh.node_box + 2 * node);
+  prefetch_l2(bvh.node_child + node);
 }
 
 template <bool kStats>
@@ -339,6 +351,8 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
       const int c1 = __ldg(&bvh.top_code[kTopOff1 + g * 32 + lane]);
       unsigned m1 = __ballot_sync(0xffffffffu, box_overlap(U1, b1));
       if (kStats) st.top_steps++;
+      if ((m1 & (m1 - 1)) && ((m1 >> lane) & 1u) && c1 >= 0)
+        prefetch_row(bvh, kTopOff2 + (uint32_t) (g * 32 + lane) * 32);
       while (m1) {
         const int h = __ffs(m1) - 1;
         m1 &= m1 - 1;
@@ -356,6 +370,10 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
         const int c2 = __ldg(&bvh.top_code[kTopOff2 + (g * 32 + h) * 32 + lane]);
         unsigned m2 = __ballot_sync(0xffffffffu, box_overlap(U2, b2));
         if (kStats) st.top_steps++;
+        if ((m2 & (m2 - 1)) && ((m2 >> lane) & 1u) && c2 >= 0) {
+          if (bvh.top_levels == 4) prefetch_row(bvh, kTopOff3 + (uint32_t) ((g * 32 + h) * 32 + lane) * 32);
+          else prefetch_node(bvh, c2);
+        }
         while (m2) {
           const int i = __ffs(m2) - 1;
           m2 &= m2 - 1;
@@ -378,6 +396,7 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
           const int c3 = __ldg(&bvh.top_code[s3]);
           unsigned m3 = __ballot_sync(0xffffffffu, box_overlap(U3, b3));
           if (kStats) st.top_steps++;
+          if ((m3 & (m3 - 1)) && ((m3 >> lane) & 1u) && c3 >= 0) prefetch_node(bvh, c3);
           while (m3) {
             const int j = __ffs(m3) - 1;
             m3 &= m3 - 1;
@@ -516,13 +535,13 @@ k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ pairs, const uint2* 
 // edge ids -> rjb_xsect (reference computes it inside the traversal callback,
 // lsi_lbvh.h:69-78; its RT backend has the same post-pass, src/app/lsi_rt.h:66-112).
 //
-// Two threads per hit: the even lane computes x, the odd lane y.  94 % of the
-// coordinates are decided without the 128-bit gcd (lsi_point_axis<true>); the rest
-// would keep every warp waiting for one or two lanes' ~10^3-instruction gcd chains,
-// so they are parked in a shared-memory list and worked off densely -- 32 deferred
-// coordinates per warp -- when the list fills up and at the end.
+// One thread per hit computes both coordinates.  94 % of the coordinates are decided
+// without the 128-bit gcd (lsi_point_axis<true>); the rest would keep every warp waiting
+// for one or two lanes' ~10^3-instruction gcd chains, so they are parked in a
+// shared-memory list and worked off densely -- 32 deferred coordinates per warp -- when
+// the list fills up and at the end.
 constexpr int kPointsThreads = 256;
-constexpr int kDeferCap = 2 * kPointsThreads;
+constexpr int kDeferCap = 3 * kPointsThreads;  // < kPointsThreads before a round, <= 2 per thread added
 
 struct DeferItem {
   uint32_t i, pq, pb, axis;
@@ -549,34 +568,22 @@ k_lsi_points(MapView Q, MapView B, int query_map_id, const unsigned int* __restr
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   const uint32_t n = min(*counter, cap);
-  const uint32_t stride = (gridDim.x * kPointsThreads) >> 1;
   // block-uniform trip count: every thread reaches the barriers
-  for (uint64_t i0 = (blockIdx.x * kPointsThreads) >> 1; i0 < n; i0 += stride) {
-    const uint32_t i = (uint32_t) min(i0 + (threadIdx.x >> 1), (uint64_t) 0xFFFFFFFFu);
-    const int axis = threadIdx.x & 1;
-    long long v = 0;
-    uint32_t pq = 0, pb = 0;
-    bool deferred = false;
-    if (i < n) {
-      pq = out[i].eid[0];
-      pb = out[i].eid[1];
+  for (uint64_t i0 = (uint64_t) blockIdx.x * kPointsThreads; i0 < n; i0 += (uint64_t) gridDim.x * kPointsThreads) {
+    const uint64_t i64 = i0 + threadIdx.x;
+    if (i64 < n) {
+      const uint32_t i = (uint32_t) i64;
+      const uint32_t pq = out[i].eid[0], pb = out[i].eid[1];
       const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
       const longlong2 c = __ldg(&B.pts[pb]), d = __ldg(&B.pts[pb + 1]);
-      const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
-      v = lsi_point_axis<true>(e1, e2, axis, &deferred);
-    }
-    if (deferred) {
-      const unsigned slot = atomicAdd(&s_n, 1u);  // < kDeferCap: flushed below kPointsThreads
-      s_list[slot] = {i, pq, pb, (uint32_t) axis};
-    }
-    const long long other = __shfl_xor_sync(0xffffffffu, v, 1);
-    // the point-index fields are overwritten below: both lanes must have read them
-    __syncwarp();
-    if (i < n && axis == 0) {
       const uint32_t eq = pq - __ldg(&Q.point_chain[pq]), eb = pb - __ldg(&B.point_chain[pb]);
+      const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
+      bool dx = false, dy = false;
       rjb_xsect r;
-      r.x = v;
-      r.y = other;
+      r.x = lsi_point_axis<true>(e1, e2, 0, &dx);
+      r.y = lsi_point_axis<true>(e1, e2, 1, &dy);
+      if (dx) s_list[atomicAdd(&s_n, 1u)] = {i, pq, pb, 0u};
+      if (dy) s_list[atomicAdd(&s_n, 1u)] = {i, pq, pb, 1u};
       r.eid[0] = query_map_id == 0 ? eq : eb;
       r.eid[1] = query_map_id == 0 ? eb : eq;
       r.mid_point_polygon_id = RJB_DONTKNOW;
@@ -585,7 +592,7 @@ k_lsi_points(MapView Q, MapView B, int query_map_id, const unsigned int* __restr
     }
     __syncthreads();  // records written, list complete for this round
     const unsigned n_list = s_n;
-    if (n_list > kDeferCap - kPointsThreads) {
+    if (n_list >= kPointsThreads) {
       points_flush(Q, B, s_list, n_list, out);
       __syncthreads();
       if (threadIdx.x == 0) s_n = 0;

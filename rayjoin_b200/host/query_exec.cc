@@ -4,13 +4,16 @@
 //
 //   query_exec -poly1 R.cdb -poly2 S.cdb -mode=lbvh|grid -query=lsi|pip
 //              [-xsect_factor f] [-grid_size n] [-warmup w] [-repeat r] [-serialize dir]
-//              [-check] [-output file] [-gen_n n -seed s]   (pip without -poly2)
+//              [-check] [-output file]
+//              [-gen_n n -gen_t t -seed s]   generated workload when -poly2 is absent:
+//                                            n random segments of length <= t (lsi), n points (pip)
 //
 // Additions over the reference: -output writes the result (LSI: sorted
 // "eid_map0 eid_map1 x y" lines; PIP: one closest eid per line), which the
 // reference parses but never uses (src/query.cc:27); -check also works for LSI
 // (pair set compared against -mode=grid).
 #include <algorithm>
+#include <cmath>
 #include <random>
 
 #include "cli_common.h"
@@ -26,21 +29,80 @@ static std::vector<rjb_xsect> fetch_xsects(rjb_ctx* ctx, const rjb_xsect* d, uin
   return h;
 }
 
+// GenerateLSIQueries, src/run_query.cu:101-144: gen_n segments, each its own 2-point
+// chain with face ids 0; start point uniform in the base map's bounding box, direction
+// towards a second uniform point, length t ~ U(0, gen_t).  Same generator, same order of
+// draws, no FMA contraction on the host; the points are scaled on the device like any
+// other map (src/map/map.h:120-127).
+struct GeneratedSegments {
+  std::vector<double> xy;
+  std::vector<uint32_t> row_index;
+  std::vector<int64_t> zero;
+  rjb_graph graph{};
+};
+
+static void generate_lsi_queries(const Flags& f, const rjb_graph& base, GeneratedSegments* out) {
+  const uint64_t ne = (uint64_t) f.i("gen_n");
+  const int seed = f.i("seed");
+  std::random_device rd;
+  std::mt19937 gen(seed == 0 ? rd() : seed);
+  std::uniform_real_distribution<> dist_x(base.min_x, base.max_x), dist_y(base.min_y, base.max_y);
+  std::uniform_real_distribution<> dist_t(0, f.d("gen_t"));
+  out->xy.resize(4 * ne);
+  out->row_index.resize(ne + 1);
+  out->zero.assign(ne, 0);
+  for (uint64_t i = 0; i < ne; i++) {
+    double x1 = dist_x(gen), y1 = dist_y(gen);
+    double x2 = dist_x(gen), y2 = dist_y(gen);
+    volatile double sx = (x2 - x1) * (x2 - x1), sy = (y2 - y1) * (y2 - y1);
+    double len = sqrt(sx + sy);
+    double d_x = (x2 - x1) / len, d_y = (y2 - y1) / len;
+    double t = dist_t(gen);
+    volatile double tx = t * d_x, ty = t * d_y;
+    out->xy[4 * i] = x1;
+    out->xy[4 * i + 1] = y1;
+    out->xy[4 * i + 2] = x1 + tx;
+    out->xy[4 * i + 3] = y1 + ty;
+    out->row_index[i] = (uint32_t) (2 * i);
+  }
+  out->row_index[ne] = (uint32_t) (2 * ne);
+  rjb_graph& g = out->graph;
+  g.n_chains = ne;
+  g.n_points = 2 * ne;
+  g.left = g.right = out->zero.data();
+  g.row_index = out->row_index.data();
+  g.xy = out->xy.data();
+}
+
 static int run_lsi(const Flags& f) {
   Timer tm;
   rjb_graph g0{}, g1{};
+  GeneratedSegments gen_q;
   tm.next("Read map 0");
   load_graph(f.s("poly1"), f.s("serialize"), &g0);
-  if (f.s("poly2").empty()) die("-query=lsi needs -poly2 (generated workloads: use -query=pip)");
-  tm.next("Read map 1");
-  load_graph(f.s("poly2"), f.s("serialize"), &g1);
+  const bool generated = f.s("poly2").empty();
+  if (generated) {
+    tm.next("Generate Workloads");
+    generate_lsi_queries(f, g0, &gen_q);
+  } else {
+    tm.next("Read map 1");
+    load_graph(f.s("poly2"), f.s("serialize"), &g1);
+  }
   tm.next("Create App");
   int mode = parse_mode(f.s("mode"));
   rjb_ctx* ctx = nullptr;
   ok(rjb_create(f.i("device"), &ctx), "rjb_create");
   ok(rjb_set_option(ctx, "lbvh_leaf_size", f.i("lbvh_leaf_size")), "rjb_set_option");
   tm.next("Load Data");
-  set_maps(ctx, &g0, &g1);
+  if (generated) {
+    // the context is built on the base map alone (run_query.cu:184-186): its box scales both
+    set_maps(ctx, &g0, nullptr);
+    g1 = gen_q.graph;
+    ok(rjb_set_map(ctx, 1, g1.xy, g1.n_points, g1.row_index, g1.left, g1.right, g1.n_chains),
+       "rjb_set_map(1)");
+  } else {
+    set_maps(ctx, &g0, &g1);
+  }
   tm.next("Init");
   uint64_t ne = (g0.n_points - g0.n_chains) + (g1.n_points - g1.n_chains);
   std::cerr << "Queue capacity: " << (uint64_t) ((float) ne * (float) f.d("xsect_factor")) << std::endl;
@@ -86,7 +148,7 @@ static int run_lsi(const Flags& f) {
   tm.next("Cleanup");
   rjb_destroy(ctx);
   rjb_graph_free(&g0);
-  rjb_graph_free(&g1);
+  if (!generated) rjb_graph_free(&g1);
   tm.end();
   return 0;
 }
