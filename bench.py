@@ -371,7 +371,10 @@ def main():
         # R vertices once, 8 B per result pair
         if args.mode == "lbvh":
             alg = 16 * S.n_points + 4 * S.n_edges + idx["bytes"] + 16 * R.n_points + 8 * n_pairs
-            kname = "k_lsi_filter+k_lsi_bvh" if ctx.last_stats()[7] else "k_lsi_bvh"
+            lst = ctx.last_stats()
+            log("last_stats (results, candidates, ..., [5] cells path, [6] long survivors, [7] survivors):", lst)
+            kname = ("k_lsi_filter+k_lsi_cells+k_lsi_bvh" if lst[5] else "k_lsi_filter+k_lsi_bvh") if lst[7] \
+                else "k_lsi_bvh"
         else:
             alg = 16 * S.n_points + 4 * S.n_edges + idx["bytes"] + 16 * R.n_points + 4 * R.n_edges + 8 * n_pairs
             kname = "k_lsi_grid"
@@ -398,7 +401,7 @@ def main():
             "e2e": {"value": all_edges / (e2e_ms / 1e3 / args.steps), "unit": "query_edges/s",
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": ((4 if kname.startswith("k_lsi_filter") else 3 if args.mode == "lbvh" else 2)
+            "gpu_launches": ((2 + len(kname.split("+")) if args.mode == "lbvh" else 2)
                              + (6 if sorted_queries else 0)) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,

@@ -131,6 +131,10 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
  *                     < 32 edges per chain; points only on request)
  *   "lsi_filter"      LBVH LSI occupancy pre-filter: -1 auto (default: on when the
  *                     base map occupies < 25 % of a 4096^2 bitmap), 0 off, 1 on
+ *   "lsi_cells"       LBVH LSI, experimental: 1 = the filter's survivors look their candidate
+ *                     leaves up in a directory of the occupied cells, built with the index
+ *                     (edges longer than a cell still walk the tree); 0 (default) = every
+ *                     survivor walks the tree.  Set it before rjb_build_index.
  *   "pip_park"        LBVH PIP: 1 (default) = lanes park the leaf their ray meets and the
  *                     warp opens the parked leaves together; 0 = open a leaf when reached
  *   "stats"           1 = collect traversal statistics (rjb_last_stats; slower)
@@ -213,7 +217,10 @@ int rjb_last_kernel_ms(const rjb_ctx* ctx, double out[2]);
 /* raw counters of the last query: [0] results, [1] candidates; with option
  * "stats" = 1 also traversal statistics ([2] binary node visits, [3] leaf visits,
  * [4] top-tree steps, [5] lane-level leaf tests, [6] warps that
- * reached a leaf, [7] deepest stack).  Replaces the reference's Debug-build
+ * reached a leaf, [7] deepest stack).  Without "stats", an LBVH LSI query reports
+ * [7] = survivors of the occupancy filter (0 = filter off), [5] = 1 when they went
+ * through the cell directory, [6] = survivors that walked the tree instead (longer
+ * than a cell).  Replaces the reference's Debug-build
  * "Total tests" / "Visited nodes" counters (src/app/lsi_lbvh.h:37-42,83-96).   */
 int rjb_last_stats(const rjb_ctx* ctx, uint64_t out[8]);
 /* index of map_id: out[0] = leaves (LBVH) / edge-cell incidences (grid),

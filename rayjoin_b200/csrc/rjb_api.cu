@@ -93,7 +93,9 @@ struct rjb_ctx {
   DBuf<uint2> cands;      // LBVH traversal output: pairs whose exact boxes overlap
   DBuf<uint32_t> survivors;  // occupancy pre-filter output (query start points)
   int use_filter = -1;    // -1 auto (by occupancy), 0 off, 1 on
-  uint32_t last_survivors = 0;
+  uint32_t last_survivors = 0, last_long = 0;
+  DBuf<uint32_t> long_edges;  // survivors longer than a cell (tree walk)
+  int use_cells = 0;      // LSI: cell directory for the filter's survivors (experimental, off)
   size_t cand_cap = 0;
   DBuf<rjb_xsect> xsects;
   DBuf<unsigned long long> counters;  // [0] = queue counter (low 32 bits), [1] = candidates
@@ -268,6 +270,17 @@ static const uint32_t* query_order_points(rjb_ctx* c, const longlong2* pts, uint
   return vb;
 }
 
+// Wait for the stream by polling: a blocking cudaStreamSynchronize wakes the host tens of
+// microseconds late, which is a tenth of a whole LSI query.  Long waits fall back to it.
+static void wait_stream(cudaStream_t s) {
+  for (int spins = 0; spins < 20000; spins++) {
+    const cudaError_t e = cudaStreamQuery(s);
+    if (e == cudaSuccess) return;
+    if (e != cudaErrorNotReady) RJB_CUDA(e);
+  }
+  RJB_CUDA(cudaStreamSynchronize(s));
+}
+
 static void ensure_load_pipeline(rjb_ctx* c) {
   if (!c->aux) RJB_CUDA(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
   for (int i = 0; i <= kLoadChunksMax; i++)
@@ -287,7 +300,7 @@ static void do_build_index(rjb_ctx* c, int map_id, int mode, uint32_t grid_size,
   ensure_events(c);
   RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
   if (mode == RJB_MODE_LBVH) {
-    build_lbvh(m.bvh, m.view(), c->leaf_size, c->sc.internal_min, c->stream);
+    build_lbvh(m.bvh, m.view(), c->leaf_size, c->sc.internal_min, c->use_cells > 0, c->stream);
   } else if (mode == RJB_MODE_GRID) {
     build_grid(m.grid, m.view(), grid_size, c->sc.internal_min, c->sc.internal_range, c->stream);
   } else if (mode == RJB_MODE_BRUTE) {
@@ -334,7 +347,11 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
     bool filter = !order && (c->use_filter == 1 || (c->use_filter < 0 && Bm.bvh.occ_fraction < 0.25 &&
                                                    !c->filter_useless));
     uint32_t* surv = filter ? c->survivors.ensure(Q.n_points) : nullptr;
-    unsigned int* surv_n = (unsigned int*) (ctr + 8);  // [0] survivors, [1] (query, leaf) pairs
+    // [0] survivors, [1] (query, leaf) pairs, [2] survivors that are longer than a cell
+    unsigned int* surv_n = (unsigned int*) (ctr + 8);
+    // cell directory instead of the tree walk for the survivors (option lsi_cells)
+    const bool cells = filter && Bm.bvh.have_cells && c->use_cells > 0 && !c->stats;
+    uint32_t* long_list = cells ? c->long_edges.ensure(Q.n_points) : nullptr;
     for (int attempt = 0;; attempt++) {
       RJB_REQUIRE(c->cand_cap < 0xFFFFFFF0ull, "rjb_lsi: candidate queue exceeds 2^32 entries");
       uint32_t ccap = (uint32_t) c->cand_cap;
@@ -349,11 +366,19 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
       const unsigned int* n_slots_dev = nullptr;
       if (filter) {
         k_lsi_filter<<<div_up(Q.n_points, kFilterCtaPoints), kFilterThreads, 0, c->stream>>>(
-            Q, Bm.bvh.occ.p, surv, surv_n);
+            Q, Bm.bvh.occ.p, surv, surv_n, long_list, surv_n + 2);
         slots = surv;
         n_slots_dev = surv_n;
         // grid for the worst case; warps beyond the survivor count exit at once
         n_slots = c->last_survivors ? min(Q.n_points, c->last_survivors + c->last_survivors / 4 + 4096) : Q.n_points;
+      }
+      if (cells) {
+        // short survivors: cell directory; the long ones (usually none) walk the tree
+        k_lsi_cells<<<kNumSMs * 48, kLsiWarps * 32, 0, c->stream>>>(Q, Bm.bvh.view(), surv, surv_n, cands, ccap,
+                                                                 surv_n + 1);
+        slots = long_list;
+        n_slots_dev = surv_n + 2;
+        n_slots = min(Q.n_points, c->last_long + c->last_long / 4 + 1024);
       }
       unsigned tiles = div_up(n_slots, 32);
       unsigned blocks = div_up(tiles, kLsiWarps);
@@ -364,7 +389,7 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
         k_lsi_bvh<false><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
             Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, cands, ccap, surv_n + 1, ctr + 2);
       RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
-      k_lsi_exact<<<kNumSMs * 8, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
+      k_lsi_exact<<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
                                                      xs, cap, (unsigned int*) ctr, ctr + 1);
       k_lsi_points<<<kNumSMs * 3, kPointsThreads, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs);
       RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
@@ -372,11 +397,13 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
       // one read-back into pinned memory: the only host round trip of the query
       RJB_CUDA(cudaMemcpyAsync(c->h_counters, ctr, 10 * sizeof(unsigned long long),
                                cudaMemcpyDeviceToHost, c->stream));
-      RJB_CUDA(cudaStreamSynchronize(c->stream));
+      wait_stream(c->stream);
       memcpy(h, c->h_counters, sizeof(h));
-      unsigned int hs[2];
+      unsigned int hs[4];
       memcpy(hs, c->h_counters + 8, sizeof(hs));
-      bool grid_too_small = filter && hs[0] > n_slots;  // launch was sized from the last query
+      // launches sized from the last query
+      bool grid_too_small = cells ? hs[2] > n_slots : (filter && hs[0] > n_slots);
+      if (cells) c->last_long = hs[2];
       if (filter) {
         c->last_survivors = hs[0];
         c->filter_useless = hs[0] > Q.n_edges / 2;  // adaptive: not worth a pass over S
@@ -386,6 +413,10 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
       if (hs[1] > ccap) c->cand_cap = (size_t) hs[1] + hs[1] / 8 + 65536;
     }
     if (filter) h[7] = c->last_survivors;
+    if (cells) {  // which path produced the candidates (no traversal statistics in this mode)
+      h[5] = 1;
+      h[6] = c->last_long;
+    }
   } else {
     RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
     RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
@@ -554,6 +585,8 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
       c->sort_queries = (int) value;
     } else if (n == "lsi_filter") {
       c->use_filter = (int) value;
+    } else if (n == "lsi_cells") {
+      c->use_cells = (int) value;
     } else if (n == "pip_park") {
       c->pip_park = value != 0;
     } else if (n == "stats") {

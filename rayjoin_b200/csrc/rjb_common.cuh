@@ -66,6 +66,15 @@ struct BvhView {
   // edge whose box touches no occupied cell cannot intersect anything.  Followed by the
   // dilated bitmap occ2 (bit (x, y) = OR of occ over {x, x+1} x {y, y+1}), see edge_desc_of.
   const uint32_t* occ;
+  // Cell directory over the OCCUPIED cells (sparse base maps only, else nullptr): cell id =
+  // occ_rank[word] + popcount of the lower bits of the word; the leaves whose box touches
+  // cell id are cell_leaf[cell_begin[id] .. cell_begin[id + 1]).  leaf_box = the quantised
+  // leaf boxes in leaf order.  A short query edge finds its candidate leaves with three
+  // dependent loads instead of a tree walk (k_lsi_cells).
+  const uint32_t* occ_rank;
+  const uint32_t* cell_begin;
+  const uint32_t* cell_leaf;
+  const int4* leaf_box;
   int top_levels;          // 3, or 4 for big trees (>= 2^18 leaves): depth 20 resolved in 4 steps
   int4 root_box;
   uint32_t n_leaves;

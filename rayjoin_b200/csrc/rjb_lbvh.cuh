@@ -32,7 +32,10 @@ struct Bvh {
   DBuf<int4> root_box_d;
   DBuf<int4> top_box;
   DBuf<int> top_code;
-  DBuf<uint32_t> occ;
+  DBuf<uint32_t> occ, occ_pop, occ_rank, cell_cnt, cell_begin, cell_leaf;
+  DBuf<unsigned long long> inc_counter;
+  bool have_cells = false;
+  uint32_t n_occ_cells = 0, n_incidences = 0;
   int top_levels = 3;
   double occ_fraction = 1.0;  // share of occupied cells (the filter pays off when it is small)
   ScanTemp scan_tmp;
@@ -48,6 +51,10 @@ struct Bvh {
     v.top_box = top_box.p;
     v.top_code = top_code.p;
     v.occ = occ.p;
+    v.occ_rank = have_cells ? occ_rank.p : nullptr;
+    v.cell_begin = cell_begin.p;
+    v.cell_leaf = cell_leaf.p;
+    v.leaf_box = leaf_box_s.p;
     v.top_levels = top_levels;
     return v;
   }
@@ -55,7 +62,9 @@ struct Bvh {
     uint32_t n_int = n_leaves > 1 ? n_leaves - 1 : 1;
     return (size_t) n_int * (2 * sizeof(int4) + sizeof(int2)) + (size_t) n_leaves * sizeof(uint2) +
            (size_t) (top_levels == 4 ? kTopSlots4 : kTopSlots3) * (sizeof(int4) + sizeof(int)) +
-           2 * (size_t) kOccDim * kOccDim / 8;
+           2 * (size_t) kOccDim * kOccDim / 8 +
+           (have_cells ? (size_t) (kOccWords + 1) * 4 + (size_t) (n_occ_cells + 1) * 4 +
+                             (size_t) n_incidences * 4 + (size_t) n_leaves * sizeof(int4) : 0);
   }
 };
 
@@ -274,16 +283,52 @@ __global__ void k_top_tree(const int4* __restrict__ node_box, const int2* __rest
 // edges: 4x fewer boxes, and the leaf box is what the traversal would test anyway.
 // (A warp-merged variant with __match_any_sync measured slower than plain atomics:
 // 71 vs 39 us for 1 M leaves.)
-__global__ void k_occ_mark(const int4* __restrict__ leaf_box, uint32_t n, uint32_t* __restrict__ occ) {
+__global__ void k_occ_mark(const int4* __restrict__ leaf_box, uint32_t n, uint32_t* __restrict__ occ,
+                           unsigned long long* __restrict__ n_incidences) {
   uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long area = 0;
+  if (l < n) {
+    const int4 b = leaf_box[l];
+    const int x0 = occ_cell(b.x), x1 = occ_cell(b.z), y0 = occ_cell(b.y), y1 = occ_cell(b.w);
+    area = (unsigned long long) (x1 - x0 + 1) * (unsigned long long) (y1 - y0 + 1);
+    for (int y = y0; y <= y1; y++)
+      for (int x = x0; x <= x1; x++) {
+        const uint32_t bit = (uint32_t) y * kOccDim + x;
+        const uint32_t m = 1u << (bit & 31);
+        if (!(occ[bit >> 5] & m)) atomicOr(&occ[bit >> 5], m);  // mostly set already
+      }
+  }
+  // (leaf, cell) incidences: the size of the cell directory
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
+  if ((threadIdx.x & 31) == 0 && area) atomicAdd(n_incidences, area);
+}
+
+__global__ void k_occ_popc(const uint32_t* __restrict__ occ, uint32_t* __restrict__ pop) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < kOccWords) pop[w] = __popc(occ[w]);
+}
+
+// id of an occupied cell (bit must be set in occ)
+static __device__ __forceinline__ uint32_t occ_cell_id(const uint32_t* __restrict__ occ,
+                                                       const uint32_t* __restrict__ rank, uint32_t bit) {
+  return __ldg(&rank[bit >> 5]) + __popc(__ldg(&occ[bit >> 5]) & ((1u << (bit & 31)) - 1));
+}
+
+// cell directory, pass 1 (fill == false): leaves per occupied cell; pass 2: the lists
+template <bool kFill>
+__global__ void k_cell_lists(const int4* __restrict__ leaf_box, uint32_t n, const uint32_t* __restrict__ occ,
+                             const uint32_t* __restrict__ rank, uint32_t* __restrict__ cnt,
+                             const uint32_t* __restrict__ begin, uint32_t* __restrict__ cell_leaf) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= n) return;
   const int4 b = leaf_box[l];
   const int x0 = occ_cell(b.x), x1 = occ_cell(b.z), y0 = occ_cell(b.y), y1 = occ_cell(b.w);
   for (int y = y0; y <= y1; y++)
     for (int x = x0; x <= x1; x++) {
-      const uint32_t bit = (uint32_t) y * kOccDim + x;
-      const uint32_t m = 1u << (bit & 31);
-      if (!(occ[bit >> 5] & m)) atomicOr(&occ[bit >> 5], m);  // mostly set already
+      const uint32_t id = occ_cell_id(occ, rank, (uint32_t) y * kOccDim + x);
+      const uint32_t k = atomicAdd(&cnt[id], 1u);
+      if (kFill) cell_leaf[__ldg(&begin[id]) + k] = l;
     }
 }
 
@@ -300,7 +345,7 @@ __global__ void k_occ_dilate(const uint32_t* __restrict__ occ, uint32_t* __restr
 }
 
 static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long imin,
-                              cudaStream_t st) {
+                              bool want_cells, cudaStream_t st) {
   RJB_REQUIRE(leaf_size >= 1 && leaf_size <= 8, "lbvh_leaf_size must be in 1..8");
   RJB_REQUIRE(m.n_chains < (1u << 28), "too many chains for the leaf record (2^28)");
   b.leaf_size = leaf_size;
@@ -350,14 +395,43 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
   const uint32_t occ_words = kOccWords;
   uint32_t* occ = b.occ.ensure(2 * occ_words);  // occ, then the dilated occ2
   RJB_CUDA(cudaMemsetAsync(occ, 0, occ_words * sizeof(uint32_t), st));
-  k_occ_mark<<<div_up(n, T), T, 0, st>>>(box_s, n, occ);
+  unsigned long long* inc = b.inc_counter.ensure(1);
+  RJB_CUDA(cudaMemsetAsync(inc, 0, sizeof(unsigned long long), st));
+  k_occ_mark<<<div_up(n, T), T, 0, st>>>(box_s, n, occ, inc);
   k_occ_dilate<<<div_up(occ_words, T), T, 0, st>>>(occ, occ + occ_words);
+  // rank of every bitmap word = number of occupied cells before it
+  uint32_t* pop = b.occ_pop.ensure(occ_words);
+  uint32_t* rank = b.occ_rank.ensure(occ_words + 1);
+  k_occ_popc<<<div_up(occ_words, T), T, 0, st>>>(occ, pop);
+  exclusive_scan_u32(pop, rank, occ_words, b.scan_tmp, st);
   RJB_CUDA(cudaGetLastError());
+  uint32_t n_occ = 0;
+  unsigned long long n_inc = 0;
   RJB_CUDA(cudaMemcpyAsync(&b.root_box, root_d, sizeof(int4), cudaMemcpyDeviceToHost, st));
+  RJB_CUDA(cudaMemcpyAsync(&n_occ, rank + occ_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  RJB_CUDA(cudaMemcpyAsync(&n_inc, inc, sizeof(n_inc), cudaMemcpyDeviceToHost, st));
   RJB_CUDA(cudaStreamSynchronize(st));
-  // upper estimate of the occupied share (a leaf touches ~1.5 cells); it only steers
-  // the first query: the filter switches itself off when it does not pay
-  b.occ_fraction = std::min(1.0, 1.5 * (double) n / ((double) kOccDim * kOccDim));
+  // share of occupied cells: it steers the first query (the filter switches itself off
+  // when it does not pay)
+  b.occ_fraction = (double) n_occ / ((double) kOccDim * kOccDim);
+  // Cell directory: only for sparse maps (the ones the occupancy filter is used for), and
+  // only when the leaves are small against the cells (else the lists explode)
+  b.have_cells = false;
+  b.n_occ_cells = n_occ;
+  b.n_incidences = 0;
+  if (want_cells && b.occ_fraction < 0.25 && n_inc <= 8ull * n + 1024) {
+    b.n_incidences = (uint32_t) n_inc;
+    uint32_t* ccnt = b.cell_cnt.ensure(n_occ + 1);
+    uint32_t* cbeg = b.cell_begin.ensure(n_occ + 1);
+    uint32_t* clist = b.cell_leaf.ensure(n_inc ? n_inc : 1);
+    RJB_CUDA(cudaMemsetAsync(ccnt, 0, (n_occ + 1) * sizeof(uint32_t), st));
+    k_cell_lists<false><<<div_up(n, T), T, 0, st>>>(box_s, n, occ, rank, ccnt, nullptr, nullptr);
+    exclusive_scan_u32(ccnt, cbeg, n_occ, b.scan_tmp, st);
+    RJB_CUDA(cudaMemsetAsync(ccnt, 0, (n_occ + 1) * sizeof(uint32_t), st));
+    k_cell_lists<true><<<div_up(n, T), T, 0, st>>>(box_s, n, occ, rank, ccnt, cbeg, clist);
+    RJB_CUDA(cudaGetLastError());
+    b.have_cells = true;
+  }
 }
 
 }  // namespace rjb

@@ -216,7 +216,7 @@ static __device__ __noinline__ bool occ_rect(const MapView& Q, const uint32_t* _
 // interleave, and every traversal warp has to follow up to 32 separate clusters.)
 __global__ void __launch_bounds__(kFilterThreads)
 k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__ survivors,
-             unsigned int* counter) {
+             unsigned int* counter, uint32_t* __restrict__ long_list, unsigned int* long_counter) {
   constexpr int kWarps = kFilterThreads / 32;
   __shared__ unsigned s_wsum[kWarps];
   __shared__ unsigned s_base;
@@ -246,7 +246,21 @@ k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__
     const uint32_t cls = d[e] >> 24;
     bool keep = cls < kDescBig && ((w[e] >> (d[e] & 31u)) & 1u);
     if (__any_sync(0xffffffffu, cls == kDescBig)) {
-      if (cls == kDescBig) keep = occ_rect(Q, occ, w0 + 32 * e + lane);
+      const bool big = cls == kDescBig && occ_rect(Q, occ, w0 + 32 * e + lane);
+      if (long_list) {
+        // edges longer than a cell go to a list of their own: the tree walk handles them,
+        // the cell directory (k_lsi_cells) everything else
+        const unsigned mb = __ballot_sync(0xffffffffu, big);
+        if (mb) {
+          unsigned base = 0;
+          const int leader = __ffs(mb) - 1;
+          if (lane == leader) base = atomicAdd(long_counter, (unsigned) __popc(mb));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (big) long_list[base + __popc(mb & ((1u << lane) - 1))] = w0 + 32 * e + lane;
+        }
+      } else if (big) {
+        keep = true;
+      }
     }
     m[e] = __ballot_sync(0xffffffffu, keep);
     cnt += __popc(m[e]);
@@ -272,6 +286,70 @@ k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__
     if ((m[e] >> lane) & 1u) survivors[pos + __popc(m[e] & lt)] = w0 + 32 * e + lane;
     pos += __popc(m[e]);
   }
+}
+
+// Candidate generation through the cell directory (sparse base maps, short query edges:
+// the survivors of the occupancy filter whose box lies within 2 x 2 cells).  Every lane
+// owns one query edge and walks ITS cells and their leaf lists independently -- three
+// dependent loads (rank, list bounds, leaf box) per candidate instead of a warp-wide tree
+// walk; the lanes only meet to stage their (query start point, leaf) pairs.  A leaf that
+// is listed in several cells of the query's box is reported once: in the cell that holds
+// the min corner of the intersection of the two cell boxes.  The pairs are exactly the
+// ones the tree walk emits (quantised boxes overlap).
+__global__ void __launch_bounds__(kLsiWarps * 32)
+k_lsi_cells(MapView Q, BvhView bvh, const uint32_t* __restrict__ survivors,
+            const unsigned int* __restrict__ n_survivors_dev, uint2* __restrict__ out, uint32_t cap,
+            unsigned int* counter) {
+  __shared__ uint2 s_emit[kLsiWarps][kEmitBuf];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Emit E = {s_emit[warp], 0u, out, cap, counter};
+  TravStats st = {0, 0, 0, 0, 0};
+  const uint32_t n = *n_survivors_dev;
+  const uint32_t n_tiles = (n + 31) / 32;
+  for (uint32_t tile = blockIdx.x * kLsiWarps + warp; tile < n_tiles; tile += gridDim.x * kLsiWarps) {
+    const uint32_t slot = tile * 32 + lane;
+    const bool valid = slot < n;
+    uint32_t p = 0;
+    int4 qb = empty_box();
+    int cx0 = 0, cy0 = 0, cx1 = -1, cy1 = -1;
+    if (valid) {
+      p = survivors[slot];
+      const longlong2 a = __ldg(&Q.pts[p]), b = __ldg(&Q.pts[p + 1]);
+      qb = make_int4(quant(min(a.x, b.x)), quant(min(a.y, b.y)), quant(max(a.x, b.x)), quant(max(a.y, b.y)));
+      cx0 = occ_cell(qb.x); cy0 = occ_cell(qb.y); cx1 = occ_cell(qb.z); cy1 = occ_cell(qb.w);
+    }
+    int cx = cx0, cy = cy0;        // next cell to look up
+    int lx = 0, ly = 0;            // cell whose list is being read
+    bool more_cells = valid;
+    uint32_t j = 0, end = 0;       // remaining part of the current list
+    while (true) {
+      const bool has_leaf = j < end;
+      if (!__any_sync(0xffffffffu, has_leaf || more_cells)) break;
+      bool hit = false;
+      uint32_t leaf = 0;
+      if (has_leaf) {
+        leaf = __ldg(&bvh.cell_leaf[j++]);
+        const int4 lb = __ldg(&bvh.leaf_box[leaf]);
+        if (box_overlap(qb, lb))
+          hit = max(cx0, occ_cell(lb.x)) == lx && max(cy0, occ_cell(lb.y)) == ly;
+      } else if (more_cells) {
+        const uint32_t bit = (uint32_t) cy * kOccDim + cx;
+        const uint32_t w = __ldg(&bvh.occ[bit >> 5]);
+        if ((w >> (bit & 31)) & 1u) {
+          const uint32_t id = __ldg(&bvh.occ_rank[bit >> 5]) + __popc(w & ((1u << (bit & 31)) - 1));
+          j = __ldg(&bvh.cell_begin[id]);
+          end = __ldg(&bvh.cell_begin[id + 1]);
+          lx = cx;
+          ly = cy;
+        }
+        if (cx < cx1) cx++;
+        else if (cy < cy1) { cy++; cx = cx0; }
+        else more_cells = false;
+      }
+      lsi_leaf<false>((int) leaf, hit, p, E, lane, st);
+    }
+  }
+  emit_flush(E, lane);
 }
 
 // The walk is a chain of dependent loads (row of level k+1 after the ballots of level k).
@@ -426,10 +504,10 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
 
 // Exact pass 1 over the (query start point, leaf) pairs of the traversal, in two dense
 // steps per CTA:
-//  (1) FOUR LANES PER PAIR: lane k of a quad tests the exact integer boxes of the query
-//      edge and base edge k (and k + 4 for leaves of > 4 edges) of the leaf -- one
-//      contiguous run of points, so a quad's loads are five consecutive 16-byte
-//      vertices.  The ~1 in 8 that overlap go to a shared-memory list;
+//  (1) one thread per pair loads the leaf's vertices (<= 9 consecutive 16-byte points, all
+//      loads of a thread in flight together) and tests the exact integer boxes of the
+//      query edge against each base edge of the leaf.  The ~1 in 8 that overlap go to a
+//      shared-memory list;
 //  (2) whenever the list holds a CTA's worth, intersect_test runs over it with every
 //      lane busy, and the hits are compacted into the result queue (one atomic per
 //      warp) as start-point index pairs.
@@ -437,7 +515,7 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
 // the int128 predicate executed by nearly every warp for one or two lanes.)
 // The pair count is read on the device: no host round trip between the kernels.
 constexpr int kExactThreads = 256;
-constexpr int kExactList = 3 * kExactThreads;  // < kExactThreads before a round, <= 2 per thread added
+constexpr int kExactList = 9 * kExactThreads;  // < kExactThreads before a round, <= 8 per thread added
 
 static __device__ __forceinline__ void exact_drain(const MapView& Q, const MapView& B, const uint2* list,
                                                    unsigned n_list, rjb_xsect* __restrict__ out,
@@ -470,6 +548,19 @@ static __device__ __forceinline__ void exact_drain(const MapView& Q, const MapVi
   }
 }
 
+// append the lanes with `pass` to the CTA's list (one shared-memory atomic per warp)
+static __device__ __forceinline__ void exact_push(bool pass, uint2 item, uint2* list, unsigned* s_n,
+                                                  int lane, unsigned& cand) {
+  const unsigned m = __ballot_sync(0xffffffffu, pass);
+  if (m == 0) return;
+  unsigned base = 0;
+  const int leader = __ffs(m) - 1;
+  if (lane == leader) base = atomicAdd(s_n, (unsigned) __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pass) list[base + __popc(m & ((1u << lane) - 1))] = item;
+  cand += __popc(m);  // counted by every lane alike
+}
+
 __global__ void __launch_bounds__(kExactThreads)
 k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ pairs, const uint2* __restrict__ leaf_rec,
             const unsigned int* __restrict__ n_pairs_dev, uint32_t pair_cap,
@@ -481,14 +572,15 @@ k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ pairs, const uint2* 
   __syncthreads();
   const uint32_t n = min(*n_pairs_dev, pair_cap);
   const int lane = threadIdx.x & 31;
-  const uint32_t sub = lane & 3;
   unsigned cand = 0;
-  constexpr uint32_t kPairsPerRound = kExactThreads / 4;
   // block-uniform trip count: every thread reaches the barriers
-  for (uint64_t i0 = (uint64_t) blockIdx.x * kPairsPerRound; i0 < n; i0 += (uint64_t) gridDim.x * kPairsPerRound) {
-    const uint64_t i = i0 + (threadIdx.x >> 2);
+  for (uint64_t i0 = (uint64_t) blockIdx.x * kExactThreads; i0 < n; i0 += (uint64_t) gridDim.x * kExactThreads) {
+    const uint64_t i = i0 + threadIdx.x;
     uint32_t pq = 0, pb0 = 0, cnt = 0;
     Seg e1 = {0, 0, 0, 0};
+    longlong2 bp[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) bp[k] = make_longlong2(0, 0);
     if (i < n) {
       const uint2 pr = pairs[i];
       pq = pr.x;
@@ -497,24 +589,27 @@ k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ pairs, const uint2* 
       pb0 = rec.x + (rec.y & 0x0FFFFFFFu);
       const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
       e1 = {a.x, a.y, b.x, b.y};
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+        if ((uint32_t) k <= cnt) bp[k] = __ldg(&B.pts[pb0 + k]);
     }
 #pragma unroll
-    for (uint32_t r = 0; r < 2; r++) {
-      const uint32_t k = sub + 4 * r;
-      bool pass = false;
-      if (k < cnt) {
-        const longlong2 p1 = __ldg(&B.pts[pb0 + k]), p2 = __ldg(&B.pts[pb0 + k + 1]);
-        const Seg e2 = {p1.x, p1.y, p2.x, p2.y};
-        pass = seg_boxes_overlap(e1, e2);
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, pass);
-      if (m) {
-        unsigned base = 0;
-        const int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(&s_n, (unsigned) __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (pass) s_list[base + __popc(m & ((1u << lane) - 1))] = make_uint2(pq, pb0 + k);
-        cand += __popc(m);  // counted by every lane alike
+    for (int k = 0; k < 4; k++) {
+      const Seg e2 = {bp[k].x, bp[k].y, bp[k + 1].x, bp[k + 1].y};
+      exact_push((uint32_t) k < cnt && seg_boxes_overlap(e1, e2), make_uint2(pq, pb0 + k), s_list, &s_n,
+                 lane, cand);
+    }
+    if (__any_sync(0xffffffffu, cnt > 4)) {  // leaves of 5..8 edges (lbvh_leaf_size > 4)
+      longlong2 p1 = bp[4];
+      for (uint32_t k = 4; k < 8; k++) {
+        bool pass = false;
+        if (k < cnt) {
+          const longlong2 p2 = __ldg(&B.pts[pb0 + k + 1]);
+          const Seg e2 = {p1.x, p1.y, p2.x, p2.y};
+          pass = seg_boxes_overlap(e1, e2);
+          p1 = p2;
+        }
+        exact_push(pass, make_uint2(pq, pb0 + k), s_list, &s_n, lane, cand);
       }
     }
     __syncthreads();

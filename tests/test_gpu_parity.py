@@ -70,6 +70,38 @@ def test_lsi_lbvh_leaf_sizes_and_sorted_queries(rjb, loaded, leaf):
         ctx.set_option("sort_queries", 0)
 
 
+@pytest.mark.parametrize("q", [1, 0])
+@pytest.mark.parametrize("name", DATASETS)
+def test_lsi_cell_directory_path(rjb, loaded, name, q):
+    """Option lsi_cells: the survivors of the occupancy filter find their candidate leaves
+    through the directory of occupied cells (k_lsi_cells), long edges through the tree
+    walk.  Same result, same number of exact-predicate evaluations as the tree walk."""
+    ctx, om = loaded(name)
+    want = om.lsi(q)
+    counts = {}
+    try:
+        for cells in (0, 1):
+            ctx.set_option("lsi_cells", cells)
+            ctx.set_option("lsi_filter", 1)
+            ctx.set_option("sort_queries", 0)
+            ctx.build_index(1 - q, "lbvh")
+            lsi = rjb.LSI(ctx, "lbvh")
+            lsi.Init(4.0)
+            for _ in range(2):  # the second query runs with launch sizes learnt from the first
+                n = lsi.Query(q)
+                got = sort_xsects(lsi.get_xsects(), q)
+                assert n == len(want[0])
+                for g, w in zip(got, want):
+                    assert np.array_equal(g, w)
+            counts[cells] = lsi.n_candidates
+            st = ctx.last_stats()
+            assert st[5] == cells or st[7] == 0  # the path that was asked for ran
+    finally:
+        ctx.set_option("lsi_cells", 0)
+        ctx.set_option("lsi_filter", -1)
+    assert counts[0] == counts[1]
+
+
 def test_lsi_queue_overflow_is_detected(rjb, loaded):
     ctx, om = loaded("voronoi")
     ctx.build_index(0, "lbvh")
