@@ -46,6 +46,11 @@ def dataset(name):
         # strongly anisotropic box -> very different rx / ry
         R = synth.voronoi_map(30, 1500, (-179.0, 10.0, 179.0, 12.0), seed=5)
         S = synth.voronoi_map(90, 2000, (-179.0, 10.0, 179.0, 12.0), seed=6)
+    elif name == "dense":
+        # many short edges (leaves touch ~6 occupancy cells): the regime of the headline workload,
+        # where the occupancy filter and the cell directory are in play
+        R = synth.voronoi_map(1500, 600000, synth.BRAZIL_BBOX, seed=7)
+        S = synth.voronoi_map(5000, 900000, synth.BRAZIL_BBOX, seed=8)
     elif name == "tiny":
         R = PlanarGraph(np.array([[0.0, 0.0], [10.0, 10.0]]), [0, 2], [1], [2])
         S = PlanarGraph(np.array([[0.0, 10.0], [10.0, 0.0], [20.0, 3.0]]), [0, 3], [3], [4])

@@ -71,7 +71,7 @@ def test_lsi_lbvh_leaf_sizes_and_sorted_queries(rjb, loaded, leaf):
 
 
 @pytest.mark.parametrize("q", [1, 0])
-@pytest.mark.parametrize("name", DATASETS)
+@pytest.mark.parametrize("name", DATASETS + ["dense"])
 def test_lsi_cell_directory_path(rjb, loaded, name, q):
     """Option lsi_cells: the survivors of the occupancy filter find their candidate leaves
     through the directory of occupied cells (k_lsi_cells), long edges through the tree
@@ -95,7 +95,10 @@ def test_lsi_cell_directory_path(rjb, loaded, name, q):
                     assert np.array_equal(g, w)
             counts[cells] = lsi.n_candidates
             st = ctx.last_stats()
-            assert st[5] == cells or st[7] == 0  # the path that was asked for ran
+            # the directory is only built where leaves are small against the cells
+            assert st[5] in (0, cells)
+            if name == "dense":
+                assert st[7] > 0 and st[5] == cells  # filter on, and the path that was asked for
     finally:
         ctx.set_option("lsi_cells", 0)
         ctx.set_option("lsi_filter", -1)
