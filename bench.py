@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--leaf-size", type=int, default=4)
     ap.add_argument("--sort-queries", type=int, default=-1)
     ap.add_argument("--filter", type=int, default=-1, help="occupancy pre-filter: -1 auto, 0 off, 1 on")
+    ap.add_argument("--cells", type=int, default=0, help="experimental cell-directory candidate path (option lsi_cells)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
@@ -264,6 +265,7 @@ def main():
     ctx.set_option("lbvh_leaf_size", args.leaf_size)
     ctx.set_option("sort_queries", args.sort_queries)
     ctx.set_option("lsi_filter", args.filter)
+    ctx.set_option("lsi_cells", args.cells)
     ctx.set_bounding_box(*bbox)
     ctx.set_map(0, R)
     # pinned host copies of the S batch for the end-to-end leg
@@ -287,20 +289,31 @@ def main():
         step_counts.append((n, lsi.n_candidates))
         return n
 
+    # fixed-size exchange buffers: the warm-up exchange has the shape of the timed one (NCCL
+    # sets its connections up lazily, 2.7 ms on first use -- tools/nccl_small.py)
+    n_rows = max(args.steps, args.warmup, 1)
+    counts_host = torch.zeros((n_rows, 2), dtype=torch.int64).pin_memory()
+    counts_dev = torch.zeros((n_rows, 2), dtype=torch.int64, device=dev)
+    counts_all = torch.zeros((world, n_rows, 2), dtype=torch.int64, device=dev)
+
     def wait_counts():
         """The only data-path collective: the per-rank {result, candidate} counts of the
         steps since the last call, ONE NCCL all-gather (16 B per step and rank).  Nothing
         in a query depends on another rank's counts, so they are exchanged once per batch
-        of steps instead of stalling every 0.35 ms step on a collective launch."""
+        of steps instead of stalling every 0.16 ms step on a collective launch."""
         if world > 1 and step_counts:
-            mine = torch.tensor(step_counts, dtype=torch.int64).to(dev, non_blocking=True)
-            out = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=dev)
+            counts_host.zero_()
+            counts_host[:len(step_counts)] = torch.tensor(step_counts[-n_rows:], dtype=torch.int64)
             with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(out, mine)
+                counts_dev.copy_(counts_host, non_blocking=True)
+                dist.all_gather_into_tensor(counts_all, counts_dev)
         step_counts.clear()
 
     for _ in range(args.warmup):
         step()
+        if world > 1 and len(step_counts) == 1:
+            wait_counts()  # twice during warm-up: connection set-up, then the steady state
+            step_counts.append((0, 0))
     wait_counts()
     torch.cuda.synchronize()
     if world > 1:
@@ -318,16 +331,31 @@ def main():
             flush_buf.zero_()  # evict L2 between timed iterations (outside the events)
             ev[i][0].record(stream)
             n_pairs = step()
-            if i == args.steps - 1:
-                wait_counts()  # every count exchange has landed inside the timed region
             ev[i][1].record(stream)
         a, b = ctx.last_kernel_ms()
         k_ms.append(a)
         p_ms.append(b)
     torch.cuda.synchronize()
+    # The count exchange of the K steps (the only data-path collective) is timed on its own,
+    # with the ranks aligned first: inside the last step's interval it would mostly measure
+    # how far the ranks had drifted apart over the untimed L2 flushes between the steps.
+    xch = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     if world > 1:
         dist.barrier()
-    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+        torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        xch[0].record(stream)
+        wait_counts()
+        xch[1].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    xch_ms = xch[0].elapsed_time(xch[1])
+    total_ms = sum(step_ms) + xch_ms
+    log("[rank %d] step ms min/median/max %.4f/%.4f/%.4f, count exchange %.4f ms; host cpus: %s (affinity %d)"
+        % (rank, min(step_ms), float(np.median(step_ms)), max(step_ms), xch_ms, os.cpu_count(),
+           len(os.sched_getaffinity(0))))
     n_cand = lsi.n_candidates
 
     # ---- end to end through the C ABI from pinned host buffers ----------------
@@ -390,7 +418,8 @@ def main():
                        "lbvh_leaf_size": args.leaf_size, "sort_queries": args.sort_queries,
                        "l2": "256 MiB flush write between timed iterations; inputs (S vertices 146 MB) also exceed L2",
                        "sharding": "R + index replicated, S sharded per rank (seed 2+rank); NCCL: one "
-                                   "all-gather of the per-step counts per timed region"},
+                                   "all-gather of the per-step counts per timed region (timed after "
+                                   "aligning the ranks, added to the K step times)"},
             "join_ms": ms_per_step, "result_pairs": int(all_pairs),
             "candidate_pairs": int(all_cand),
             "candidate_pairs_per_s": all_cand / (ms_per_step / 1e3),

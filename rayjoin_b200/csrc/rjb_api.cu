@@ -9,6 +9,8 @@
 
 #include "rjb_grid.cuh"
 #include "rjb_lbvh.cuh"
+#include <sched.h>
+
 #include "rjb_lsi.cuh"
 #include "rjb_pip.cuh"
 
@@ -270,13 +272,14 @@ static const uint32_t* query_order_points(rjb_ctx* c, const longlong2* pts, uint
   return vb;
 }
 
-// Wait for the stream by polling: a blocking cudaStreamSynchronize wakes the host tens of
+// Wait for the stream by polling (yielding the core between polls): a blocking cudaStreamSynchronize wakes the host tens of
 // microseconds late, which is a tenth of a whole LSI query.  Long waits fall back to it.
 static void wait_stream(cudaStream_t s) {
   for (int spins = 0; spins < 20000; spins++) {
     const cudaError_t e = cudaStreamQuery(s);
     if (e == cudaSuccess) return;
     if (e != cudaErrorNotReady) RJB_CUDA(e);
+    sched_yield();  // other ranks of the job may share this core
   }
   RJB_CUDA(cudaStreamSynchronize(s));
 }
@@ -380,14 +383,16 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
         n_slots_dev = surv_n + 2;
         n_slots = min(Q.n_points, c->last_long + c->last_long / 4 + 1024);
       }
-      unsigned tiles = div_up(n_slots, 32);
+      // the long-edge list comes from all over the map: two queries per warp while it is short
+      const uint32_t spw = cells && n_slots <= 16384 ? 2 : 32;
+      unsigned tiles = div_up(n_slots, spw);
       unsigned blocks = div_up(tiles, kLsiWarps);
       if (c->stats)
         k_lsi_bvh<true><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-            Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, cands, ccap, surv_n + 1, ctr + 2);
+            Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
       else
         k_lsi_bvh<false><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-            Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, cands, ccap, surv_n + 1, ctr + 2);
+            Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
       RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
       k_lsi_exact<<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
                                                      xs, cap, (unsigned int*) ctr, ctr + 1);
