@@ -16,6 +16,7 @@ Multi-GPU: R and its LBVH are replicated, S is sharded (rank r owns its own
 all-gather.  Prints ONE JSON line on rank 0.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -326,6 +327,7 @@ def main():
     k_ms, p_ms = [], []
     n_pairs = 0
     torch.cuda.synchronize()
+    gc.disable()  # a collection inside a 0.16 ms step shows up as a 5x outlier
     for i in range(args.steps):
         with torch.cuda.stream(stream):
             flush_buf.zero_()  # evict L2 between timed iterations (outside the events)
@@ -336,6 +338,7 @@ def main():
         k_ms.append(a)
         p_ms.append(b)
     torch.cuda.synchronize()
+    gc.enable()
     # The count exchange of the K steps (the only data-path collective) is timed on its own,
     # with the ranks aligned first: inside the last step's interval it would mostly measure
     # how far the ranks had drifted apart over the untimed L2 flushes between the steps.
