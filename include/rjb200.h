@@ -135,6 +135,8 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
  *                     leaves up in a directory of the occupied cells, built with the index
  *                     (edges longer than a cell still walk the tree); 0 (default) = every
  *                     survivor walks the tree.  Set it before rjb_build_index.
+ *   "load_chunk_points" points per upload chunk of rjb_set_map (multiple of 1024, default 2^20):
+ *                     the load kernel of chunk k runs while chunk k+1 is copied
  *   "pip_park"        LBVH PIP: 1 (default) = lanes park the leaf their ray meets and the
  *                     warp opens the parked leaves together; 0 = open a leaf when reached
  *   "stats"           1 = collect traversal statistics (rjb_last_stats; slower)

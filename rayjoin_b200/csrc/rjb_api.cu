@@ -97,6 +97,7 @@ struct rjb_ctx {
   int use_filter = -1;    // -1 auto (by occupancy), 0 off, 1 on
   uint32_t last_survivors = 0, last_long = 0;
   DBuf<uint32_t> long_edges;  // survivors longer than a cell (tree walk)
+  uint32_t load_chunk = kLoadChunkPoints;  // points per upload chunk (option load_chunk_points)
   int use_cells = 0;      // LSI: cell directory for the filter's survivors (experimental, off)
   size_t cand_cap = 0;
   DBuf<rjb_xsect> xsects;
@@ -376,18 +377,20 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
         n_slots = c->last_survivors ? min(Q.n_points, c->last_survivors + c->last_survivors / 4 + 4096) : Q.n_points;
       }
       if (cells) {
-        // short survivors: cell directory; the long ones (usually none) walk the tree
+        // survivors: cell directory; the long ones (usually none) walk the tree
         k_lsi_cells<<<kNumSMs * 48, kLsiWarps * 32, 0, c->stream>>>(Q, Bm.bvh.view(), surv, surv_n, cands, ccap,
-                                                                 surv_n + 1);
+                                                                  surv_n + 1);
         slots = long_list;
         n_slots_dev = surv_n + 2;
-        n_slots = min(Q.n_points, c->last_long + c->last_long / 4 + 1024);
+        n_slots = c->last_long ? min(Q.n_points, c->last_long + c->last_long / 4 + 1024) : 0;
       }
       // the long-edge list comes from all over the map: two queries per warp while it is short
       const uint32_t spw = cells && n_slots <= 16384 ? 2 : 32;
       unsigned tiles = div_up(n_slots, spw);
       unsigned blocks = div_up(tiles, kLsiWarps);
-      if (c->stats)
+      if (blocks == 0) {
+        // nothing to walk (no long edges last time; a non-empty list triggers the retry below)
+      } else if (c->stats)
         k_lsi_bvh<true><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
             Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
       else
@@ -590,6 +593,10 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
       c->sort_queries = (int) value;
     } else if (n == "lsi_filter") {
       c->use_filter = (int) value;
+    } else if (n == "load_chunk_points") {
+      RJB_REQUIRE(value >= 1024 && value <= (1ll << 30) && value % 1024 == 0,
+                  "load_chunk_points must be a multiple of 1024");
+      c->load_chunk = (uint32_t) value;
     } else if (n == "lsi_cells") {
       c->use_cells = (int) value;
     } else if (n == "pip_park") {
@@ -667,7 +674,7 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
       RJB_CUDA(cudaMemsetAsync(lb + (n_words - 2), 0, 2 * sizeof(uint32_t), st));
       RJB_CUDA(cudaMemsetAsync(cc + n_points, 0xFF, 16 * sizeof(uint32_t), st));
       ensure_load_pipeline(c);
-      uint32_t chunk = kLoadChunkPoints;
+      uint32_t chunk = c->load_chunk;
       if (div_up(n_points, chunk) > (unsigned) kLoadChunksMax)
         chunk = (div_up(n_points, kLoadChunksMax) + 1023u) & ~1023u;
       int k = 0;

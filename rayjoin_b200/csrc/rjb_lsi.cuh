@@ -197,12 +197,14 @@ constexpr int kFilterPerThread = 16;
 constexpr int kFilterCtaPoints = kFilterThreads * kFilterPerThread;
 
 // edge longer than a cell (rare): every cell of its box
-static __device__ __noinline__ bool occ_rect(const MapView& Q, const uint32_t* __restrict__ occ, uint32_t p) {
+static __device__ __noinline__ bool occ_rect(const MapView& Q, const uint32_t* __restrict__ occ, uint32_t p,
+                                             bool* within3) {
   const longlong2 a = __ldg(&Q.pts[p]), b = __ldg(&Q.pts[p + 1]);
   const uint32_t c1 = occ_code(a.x, a.y), c2 = occ_code(b.x, b.y);
   const uint32_t x0 = min(c1 & (kOccDim - 1), c2 & (kOccDim - 1));
   const uint32_t x1 = max(c1 & (kOccDim - 1), c2 & (kOccDim - 1));
   const uint32_t y0 = min(c1 >> kOccBits, c2 >> kOccBits), y1 = max(c1 >> kOccBits, c2 >> kOccBits);
+  *within3 = x1 - x0 <= 2 && y1 - y0 <= 2;
   for (uint32_t y = y0; y <= y1; y++)
     for (uint32_t x = x0; x <= x1; x++) {
       const uint32_t bit = y * kOccDim + x;
@@ -248,10 +250,15 @@ k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__
     const uint32_t cls = d[e] >> 24;
     bool keep = cls < kDescBig && ((w[e] >> (d[e] & 31u)) & 1u);
     if (__any_sync(0xffffffffu, cls == kDescBig)) {
-      const bool big = cls == kDescBig && occ_rect(Q, occ, w0 + 32 * e + lane);
+      bool within3 = false;
+      bool big = cls == kDescBig && occ_rect(Q, occ, w0 + 32 * e + lane, &within3);
       if (long_list) {
-        // edges longer than a cell go to a list of their own: the tree walk handles them,
-        // the cell directory (k_lsi_cells) everything else
+        // edges whose box exceeds 3 x 3 cells go to a list of their own: the tree walk
+        // handles them, the cell directory (k_lsi_cells) everything else
+        if (big && within3) {
+          keep = true;
+          big = false;
+        }
         const unsigned mb = __ballot_sync(0xffffffffu, big);
         if (mb) {
           unsigned base = 0;
@@ -291,9 +298,10 @@ k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__
 }
 
 // Candidate generation through the cell directory (sparse base maps, short query edges:
-// the survivors of the occupancy filter whose box lies within 2 x 2 cells).  A warp owns 32
-// query edges.  Every lane looks up the (at most four) cells of ITS edge -- rank, list
-// bounds: two rounds of independent loads -- and the warp then works through the
+// the survivors of the occupancy filter whose box lies within 3 x 3 cells).  A warp owns 32
+// query edges.  Every lane looks up the cells of ITS edge -- rank, list bounds: two rounds
+// of independent loads for the 2 x 2 cells at the min corner, two more only if some edge
+// spans three cells -- and the warp then works through the
 // concatenation of all the leaf lists with one lane per (query, leaf) item, 128 items at a
 // time: the owner of an item is found by binary search over the prefix sums, the leaf ids
 // and then the leaf boxes of a batch are loaded together.  Five dependent rounds of loads
@@ -305,12 +313,120 @@ k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__
 struct CellWork {
   int4 qb[32];           // query boxes of the lanes
   uint32_t p[32];        // query start points
-  uint32_t beg[32][4];   // list begin per cell (cell k = (cx0 + (k & 1), cy0 + (k >> 1)))
-  uint32_t cum[32][4];   // inclusive prefix of the list lengths over the lane's cells
+  uint32_t beg[32][9];   // list begin per cell (cell k = (cx0 + k % 3, cy0 + k / 3))
+  uint32_t cum[32][9];   // inclusive prefix of the list lengths over the lane's cells
   uint32_t pre[33];      // exclusive prefix of the lanes' totals
 };
 
 constexpr int kCellBatch = 4;  // items per lane and batch
+
+// list bounds of cell (cx, cy) if it is occupied, else an empty range
+static __device__ __forceinline__ void cell_range(const BvhView& bvh, bool in, int cx, int cy,
+                                                  uint32_t& beg, uint32_t& end) {
+  const uint32_t bit = in ? (uint32_t) cy * kOccDim + cx : 0u;
+  const uint32_t wd = __ldg(&bvh.occ[bit >> 5]);
+  const uint32_t rk = __ldg(&bvh.occ_rank[bit >> 5]);
+  const bool set = in && ((wd >> (bit & 31)) & 1u);
+  const uint32_t id = set ? rk + __popc(wd & ((1u << (bit & 31)) - 1)) : 0u;
+  beg = __ldg(&bvh.cell_begin[id]);
+  end = set ? __ldg(&bvh.cell_begin[id + 1]) : beg;
+}
+
+// One tile: lane = one query edge (start point p) whose box spans at most 3 x 3 cells.
+static __device__ __forceinline__ void cells_tile(const MapView& Q, const BvhView& bvh, uint32_t p, bool valid,
+                                                  CellWork& W, Emit& E, int lane, TravStats& st) {
+  int4 qb = empty_box();
+  int cx0 = 0, cy0 = 0, cx1 = -1, cy1 = -1;
+  if (valid) {
+    const longlong2 a = __ldg(&Q.pts[p]), b = __ldg(&Q.pts[p + 1]);
+    qb = make_int4(quant(min(a.x, b.x)), quant(min(a.y, b.y)), quant(max(a.x, b.x)), quant(max(a.y, b.y)));
+    cx0 = occ_cell(qb.x); cy0 = occ_cell(qb.y); cx1 = occ_cell(qb.z); cy1 = occ_cell(qb.w);
+  }
+  // the 2 x 2 cells at the min corner: all look-ups in flight together (two rounds of loads)
+  uint32_t lb[9], le[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) lb[k] = le[k] = 0;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    if (k % 3 == 2 || k / 3 == 2) continue;
+    cell_range(bvh, valid && cx0 + k % 3 <= cx1 && cy0 + k / 3 <= cy1, cx0 + k % 3, cy0 + k / 3, lb[k], le[k]);
+  }
+  // third column / row: only for the rare edge spanning three cells
+  if (__any_sync(0xffffffffu, valid && (cx1 - cx0 == 2 || cy1 - cy0 == 2))) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      if (!(k % 3 == 2 || k / 3 == 2)) continue;
+      cell_range(bvh, valid && cx0 + k % 3 <= cx1 && cy0 + k / 3 <= cy1, cx0 + k % 3, cy0 + k / 3, lb[k], le[k]);
+    }
+  }
+  uint32_t total = 0;
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    total += le[k] - lb[k];
+    W.beg[lane][k] = lb[k];
+    W.cum[lane][k] = total;
+  }
+  W.qb[lane] = qb;
+  W.p[lane] = p;
+  uint32_t inc = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  W.pre[lane] = inc - total;
+  if (lane == 31) W.pre[32] = inc;
+  __syncwarp();
+  const uint32_t all = W.pre[32];
+  for (uint32_t base = 0; base < all; base += 32 * kCellBatch) {
+    uint32_t owner[kCellBatch], cell[kCellBatch], leaf[kCellBatch];
+    bool act[kCellBatch];
+#pragma unroll
+    for (int s2 = 0; s2 < kCellBatch; s2++) {
+      const uint32_t i = base + s2 * 32 + lane;
+      act[s2] = i < all;
+      // owner = last lane whose prefix is <= i
+      int lo = 0, hi = 32;
+#pragma unroll
+      for (int it = 0; it < 5; it++) {
+        const int mid = (lo + hi) >> 1;
+        if (W.pre[mid] <= i) lo = mid; else hi = mid;
+      }
+      owner[s2] = (uint32_t) lo;
+      const uint32_t r = i - W.pre[lo];
+      uint32_t k = 0, before = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t cj = W.cum[lo][j];
+        if (r >= cj) {
+          k = j + 1;
+          before = cj;
+        }
+      }
+      cell[s2] = k;
+      leaf[s2] = act[s2] ? __ldg(&bvh.cell_leaf[W.beg[lo][k] + (r - before)]) : 0u;
+    }
+    int4 box[kCellBatch];
+#pragma unroll
+    for (int s2 = 0; s2 < kCellBatch; s2++) box[s2] = __ldg(&bvh.leaf_box[leaf[s2]]);
+#pragma unroll
+    for (int s2 = 0; s2 < kCellBatch; s2++) {
+      bool hit = false;
+      uint32_t qp = 0;
+      if (act[s2]) {
+        const int4 oq = W.qb[owner[s2]];
+        qp = W.p[owner[s2]];
+        if (box_overlap(oq, box[s2])) {
+          const int ox = occ_cell(oq.x), oy = occ_cell(oq.y);
+          hit = max(ox, occ_cell(box[s2].x)) == ox + (int) (cell[s2] % 3u) &&
+                max(oy, occ_cell(box[s2].y)) == oy + (int) (cell[s2] / 3u);
+        }
+      }
+      lsi_leaf<false>((int) leaf[s2], hit, qp, E, lane, st);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kLsiWarps * 32)
 k_lsi_cells(MapView Q, BvhView bvh, const uint32_t* __restrict__ survivors,
@@ -320,102 +436,13 @@ k_lsi_cells(MapView Q, BvhView bvh, const uint32_t* __restrict__ survivors,
   __shared__ CellWork s_work[kLsiWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Emit E = {s_emit[warp], 0u, out, cap, counter};
-  CellWork& W = s_work[warp];
   TravStats st = {0, 0, 0, 0, 0};
   const uint32_t n = *n_survivors_dev;
   const uint32_t n_tiles = (n + 31) / 32;
   for (uint32_t tile = blockIdx.x * kLsiWarps + warp; tile < n_tiles; tile += gridDim.x * kLsiWarps) {
     const uint32_t slot = tile * 32 + lane;
     const bool valid = slot < n;
-    uint32_t p = 0;
-    int4 qb = empty_box();
-    int cx0 = 0, cy0 = 0, cx1 = -1, cy1 = -1;
-    if (valid) {
-      p = survivors[slot];
-      const longlong2 a = __ldg(&Q.pts[p]), b = __ldg(&Q.pts[p + 1]);
-      qb = make_int4(quant(min(a.x, b.x)), quant(min(a.y, b.y)), quant(max(a.x, b.x)), quant(max(a.y, b.y)));
-      cx0 = occ_cell(qb.x); cy0 = occ_cell(qb.y); cx1 = occ_cell(qb.z); cy1 = occ_cell(qb.w);
-    }
-    // round 1: bitmap word and rank of every cell; round 2: the list bounds
-    uint32_t wd[4], rk[4], bit[4];
-    bool in[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int cx = cx0 + (k & 1), cy = cy0 + (k >> 1);
-      in[k] = valid && cx <= cx1 && cy <= cy1;
-      bit[k] = in[k] ? (uint32_t) cy * kOccDim + cx : 0u;
-      wd[k] = __ldg(&bvh.occ[bit[k] >> 5]);
-      rk[k] = __ldg(&bvh.occ_rank[bit[k] >> 5]);
-    }
-    uint32_t lb[4], le[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const bool set = in[k] && ((wd[k] >> (bit[k] & 31)) & 1u);
-      const uint32_t id = set ? rk[k] + __popc(wd[k] & ((1u << (bit[k] & 31)) - 1)) : 0u;
-      lb[k] = __ldg(&bvh.cell_begin[id]);
-      le[k] = set ? __ldg(&bvh.cell_begin[id + 1]) : lb[k];
-    }
-    uint32_t total = 0;
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      total += le[k] - lb[k];
-      W.beg[lane][k] = lb[k];
-      W.cum[lane][k] = total;
-    }
-    W.qb[lane] = qb;
-    W.p[lane] = p;
-    uint32_t inc = total;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += v;
-    }
-    W.pre[lane] = inc - total;
-    if (lane == 31) W.pre[32] = inc;
-    __syncwarp();
-    const uint32_t all = W.pre[32];
-    for (uint32_t base = 0; base < all; base += 32 * kCellBatch) {
-      uint32_t owner[kCellBatch], cell[kCellBatch], leaf[kCellBatch];
-      bool act[kCellBatch];
-#pragma unroll
-      for (int s2 = 0; s2 < kCellBatch; s2++) {
-        const uint32_t i = base + s2 * 32 + lane;
-        act[s2] = i < all;
-        // owner = last lane whose prefix is <= i
-        int lo = 0, hi = 32;
-#pragma unroll
-        for (int it = 0; it < 5; it++) {
-          const int mid = (lo + hi) >> 1;
-          if (W.pre[mid] <= i) lo = mid; else hi = mid;
-        }
-        owner[s2] = (uint32_t) lo;
-        const uint32_t r = i - W.pre[lo];
-        const uint32_t c0 = W.cum[lo][0], c1 = W.cum[lo][1], c2 = W.cum[lo][2];
-        const uint32_t k = (r >= c0) + (r >= c1) + (r >= c2);
-        const uint32_t before = k == 0 ? 0u : k == 1 ? c0 : k == 2 ? c1 : c2;
-        cell[s2] = k;
-        leaf[s2] = act[s2] ? __ldg(&bvh.cell_leaf[W.beg[lo][k] + (r - before)]) : 0u;
-      }
-      int4 box[kCellBatch];
-#pragma unroll
-      for (int s2 = 0; s2 < kCellBatch; s2++) box[s2] = __ldg(&bvh.leaf_box[leaf[s2]]);
-#pragma unroll
-      for (int s2 = 0; s2 < kCellBatch; s2++) {
-        bool hit = false;
-        uint32_t qp = 0;
-        if (act[s2]) {
-          const int4 oq = W.qb[owner[s2]];
-          qp = W.p[owner[s2]];
-          if (box_overlap(oq, box[s2])) {
-            const int ox = occ_cell(oq.x), oy = occ_cell(oq.y);
-            hit = max(ox, occ_cell(box[s2].x)) == ox + (int) (cell[s2] & 1u) &&
-                  max(oy, occ_cell(box[s2].y)) == oy + (int) (cell[s2] >> 1);
-          }
-        }
-        lsi_leaf<false>((int) leaf[s2], hit, qp, E, lane, st);
-      }
-    }
+    cells_tile(Q, bvh, valid ? survivors[slot] : 0u, valid, s_work[warp], E, lane, st);
   }
   emit_flush(E, lane);
 }

@@ -105,6 +105,39 @@ def test_lsi_cell_directory_path(rjb, loaded, name, q):
     assert counts[0] == counts[1]
 
 
+def test_chunked_upload_matches_single_chunk(rjb, oracle):
+    """rjb_set_map uploads in chunks and runs the load kernel per chunk; the edge descriptors,
+    chain maps and last-point bits must not depend on where the chunk boundaries fall."""
+    R, S = dataset("voronoi")
+    om = OracleMaps(oracle, [R, S])
+    want = om.lsi(1)
+    for chunk in (1024, 3072, 1 << 20):
+        ctx = rjb.Context(device=0)
+        try:
+            ctx.set_option("load_chunk_points", chunk)
+            ctx.set_bounding_box(*om.bbox)
+            ctx.set_map(0, R)
+            ctx.set_map(1, S)
+            for im in range(2):
+                assert np.array_equal(ctx.map_points(im), om.pts[im])
+            ctx.set_option("lsi_filter", 1)  # the filter reads the per-edge descriptors
+            ctx.build_index(0, "lbvh")
+            lsi = rjb.LSI(ctx, "lbvh")
+            lsi.Init(4.0)
+            assert lsi.Query(1) == len(want[0])
+            for g, w in zip(sort_xsects(lsi.get_xsects(), 1), want):
+                assert np.array_equal(g, w)
+            ctx.build_index(0, "grid", grid_size=64)  # the grid path reads edge_chain
+            lsi = rjb.LSI(ctx, "grid")
+            lsi.Init(4.0)
+            assert lsi.Query(1) == len(want[0])
+            pip = rjb.PIP(ctx, "lbvh")
+            pip.Query(1)
+            assert np.array_equal(pip.get_closest_eids(), om.pip(1, om.pts[1]))
+        finally:
+            ctx.close()
+
+
 def test_lsi_queue_overflow_is_detected(rjb, loaded):
     ctx, om = loaded("voronoi")
     ctx.build_index(0, "lbvh")
