@@ -399,21 +399,26 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
   RJB_CUDA(cudaMemsetAsync(inc, 0, sizeof(unsigned long long), st));
   k_occ_mark<<<div_up(n, T), T, 0, st>>>(box_s, n, occ, inc);
   k_occ_dilate<<<div_up(occ_words, T), T, 0, st>>>(occ, occ + occ_words);
-  // rank of every bitmap word = number of occupied cells before it
-  uint32_t* pop = b.occ_pop.ensure(occ_words);
-  uint32_t* rank = b.occ_rank.ensure(occ_words + 1);
-  k_occ_popc<<<div_up(occ_words, T), T, 0, st>>>(occ, pop);
-  exclusive_scan_u32(pop, rank, occ_words, b.scan_tmp, st);
   RJB_CUDA(cudaGetLastError());
   uint32_t n_occ = 0;
   unsigned long long n_inc = 0;
+  uint32_t* rank = nullptr;
   RJB_CUDA(cudaMemcpyAsync(&b.root_box, root_d, sizeof(int4), cudaMemcpyDeviceToHost, st));
-  RJB_CUDA(cudaMemcpyAsync(&n_occ, rank + occ_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  RJB_CUDA(cudaMemcpyAsync(&n_inc, inc, sizeof(n_inc), cudaMemcpyDeviceToHost, st));
+  if (want_cells) {
+    // rank of every bitmap word = number of occupied cells before it
+    uint32_t* pop = b.occ_pop.ensure(occ_words);
+    rank = b.occ_rank.ensure(occ_words + 1);
+    k_occ_popc<<<div_up(occ_words, T), T, 0, st>>>(occ, pop);
+    exclusive_scan_u32(pop, rank, occ_words, b.scan_tmp, st);
+    RJB_CUDA(cudaMemcpyAsync(&n_occ, rank + occ_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    RJB_CUDA(cudaMemcpyAsync(&n_inc, inc, sizeof(n_inc), cudaMemcpyDeviceToHost, st));
+  }
   RJB_CUDA(cudaStreamSynchronize(st));
-  // share of occupied cells: it steers the first query (the filter switches itself off
-  // when it does not pay)
-  b.occ_fraction = (double) n_occ / ((double) kOccDim * kOccDim);
+  // share of occupied cells (exact with the directory, else an upper estimate: a leaf
+  // touches ~1.5 cells): it steers the first query, the filter switches itself off when it
+  // does not pay
+  b.occ_fraction = want_cells ? (double) n_occ / ((double) kOccDim * kOccDim)
+                              : std::min(1.0, 1.5 * (double) n / ((double) kOccDim * kOccDim));
   // Cell directory: only for sparse maps (the ones the occupancy filter is used for), and
   // only when the leaves are small against the cells (else the lists explode)
   b.have_cells = false;

@@ -173,7 +173,7 @@ static __device__ __forceinline__ int lowest_slot(unsigned m, int ymin, int lane
 }
 
 template <bool kStats, bool kPark>
-__global__ void __launch_bounds__(kLsiWarps * 32, kPark ? 6 : 8)
+__global__ void __launch_bounds__(kLsiWarps * 32, 8)
 k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __restrict__ order,
           MapView B, BvhView bvh, int query_map_id, uint32_t* __restrict__ out_eid,
           int32_t* __restrict__ out_face, unsigned long long* counters) {
