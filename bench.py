@@ -145,6 +145,7 @@ def ncu_traffic(kernel):
 def cpu_oracle_lsi(R, S, bbox, repeats=1):
     """The multithreaded host exact-predicate oracle on the same workload."""
     from oracle import oracle as O
+    O.set_num_threads(len(os.sched_getaffinity(0)))  # torch.set_num_threads(1) above lowered it
     sc = O.scaling_init(*bbox)
     r, s = O.scale_points(sc, R.xy), O.scale_points(sc, S.xy)
     rp1, _ = O.build_edges(R.row_index)

@@ -605,6 +605,16 @@ void orc_face_ids(const int64_t* xyb, const uint32_t* b_p1,
   }
 }
 
+/* bench.py pins torch to one thread per rank, which also lowers the OpenMP default of
+ * this library when both share one libgomp: the CPU baseline asks for all cores again */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void) n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

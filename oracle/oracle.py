@@ -64,6 +64,11 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n):
+    """OpenMP threads of the oracle's drivers (bench.py: all the cores the process may use)."""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+
+
 def scaling_init(min_x, min_y, max_x, max_y):
     s = Scaling()
     lib().orc_scaling_init(C.byref(s), C.c_double(min_x), C.c_double(min_y),

@@ -298,10 +298,12 @@ __global__ void k_occ_mark(const int4* __restrict__ leaf_box, uint32_t n, uint32
         if (!(occ[bit >> 5] & m)) atomicOr(&occ[bit >> 5], m);  // mostly set already
       }
   }
-  // (leaf, cell) incidences: the size of the cell directory
+  // (leaf, cell) incidences: the size of the cell directory (only when one is wanted)
+  if (n_incidences) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
-  if ((threadIdx.x & 31) == 0 && area) atomicAdd(n_incidences, area);
+    for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
+    if ((threadIdx.x & 31) == 0 && area) atomicAdd(n_incidences, area);
+  }
 }
 
 __global__ void k_occ_popc(const uint32_t* __restrict__ occ, uint32_t* __restrict__ pop) {
@@ -397,7 +399,7 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
   RJB_CUDA(cudaMemsetAsync(occ, 0, occ_words * sizeof(uint32_t), st));
   unsigned long long* inc = b.inc_counter.ensure(1);
   RJB_CUDA(cudaMemsetAsync(inc, 0, sizeof(unsigned long long), st));
-  k_occ_mark<<<div_up(n, T), T, 0, st>>>(box_s, n, occ, inc);
+  k_occ_mark<<<div_up(n, T), T, 0, st>>>(box_s, n, occ, want_cells ? inc : nullptr);
   k_occ_dilate<<<div_up(occ_words, T), T, 0, st>>>(occ, occ + occ_words);
   RJB_CUDA(cudaGetLastError());
   uint32_t n_occ = 0;
