@@ -36,6 +36,14 @@ void hx_intersect_batch(const long long* pts, unsigned long long n, int mode, un
   if (n_deferred) *n_deferred = nd;
 }
 
+// occupancy cell code of a vertex and descriptor of an edge (what k_load_points writes and
+// k_lsi_filter reads)
+unsigned hx_occ_code(long long x, long long y) { return occ_code(x, y); }
+unsigned hx_edge_desc(long long x1, long long y1, long long x2, long long y2) {
+  return edge_desc_of(occ_code(x1, y1), occ_code(x2, y2));
+}
+int hx_occ_cell_of_quant(long long v) { return occ_cell((int) (v >> kQuantShift)); }
+
 // PIP update rule over a list of edges for one point (returns the chosen index or -1)
 int hx_pip_scan(const long long* edges, unsigned long long n, int q, long long px, long long py) {
   PipBest st;

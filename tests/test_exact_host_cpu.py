@@ -104,3 +104,33 @@ def test_gcd_free_point_path_special_cases(hx, oracle):
             h2, x2, y2, _ = run(hx, pts, mode)
             assert np.array_equal(hit, h2)
             assert np.array_equal(x[m], x2[m]) and np.array_equal(y[m], y2[m])
+
+
+def test_edge_descriptor_covers_the_edge_box(hx):
+    """The LSI filter decides from a 4-byte descriptor per edge: min-corner cell + class.
+    Same / Small must describe a box inside the 2 x 2 cells at the min corner (what the
+    dilated bitmap covers); the cell code must agree with the cell of the quantised box
+    coordinate the index is built from (occ_cell(quant(v)))."""
+    rng = np.random.default_rng(3)
+    n = 200000
+    p1 = rng.integers(-2**46, 2**46, size=(n, 2))
+    step = rng.integers(-2**36, 2**36, size=(n, 2)) >> rng.integers(0, 30, size=(n, 1))
+    p2 = np.clip(p1 + step, -2**46, 2**46 - 1)
+    hx.hx_occ_code.restype = C.c_uint32
+    hx.hx_edge_desc.restype = C.c_uint32
+    seen = set()
+    for (x1, y1), (x2, y2) in zip(p1[:20000].tolist(), p2[:20000].tolist()):
+        c1 = hx.hx_occ_code(C.c_longlong(x1), C.c_longlong(y1))
+        c2 = hx.hx_occ_code(C.c_longlong(x2), C.c_longlong(y2))
+        assert (c1 & 4095) == hx.hx_occ_cell_of_quant(C.c_longlong(x1))
+        assert (c1 >> 12) == hx.hx_occ_cell_of_quant(C.c_longlong(y1))
+        d = hx.hx_edge_desc(C.c_longlong(x1), C.c_longlong(y1), C.c_longlong(x2), C.c_longlong(y2))
+        cls, corner = d >> 24, d & 0xFFFFFF
+        cx0, cx1 = sorted((c1 & 4095, c2 & 4095))
+        cy0, cy1 = sorted((c1 >> 12, c2 >> 12))
+        assert corner == (cy0 << 12 | cx0)
+        ex, ey = cx1 - cx0, cy1 - cy0
+        want = 0 if (ex, ey) == (0, 0) else 1 if ex <= 1 and ey <= 1 else 2
+        assert cls == want
+        seen.add(cls)
+    assert seen == {0, 1, 2}
