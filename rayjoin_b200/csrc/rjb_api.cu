@@ -116,6 +116,7 @@ struct rjb_ctx {
   // timing of the kernels of the last query call
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_ms[4] = {0, 0, 0, 0};
+  int timing_pending = 0;  // 1: ev[0..1], 2: ev[0..2] recorded by the last query, not read yet
 };
 
 namespace rjb {
@@ -453,8 +454,7 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
     RJB_CUDA(cudaStreamSynchronize(c->stream));
   }
   memcpy(c->last_stats, h, sizeof(h));
-  RJB_CUDA(cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]));
-  RJB_CUDA(cudaEventElapsedTime(&c->last_ms[1], c->ev[1], c->ev[2]));
+  c->timing_pending = 2;  // event times are fetched when rjb_last_kernel_ms asks for them
   uint64_t n = (uint32_t) h[0];
   if (n_candidates) *n_candidates = h[1];
   if (n > cap) {
@@ -505,8 +505,7 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
   RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   RJB_CUDA(cudaStreamSynchronize(c->stream));
   memcpy(c->last_stats, h, sizeof(h));
-  RJB_CUDA(cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]));
-  c->last_ms[1] = 0;
+  c->timing_pending = 1;
   if (n_candidates) *n_candidates = h[1];
 }
 
@@ -826,6 +825,13 @@ int rjb_pip_host_scaled(rjb_ctx* c, int query_map_id, int mode, const int64_t* h
 int rjb_last_kernel_ms(const rjb_ctx* c, double out[2]) {
   return guarded([&] {
     RJB_REQUIRE(c && out, "NULL argument");
+    rjb_ctx* m = const_cast<rjb_ctx*>(c);
+    if (m->timing_pending) {  // the events have completed: every query ends with a stream wait
+      RJB_CUDA(cudaEventElapsedTime(&m->last_ms[0], m->ev[0], m->ev[1]));
+      m->last_ms[1] = 0;
+      if (m->timing_pending == 2) RJB_CUDA(cudaEventElapsedTime(&m->last_ms[1], m->ev[1], m->ev[2]));
+      m->timing_pending = 0;
+    }
     out[0] = c->last_ms[0];
     out[1] = c->last_ms[1];
   });
