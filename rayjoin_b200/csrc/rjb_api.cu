@@ -24,6 +24,10 @@ struct DeviceMap {
   DBuf<double2> raw;
   DBuf<longlong2> pts;
   DBuf<uint32_t> edge_chain, point_chain, edge_desc, row_index, last_bits;
+  // Morton order of the map's edges as query start points (maps of short chains): computed
+  // by the first query that wants it, reused until the map is replaced
+  DBuf<uint32_t> edge_order;
+  bool edge_order_valid = false;
   DBuf<int32_t> left, right;
   std::vector<int32_t> h_left, h_right;
   // host copy of the source graph kept for the overlay writer (points as
@@ -244,13 +248,14 @@ static void scaling_init(rjb_scaling& s, double bminx, double bminy, double bmax
 
 static void check_map_id(int id) { RJB_REQUIRE(id == 0 || id == 1, "map id must be 0 or 1"); }
 
-static const uint32_t* query_order_edges(rjb_ctx* c, const MapView& Q) {
+static const uint32_t* query_order_edges(rjb_ctx* c, DeviceMap& Qm, const MapView& Q) {
   // Consecutive edges of a long chain are spatial neighbours already; maps made of
   // short chains in arbitrary order (polygon soups: ~7 edges per chain) are not, and a
   // warp would walk one cluster after the other.  auto = sort below 32 edges per chain.
   bool want = c->sort_queries > 0 ||
               (c->sort_queries < 0 && Q.n_chains > 0 && Q.n_edges / Q.n_chains < 32);
   if (!want || Q.n_edges == 0) return nullptr;
+  if (Qm.edge_order_valid) return Qm.edge_order.p;
   uint32_t n = Q.n_edges;
   uint64_t* ka = c->ord_keys_a.ensure(n);
   uint64_t* kb = c->ord_keys_b.ensure(n);
@@ -258,7 +263,12 @@ static const uint32_t* query_order_edges(rjb_ctx* c, const MapView& Q) {
   uint32_t* vb = c->ord_vals_b.ensure(n);
   k_query_keys_edges<<<div_up(n, 256), 256, 0, c->stream>>>(Q, c->sc.internal_min, ka, va);
   sort_pairs_u64_u32(ka, kb, va, vb, n, 40, 64, c->ord_sort, c->stream);
-  return vb;
+  // the order belongs to the map, not to the query: keep it (the scratch buffers are
+  // shared with the point ordering of PIP)
+  uint32_t* keep = Qm.edge_order.ensure(n);
+  RJB_CUDA(cudaMemcpyAsync(keep, vb, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+  Qm.edge_order_valid = true;
+  return keep;
 }
 
 static const uint32_t* query_order_points(rjb_ctx* c, const longlong2* pts, uint32_t n) {
@@ -346,7 +356,7 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
     // The candidate buffer is internal: it grows and the query is repeated if it
     // was too small (the needed size is known exactly after the first attempt).
     if (c->cand_cap < (size_t) cap + 65536) c->cand_cap = 2 * (size_t) cap + 65536;
-    const uint32_t* order = query_order_edges(c, Q);
+    const uint32_t* order = query_order_edges(c, Qm, Q);
     // occupancy pre-filter: worthwhile when the base map covers a small part of the
     // plane; it replaces the Morton order (survivors come out in map order)
     bool filter = !order && (c->use_filter == 1 || (c->use_filter < 0 && Bm.bvh.occ_fraction < 0.25 &&
@@ -569,7 +579,12 @@ int rjb_set_bounding_box(rjb_ctx* c, double min_x, double min_y, double max_x, d
     scaling_init(c->sc, min_x, min_y, max_x, max_y);
     c->have_scaling = true;
     // scaled coordinates of loaded maps are stale now
-    for (auto& m : c->maps) { m.loaded = false; m.bvh.built = false; m.grid.built = false; }
+    for (auto& m : c->maps) {
+      m.loaded = false;
+      m.edge_order_valid = false;
+      m.bvh.built = false;
+      m.grid.built = false;
+    }
   });
 }
 
@@ -622,6 +637,7 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
     RJB_CUDA(cudaSetDevice(c->device));
     DeviceMap& m = c->maps[map_id];
     m.loaded = false;
+    m.edge_order_valid = false;
     m.bvh.built = false;
     m.grid.built = false;
     c->filter_useless = false;  // new data: let the occupancy filter prove itself again

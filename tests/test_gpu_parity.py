@@ -4,6 +4,11 @@ import numpy as np
 import pytest
 
 from helpers import DATASETS, OracleMaps, dataset, sort_xsects
+from rayjoin_b200 import synth
+
+
+def synth_soup(n, seed):
+    return synth.polygon_soup(n, "gaussian", seed=seed, polysize=0.2)
 
 pytestmark = pytest.mark.gpu
 
@@ -103,6 +108,34 @@ def test_lsi_cell_directory_path(rjb, loaded, name, q):
         ctx.set_option("lsi_cells", 0)
         ctx.set_option("lsi_filter", -1)
     assert counts[0] == counts[1]
+
+
+def test_cached_query_order_follows_the_map(rjb, oracle):
+    """The Morton order of a short-chain query map is computed once and kept with the map: a
+    second query reuses it, replacing the map drops it."""
+    R = synth_soup(3000, 1)
+    S1, S2 = synth_soup(2500, 2), synth_soup(2600, 3)
+    ctx = rjb.Context(device=0)
+    try:
+        bbox = synth.union_bbox(R, S1, S2)
+        ctx.set_bounding_box(*bbox)
+        ctx.set_option("sort_queries", 1)
+        ctx.set_map(0, R)
+        ctx.build_index(0, "lbvh")
+        lsi = rjb.LSI(ctx, "lbvh")
+        lsi.Init(4.0)
+        for S in (S1, S2, S1):
+            ctx.set_map(1, S)
+            sc = oracle.scaling_init(*bbox)
+            pts = [oracle.scale_points(sc, g.xy) for g in (R, S)]
+            p1 = [oracle.build_edges(g.row_index)[0] for g in (R, S)]
+            want = oracle.lsi_grid(pts[1], p1[1], pts[0], p1[0], sc)
+            for _ in range(2):
+                assert lsi.Query(1) == len(want[0])
+                for g, w in zip(sort_xsects(lsi.get_xsects(), 1), want):
+                    assert np.array_equal(g, w)
+    finally:
+        ctx.close()
 
 
 def test_chunked_upload_matches_single_chunk(rjb, oracle):
