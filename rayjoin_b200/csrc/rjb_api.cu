@@ -707,7 +707,7 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
       RJB_CUDA(cudaEventRecord(c->chunk_ev[kLoadChunksMax], c->aux));
       RJB_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[kLoadChunksMax], 0));
     }
-    RJB_CUDA(cudaStreamSynchronize(st));
+    wait_stream(st);
     m.loaded = true;
   });
 }
@@ -961,7 +961,7 @@ int rjb_copy_to_host(rjb_ctx* c, const void* d_src, void* h_dst, uint64_t bytes)
     if (bytes == 0) return;
     RJB_CUDA(cudaSetDevice(c->device));
     RJB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
-    RJB_CUDA(cudaStreamSynchronize(c->stream));
+    wait_stream(c->stream);
   });
 }
 
