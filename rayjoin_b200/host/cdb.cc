@@ -33,18 +33,39 @@
 
 #include <charconv>
 #include <limits>
+#include <memory>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "rjb200.h"
 
 namespace {
 
+// vector<double> whose resize() does not touch the memory: the pages of a 150 MB vertex
+// array are first touched by the threads that fill it, not zero-filled by one thread first
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = NoInitAlloc<U>;
+  };
+  template <class U>
+  void construct(U* p) noexcept {
+    ::new (static_cast<void*>(p)) U;  // default-init: nothing for double
+  }
+  template <class U, class... A>
+  void construct(U* p, A&&... a) {
+    ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+  }
+};
+using DVec = std::vector<double, NoInitAlloc<double>>;
+
 struct GraphOwner {
   std::vector<int64_t> chain_id, first_point, last_point, left, right;
   std::vector<uint32_t> row_index;
-  std::vector<double> xy;
+  DVec xy;
   double min_x = std::numeric_limits<double>::max();
   double min_y = std::numeric_limits<double>::max();
   double max_x = -std::numeric_limits<double>::max();
@@ -79,7 +100,7 @@ int fail(const std::string& msg) {
 
 // ---- parallel fast path -----------------------------------------------------
 struct Piece {
-  std::vector<double> xy;
+  DVec xy;
   std::vector<int64_t> hdr;       // 6 per header
   std::vector<uint64_t> hdr_pos;  // vertices of this piece seen before the header
   double min_x = std::numeric_limits<double>::max(), min_y = min_x;
@@ -243,6 +264,19 @@ int read_text(const char* path, GraphOwner* o) {
     return fail(std::string("Cannot stat file ") + path);
   }
   size_t len = (size_t) sb.st_size;
+  // Fast path straight from the page cache: no 250 MB buffer to allocate, zero and fill.
+  if (len > 0 && getenv("RJB_CDB_SEQUENTIAL") == nullptr) {
+    void* m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    if (m != MAP_FAILED) {
+      const bool ok = read_text_parallel((const char*) m, len, o);
+      munmap(m, len);
+      if (ok) {
+        close(fd);
+        return RJB_OK;
+      }
+      *o = GraphOwner();  // anything unusual: the sequential parser decides and reports
+    }
+  }
   std::vector<char> buf(len + 1);
   size_t got = 0;
   while (got < len) {
@@ -253,11 +287,6 @@ int read_text(const char* path, GraphOwner* o) {
   close(fd);
   if (got != len) return fail(std::string("Short read on ") + path);
   buf[len] = '\0';
-
-  if (getenv("RJB_CDB_SEQUENTIAL") == nullptr) {
-    if (read_text_parallel(buf.data(), len, o)) return RJB_OK;
-    *o = GraphOwner();  // anything unusual: the sequential parser decides and reports
-  }
 
   int64_t np = 0;
   bool have_last = false;
