@@ -133,11 +133,11 @@ static __device__ __forceinline__ void lsi_subtree(const BvhView& bvh, int root,
   }
 }
 
-// One warp = 32 query edges.  The warp first resolves the top 15 levels of the
-// tree in three steps of a 32-ary top tree (one LANE PER CHILD SLOT tests the
-// warp's union box; loads are coalesced and the 21 KB of the first two levels
-// stay L1-resident), then walks the remaining binary subtrees with per-lane
-// boxes.  Output: candidate pairs whose exact integer boxes overlap.
+// One warp = 32 query edges.  The warp first resolves the top 15 (20 for trees of
+// >= 2^18 leaves) levels of the tree in three (four) steps of a 32-ary top tree (one
+// LANE PER CHILD SLOT tests the warp's union box; loads are coalesced and the 21 KB
+// of the first two levels stay L1-resident), then walks the remaining binary subtrees
+// with per-lane boxes.  Output: (query, leaf) pairs whose quantised boxes overlap.
 //
 // Query slots are POINT indices: lane p owns the edge (pts[p], pts[p+1]) unless p
 // is the last point of a chain (one bit per point), so a tile is two coalesced
@@ -214,7 +214,8 @@ static __device__ __noinline__ bool occ_rect(const MapView& Q, const uint32_t* _
 }
 
 // A CTA filters 4096 consecutive points and appends its survivors as ONE contiguous,
-// map-ordered run (block scan of the per-thread counts, one atomic per CTA): the 32
+// map-ordered run (positions from the ballots, scan over the 8 warp totals, one atomic per
+// CTA): the 32
 // survivors a traversal warp picks up are then neighbours on the map.  (With one
 // atomic per warp the runs of concurrently running warps from all over the map
 // interleave, and every traversal warp has to follow up to 32 separate clusters.)
