@@ -44,6 +44,21 @@ unsigned hx_edge_desc(long long x1, long long y1, long long x2, long long y2) {
 }
 int hx_occ_cell_of_quant(long long v) { return occ_cell((int) (v >> kQuantShift)); }
 
+// PIP: the update rule scanned over all edges in eid order for a batch of points
+// (edges: nb x 4 int64 {x1, y1, x2, y2}; out: chosen edge index or 0xFFFFFFFF)
+void hx_pip_batch(const long long* edges, unsigned long long nb, const long long* pts,
+                  unsigned long long n, int q, unsigned* out) {
+  for (unsigned long long i = 0; i < n; i++) {
+    PipBest st;
+    pip_init(st);
+    for (unsigned long long j = 0; j < nb; j++) {
+      const Seg e = {edges[4 * j], edges[4 * j + 1], edges[4 * j + 2], edges[4 * j + 3]};
+      pip_update(st, q, pts[2 * i], pts[2 * i + 1], e, (uint32_t) j);
+    }
+    out[i] = st.eid;
+  }
+}
+
 // PIP update rule over a list of edges for one point (returns the chosen index or -1)
 int hx_pip_scan(const long long* edges, unsigned long long n, int q, long long px, long long py) {
   PipBest st;

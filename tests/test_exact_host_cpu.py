@@ -134,3 +134,33 @@ def test_edge_descriptor_covers_the_edge_box(hx):
         assert cls == want
         seen.add(cls)
     assert seen == {0, 1, 2}
+
+
+@pytest.mark.parametrize("q", [0, 1])
+def test_pip_update_rule_matches_oracle(hx, oracle, q):
+    """The kernels' pip_update (closest edge above, src/algo/pip.h:27-96) scanned in eid order
+    against the oracle's brute force: lattice maps (points with x equal to a vertex x,
+    horizontal / vertical / coincident edges) and a Voronoi map with random points."""
+    import sys
+    sys.path.insert(0, HERE)
+    from helpers import dataset, OracleMaps
+    for name in ("lattice", "voronoi", "shared"):
+        R, S = dataset(name)
+        om = OracleMaps(oracle, [R, S])
+        b = 1 - q
+        xyb, p1 = om.pts[b], om.p1[b]
+        edges = np.concatenate([xyb[p1], xyb[p1 + 1]], axis=1).astype(np.int64)
+        rng = np.random.default_rng(17)
+        pts = om.pts[q][:1500]
+        lo, hi = xyb.min(0), xyb.max(0)
+        rnd = np.column_stack([rng.integers(lo[0], hi[0] + 1, 800), rng.integers(lo[1], hi[1] + 1, 800)])
+        pts = np.ascontiguousarray(np.concatenate([pts, rnd]), np.int64)
+        if len(edges) > 4000:  # keep the brute-force scan short
+            edges, p1 = edges[:4000], p1[:4000]
+        want = oracle.pip_brute(xyb, p1, pts, q)
+        got = np.zeros(len(pts), np.uint32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        edges = np.ascontiguousarray(edges)
+        hx.hx_pip_batch(p(edges), C.c_uint64(len(edges)), p(pts), C.c_uint64(len(pts)), C.c_int(q), p(got))
+        assert np.array_equal(got, want), name
+        assert (got != 0xFFFFFFFF).any()
