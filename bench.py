@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """Headline benchmark: LSI join of County x Zipcode-scale synthetic maps
-(BASELINE.json configs[1]: ~4M base edges R vs ~9M query edges S) on B200.
+(BASELINE.json configs[1]: ~4M base edges R vs ~9M query edges S) on B200, with the
+metric's other quantities -- PIP (configs[2]), polygon overlay, index build -- as extra
+keys of the same JSON line.
 
   python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun)
-  python bench.py --impl reference ...                   reference arm (see below)
+  python bench.py --impl reference ...                   reference arm (see run_reference)
 
-One "step" = one LSI Query(): every S edge against the LBVH of R, including
-the exact intersection points (the reference's "Query" phase,
-src/run_query.cu:297-303).  `value` times it with S resident in HBM; `e2e`
-times the same query through the C ABI from pinned HOST buffers: H2D of the S
-batch + scaling + query + D2H of the rjb_xsect results, every step.
+One "step" = one LSI Query(): every S edge against the LBVH of R, including the exact
+intersection points (the reference's "Query" phase, src/run_query.cu:297-303).  `value`
+times it on the device (CUDA events around the enqueued query, rjb_lsi_launch /
+rjb_lsi_wait) with S resident in HBM; `e2e` times the same query through the synchronous
+C ABI from pinned HOST buffers: H2D of the S batch + scaling + query + D2H of the
+rjb_xsect results, every step.
 
-Multi-GPU: R and its LBVH are replicated, S is sharded (rank r owns its own
-9M-edge shard, seed 2 + r: weak scaling); NCCL carries only the per-step count
-all-gather.  Prints ONE JSON line on rank 0.
+Multi-GPU: R and its LBVH are replicated, S is sharded.  Default = weak scaling (rank r
+owns its own 9M-edge S, seed 2 + r); the line also carries a strong-scaling leg (ONE
+9M-edge S cut by whole chains over the ranks, rayjoin_b200.dist.shard_graph).  NCCL
+carries only the per-step count all-gather, issued on a side stream while the next
+step runs.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import gc
@@ -30,8 +35,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = "synthetic County x Zipcode-scale LSI: |R|~4.0M edges (3100 faces), |S|~9.0M edges (33000 faces) per GPU, US bbox"
+PIP_WORKLOAD = "PIP: 100M uniform random points vs BlockGroup-scale synthetic map (220k faces, ~28.0M edges), US bbox"
+OVERLAY_WORKLOAD = "polygon overlay (polyover_exec protocol) of the County x Zipcode-scale pair, xsect_factor 0.5"
 R_FACES, R_EDGES, S_FACES, S_EDGES = 3100, 4_000_000, 33_000, 9_000_000
+PIP_FACES, PIP_EDGES, PIP_POINTS = 220_000, 28_000_000, 100_000_000
 XSECT_FACTOR = 0.1  # expr/env.sh:16 of the reference
+OVERLAY_XSECT_FACTOR = 0.5
 CACHE = os.environ.get("RJB_CACHE", "/tmp/rjb200_cache")
 
 
@@ -39,21 +48,27 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def get_map(kind, seed, scale=1.0):
-    """Seeded synthetic map, cached as .npz for the second arm on the same box."""
-    from rayjoin_b200 import synth
+def make_config(args, world):
+    """The workload description -- identical keys and values on both arms."""
+    legs = args.legs if args.legs else ("lsi,pip,overlay" if world == 1 else "lsi")
+    cfg = {"workload": WORKLOAD, "xsect_factor": XSECT_FACTOR, "scaling": "weak", "legs": legs}
+    if "pip" in legs:
+        cfg["pip_workload"] = PIP_WORKLOAD
+    if "overlay" in legs:
+        cfg["overlay_workload"] = OVERLAY_WORKLOAD
+    return cfg
+
+
+def _cached_map(path, make):
     from rayjoin_b200.capi import PlanarGraph
-    faces, edges = (R_FACES, R_EDGES) if kind == "R" else (S_FACES, S_EDGES)
-    faces, edges = max(8, int(faces * scale)), max(64, int(edges * scale))
     os.makedirs(CACHE, exist_ok=True)
-    path = os.path.join(CACHE, "%s_%d_%d_%d.npz" % (kind, faces, edges, seed))
     if os.path.exists(path):
         try:
             z = np.load(path)
             return PlanarGraph(z["xy"], z["row_index"], z["left"], z["right"])
         except Exception:
             pass
-    g = synth.voronoi_map(faces, edges, synth.US_BBOX, seed=seed)
+    g = make()
     try:
         tmp = path + ".%d.tmp.npz" % os.getpid()
         np.savez(tmp, xy=g.xy, row_index=g.row_index, left=g.left, right=g.right)
@@ -61,6 +76,31 @@ def get_map(kind, seed, scale=1.0):
     except Exception:
         pass
     return g
+
+
+def get_map(kind, seed, scale=1.0):
+    """Seeded synthetic map, cached as .npz for the second arm on the same box."""
+    from rayjoin_b200 import synth
+    faces, edges = (R_FACES, R_EDGES) if kind == "R" else (S_FACES, S_EDGES)
+    faces, edges = max(8, int(faces * scale)), max(64, int(edges * scale))
+    path = os.path.join(CACHE, "%s_%d_%d_%d.npz" % (kind, faces, edges, seed))
+    return _cached_map(path, lambda: synth.voronoi_map(faces, edges, synth.US_BBOX, seed=seed))
+
+
+def get_pip_map(scale=1.0):
+    from rayjoin_b200 import synth
+    faces, edges = max(8, int(PIP_FACES * scale)), max(64, int(PIP_EDGES * scale))
+    path = os.path.join(CACHE, "pipmap_%d_%d.npz" % (faces, edges))
+    g = _cached_map(path, lambda: synth.voronoi_map(faces, edges, synth.US_BBOX, seed=1))
+    g.bbox = synth.US_BBOX
+    return g
+
+
+def pip_points_host(n, seed=1):
+    """Uniform random query points inside the scaled US box (int64 internal coordinates)."""
+    rng = np.random.default_rng(seed)
+    lim = int(2**46 * 0.97)
+    return np.column_stack([rng.integers(-lim, lim, n), rng.integers(-lim, lim, n)]).astype(np.int64)
 
 
 class ClockSampler(threading.Thread):
@@ -142,6 +182,21 @@ def ncu_traffic(kernel):
         return None
 
 
+def pin_to_cores(local_rank, world):
+    """Each rank gets its own slice of the host cores: the completion wait polls the
+    stream, and eight unpinned pollers next to each other showed up as single steps of
+    1-2 ms (round 1, N = 8)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        per = len(cpus) // max(1, local_world)
+        if local_world > 1 and per >= 1:
+            os.sched_setaffinity(0, cpus[local_rank * per:(local_rank + 1) * per])
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def cpu_oracle_lsi(R, S, bbox, repeats=1):
     """The multithreaded host exact-predicate oracle on the same workload."""
     from oracle import oracle as O
@@ -159,33 +214,41 @@ def cpu_oracle_lsi(R, S, bbox, repeats=1):
     return best, len(res[0]), res[4], O.num_threads(), res
 
 
+# ---------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------
 def run_reference(args, rank, world, json_out):
-    """Reference arm.  RayJoin has no CPU implementation of this path; its only
-    code that can run on a B200 box are the -mode=lbvh / -mode=grid CUDA
-    backends, built unmodified from /root/reference with stub OptiX/glog headers
-    into oracle/_ref/ref_exec (oracle/Makefile).  When that binary is present it
-    is timed (GPU, the reference's own 'Query' phase timer); otherwise the host
-    oracle port is timed on all host cores."""
+    """Reference arm.  RayJoin has no CPU implementation of this path; its only code that
+    can run on a B200 box are the -mode=lbvh / -mode=grid CUDA backends, built unmodified
+    from /root/reference with stub OptiX/glog headers into oracle/_ref/ref_exec
+    (oracle/Makefile).  When that binary is present it is timed (GPU, the reference's own
+    phase timers: Query = wall clock over `repeat` iterations); otherwise the host oracle
+    port is timed on all host cores.  At N = 1 the line also carries the reference's PIP
+    (bounded samples: its lbvh PIP visits every leaf above the point) and overlay phases."""
     if rank != 0:
         return
     from rayjoin_b200 import synth
+    from rayjoin_b200.capi import PlanarGraph
+    cfg = make_config(args, world)
     R, S = get_map("R", 1, args.scale), get_map("S", 2, args.scale)
     bbox = synth.union_bbox(R, S)
     line = {"impl": "reference", "metric": "LSI join throughput", "unit": "query_edges/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/int128",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "xsect_factor": XSECT_FACTOR}}
+            "data": "synthetic", "config": cfg}
     ref_exec = os.path.join(ROOT, "oracle", "_ref", "ref_exec")
     used = None
-    if os.path.exists(ref_exec) and args.ref_mode != "cpu":
+    have_ref = os.path.exists(ref_exec) and args.ref_mode != "cpu"
+    if have_ref:
         try:
             from tools import ref_runner
             out = ref_runner.run_lsi(ref_exec, R, S, mode=args.ref_mode, warmup=args.warmup,
                                      repeat=args.steps, xsect_factor=max(XSECT_FACTOR, 0.1),
                                      workdir=CACHE)
             ms = out["query_ms"]
-            line.update({"value": S.n_edges / (ms / 1e3), "ms_per_step": ms,
+            line.update({"value": S.n_edges / (ms / 1e3), "ms_per_step": ms, "join_ms": ms,
                          "result_pairs": out.get("intersections"),
+                         "index_build_ms": out["phases"].get("build_index_ms"),
                          "reference_phases_ms": out.get("phases"),
                          "cpu_baseline": {"value": S.n_edges / (ms / 1e3), "unit": "query_edges/s",
                                           "cores": 0, "kind": "reference",
@@ -198,7 +261,7 @@ def run_reference(args, rank, world, json_out):
             log("reference binary failed (%s); timing the oracle port instead" % e)
     if used is None:
         dt, n, cand, cores, _ = cpu_oracle_lsi(R, S, bbox, repeats=max(1, min(args.steps, 3)))
-        line.update({"value": S.n_edges / dt, "ms_per_step": dt * 1e3, "result_pairs": n,
+        line.update({"value": S.n_edges / dt, "ms_per_step": dt * 1e3, "join_ms": dt * 1e3, "result_pairs": n,
                      "candidate_pairs": cand,
                      "cpu_baseline": {"value": S.n_edges / dt, "unit": "query_edges/s", "cores": cores,
                                       "kind": "port",
@@ -207,7 +270,155 @@ def run_reference(args, rank, world, json_out):
                                                 % (R.n_edges, S.n_edges, max(1, min(args.steps, 3)))}})
     line["e2e"] = {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
                    "d2h_bytes_per_step": 0}
+    if used == "ref_exec":
+        from tools import ref_runner
+        if "lsi" in cfg["legs"] and world == 1:
+            try:  # the reference's other backend on the same input
+                other = "grid" if args.ref_mode == "lbvh" else "lbvh"
+                out = ref_runner.run_lsi(ref_exec, R, S, mode=other, warmup=2, repeat=3,
+                                         xsect_factor=max(XSECT_FACTOR, 0.1), grid_size=2048, workdir=CACHE)
+                line["lsi_%s" % other] = {"query_ms": out["query_ms"], "build_index_ms": out["phases"]["build_index_ms"],
+                                          "result_pairs": out.get("intersections"), "grid_size": 2048}
+            except Exception as e:
+                line["lsi_other_error"] = str(e)[:200]
+        if "pip" in cfg["legs"]:
+            try:
+                M = get_pip_map(args.scale)
+                pip = {"workload": PIP_WORKLOAD, "edges": M.n_edges}
+                x0, y0, x1, y1 = synth.US_BBOX
+                for mode, n in (("grid", int(10_000_000 * args.scale)), ("lbvh", int(1_000_000 * args.scale))):
+                    n = max(2, n // 2 * 2)
+                    rng = np.random.default_rng(1)
+                    xy = np.column_stack([rng.uniform(x0, x1, n), rng.uniform(y0, y1, n)])
+                    Q = PlanarGraph(xy, np.arange(0, n + 1, 2, dtype=np.uint32), np.ones(n // 2, np.int64),
+                                    np.full(n // 2, 2, np.int64), bbox=synth.US_BBOX)
+                    out = ref_runner.run_pip(ref_exec, M, Q, mode=mode, warmup=1, repeat=2, grid_size=4096,
+                                             workdir=CACHE)
+                    pip[mode] = {"points": n, "query_ms": out["query_ms"],
+                                 "points_per_s": n / (out["query_ms"] / 1e3),
+                                 "build_index_ms": out["phases"]["build_index_ms"],
+                                 "sample": "bounded: %d of the 100M points (vertices of a 2-point-chain map)" % n}
+                line["pip"] = pip
+            except Exception as e:
+                line["pip"] = {"error": str(e)[:300]}
+        if "overlay" in cfg["legs"]:
+            ov = {"workload": OVERLAY_WORKLOAD}
+            for mode in ("lbvh", "grid"):
+                try:
+                    out = ref_runner.run_overlay(ref_exec, R, S, mode=mode, xsect_factor=OVERLAY_XSECT_FACTOR,
+                                                 grid_size=2048, workdir=CACHE)
+                    ph = out["phases"]
+                    ov[mode] = {"phase_ms": ph, "intersections": out["intersections"],
+                                "device_total_ms": sum(ph[k] for k in ("build_index_ms", "lsi_ms", "pip0_ms",
+                                                                       "pip1_ms", "polygons_ms"))}
+                except Exception as e:
+                    ov[mode] = {"error": str(e)[:300]}
+            line["overlay"] = ov
     print(json.dumps(line), file=json_out, flush=True)
+
+
+# ---------------------------------------------------------------------------------
+# extra legs of the repo arm (N = 1)
+# ---------------------------------------------------------------------------------
+def pip_leg(args, RJ, torch, dev, stream, peak):
+    """BASELINE.json configs[2]: 100M uniform random points against the 28M-edge map."""
+    from oracle import oracle as O
+    M = get_pip_map(args.scale)
+    n = max(1024, int(PIP_POINTS * args.scale))
+    ctx = RJ.Context(device=dev.index, stream=stream.cuda_stream)
+    out = {"workload": PIP_WORKLOAD, "points": n, "edges": M.n_edges, "chains": M.n_chains}
+    try:
+        ctx.set_option("keep_host_graph", 0)
+        ctx.set_bounding_box(*M.bbox)
+        ctx.set_map(0, M)
+        h_pts = torch.from_numpy(pip_points_host(n)).pin_memory()
+        with torch.cuda.stream(stream):
+            d_pts = h_pts.to(dev, non_blocking=True)
+        stream.synchronize()
+        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for mode in args.pip_modes.split(","):
+            res = {}
+            build = [ctx.build_index(0, mode, args.pip_grid_size) for _ in range(3)]
+            res["index_build_ms"] = float(np.min(build))
+            idx = ctx.index_info(0, mode)
+            res["index_bytes"] = int(idx["bytes"])
+            ctx.set_option("sort_queries", 1)
+            steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            kms = []
+            de = df = None
+            for i in range(warm + steps):
+                with torch.cuda.stream(stream):
+                    flush_buf.zero_()
+                    if i >= warm:
+                        ev[i - warm][0].record(stream)
+                    de, df, cand = ctx.pip_device(1, mode, d_pts.data_ptr(), n)
+                    if i >= warm:
+                        ev[i - warm][1].record(stream)
+                if i >= warm:
+                    kms.append(ctx.last_stage_ms()[0][:2])
+            stream.synchronize()
+            ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+            kms = np.mean(np.asarray(kms), axis=0)
+            res.update({"query_ms": ms, "points_per_s": n / (ms / 1e3), "order_ms": float(kms[0]),
+                        "kernel_ms": float(kms[1]), "candidates": int(cand), "gpu_launches": ctx.last_launches()})
+            # compulsory traffic of the query with this layout: 16 B per point in, eid + face id out,
+            # the index and the base vertices once (SURVEY 8(d) pip_bvh_traverse / pip_grid)
+            alg = 16 * n + 8 * n + idx["bytes"] + 16 * M.n_points
+            res["roofline"] = {"bound": "hbm", "algorithmic_bytes": int(alg), "achieved": alg / (ms / 1e3) / 1e9,
+                               "peak": peak, "unit": "GB/s", "frac": alg / (ms / 1e3) / 1e9 / peak,
+                               "traffic": ncu_traffic("k_pip_%s" % mode)}
+            # every point against the oracle (host grid filter + the restated update rule)
+            if not args.no_check:
+                ncheck = n if args.pip_check < 0 else min(n, args.pip_check)
+                eids = ctx.copy_to_host(de, np.empty(n, np.uint32))[:ncheck]
+                sc = O.scaling_init(*M.bbox)
+                O.set_num_threads(len(os.sched_getaffinity(0)))
+                t = time.perf_counter()
+                want = O.pip_grid(O.scale_points(sc, M.xy), O.build_edges(M.row_index)[0], sc,
+                                  h_pts.numpy()[:ncheck], 1)
+                res["oracle_s"] = time.perf_counter() - t
+                bad = int((eids != want).sum())
+                res["parity_vs_oracle"] = ("bit-exact (%d points checked)" % ncheck) if bad == 0 else \
+                    "MISMATCH (%d of %d)" % (bad, ncheck)
+                res["hit_fraction"] = float((eids != 0xFFFFFFFF).mean())
+            out[mode] = res
+        # end to end: scaled int64 points from pinned host memory, eids + face ids back
+        mode = args.pip_modes.split(",")[0]
+        h_e = torch.empty(n, dtype=torch.int32).pin_memory()
+        h_f = torch.empty(n, dtype=torch.int32).pin_memory()
+        ctx.build_index(0, mode, args.pip_grid_size)
+        ts = []
+        for _ in range(3):
+            t = time.perf_counter()
+            ctx.pip_host_scaled(1, mode, h_pts.data_ptr(), n, h_e.data_ptr(), h_f.data_ptr())
+            ts.append(time.perf_counter() - t)
+        out["e2e"] = {"mode": mode, "ms": float(np.min(ts[1:])) * 1e3,
+                      "points_per_s": n / float(np.min(ts[1:])), "h2d_bytes": 16 * n, "d2h_bytes": 8 * n}
+        out["best_mode"] = min((m for m in args.pip_modes.split(",")), key=lambda m: out[m]["query_ms"])
+        out["query_ms"] = out[out["best_mode"]]["query_ms"]
+        out["points_per_s"] = out[out["best_mode"]]["points_per_s"]
+    finally:
+        ctx.close()
+    return out
+
+
+def overlay_leg(args, RJ, R, S, dev, stream):
+    ctx = RJ.Context([R, S], device=dev.index, stream=stream.cuda_stream)
+    out = {"workload": OVERLAY_WORKLOAD}
+    try:
+        for mode in ("lbvh", "grid"):
+            ov = RJ.MapOverlay(ctx, mode, grid_size=args.grid_size, xsect_factor=OVERLAY_XSECT_FACTOR)
+            best = None
+            for _ in range(3):
+                ms = ov.Run()
+                if best is None or ms["total"] < best["total"]:
+                    best = dict(ms)
+            out[mode] = {"phase_ms": best, "device_total_ms": best["total"],
+                         "intersections": int(len(ov.get_xsect_edges(0)))}
+    finally:
+        ctx.close()
+    return out
 
 
 def main():
@@ -223,9 +434,15 @@ def main():
     ap.add_argument("--sort-queries", type=int, default=-1)
     ap.add_argument("--filter", type=int, default=-1, help="occupancy pre-filter: -1 auto, 0 off, 1 on")
     ap.add_argument("--cells", type=int, default=0, help="experimental cell-directory candidate path (option lsi_cells)")
+    ap.add_argument("--stage-timing", type=int, default=1, help="CUDA event after every kernel of the query")
+    ap.add_argument("--legs", default="", help="lsi,pip,overlay (default: all at N = 1, lsi at N > 1)")
+    ap.add_argument("--pip-modes", default="lbvh,grid")
+    ap.add_argument("--pip-grid-size", type=int, default=4096)
+    ap.add_argument("--pip-check", type=int, default=10_000_000, help="points checked against the oracle (-1: all)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg at N > 1")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
 
@@ -241,9 +458,11 @@ def main():
         run_reference(args, rank, world, json_out)
         return
 
+    n_cores = pin_to_cores(local_rank, world)
     import torch
     import torch.distributed as dist
     import rayjoin_b200 as RJ
+    from rayjoin_b200 import dist as rdist
     from rayjoin_b200 import synth
 
     RJ.load_library()  # fail loudly when the CUDA extension is missing
@@ -253,194 +472,237 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    cfg = make_config(args, world)
+    legs = cfg["legs"].split(",")
 
     t0 = time.time()
     R = get_map("R", 1, args.scale)
     S = get_map("S", 2 + rank, args.scale)
     bbox = synth.US_BBOX  # same scaling on every rank
-    log("[rank %d] maps ready in %.1fs: R %d edges / %d chains, S %d edges / %d chains"
-        % (rank, time.time() - t0, R.n_edges, R.n_chains, S.n_edges, S.n_chains))
+    log("[rank %d] maps ready in %.1fs: R %d edges / %d chains, S %d edges / %d chains; host cores of this rank: %s"
+        % (rank, time.time() - t0, R.n_edges, R.n_chains, S.n_edges, S.n_chains, n_cores))
 
     stream = torch.cuda.Stream(device=dev)
+    side = torch.cuda.Stream(device=dev)  # count exchange: off the critical path of the queries
     ctx = RJ.Context(device=local_rank, stream=stream.cuda_stream)
     ctx.set_option("keep_host_graph", 0)
     ctx.set_option("lbvh_leaf_size", args.leaf_size)
     ctx.set_option("sort_queries", args.sort_queries)
     ctx.set_option("lsi_filter", args.filter)
     ctx.set_option("lsi_cells", args.cells)
+    ctx.set_option("stage_timing", args.stage_timing)
     ctx.set_bounding_box(*bbox)
     ctx.set_map(0, R)
-    # pinned host copies of the S batch for the end-to-end leg
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_xy, h_row, h_left, h_right = pin(S.xy), pin(S.row_index), pin(S.left), pin(S.right)
 
-    def upload_S():
-        ctx.set_map_raw(1, h_xy.data_ptr(), S.n_points, h_row.data_ptr(), h_left.data_ptr(),
-                        h_right.data_ptr(), S.n_chains)
-    upload_S()
+    def host_buffers(g):
+        # pinned host copies of a query map for the end-to-end leg
+        return g, (pin(g.xy), pin(g.row_index), pin(g.left), pin(g.right))
+
+    def upload(hb):
+        g, (xy, row, left, right) = hb
+        ctx.set_map_raw(1, xy.data_ptr(), g.n_points, row.data_ptr(), left.data_ptr(), right.data_ptr(),
+                        g.n_chains)
+
+    hb_S = host_buffers(S)
+    upload(hb_S)
     build_ms = [ctx.build_index(0, args.mode, args.grid_size) for _ in range(3)]
     idx = ctx.index_info(0, args.mode)
     lsi = RJ.LSI(ctx, args.mode)
     lsi.Init(XSECT_FACTOR)
-
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    step_counts = []  # (results, candidates) of every step, exchanged in one all-gather
 
-    def step():
-        n = lsi.Query(1)
-        step_counts.append((n, lsi.n_candidates))
-        return n
+    # the only data-path collective: the per-rank {result, candidate} counts of a step, one
+    # NCCL all-gather of 16 B per rank, issued on the side stream right after the step's
+    # wait -- it travels while the next step's kernels run, only the last one is exposed
+    counts_host = torch.zeros((max(args.steps, args.warmup, 1) + 4, 2), dtype=torch.int64).pin_memory()
+    counts_dev = torch.zeros_like(counts_host, device=dev)
+    counts_all = torch.zeros((counts_host.shape[0], world, 2), dtype=torch.int64, device=dev)
 
-    # fixed-size exchange buffers: the warm-up exchange has the shape of the timed one (NCCL
-    # sets its connections up lazily, 2.7 ms on first use -- tools/nccl_small.py)
-    n_rows = max(args.steps, args.warmup, 1)
-    counts_host = torch.zeros((n_rows, 2), dtype=torch.int64).pin_memory()
-    counts_dev = torch.zeros((n_rows, 2), dtype=torch.int64, device=dev)
-    counts_all = torch.zeros((world, n_rows, 2), dtype=torch.int64, device=dev)
+    def exchange(i, n, cand):
+        if world == 1:
+            return
+        counts_host[i, 0], counts_host[i, 1] = n, cand
+        with torch.cuda.stream(side):
+            counts_dev[i].copy_(counts_host[i], non_blocking=True)
+            dist.all_gather_into_tensor(counts_all[i], counts_dev[i])
 
-    def wait_counts():
-        """The only data-path collective: the per-rank {result, candidate} counts of the
-        steps since the last call, ONE NCCL all-gather (16 B per step and rank).  Nothing
-        in a query depends on another rank's counts, so they are exchanged once per batch
-        of steps instead of stalling every 0.16 ms step on a collective launch."""
-        if world > 1 and step_counts:
-            counts_host.zero_()
-            counts_host[:len(step_counts)] = torch.tensor(step_counts[-n_rows:], dtype=torch.int64)
+    def timed_steps(n_steps, n_warm):
+        """-> (per-step device ms, drain ms of the last count exchange, per-kernel ms, pairs, cand)"""
+        for i in range(n_warm):
+            lsi.Launch(1)
+            n = lsi.Wait()
+            exchange(i, n, lsi.n_candidates)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(n_steps)]
+        fin = torch.cuda.Event(enable_timing=True)
+        stage = []
+        n = 0
+        gc.disable()  # a collection inside a 0.16 ms step shows up as a 5x outlier
+        for i in range(n_steps):
             with torch.cuda.stream(stream):
-                counts_dev.copy_(counts_host, non_blocking=True)
-                dist.all_gather_into_tensor(counts_all, counts_dev)
-        step_counts.clear()
+                flush_buf.zero_()  # evict L2 between timed iterations (outside the events)
+                ev[i][0].record(stream)
+                lsi.Launch(1)     # the whole query is enqueued ...
+                ev[i][1].record(stream)
+            n = lsi.Wait()        # ... and completed; the events bracket its device time
+            exchange(i, n, lsi.n_candidates)
+            stage.append(ctx.last_stage_ms()[0])
+        fin.record(side)
+        torch.cuda.synchronize()
+        gc.enable()
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        drain = max(0.0, ev[-1][1].elapsed_time(fin)) if world > 1 else 0.0
+        return step_ms, drain, np.mean(np.asarray(stage), axis=0), n, lsi.n_candidates
 
-    for _ in range(args.warmup):
-        step()
-        if world > 1 and len(step_counts) == 1:
-            wait_counts()  # twice during warm-up: connection set-up, then the steady state
-            step_counts.append((0, 0))
-    wait_counts()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:  # one sampler per job: NVML calls from N processes serialise in the driver
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    k_ms, p_ms = [], []
-    n_pairs = 0
-    torch.cuda.synchronize()
-    gc.disable()  # a collection inside a 0.16 ms step shows up as a 5x outlier
-    for i in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush_buf.zero_()  # evict L2 between timed iterations (outside the events)
-            ev[i][0].record(stream)
-            n_pairs = step()
-            ev[i][1].record(stream)
-        a, b = ctx.last_kernel_ms()
-        k_ms.append(a)
-        p_ms.append(b)
-    torch.cuda.synchronize()
-    gc.enable()
-    # The count exchange of the K steps (the only data-path collective) is timed on its own,
-    # with the ranks aligned first: inside the last step's interval it would mostly measure
-    # how far the ranks had drifted apart over the untimed L2 flushes between the steps.
-    xch = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-    with torch.cuda.stream(stream):
-        xch[0].record(stream)
-        wait_counts()
-        xch[1].record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
-    xch_ms = xch[0].elapsed_time(xch[1])
-    total_ms = sum(step_ms) + xch_ms
-    log("[rank %d] step ms min/median/max %.4f/%.4f/%.4f, count exchange %.4f ms; host cpus: %s (affinity %d)"
-        % (rank, min(step_ms), float(np.median(step_ms)), max(step_ms), xch_ms, os.cpu_count(),
-           len(os.sched_getaffinity(0))))
-    n_cand = lsi.n_candidates
+    step_ms, drain_ms, stage_ms, n_pairs, n_cand = timed_steps(args.steps, args.warmup)
+    total_ms = sum(step_ms) + drain_ms
+    launches = ctx.last_launches()
+    lst = ctx.last_stats()
+    log("[rank %d] step ms min/median/max %.4f/%.4f/%.4f, exposed count exchange %.4f ms"
+        % (rank, min(step_ms), float(np.median(step_ms)), max(step_ms), drain_ms))
 
-    # ---- end to end through the C ABI from pinned host buffers ----------------
+    # ---- end to end through the synchronous C ABI from pinned host buffers ---------
     out_host = torch.empty(max(1, n_pairs) * 32, dtype=torch.uint8).pin_memory()
     out_np = out_host.numpy().view(RJ.XSECT_DTYPE)
 
-    def e2e_step():
-        upload_S()                                   # H2D + scale + edge numbering
-        n = lsi.Query(1)                             # traversal + intersection points
-        ctx.copy_to_host(lsi._res[0], out_np[:n])    # D2H of the rjb_xsect records
-        return n
-    for _ in range(min(3, args.warmup)):
-        e2e_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t
+    def e2e_run(hb, n_steps):
+        def e2e_step():
+            upload(hb)                                   # H2D + scale + edge numbering
+            n = lsi.Query(1)                             # traversal + intersection points
+            ctx.copy_to_host(lsi._res[0], out_np[:n])    # D2H of the rjb_xsect records
+            return n
+        for _ in range(min(3, args.warmup)):
+            e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = time.perf_counter()
+        for _ in range(n_steps):
+            n = e2e_step()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t) * 1e3, n
+    e2e_total_ms, _ = e2e_run(hb_S, args.steps)
     clocks = sampler.summary()
 
-    times = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([total_ms, e2e_total_ms, max(step_ms), float(np.median(step_ms))], dtype=torch.float64, device=dev)
     sizes = torch.tensor([S.n_edges, n_pairs, n_cand], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(sizes, op=dist.ReduceOp.SUM)
-    total_ms, e2e_ms = times.tolist()
+    total_ms, e2e_ms, worst_step, worst_median = times.tolist()
     all_edges, all_pairs, all_cand = sizes.tolist()
-
     h2d = S.xy.nbytes + S.row_index.nbytes + 4 * 2 * S.n_chains
     d2h = n_pairs * 32 + 16
+
+    # ---- strong scaling: ONE S map cut by whole chains over the ranks ------------------
+    strong = None
+    if world > 1 and not args.no_strong:
+        S_full = get_map("S", 2, args.scale)
+        shard, _, _ = rdist.shard_graph(S_full, rank, world)
+        hb_sh = host_buffers(shard)
+        upload(hb_sh)
+        s_ms, s_drain, _, s_pairs, _ = timed_steps(args.steps, args.warmup)
+        s_e2e, _ = e2e_run(hb_sh, args.steps)
+        t = torch.tensor([sum(s_ms) + s_drain, s_e2e], dtype=torch.float64, device=dev)
+        z = torch.tensor([s_pairs], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(z, op=dist.ReduceOp.SUM)
+        strong = {"workload": "ONE |S|=%d-edge map sharded by whole chains over %d ranks, R replicated"
+                              % (S_full.n_edges, world),
+                  "join_ms": t[0].item() / args.steps, "value": S_full.n_edges / (t[0].item() / args.steps / 1e3),
+                  "unit": "query_edges/s", "e2e_ms_per_step": t[1].item() / args.steps,
+                  "e2e_value": S_full.n_edges / (t[1].item() / args.steps / 1e3),
+                  "result_pairs": int(z[0].item()), "h2d_bytes_per_step_per_rank": int(shard.xy.nbytes)}
+        upload(hb_S)
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = all_edges / (ms_per_step / 1e3)
         peak, peak_src = measured_peak()
-        # algorithmic (compulsory) bytes of one traversal launch with this layout
-        # (DESIGN.md "Kernels"): S vertices + S edge->chain ids, the index once,
-        # R vertices once, 8 B per result pair
+        f_ms, t_ms, x_ms, p_ms = [float(v) for v in stage_ms]
+        surv, ql_pairs = (lst[7] or S.n_edges), lst[2]
+        n_leaves = idx["units"]
         if args.mode == "lbvh":
-            alg = 16 * S.n_points + 4 * S.n_edges + idx["bytes"] + 16 * R.n_points + 8 * n_pairs
-            lst = ctx.last_stats()
-            log("last_stats (results, candidates, ..., [5] cells path, [6] long survivors, [7] survivors):", lst)
-            kname = ("k_lsi_filter+k_lsi_cells+k_lsi_bvh" if lst[5] else "k_lsi_filter+k_lsi_bvh") if lst[7] \
-                else "k_lsi_bvh"
+            # Algorithmic (compulsory) bytes per kernel with this layout (DESIGN.md section 4).
+            #  filter   : 4 B descriptor per S point, both 2 MiB bitmaps, 4 B per survivor out
+            #  traversal: 4 B slot + one 16 B vertex per survivor (the second is the neighbour's),
+            #             the tree once (node boxes + children + top tree), 8 B per (query, leaf) pair out
+            #  exact    : the pair list, per distinct leaf its record and <= 5 vertices, per distinct
+            #             query edge its two vertices, 8 B per hit out
+            #  points   : per hit 8 B in, four vertices, two chain ids, 32 B record out
+            tree_bytes = idx["bytes"] - 2 * (4096 * 4096 // 8) - 8 * n_leaves
+            kern = [
+                ("k_lsi_filter", f_ms, 4 * S.n_points + 2 * (4096 * 4096 // 8) + 4 * surv),
+                ("k_lsi_bvh", t_ms, 20 * surv + tree_bytes + 8 * ql_pairs),
+                ("k_lsi_exact", x_ms, 8 * ql_pairs + 88 * min(ql_pairs, n_leaves) + 32 * min(ql_pairs, surv) + 8 * n_pairs),
+                ("k_lsi_points", p_ms, (8 + 64 + 8 + 32) * n_pairs),
+            ]
+            if not lst[7]:
+                kern = kern[1:]
+                kern[0] = ("k_lsi_bvh", t_ms, 4 * S.n_edges + 16 * S.n_points + tree_bytes + 8 * ql_pairs)
+            # whole query, SURVEY 8(d): every S vertex, every S edge id, the index and every R vertex once
+            alg_query = 16 * S.n_points + 4 * S.n_edges + idx["bytes"] + 16 * R.n_points + 8 * n_pairs
         else:
-            alg = 16 * S.n_points + 4 * S.n_edges + idx["bytes"] + 16 * R.n_points + 4 * R.n_edges + 8 * n_pairs
-            kname = "k_lsi_grid"
-        sorted_queries = args.sort_queries > 0 or (args.sort_queries < 0 and S.n_edges / max(1, S.n_chains) < 32)
-        k_avg = float(np.mean(k_ms))
-        achieved = alg / (k_avg / 1e3) / 1e9
+            kern = [("k_lsi_grid", f_ms, 16 * S.n_points + 4 * S.n_edges + idx["bytes"] + 16 * R.n_points + 8 * n_pairs),
+                    ("k_xsect_points_dyn", t_ms, (8 + 64 + 8 + 32) * n_pairs)]
+            alg_query = kern[0][2]
+        rk = []
+        for name, ms, b in kern:
+            rk.append({"kernel": name, "ms": ms, "algorithmic_bytes": int(b),
+                       "achieved": (b / (ms / 1e3) / 1e9) if ms > 0 else None,
+                       "frac": (b / (ms / 1e3) / 1e9 / peak) if ms > 0 else None,
+                       "traffic": ncu_traffic(name)})
+        dom = max(rk, key=lambda r: r["ms"])
         line = {
             "metric": "LSI join throughput", "value": value, "unit": "query_edges/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64/int128", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "mode": args.mode, "xsect_factor": XSECT_FACTOR,
-                       "lbvh_leaf_size": args.leaf_size, "sort_queries": args.sort_queries,
-                       "l2": "256 MiB flush write between timed iterations; inputs (S vertices 146 MB) also exceed L2",
-                       "sharding": "R + index replicated, S sharded per rank (seed 2+rank); NCCL: one "
-                                   "all-gather of the per-step counts per timed region (timed after "
-                                   "aligning the ranks, added to the K step times)"},
+            "config": cfg,
+            "engine": {"mode": args.mode, "lbvh_leaf_size": args.leaf_size, "sort_queries": args.sort_queries,
+                       "timing": "CUDA events on the launch stream around the enqueued query (rjb_lsi_launch); "
+                                 "max over ranks of the sum of the K step times + the exposed part of the last "
+                                 "count exchange",
+                       "l2": "256 MiB flush write between timed iterations; inputs (S descriptors + survivors' "
+                             "vertices + index, ~150 MB) also exceed L2",
+                       "sharding": "R + index replicated, S sharded per rank (seed 2+rank); NCCL: one 16 B "
+                                   "all-gather of the step's counts per step on a side stream",
+                       "host_cores_per_rank": n_cores},
             "join_ms": ms_per_step, "result_pairs": int(all_pairs),
             "candidate_pairs": int(all_cand),
             "candidate_pairs_per_s": all_cand / (ms_per_step / 1e3),
             "index_build_ms": float(np.min(build_ms)), "index_bytes": int(idx["bytes"]),
             "index_units": int(idx["units"]),
-            "kernel_ms": {kname: k_avg, "exact_pass(k_lsi_exact+k_lsi_points)" if args.mode == "lbvh"
-                          else "k_xsect_points_dyn": float(np.mean(p_ms))},
+            "kernel_ms": {r["kernel"]: r["ms"] for r in rk},
+            "step_ms": {"median_worst_rank": worst_median, "max_worst_rank": worst_step,
+                        "exposed_count_exchange": drain_ms},
             "e2e": {"value": all_edges / (e2e_ms / 1e3 / args.steps), "unit": "query_edges/s",
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": ((2 + len(kname.split("+")) if args.mode == "lbvh" else 2)
-                             + (6 if sorted_queries else 0)) * args.steps,
+            "gpu_launches": int(launches) * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(kname),
-                         "algorithmic_bytes": int(alg), "peak_source": peak_src},
+            "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak,
+                         "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"],
+                         "algorithmic_bytes": dom["algorithmic_bytes"], "peak_source": peak_src,
+                         "note": "dominant kernel of the query: its own algorithmic bytes over its own "
+                                 "CUDA-event time; latency bound by design (a chain of dependent loads per "
+                                 "warp), see roofline_kernels / roofline_query"},
+            "roofline_kernels": rk,
+            "roofline_query": {"algorithmic_bytes": int(alg_query), "ms": ms_per_step,
+                               "achieved": alg_query / (ms_per_step / 1e3) / 1e9,
+                               "frac": alg_query / (ms_per_step / 1e3) / 1e9 / peak,
+                               "formula": "16*Np(S) + 4*Ne(S) + index + 16*Np(R) + 8*K over ms_per_step (SURVEY 8d)"},
         }
+        if strong:
+            line["strong_scaling"] = strong
         # check the last result against the host oracle, and time it: the CPU baseline
         if not args.no_cpu_baseline:
             dt, n_ref, cand_ref, cores, res = cpu_oracle_lsi(R, S, bbox)
@@ -456,8 +718,23 @@ def main():
                 line["parity_vs_oracle"] = "bit-exact" if ok else "MISMATCH"
                 if not ok:
                     log("PARITY MISMATCH against the oracle: %d vs %d pairs" % (n_pairs, n_ref))
-        print(json.dumps(line), file=json_out, flush=True)
+            del res
     ctx.close()
+    if rank == 0 and world == 1:
+        del flush_buf
+        torch.cuda.empty_cache()
+        if "pip" in legs:
+            try:
+                line["pip"] = pip_leg(args, RJ, torch, dev, stream, peak)
+            except Exception as e:  # the headline line must survive a failing extra leg
+                line["pip"] = {"error": repr(e)[:300]}
+        if "overlay" in legs:
+            try:
+                line["overlay"] = overlay_leg(args, RJ, R, get_map("S", 2, args.scale), dev, stream)
+            except Exception as e:
+                line["overlay"] = {"error": repr(e)[:300]}
+    if rank == 0:
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -139,6 +139,8 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
  *                     the load kernel of chunk k runs while chunk k+1 is copied
  *   "pip_park"        LBVH PIP: 1 (default) = lanes park the leaf their ray meets and the
  *                     warp opens the parked leaves together; 0 = open a leaf when reached
+ *   "stage_timing"    LBVH LSI: 1 (default) = a CUDA event after every kernel
+ *                     (rjb_last_stage_ms), 0 = after every phase only
  *   "stats"           1 = collect traversal statistics (rjb_last_stats; slower)
  *   "keep_host_graph" 0 = rjb_set_map keeps no host copy of the source graph
  *                     (saves a memcpy; rjb_overlay_write then refuses)     */
@@ -158,6 +160,15 @@ int rjb_set_option(rjb_ctx* ctx, const char* name, int64_t value);
 int rjb_lsi(rjb_ctx* ctx, int query_map_id, int mode, double xsect_factor,
             const rjb_xsect** d_xsects, uint64_t* n_xsects,
             uint64_t* n_candidates);
+
+/* The same query in two halves, for callers that overlap host work (or several GPUs driven by
+ * one thread) with the query: rjb_lsi_launch puts the kernels and the read-back of the counts on
+ * the context's stream and returns without waiting; rjb_lsi_wait completes it with the result
+ * contract of rjb_lsi (and repeats the query internally if an internal queue was too small).
+ * Nothing else may be called on the context in between.  rjb_lsi == launch + wait.          */
+int rjb_lsi_launch(rjb_ctx* ctx, int query_map_id, int mode, double xsect_factor);
+int rjb_lsi_wait(rjb_ctx* ctx, const rjb_xsect** d_xsects, uint64_t* n_xsects,
+                 uint64_t* n_candidates);
 
 /* ---- PIP ------------------------------------------------------------------
  * PIP<CTX>::Query + get_closest_eids (src/app/pip.h:26-36,
@@ -216,15 +227,26 @@ int rjb_overlay_write(rjb_ctx* ctx, const char* path);
  * out[1] = intersection-point pass.  Replaces the reference's Stopwatch /
  * -profile sub-stage timers (src/util/stopwatch.h).                            */
 int rjb_last_kernel_ms(const rjb_ctx* ctx, double out[2]);
+/* per-kernel device times (ms) of the last query, by *layout:
+ *   1  LBVH LSI : {k_lsi_filter, k_lsi_bvh (+ k_lsi_cells), k_lsi_exact, k_lsi_points}
+ *                 (option "stage_timing" = 0: one event per phase only,
+ *                  {filter + traversal, 0, exact + points, 0})
+ *   3  grid LSI : {k_grid_lsi_filter (+ big), k_grid_lsi_exact, k_lsi_points, 0}
+ *   4  PIP      : {ordering of the points (0 when not ordered), query kernel (+ split), 0, 0}
+ *   0  brute LSI: {all-pairs kernel, point pass, 0, 0}                                     */
+int rjb_last_stage_ms(const rjb_ctx* ctx, double out[4], int* layout);
 /* raw counters of the last query: [0] results, [1] candidates; with option
  * "stats" = 1 also traversal statistics ([2] binary node visits, [3] leaf visits,
  * [4] top-tree steps, [5] lane-level leaf tests, [6] warps that
  * reached a leaf, [7] deepest stack).  Without "stats", an LBVH LSI query reports
+ * [2] = (query edge, leaf) pairs handed from the traversal to the exact pass,
  * [7] = survivors of the occupancy filter (0 = filter off), [5] = 1 when they went
  * through the cell directory, [6] = survivors that walked the tree instead (longer
  * than a cell).  Replaces the reference's Debug-build
  * "Total tests" / "Visited nodes" counters (src/app/lsi_lbvh.h:37-42,83-96).   */
 int rjb_last_stats(const rjb_ctx* ctx, uint64_t out[8]);
+/* number of kernels the last completed rjb_lsi / rjb_pip put on the stream (all attempts) */
+int rjb_last_launches(const rjb_ctx* ctx, uint32_t* out);
 /* index of map_id: out[0] = leaves (LBVH) / edge-cell incidences (grid),
  * out[1] = bytes of the index, out[2] = leaf size / grid size, out[3] = 0      */
 int rjb_index_info(const rjb_ctx* ctx, int map_id, int mode, uint64_t out[4]);
@@ -233,6 +255,24 @@ int rjb_index_info(const rjb_ctx* ctx, int map_id, int mode, uint64_t out[4]);
  * bits [begin_bit, end_bit), stable; arrays are sorted in place                 */
 int rjb_debug_sort_pairs(rjb_ctx* ctx, uint64_t* h_keys, uint32_t* h_vals,
                          uint64_t n, int begin_bit, int end_bit);
+
+/* test hooks: the exact arithmetic of the query kernels (the same device functions) over
+ * caller-supplied HOST arrays, so that the golden vectors of the reference's
+ * src/algo/lsi.h:27-143 + src/util/rational.h:190-203 and known-answer tests of the
+ * (double)(__int128) conversions go through the sm_100a compile.
+ *  intersect: pts = n x 8 int64 {e1.p1, e1.p2, e2.p1, e2.p2} (e1 = query side); mode 0 = always
+ *    through the gcd, 1 = the deferring path of the point kernel; flags bit 0 = intersects,
+ *    bits 1 / 2 = x / y went through the deferred pass; x, y = the stored intersection point.
+ *  i128: v, d = n x {lo, hi} words; cvt = (double) v, div = (double) v / (double) d,
+ *    trunc = (int64) div  (d, div, trunc may be NULL together).
+ *  pip: the update rule of src/algo/pip.h:27-96 scanned over the edges (n_edges x 4 int64) in
+ *    order for every point (n x 2 int64); out = index of the chosen edge or RJB_NO_HIT.    */
+int rjb_debug_intersect_batch(rjb_ctx* ctx, const int64_t* h_pts, uint64_t n, int mode,
+                              uint8_t* h_flags, int64_t* h_x, int64_t* h_y);
+int rjb_debug_i128_batch(rjb_ctx* ctx, const uint64_t* h_v, const uint64_t* h_d, uint64_t n,
+                         double* h_cvt, double* h_div, int64_t* h_trunc);
+int rjb_debug_pip_batch(rjb_ctx* ctx, const int64_t* h_edges, uint64_t n_edges,
+                        const int64_t* h_pts, uint64_t n, int query_map_id, uint32_t* h_out);
 
 /* ---- transfers --------------------------------------------------------------- */
 int rjb_copy_to_host(rjb_ctx* ctx, const void* d_src, void* h_dst,

@@ -486,6 +486,163 @@ uint64_t orc_lsi_grid(const int64_t* xyq, const uint32_t* q_p1, uint64_t nq,
 }
 
 /* ------------------------------------------------------------------ */
+/* LSI with the semantics of the reference's GRID backend               */
+/*   src/app/lsi_grid.h:19-78: for every cell, every (map-0 edge,       */
+/*   map-1 edge) pair registered in it: intersect_test(e1 = map 0,      */
+/*   e2 = map 1) -- the query map id is ignored (:96-104) -- and the    */
+/*   pair is kept only if calculate_cell(xsect) is this very cell       */
+/*   (:62-67).  Cells of an edge: the cell-box of its end points        */
+/*   (src/grid/uniform_grid.h:44-86).  So a pair is reported iff the    */
+/*   predicate holds and the cell of the intersection point lies in the */
+/*   cell-boxes of both edges.                                          */
+/* ------------------------------------------------------------------ */
+/* calculate_cell for an integer coordinate (src/grid/cell.h:15-22) */
+static inline int ref_cell_int(int64_t v, int64_t imin, double cell_scale) {
+  return (int) ((double) (v - imin) * cell_scale);
+}
+
+/* calculate_cell for the rational intersection coordinate: `val - internal_min` is
+ * rational{num*1 - imin*den, den*1} simplified (rational.h:399-407), `* cell_scale` has no
+ * rational overload, so the value converts through operator double (rational.h:94-97) */
+static inline int ref_cell_rat(i128 num, i128 den, int64_t imin, double cell_scale) {
+  i128 n1 = num - (i128) imin * den, n2, d2;
+  rat_make(n1, den, &n2, &d2);
+  return (int) (((double) n2 / (double) d2) * cell_scale);
+}
+
+/* lsi.h:105-143 without the final truncation: the clamped rationals */
+static inline void xsect_rational_eq(const edge_eq* e1, int64_t e1p1x, int64_t e1p1y, int64_t e1p2x,
+                                     int64_t e1p2y, const edge_eq* e2, int64_t e2p1x, int64_t e2p1y,
+                                     int64_t e2p2x, int64_t e2p2y, i128* xn, i128* xd, i128* yn,
+                                     i128* yd) {
+  i128 denom = e1->a * e2->b - e2->a * e1->b;
+  i128 numx = e2->c * e1->b - e1->c * e2->b;
+  i128 numy = e2->a * e1->c - e1->a * e2->c;
+  rat_make(numx, denom, xn, xd);
+  rat_make(numy, denom, yn, yd);
+  int64_t t = min4(e1p1x, e1p2x, e2p1x, e2p2x);
+  if (*xn < (i128) t * *xd) { *xn = t; *xd = 1; }
+  t = max4(e1p1x, e1p2x, e2p1x, e2p2x);
+  if ((i128) t * *xd < *xn) { *xn = t; *xd = 1; }
+  t = min4(e1p1y, e1p2y, e2p1y, e2p2y);
+  if (*yn < (i128) t * *yd) { *yn = t; *yd = 1; }
+  t = max4(e1p1y, e1p2y, e2p1y, e2p2y);
+  if ((i128) t * *yd < *yn) { *yn = t; *yd = 1; }
+}
+
+/* a = map-0 edge (4 coords), b = map-1 edge; returns 1 and the stored point when the
+ * reference's grid backend reports the pair */
+static inline int refgrid_pair(const int64_t* a, const int64_t* b, int gsize, int64_t imin,
+                               double cell_scale, int64_t* ox, int64_t* oy) {
+  edge_eq e1 = make_eq(a[0], a[1], a[2], a[3]);
+  edge_eq e2 = make_eq(b[0], b[1], b[2], b[3]);
+  if (!intersect_test_eq(&e1, a[0], a[1], a[2], a[3], &e2, b[0], b[1], b[2], b[3])) return 0;
+  i128 xn, xd, yn, yd;
+  xsect_rational_eq(&e1, a[0], a[1], a[2], a[3], &e2, b[0], b[1], b[2], b[3], &xn, &xd, &yn, &yd);
+  int cx = ref_cell_rat(xn, xd, imin, cell_scale), cy = ref_cell_rat(yn, yd, imin, cell_scale);
+  (void) gsize;
+#define CMIN(u, v) ref_cell_int((u) < (v) ? (u) : (v), imin, cell_scale)
+#define CMAX(u, v) ref_cell_int((u) < (v) ? (v) : (u), imin, cell_scale)
+  int ok = cx >= CMIN(a[0], a[2]) && cx <= CMAX(a[0], a[2]) && cx >= CMIN(b[0], b[2]) && cx <= CMAX(b[0], b[2]) &&
+           cy >= CMIN(a[1], a[3]) && cy <= CMAX(a[1], a[3]) && cy >= CMIN(b[1], b[3]) && cy <= CMAX(b[1], b[3]);
+#undef CMIN
+#undef CMAX
+  if (!ok) return 0;
+  *ox = (int64_t) ((double) xn / (double) xd);
+  *oy = (int64_t) ((double) yn / (double) yd);
+  return 1;
+}
+
+/* batch form for known-answer tests: pts = n x 8 {map-0 edge, map-1 edge}; cx, cy = cell of the
+ * intersection point as the reference computes it (valid where hit), owned = pair reported */
+void orc_refgrid_cells(const int64_t* pts, uint64_t n, int gsize, int64_t imin, int64_t irange,
+                       uint8_t* hit, int32_t* cx, int32_t* cy, uint8_t* owned) {
+  double cell_scale = (double) gsize / irange * 0.999;
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < n; i++) {
+    const int64_t* a = pts + 8 * i;
+    const int64_t* b = a + 4;
+    edge_eq e1 = make_eq(a[0], a[1], a[2], a[3]);
+    edge_eq e2 = make_eq(b[0], b[1], b[2], b[3]);
+    hit[i] = (uint8_t) intersect_test_eq(&e1, a[0], a[1], a[2], a[3], &e2, b[0], b[1], b[2], b[3]);
+    cx[i] = cy[i] = 0;
+    owned[i] = 0;
+    if (!hit[i]) continue;
+    i128 xn, xd, yn, yd;
+    xsect_rational_eq(&e1, a[0], a[1], a[2], a[3], &e2, b[0], b[1], b[2], b[3], &xn, &xd, &yn, &yd);
+    cx[i] = ref_cell_rat(xn, xd, imin, cell_scale);
+    cy[i] = ref_cell_rat(yn, yd, imin, cell_scale);
+    int64_t x, y;
+    owned[i] = (uint8_t) refgrid_pair(a, b, gsize, imin, cell_scale, &x, &y);
+  }
+}
+
+/* xy0/p1_0 = map 0, xy1/p1_1 = map 1.  Output sorted by (first, second) where first is the
+ * edge of map `sort_map`: out_first = eids of that map, out_second = eids of the other.
+ * The candidate filter (a host grid over map 0, all-pairs when brute != 0) loses nothing:
+ * the predicate implies overlapping boxes. */
+uint64_t orc_lsi_refgrid(const int64_t* xy0, const uint32_t* p1_0, uint64_t n0, const int64_t* xy1,
+                         const uint32_t* p1_1, uint64_t n1, int64_t imin, int64_t irange, int gsize,
+                         int sort_map, int brute, uint32_t* out_first, uint32_t* out_second,
+                         int64_t* out_x, int64_t* out_y, uint64_t cap) {
+  double cell_scale = (double) gsize / irange * 0.999; /* cell.h:19 */
+  host_grid g;
+  if (!brute) grid_build(&g, xy0, p1_0, n0, imin, irange);
+  int nt = 1;
+#ifdef _OPENMP
+  nt = omp_get_max_threads();
+#endif
+  pair_vec* pvs = (pair_vec*) calloc(nt, sizeof(pair_vec));
+#pragma omp parallel
+  {
+    int tid = 0;
+#ifdef _OPENMP
+    tid = omp_get_thread_num();
+#endif
+#pragma omp for schedule(dynamic, 256)
+    for (uint64_t i = 0; i < n1; i++) {
+      const int64_t* q = xy1 + 2 * (uint64_t) p1_1[i];
+      if (brute) {
+        for (uint64_t j = 0; j < n0; j++) {
+          int64_t x, y;
+          if (refgrid_pair(xy0 + 2 * (uint64_t) p1_0[j], q, gsize, imin, cell_scale, &x, &y)) {
+            pair_rec r = {sort_map == 1 ? (uint32_t) i : (uint32_t) j, sort_map == 1 ? (uint32_t) j : (uint32_t) i, x, y};
+            pv_push(&pvs[tid], r);
+          }
+        }
+        continue;
+      }
+      int64_t qx0 = q[0] < q[2] ? q[0] : q[2], qx1 = q[0] < q[2] ? q[2] : q[0];
+      int64_t qy0 = q[1] < q[3] ? q[1] : q[3], qy1 = q[1] < q[3] ? q[3] : q[1];
+      int cx0 = cell_of(&g, qx0), cx1 = cell_of(&g, qx1);
+      int cy0 = cell_of(&g, qy0), cy1 = cell_of(&g, qy1);
+      for (int cy = cy0; cy <= cy1; cy++)
+        for (int cx = cx0; cx <= cx1; cx++) {
+          uint64_t c = (uint64_t) cy * g.gsize + cx;
+          for (uint64_t k = g.cell_begin[c]; k < g.cell_begin[c + 1]; k++) {
+            uint32_t j = g.items[k];
+            const int64_t* b = xy0 + 2 * (uint64_t) p1_0[j];
+            int64_t bx0 = b[0] < b[2] ? b[0] : b[2], bx1 = b[0] < b[2] ? b[2] : b[0];
+            int64_t by0 = b[1] < b[3] ? b[1] : b[3], by1 = b[1] < b[3] ? b[3] : b[1];
+            if (bx1 < qx0 || qx1 < bx0 || by1 < qy0 || qy1 < by0) continue;
+            int64_t lx = qx0 > bx0 ? qx0 : bx0, ly = qy0 > by0 ? qy0 : by0;
+            if (cell_of(&g, lx) != cx || cell_of(&g, ly) != cy) continue;
+            int64_t x, y;
+            if (refgrid_pair(b, q, gsize, imin, cell_scale, &x, &y)) {
+              pair_rec r = {sort_map == 1 ? (uint32_t) i : j, sort_map == 1 ? j : (uint32_t) i, x, y};
+              pv_push(&pvs[tid], r);
+            }
+          }
+        }
+    }
+  }
+  uint64_t total = emit_sorted(pvs, nt, out_first, out_second, out_x, out_y, cap);
+  free(pvs);
+  if (!brute) grid_free(&g);
+  return total;
+}
+
+/* ------------------------------------------------------------------ */
 /* PIP: closest edge above the point                                   */
 /*   rule text identical in src/algo/pip.h:27-96,                      */
 /*   src/app/pip_lbvh.h:57-123, src/algo/rt_pip_custom.cu:44-106       */
@@ -607,6 +764,16 @@ void orc_face_ids(const int64_t* xyb, const uint32_t* b_p1,
 
 /* bench.py pins torch to one thread per rank, which also lowers the OpenMP default of
  * this library when both share one libgomp: the CPU baseline asks for all cores again */
+/* (double)(__int128) as this host compiles it (libgcc __floattidf, round to nearest even):
+ * what tcb::rational's operator double (src/util/rational.h:94-97) and the PIP y*
+ * (src/algo/pip.h:56-58) do per operand.  v = n x {lo, hi} words. */
+void orc_i128_to_double(const uint64_t* v, uint64_t n, double* out) {
+  for (uint64_t i = 0; i < n; i++) {
+    i128 a = (i128) (((unsigned __int128) v[2 * i + 1] << 64) | v[2 * i]);
+    out[i] = (double) a;
+  }
+}
+
 void orc_set_num_threads(int n) {
 #ifdef _OPENMP
   if (n > 0) omp_set_num_threads(n);

@@ -37,7 +37,8 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB):
+        src = os.path.join(_HERE, "oracle.c")
+        if not os.path.exists(_LIB) or os.path.getmtime(src) > os.path.getmtime(_LIB):
             build(ref=False)
         _lib = C.CDLL(_LIB)
         _lib.orc_lsi_brute.restype = C.c_uint64
@@ -110,6 +111,45 @@ def intersect_batch(pts):
     y = np.zeros(n, dtype=np.int64)
     lib().orc_intersect_batch(_p(pts), C.c_uint64(n), _p(hit), _p(x), _p(y))
     return hit, x, y
+
+
+def i128_to_double(words):
+    """(n, 2) uint64 {lo, hi} words of signed 128-bit integers -> (double) value (host libgcc)."""
+    words = np.ascontiguousarray(words, dtype=np.uint64).reshape(-1, 2)
+    out = np.zeros(len(words), np.float64)
+    lib().orc_i128_to_double(_p(words), C.c_uint64(len(words)), _p(out))
+    return out
+
+
+def lsi_refgrid(xy0, p1_0, xy1, p1_1, s, gsize, sort_map=1, brute=False, cap=None):
+    """LSI with the semantics of the reference's GRID backend (src/app/lsi_grid.h:19-78):
+    intersect_test(map-0 edge, map-1 edge), kept iff the cell of the intersection point is a
+    cell both edges are registered in.  -> (eids of map sort_map, eids of the other map, x, y)
+    sorted by (first, second)."""
+    xy0, xy1, p1_0, p1_1 = _i64(xy0), _i64(xy1), _u32(p1_0), _u32(p1_1)
+    cap = cap or max(1024, 2 * (len(p1_0) + len(p1_1)))
+    a, b, x, y = _lsi_out(cap)
+    lib().orc_lsi_refgrid.restype = C.c_uint64
+    n = lib().orc_lsi_refgrid(_p(xy0), _p(p1_0), C.c_uint64(len(p1_0)), _p(xy1), _p(p1_1),
+                              C.c_uint64(len(p1_1)), C.c_int64(s.imin), C.c_int64(s.irange),
+                              C.c_int(gsize), C.c_int(sort_map), C.c_int(1 if brute else 0),
+                              _p(a), _p(b), _p(x), _p(y), C.c_uint64(cap))
+    if n > cap:
+        return lsi_refgrid(xy0, p1_0, xy1, p1_1, s, gsize, sort_map, brute, cap=int(n))
+    return a[:n], b[:n], x[:n], y[:n]
+
+
+def refgrid_cells(pts, s, gsize):
+    """pts: (n, 8) int64 {map-0 edge, map-1 edge} -> hit, cell x, cell y of the intersection
+    point as the reference's grid computes it (src/grid/cell.h:15-22), and whether its grid
+    backend reports the pair (src/app/lsi_grid.h:62-67)."""
+    pts = _i64(pts).reshape(-1, 8)
+    n = len(pts)
+    hit, owned = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    cx, cy = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    lib().orc_refgrid_cells(_p(pts), C.c_uint64(n), C.c_int(gsize), C.c_int64(s.imin), C.c_int64(s.irange),
+                            _p(hit), _p(cx), _p(cy), _p(owned))
+    return hit, cx, cy, owned
 
 
 def ref_lsi_available():

@@ -15,7 +15,11 @@ DONTKNOW = -1
 
 
 class OverlayOracle:
-    def __init__(self, graphs, bbox=None):
+    def __init__(self, graphs, bbox=None, grid_size=None):
+        """grid_size: None = the LBVH / RT pair set (pure predicate); a number = the pair set of
+        the reference's GRID backend at that -grid_size (src/app/lsi_grid.h:62-67: a pair is
+        kept only in the cell of its intersection point)."""
+        self.grid_size = grid_size
         from rayjoin_b200 import synth  # only the bbox helper, no compute
         self.g = graphs
         self.bbox = bbox or synth.union_bbox(*graphs)
@@ -33,7 +37,11 @@ class OverlayOracle:
 
     def run(self):
         # LSI with map 0 as the query side: pairs (eid0, eid1, x, y)
-        e0, e1, x, y = O.lsi_grid(self.pts[0], self.p1[0], self.pts[1], self.p1[1], self.sc)
+        if self.grid_size:
+            e0, e1, x, y = O.lsi_refgrid(self.pts[0], self.p1[0], self.pts[1], self.p1[1], self.sc,
+                                         self.grid_size, sort_map=0)
+        else:
+            e0, e1, x, y = O.lsi_grid(self.pts[0], self.p1[0], self.pts[1], self.p1[1], self.sc)
         self.xs = np.column_stack([e0.astype(np.int64), e1.astype(np.int64), x, y])
         self.closest = [None, None]
         self.pip = [None, None]

@@ -21,9 +21,11 @@ ERR_QUEUE_OVERFLOW = 3
 EXPORTS = [
     "rjb_last_error", "rjb_version", "rjb_create", "rjb_destroy", "rjb_set_stream",
     "rjb_set_bounding_box", "rjb_get_scaling", "rjb_set_map", "rjb_map_info",
-    "rjb_map_device_views", "rjb_build_index", "rjb_set_option", "rjb_lsi", "rjb_pip",
+    "rjb_map_device_views", "rjb_build_index", "rjb_set_option", "rjb_lsi", "rjb_lsi_launch", "rjb_lsi_wait",
+    "rjb_last_launches", "rjb_pip",
     "rjb_pip_host", "rjb_pip_host_scaled", "rjb_overlay_run", "rjb_overlay_finish", "rjb_overlay_results", "rjb_overlay_write",
-    "rjb_debug_sort_pairs", "rjb_last_kernel_ms", "rjb_last_stats", "rjb_index_info", "rjb_copy_to_host", "rjb_sync",
+    "rjb_debug_sort_pairs", "rjb_debug_intersect_batch", "rjb_debug_i128_batch", "rjb_debug_pip_batch",
+    "rjb_last_kernel_ms", "rjb_last_stage_ms", "rjb_last_stats", "rjb_index_info", "rjb_copy_to_host", "rjb_sync",
     "rjb_graph_load", "rjb_graph_read_text", "rjb_graph_read_bin", "rjb_graph_write_bin",
     "rjb_graph_free",
 ]
@@ -280,6 +282,45 @@ class Context:
         _check(self.lib.rjb_last_kernel_ms(self._h, out))
         return out[0], out[1]
 
+    def last_stage_ms(self):
+        """(times[4], layout): per-kernel device times of the last query (rjb_last_stage_ms)."""
+        out = (C.c_double * 4)()
+        layout = C.c_int(0)
+        _check(self.lib.rjb_last_stage_ms(self._h, out, C.byref(layout)))
+        return list(out), layout.value
+
+    def debug_intersect_batch(self, pts, mode=1):
+        """Device run of lsi_intersect + the intersection point on (n, 8) int64 cases."""
+        pts = np.ascontiguousarray(pts, dtype=np.int64).reshape(-1, 8)
+        n = len(pts)
+        flags, x, y = np.zeros(n, np.uint8), np.zeros(n, np.int64), np.zeros(n, np.int64)
+        _check(self.lib.rjb_debug_intersect_batch(self._h, _ptr(pts), C.c_uint64(n), C.c_int(mode),
+                                                  _ptr(flags), _ptr(x), _ptr(y)))
+        return flags, x, y
+
+    def debug_i128_batch(self, v, d=None):
+        """v, d: (n, 2) uint64 {lo, hi} words of signed 128-bit integers -> (double) v,
+        (double) v / (double) d, (int64) of the quotient -- computed on the device."""
+        v = np.ascontiguousarray(v, dtype=np.uint64).reshape(-1, 2)
+        n = len(v)
+        cvt = np.zeros(n, np.float64)
+        if d is None:
+            _check(self.lib.rjb_debug_i128_batch(self._h, _ptr(v), None, C.c_uint64(n), _ptr(cvt), None, None))
+            return cvt
+        d = np.ascontiguousarray(d, dtype=np.uint64).reshape(-1, 2)
+        div, tr = np.zeros(n, np.float64), np.zeros(n, np.int64)
+        _check(self.lib.rjb_debug_i128_batch(self._h, _ptr(v), _ptr(d), C.c_uint64(n), _ptr(cvt), _ptr(div),
+                                             _ptr(tr)))
+        return cvt, div, tr
+
+    def debug_pip_batch(self, edges, pts, query_map_id):
+        edges = np.ascontiguousarray(edges, dtype=np.int64).reshape(-1, 4)
+        pts = np.ascontiguousarray(pts, dtype=np.int64).reshape(-1, 2)
+        out = np.zeros(len(pts), np.uint32)
+        _check(self.lib.rjb_debug_pip_batch(self._h, _ptr(edges), C.c_uint64(len(edges)), _ptr(pts),
+                                            C.c_uint64(len(pts)), C.c_int(query_map_id), _ptr(out)))
+        return out
+
     def debug_sort_pairs(self, keys, vals, begin_bit=0, end_bit=64):
         keys = np.ascontiguousarray(keys, dtype=np.uint64).copy()
         vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()
@@ -314,6 +355,33 @@ class Context:
             raise err
         return d.value, n.value, cand.value
 
+    def lsi_launch(self, query_map_id, mode, xsect_factor):
+        _check(self.lib.rjb_lsi_launch(self._h, C.c_int(query_map_id), C.c_int(MODES.get(mode, mode)),
+                                       C.c_double(xsect_factor)))
+
+    def lsi_wait(self):
+        d = C.c_void_p()
+        n = C.c_uint64(0)
+        cand = C.c_uint64(0)
+        rc = self.lib.rjb_lsi_wait(self._h, C.byref(d), C.byref(n), C.byref(cand))
+        if rc != 0:
+            err = RjbError(rc, self.lib.rjb_last_error().decode("utf-8", "replace"))
+            err.needed = n.value
+            raise err
+        return d.value, n.value, cand.value
+
+    def last_launches(self):
+        out = C.c_uint32(0)
+        _check(self.lib.rjb_last_launches(self._h, C.byref(out)))
+        return out.value
+
+    def pip_host_scaled(self, query_map_id, mode, h_points_ptr, n_points, h_eid_ptr, h_face_ptr):
+        """End-to-end PIP from (pinned) host buffers: scaled int64 points in, closest edge ids
+        and face ids out (rjb_pip_host_scaled); raw pointers, e.g. torch tensors' data_ptr()."""
+        _check(self.lib.rjb_pip_host_scaled(self._h, C.c_int(query_map_id), C.c_int(MODES.get(mode, mode)),
+                                            C.c_void_p(h_points_ptr), C.c_uint64(n_points),
+                                            C.c_void_p(h_eid_ptr), C.c_void_p(h_face_ptr)))
+
     def pip_device(self, query_map_id, mode, d_points_ptr=None, n_points=0):
         de, df = C.c_void_p(), C.c_void_p()
         cand = C.c_uint64(0)
@@ -337,6 +405,17 @@ class LSI:
 
     def Query(self, query_map_id):
         d, n, cand = self.ctx.lsi_device(query_map_id, self.mode, self.xsect_factor)
+        self._res = (d, n)
+        self.n_candidates = cand
+        return n
+
+    def Launch(self, query_map_id):
+        """First half of Query: enqueue only (rjb_lsi_launch)."""
+        self.ctx.lsi_launch(query_map_id, self.mode, self.xsect_factor)
+
+    def Wait(self):
+        """Second half of Query: complete the launched query (rjb_lsi_wait)."""
+        d, n, cand = self.ctx.lsi_wait()
         self._res = (d, n)
         self.n_candidates = cand
         return n

@@ -13,6 +13,7 @@
 
 #include "rjb_lsi.cuh"
 #include "rjb_pip.cuh"
+#include "rjb_debug.cuh"
 
 namespace rjb {
 
@@ -75,7 +76,18 @@ struct OverlayState {
 using namespace rjb;
 
 constexpr int kLoadChunksMax = 16;
+constexpr int kTimedStages = 4;
 constexpr uint32_t kLoadChunkPoints = 1u << 20;  // 16 MB of double2 per chunk
+
+// an LSI query that is on the stream and has not been waited for (rjb_lsi_launch)
+struct LsiPending {
+  bool active = false;
+  int q = 0, mode = 0, attempt = 0;
+  double xsect_factor = 0;
+  uint32_t cap = 0, ccap = 0, n_slots = 0;
+  bool lbvh = false, grid = false, filter = false, cells = false;
+  unsigned launches = 0;  // kernels this attempt put on the stream
+};
 
 struct rjb_ctx {
   int device = 0;
@@ -91,8 +103,11 @@ struct rjb_ctx {
   int sort_queries = -1;  // -1 auto: Morton-order query EDGES when the chains are short
   bool filter_useless = false;  // the occupancy filter kept > 50 % last time: skip it
   int stats = 0;  // collect traversal statistics (slower)
+  int stage_timing = 1;  // LBVH LSI: an event after every kernel (rjb_last_stage_ms), else after every phase
   bool pip_park = true;  // PIP: park leaves per lane and open them together (rjb_pip.cuh)
   unsigned long long last_stats[8] = {0};
+  LsiPending lsi_pending;
+  unsigned last_launches = 0;  // kernels launched by the last completed query
   int keep_host_graph = 1;  // overlay writer needs the source coordinates
   // LSI result queue
   DBuf<uint2> pairs;
@@ -104,12 +119,14 @@ struct rjb_ctx {
   uint32_t load_chunk = kLoadChunkPoints;  // points per upload chunk (option load_chunk_points)
   int use_cells = 0;      // LSI: cell directory for the filter's survivors (experimental, off)
   size_t cand_cap = 0;
+  size_t grid_work_cap = 0;  // grid LSI: capacity of the (query edge, cell) work list
   DBuf<rjb_xsect> xsects;
   DBuf<unsigned long long> counters;  // [0] = queue counter (low 32 bits), [1] = candidates
   // PIP results
   DBuf<uint32_t> pip_eid;
   DBuf<int32_t> pip_face;
   DBuf<longlong2> pip_pts;
+  DBuf<uint2> pip_packed;  // {eid, face} per point: the scattered write of ordered queries
   DBuf<double2> pip_raw;
   // query ordering scratch
   DBuf<uint64_t> ord_keys_a, ord_keys_b;
@@ -117,10 +134,14 @@ struct rjb_ctx {
   SortTemp ord_sort;
   // overlay state
   OverlayState ov;
-  // timing of the kernels of the last query call
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  float last_ms[4] = {0, 0, 0, 0};
-  int timing_pending = 0;  // 1: ev[0..1], 2: ev[0..2] recorded by the last query, not read yet
+  // timing of the kernels of the last query call: ev[k] .. ev[k + 1] brackets stage k
+  // (LBVH LSI: filter, traversal, exact pass, point pass; other queries: query kernel,
+  // point pass).  Index builds have events of their own (bev).
+  cudaEvent_t ev[kTimedStages + 1] = {};
+  cudaEvent_t bev[2] = {nullptr, nullptr};
+  float last_ms[kTimedStages] = {};
+  int timing_pending = 0;  // number of stages recorded by the last query and not read yet
+  int timing_layout = 0;   // 0: {query kernel, point pass}; 1: {filter, traversal, exact, points}
 };
 
 namespace rjb {
@@ -271,19 +292,6 @@ static const uint32_t* query_order_edges(rjb_ctx* c, DeviceMap& Qm, const MapVie
   return keep;
 }
 
-static const uint32_t* query_order_points(rjb_ctx* c, const longlong2* pts, uint32_t n) {
-  if (c->sort_queries <= 0 || n == 0) return nullptr;  // points: only on request
-  uint64_t* ka = c->ord_keys_a.ensure(n);
-  uint64_t* kb = c->ord_keys_b.ensure(n);
-  uint32_t* va = c->ord_vals_a.ensure(n);
-  uint32_t* vb = c->ord_vals_b.ensure(n);
-  k_query_keys_points<<<div_up(n, 256), 256, 0, c->stream>>>(pts, n, c->sc.internal_min, ka, va);
-  // only coherence is needed, not a total order: the top 24 Morton bits (4096 x 4096
-  // cells) = 3 radix passes instead of 8
-  sort_pairs_u64_u32(ka, kb, va, vb, n, 40, 64, c->ord_sort, c->stream);
-  return vb;
-}
-
 // Wait for the stream by polling (yielding the core between polls): a blocking cudaStreamSynchronize wakes the host tens of
 // microseconds late, which is a tenth of a whole LSI query.  Long waits fall back to it.
 static void wait_stream(cudaStream_t s) {
@@ -304,8 +312,10 @@ static void ensure_load_pipeline(rjb_ctx* c) {
 
 static void ensure_events(rjb_ctx* c) {
   if (!c->h_counters) RJB_CUDA(cudaHostAlloc((void**) &c->h_counters, 16 * sizeof(unsigned long long), cudaHostAllocDefault));
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i <= kTimedStages; i++)
     if (!c->ev[i]) RJB_CUDA(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < 2; i++)
+    if (!c->bev[i]) RJB_CUDA(cudaEventCreate(&c->bev[i]));
 }
 
 static void do_build_index(rjb_ctx* c, int map_id, int mode, uint32_t grid_size, double* build_ms) {
@@ -313,7 +323,7 @@ static void do_build_index(rjb_ctx* c, int map_id, int mode, uint32_t grid_size,
   DeviceMap& m = c->maps[map_id];
   RJB_REQUIRE(m.loaded, "rjb_build_index: map not loaded");
   ensure_events(c);
-  RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  RJB_CUDA(cudaEventRecord(c->bev[0], c->stream));
   if (mode == RJB_MODE_LBVH) {
     build_lbvh(m.bvh, m.view(), c->leaf_size, c->sc.internal_min, c->use_cells > 0, c->stream);
   } else if (mode == RJB_MODE_GRID) {
@@ -323,148 +333,247 @@ static void do_build_index(rjb_ctx* c, int map_id, int mode, uint32_t grid_size,
   } else {
     throw Error(RJB_ERR_INVALID, "rjb_build_index: unknown mode");
   }
-  RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
-  RJB_CUDA(cudaEventSynchronize(c->ev[1]));
+  RJB_CUDA(cudaEventRecord(c->bev[1], c->stream));
+  RJB_CUDA(cudaEventSynchronize(c->bev[1]));
   float ms = 0;
-  RJB_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+  RJB_CUDA(cudaEventElapsedTime(&ms, c->bev[0], c->bev[1]));
   if (build_ms) *build_ms = ms;
 }
 
-// LSI into c->pairs / c->xsects.  Returns the number found.
-static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_t* n_candidates) {
+// LSI into c->xsects, in two halves so that a caller can keep the device busy while its host
+// thread does something else (rjb_lsi_launch / rjb_lsi_wait): lsi_enqueue puts the whole query
+// on the stream -- kernels, and the read-back of the counters into pinned memory -- and returns;
+// lsi_finish waits for the stream, and repeats the query if an internal queue was too small
+// (the needed size is known exactly after the first attempt).  Between the kernels nothing
+// goes through the host: the counts stay on the device.
+static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
   check_map_id(q);
   DeviceMap& Qm = c->maps[q];
   DeviceMap& Bm = c->maps[1 - q];
   RJB_REQUIRE(Qm.loaded && Bm.loaded, "rjb_lsi: both maps must be loaded");
+  RJB_REQUIRE(mode == RJB_MODE_LBVH || mode == RJB_MODE_GRID || mode == RJB_MODE_BRUTE, "rjb_lsi: unknown mode");
   // queue capacity as in src/run_query.cu:226-228 (float arithmetic)
   float total_e = (float) ((size_t) Qm.n_edges + (size_t) Bm.n_edges);
   uint64_t cap64 = (uint64_t) (total_e * (float) xsect_factor);
   RJB_REQUIRE(cap64 < 0xFFFFFFFFull, "rjb_lsi: xsect queue exceeds 2^32 entries");
   uint32_t cap = (uint32_t) cap64;
-  uint2* pairs = c->pairs.ensure(cap ? cap : 1);
   rjb_xsect* xs = c->xsects.ensure(cap ? cap : 1);
   // counters: [0] results, [1] candidates (= exact-predicate evaluations),
   // [2..7] traversal statistics
-  // [8], [9]: {filter survivors, (query, leaf) pairs} as 32-bit counters
+  // [8], [9]: {filter survivors, (query, leaf) pairs, long survivors} as 32-bit counters
   unsigned long long* ctr = c->counters.ensure(10);
   ensure_events(c);
   MapView Q = Qm.view(), B = Bm.view();
-  unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (mode == RJB_MODE_LBVH && Q.n_edges > 0 && B.n_edges > 0) {
-    if (!Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no LBVH on the base map");
+  LsiPending& P = c->lsi_pending;
+  const int attempt = P.active ? P.attempt : 0;  // a retry keeps its attempt number
+  P = LsiPending();
+  P.q = q;
+  P.mode = mode;
+  P.xsect_factor = xsect_factor;
+  P.cap = cap;
+  P.attempt = attempt;
+  const bool nonempty = Q.n_edges > 0 && B.n_edges > 0;
+  if (mode == RJB_MODE_LBVH && !Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no LBVH on the base map");
+  if (mode == RJB_MODE_GRID && nonempty && !Bm.grid.built)
+    throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no grid on the base map");
+  if (mode == RJB_MODE_LBVH && nonempty) {
     // traversal -> candidate pairs (exact integer boxes overlap) -> dense exact pass.
-    // The candidate buffer is internal: it grows and the query is repeated if it
-    // was too small (the needed size is known exactly after the first attempt).
+    // The candidate buffer is internal: it grows and the query is repeated if it was too small.
     if (c->cand_cap < (size_t) cap + 65536) c->cand_cap = 2 * (size_t) cap + 65536;
     const uint32_t* order = query_order_edges(c, Qm, Q);
     // occupancy pre-filter: worthwhile when the base map covers a small part of the
     // plane; it replaces the Morton order (survivors come out in map order)
-    bool filter = !order && (c->use_filter == 1 || (c->use_filter < 0 && Bm.bvh.occ_fraction < 0.25 &&
-                                                   !c->filter_useless));
+    const bool filter = !order && (c->use_filter == 1 || (c->use_filter < 0 && Bm.bvh.occ_fraction < 0.25 &&
+                                                         !c->filter_useless));
     uint32_t* surv = filter ? c->survivors.ensure(Q.n_points) : nullptr;
     // [0] survivors, [1] (query, leaf) pairs, [2] survivors that are longer than a cell
     unsigned int* surv_n = (unsigned int*) (ctr + 8);
     // cell directory instead of the tree walk for the survivors (option lsi_cells)
     const bool cells = filter && Bm.bvh.have_cells && c->use_cells > 0 && !c->stats;
     uint32_t* long_list = cells ? c->long_edges.ensure(Q.n_points) : nullptr;
-    for (int attempt = 0;; attempt++) {
-      RJB_REQUIRE(c->cand_cap < 0xFFFFFFF0ull, "rjb_lsi: candidate queue exceeds 2^32 entries");
-      uint32_t ccap = (uint32_t) c->cand_cap;
-      uint2* cands = c->cands.ensure(ccap);
-      RJB_CUDA(cudaMemsetAsync(ctr, 0, 10 * sizeof(unsigned long long), c->stream));
-      RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
-      // query slots: point indices (edge = slot, slot + 1), or a list of start points
-      // (Morton-sorted edges, or the survivors of the occupancy filter, whose count
-      // stays on the device)
-      uint32_t n_slots = order ? Q.n_edges : Q.n_points;
-      const uint32_t* slots = order;
-      const unsigned int* n_slots_dev = nullptr;
-      if (filter) {
-        k_lsi_filter<<<div_up(Q.n_points, kFilterCtaPoints), kFilterThreads, 0, c->stream>>>(
-            Q, Bm.bvh.occ.p, surv, surv_n, long_list, surv_n + 2);
-        slots = surv;
-        n_slots_dev = surv_n;
-        // grid for the worst case; warps beyond the survivor count exit at once
-        n_slots = c->last_survivors ? min(Q.n_points, c->last_survivors + c->last_survivors / 4 + 4096) : Q.n_points;
-      }
-      if (cells) {
-        // survivors: cell directory; the long ones (usually none) walk the tree
-        k_lsi_cells<<<kNumSMs * 48, kLsiWarps * 32, 0, c->stream>>>(Q, Bm.bvh.view(), surv, surv_n, cands, ccap,
-                                                                  surv_n + 1);
-        slots = long_list;
-        n_slots_dev = surv_n + 2;
-        n_slots = c->last_long ? min(Q.n_points, c->last_long + c->last_long / 4 + 1024) : 0;
-      }
-      // the long-edge list comes from all over the map: two queries per warp while it is short
-      const uint32_t spw = cells && n_slots <= 16384 ? 2 : 32;
-      unsigned tiles = div_up(n_slots, spw);
-      unsigned blocks = div_up(tiles, kLsiWarps);
-      if (blocks == 0) {
-        // nothing to walk (no long edges last time; a non-empty list triggers the retry below)
-      } else if (c->stats)
-        k_lsi_bvh<true><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-            Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
-      else
-        k_lsi_bvh<false><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-            Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
-      RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
-      k_lsi_exact<<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
-                                                     xs, cap, (unsigned int*) ctr, ctr + 1);
-      k_lsi_points<<<kNumSMs * 3, kPointsThreads, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs);
-      RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
-      RJB_CUDA(cudaGetLastError());
-      // one read-back into pinned memory: the only host round trip of the query
-      RJB_CUDA(cudaMemcpyAsync(c->h_counters, ctr, 10 * sizeof(unsigned long long),
-                               cudaMemcpyDeviceToHost, c->stream));
-      wait_stream(c->stream);
-      memcpy(h, c->h_counters, sizeof(h));
-      unsigned int hs[4];
-      memcpy(hs, c->h_counters + 8, sizeof(hs));
-      // launches sized from the last query
-      bool grid_too_small = cells ? hs[2] > n_slots : (filter && hs[0] > n_slots);
-      if (cells) c->last_long = hs[2];
-      if (filter) {
-        c->last_survivors = hs[0];
-        c->filter_useless = hs[0] > Q.n_edges / 2;  // adaptive: not worth a pass over S
-      }
-      if (hs[1] <= ccap && !grid_too_small) break;
-      RJB_REQUIRE(attempt < 2, "rjb_lsi: internal queues overflowed repeatedly");
-      if (hs[1] > ccap) c->cand_cap = (size_t) hs[1] + hs[1] / 8 + 65536;
-    }
-    if (filter) h[7] = c->last_survivors;
-    if (cells) {  // which path produced the candidates (no traversal statistics in this mode)
-      h[5] = 1;
-      h[6] = c->last_long;
-    }
-  } else {
-    RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
+    RJB_REQUIRE(c->cand_cap < 0xFFFFFFF0ull, "rjb_lsi: candidate queue exceeds 2^32 entries");
+    const uint32_t ccap = (uint32_t) c->cand_cap;
+    uint2* cands = c->cands.ensure(ccap);
+    RJB_CUDA(cudaMemsetAsync(ctr, 0, 10 * sizeof(unsigned long long), c->stream));
     RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    if (Q.n_edges > 0 && B.n_edges > 0) {
-      if (mode == RJB_MODE_GRID) {
-        if (!Bm.grid.built) throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no grid on the base map");
-        lsi_grid(Bm.grid, Q, B, pairs, cap, (unsigned int*) ctr, ctr + 1, c->stream);
-      } else if (mode == RJB_MODE_BRUTE) {
-        dim3 g(div_up(Q.n_edges, 256), min(64u, div_up(B.n_edges, 256)));
-        k_lsi_brute<<<g, 256, 0, c->stream>>>(Q, B, pairs, cap, (unsigned int*) ctr, ctr + 1);
-      } else if (mode != RJB_MODE_LBVH) {
-        throw Error(RJB_ERR_INVALID, "rjb_lsi: unknown mode");
-      }
-    } else if (mode == RJB_MODE_LBVH && !Bm.bvh.built) {
-      throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no LBVH on the base map");
+    // query slots: point indices (edge = slot, slot + 1), or a list of start points
+    // (Morton-sorted edges, or the survivors of the occupancy filter, whose count
+    // stays on the device)
+    uint32_t n_slots = order ? Q.n_edges : Q.n_points;
+    const uint32_t* slots = order;
+    const unsigned int* n_slots_dev = nullptr;
+    if (filter) {
+      k_lsi_filter<<<div_up(Q.n_points, kFilterCtaPoints), kFilterThreads, 0, c->stream>>>(
+          Q, Bm.bvh.occ.p, surv, surv_n, long_list, surv_n + 2);
+      slots = surv;
+      n_slots_dev = surv_n;
+      // grid for the worst case; warps beyond the survivor count exit at once
+      n_slots = c->last_survivors ? min(Q.n_points, c->last_survivors + c->last_survivors / 4 + 4096) : Q.n_points;
+    }
+    if (c->stage_timing) RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    if (cells) {
+      // survivors: cell directory; the long ones (usually none) walk the tree
+      k_lsi_cells<<<kNumSMs * 48, kLsiWarps * 32, 0, c->stream>>>(Q, Bm.bvh.view(), surv, surv_n, cands, ccap,
+                                                                surv_n + 1);
+      slots = long_list;
+      n_slots_dev = surv_n + 2;
+      n_slots = c->last_long ? min(Q.n_points, c->last_long + c->last_long / 4 + 1024) : 0;
+    }
+    // the long-edge list comes from all over the map: two queries per warp while it is short
+    const uint32_t spw = cells && n_slots <= 16384 ? 2 : 32;
+    unsigned tiles = div_up(n_slots, spw);
+    unsigned blocks = div_up(tiles, kLsiWarps);
+    if (blocks == 0) {
+      // nothing to walk (no long edges last time; a non-empty list triggers the retry in lsi_finish)
+    } else if (c->stats)
+      k_lsi_bvh<true><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
+          Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
+    else
+      k_lsi_bvh<false><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
+          Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
+    RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    k_lsi_exact<<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
+                                                   xs, cap, (unsigned int*) ctr, ctr + 1);
+    if (c->stage_timing) RJB_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    k_lsi_points<<<kNumSMs * 3, kPointsThreads, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs, false);
+    RJB_CUDA(cudaEventRecord(c->ev[4], c->stream));
+    RJB_CUDA(cudaGetLastError());
+    P.lbvh = true;
+    P.filter = filter;
+    P.cells = cells;
+    P.ccap = ccap;
+    P.n_slots = n_slots;
+    P.launches = 3 + (filter ? 1 : 0) + (cells ? 1 : 0) - (blocks == 0 ? 1 : 0);
+    c->timing_pending = 4;
+    c->timing_layout = c->stage_timing ? 1 : 2;
+  } else if (mode == RJB_MODE_GRID && nonempty) {
+    // cell filter -> (query edge, occupied cell) work items -> dense exact pass -> point pass.
+    // Reference semantics of LSIGrid: intersect_test(map-0 edge, map-1 edge) whatever the query
+    // side, a pair kept iff the cell of its intersection point holds both edges.
+    if (c->grid_work_cap < 65536) c->grid_work_cap = (size_t) Q.n_edges / 4 + 65536;
+    RJB_REQUIRE(c->grid_work_cap < 0xFFFFFFF0ull, "rjb_lsi: work list exceeds 2^32 entries");
+    const uint32_t wcap = (uint32_t) c->grid_work_cap;
+    uint2* work = c->cands.ensure(wcap);
+    uint32_t* big = c->long_edges.ensure(Q.n_points);
+    unsigned int* wn = (unsigned int*) (ctr + 8);  // [0] work items, [2] long query edges
+    const GridView gv = Bm.grid.view();
+    RJB_CUDA(cudaMemsetAsync(ctr, 0, 10 * sizeof(unsigned long long), c->stream));
+    RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    k_grid_lsi_filter<<<div_up(Q.n_points, 256), 256, 0, c->stream>>>(Q, gv, work, wcap, wn, big, wn + 2);
+    k_grid_lsi_big<<<kNumSMs, 256, 0, c->stream>>>(Q, gv, big, wn + 2, work, wcap, wn);
+    RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    k_grid_lsi_exact<<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, gv, q, work, wn, wcap, xs, cap,
+                                                                 (unsigned int*) ctr, ctr + 1);
+    RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    k_lsi_points<<<kNumSMs * 3, kPointsThreads, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs, q == 1);
+    RJB_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    RJB_CUDA(cudaGetLastError());
+    P.grid = true;
+    P.ccap = wcap;
+    P.launches = 4;
+    c->timing_pending = 3;
+    c->timing_layout = 3;
+  } else {
+    RJB_CUDA(cudaMemsetAsync(ctr, 0, 10 * sizeof(unsigned long long), c->stream));
+    RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    uint2* pairs = c->pairs.ensure(cap ? cap : 1);
+    if (nonempty && mode == RJB_MODE_BRUTE) {
+      dim3 g(div_up(Q.n_edges, 256), min(64u, div_up(B.n_edges, 256)));
+      k_lsi_brute<<<g, 256, 0, c->stream>>>(Q, B, pairs, cap, (unsigned int*) ctr, ctr + 1);
+      P.launches++;
     }
     RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
     // the point pass reads the count on the device: no host round trip between
     // the two kernels
-    if (cap > 0)
+    if (cap > 0 && nonempty) {
       k_xsect_points_dyn<<<div_up(cap, 128), 128, 0, c->stream>>>(
           Q, B, q, pairs, (const unsigned int*) ctr, cap, xs);
+      P.launches++;
+    }
     RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
     RJB_CUDA(cudaGetLastError());
-    RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    RJB_CUDA(cudaStreamSynchronize(c->stream));
+    c->timing_pending = 2;  // event times are fetched when rjb_last_kernel_ms asks for them
+    c->timing_layout = 0;
   }
+  // one read-back into pinned memory: the only host round trip of the query
+  RJB_CUDA(cudaMemcpyAsync(c->h_counters, ctr, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                           c->stream));
+  P.active = true;
+}
+
+// Returns the number of intersections found.
+static uint64_t lsi_finish(rjb_ctx* c, uint64_t* n_candidates) {
+  LsiPending& P = c->lsi_pending;
+  RJB_REQUIRE(P.active, "rjb_lsi_wait: no query was launched");
+  unsigned long long h[8];
+  unsigned launches = 0;
+  while (true) {
+    try {
+      wait_stream(c->stream);
+    } catch (...) {
+      P.active = false;
+      throw;
+    }
+    launches += P.launches;
+    memcpy(h, c->h_counters, sizeof(h));
+    unsigned int hs[4];
+    memcpy(hs, c->h_counters + 8, sizeof(hs));
+    if (P.grid) {
+      h[2] = hs[0];  // (query edge, occupied cell) work items
+      h[6] = hs[2];  // query edges longer than kGridSmallCells cells
+      if (hs[0] <= P.ccap) break;
+      if (P.attempt >= 2) {
+        P.active = false;
+        throw Error(RJB_ERR_INVALID, "rjb_lsi: internal queues overflowed repeatedly");
+      }
+      c->grid_work_cap = (size_t) hs[0] + hs[0] / 8 + 65536;
+      P.attempt++;
+      const int q = P.q, mode = P.mode;
+      const double xf = P.xsect_factor;
+      try {
+        lsi_enqueue(c, q, mode, xf);
+      } catch (...) {
+        P.active = false;
+        throw;
+      }
+      continue;
+    }
+    if (!P.lbvh) break;
+    // launches sized from the last query
+    const bool grid_too_small = P.cells ? hs[2] > P.n_slots : (P.filter && hs[0] > P.n_slots);
+    if (P.cells) c->last_long = hs[2];
+    if (P.filter) {
+      c->last_survivors = hs[0];
+      // adaptive: not worth a pass over S
+      c->filter_useless = hs[0] > c->maps[P.q].n_edges / 2;
+    }
+    if (!c->stats) h[2] = hs[1];  // (query, leaf) pairs the traversal handed to the exact pass
+    if (P.filter) h[7] = c->last_survivors;
+    if (P.cells) {  // which path produced the candidates (no traversal statistics in this mode)
+      h[5] = 1;
+      h[6] = c->last_long;
+    }
+    if (hs[1] <= P.ccap && !grid_too_small) break;
+    if (P.attempt >= 2) {
+      P.active = false;
+      throw Error(RJB_ERR_INVALID, "rjb_lsi: internal queues overflowed repeatedly");
+    }
+    if (hs[1] > P.ccap) c->cand_cap = (size_t) hs[1] + hs[1] / 8 + 65536;
+    P.attempt++;
+    const int q = P.q, mode = P.mode;
+    const double xf = P.xsect_factor;
+    try {
+      lsi_enqueue(c, q, mode, xf);
+    } catch (...) {
+      P.active = false;
+      throw;
+    }
+  }
+  const uint32_t cap = P.cap;
+  P.active = false;
+  P.attempt = 0;
+  c->last_launches = launches;
   memcpy(c->last_stats, h, sizeof(h));
-  c->timing_pending = 2;  // event times are fetched when rjb_last_kernel_ms asks for them
   uint64_t n = (uint32_t) h[0];
   if (n_candidates) *n_candidates = h[1];
   if (n > cap) {
@@ -475,48 +584,104 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
   return n;
 }
 
+static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_t* n_candidates) {
+  c->lsi_pending.active = false;  // an abandoned launch is superseded
+  lsi_enqueue(c, q, mode, xsect_factor);
+  return lsi_finish(c, n_candidates);
+}
+
+// order of the query points for coherent warps: key = the 4096 x 4096 cell of the point in
+// Morton order (LBVH) or its grid cell in the grid's own column-major numbering (grid: a warp
+// then walks one column together).  Only coherence is needed, not a total order.
+__global__ void k_query_keys_points_grid(const longlong2* __restrict__ pts, uint32_t n, GridView g,
+                                         uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const longlong2 p = pts[i];
+  key[i] = (uint64_t) grid_cell(g, p.x) * g.gs + (uint64_t) grid_cell(g, p.y - 1);
+  val[i] = i;
+}
+
+// `user_points`: the caller handed its own points (not the vertices of a map, which are
+// coherent along their chains): with sort_queries = -1 (auto) those are ordered when there are
+// enough of them to pay for the sort.
 static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t n,
-                   uint64_t* n_candidates) {
+                   uint64_t* n_candidates, bool user_points = false) {
   check_map_id(q);
   DeviceMap& Bm = c->maps[1 - q];
   RJB_REQUIRE(Bm.loaded, "rjb_pip: base map not loaded");
+  RJB_REQUIRE(mode == RJB_MODE_LBVH || mode == RJB_MODE_GRID || mode == RJB_MODE_BRUTE, "rjb_pip: unknown mode");
   uint32_t* eid = c->pip_eid.ensure(n ? n : 1);
   int32_t* face = c->pip_face.ensure(n ? n : 1);
-  // [8], [9]: {filter survivors, (query, leaf) pairs} as 32-bit counters
   unsigned long long* ctr = c->counters.ensure(10);
   ensure_events(c);
   RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
   MapView B = Bm.view();
+  if (mode == RJB_MODE_LBVH && !Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no LBVH on the base map");
+  if (mode == RJB_MODE_GRID && !Bm.grid.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no grid on the base map");
+  unsigned launches = 0;
   RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
-  if (n > 0) {
-    if (mode == RJB_MODE_LBVH) {
-      if (!Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no LBVH on the base map");
-      const uint32_t* order = query_order_points(c, d_pts, n);
-      RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
-      const unsigned pb = div_up(n, kLsiWarps * 32), pt = kLsiWarps * 32;
-      if (c->stats)
-        k_pip_bvh<true, false><<<pb, pt, 0, c->stream>>>(d_pts, n, order, B, Bm.bvh.view(), q, eid, face, ctr);
-      else if (c->pip_park)
-        k_pip_bvh<false, true><<<pb, pt, 0, c->stream>>>(d_pts, n, order, B, Bm.bvh.view(), q, eid, face, ctr);
-      else
-        k_pip_bvh<false, false><<<pb, pt, 0, c->stream>>>(d_pts, n, order, B, Bm.bvh.view(), q, eid, face, ctr);
-    } else if (mode == RJB_MODE_GRID) {
-      if (!Bm.grid.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no grid on the base map");
-      pip_grid(Bm.grid, d_pts, n, B, q, eid, face, ctr + 1, c->stream);
-    } else if (mode == RJB_MODE_BRUTE) {
-      k_pip_brute<<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, B, q, eid, face);
+  const uint32_t* order = nullptr;
+  const bool sort = n > 0 && mode != RJB_MODE_BRUTE && B.n_edges > 0 &&
+                    (c->sort_queries > 0 || (c->sort_queries < 0 && user_points && n >= 65536));
+  if (sort) {
+    uint64_t* ka = c->ord_keys_a.ensure(n);
+    uint64_t* kb = c->ord_keys_b.ensure(n);
+    uint32_t* va = c->ord_vals_a.ensure(n);
+    uint32_t* vb = c->ord_vals_b.ensure(n);
+    if (mode == RJB_MODE_GRID) {
+      const GridView gv = Bm.grid.view();
+      k_query_keys_points_grid<<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, gv, ka, va);
+      int bits = 1;
+      while (bits < 40 && (((uint64_t) gv.gsize * gv.gs) >> bits)) bits++;
+      // the low (row) bits beyond 24 key bits buy nothing: three radix passes at most
+      const int lo = bits > 24 ? bits - 24 : 0;
+      sort_pairs_u64_u32(ka, kb, va, vb, n, lo, bits, c->ord_sort, c->stream);
+      launches += 2 + (bits - lo + 7) / 8 + 1;
     } else {
-      throw Error(RJB_ERR_INVALID, "rjb_pip: unknown mode");
+      k_query_keys_points<<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, c->sc.internal_min, ka, va);
+      // the top 24 Morton bits (4096 x 4096 cells) = 3 radix passes instead of 8
+      sort_pairs_u64_u32(ka, kb, va, vb, n, 40, 64, c->ord_sort, c->stream);
+      launches += 2 + 3 + 1;
     }
+    order = vb;
   }
   RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  // ordered queries write their results through ONE scattered 8-byte store per point
+  uint2* packed = order ? c->pip_packed.ensure(n) : nullptr;
+  if (n > 0) {
+    if (mode == RJB_MODE_LBVH) {
+      const unsigned pb = div_up(n, kLsiWarps * 32), pt = kLsiWarps * 32;
+      if (c->stats)
+        k_pip_bvh<true, false><<<pb, pt, 0, c->stream>>>(d_pts, n, order, B, Bm.bvh.view(), q, eid, face, packed, ctr);
+      else if (c->pip_park)
+        k_pip_bvh<false, true><<<pb, pt, 0, c->stream>>>(d_pts, n, order, B, Bm.bvh.view(), q, eid, face, packed, ctr);
+      else
+        k_pip_bvh<false, false><<<pb, pt, 0, c->stream>>>(d_pts, n, order, B, Bm.bvh.view(), q, eid, face, packed, ctr);
+    } else if (mode == RJB_MODE_GRID) {
+      const GridView gv = Bm.grid.view();
+      if (packed)
+        k_pip_grid<true><<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, order, B, gv, q, eid, face, packed, ctr + 1);
+      else
+        k_pip_grid<false><<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, order, B, gv, q, eid, face, nullptr, ctr + 1);
+    } else {
+      k_pip_brute<<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, B, q, eid, face);
+    }
+    launches++;
+    if (packed) {
+      k_pip_split<<<div_up(n, 256), 256, 0, c->stream>>>(packed, n, eid, face);
+      launches++;
+    }
+  }
+  RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
   RJB_CUDA(cudaGetLastError());
-  unsigned long long h[8];
-  RJB_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  RJB_CUDA(cudaMemcpyAsync(c->h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   RJB_CUDA(cudaStreamSynchronize(c->stream));
-  memcpy(c->last_stats, h, sizeof(h));
-  c->timing_pending = 1;
-  if (n_candidates) *n_candidates = h[1];
+  memcpy(c->last_stats, c->h_counters, 8 * sizeof(unsigned long long));
+  c->last_launches = launches;
+  c->timing_pending = 2;
+  c->timing_layout = 4;  // {ordering of the points, query kernel (+ result split)}
+  if (n_candidates) *n_candidates = c->last_stats[1];
 }
 
 }  // namespace rjb
@@ -554,8 +719,10 @@ void rjb_destroy(rjb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i <= kTimedStages; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2; i++)
+    if (c->bev[i]) cudaEventDestroy(c->bev[i]);
   for (int i = 0; i <= kLoadChunksMax; i++)
     if (c->chunk_ev[i]) cudaEventDestroy(c->chunk_ev[i]);
   if (c->aux) cudaStreamDestroy(c->aux);
@@ -578,7 +745,9 @@ int rjb_set_bounding_box(rjb_ctx* c, double min_x, double min_y, double max_x, d
     RJB_REQUIRE(min_x <= max_x && min_y <= max_y, "rjb_set_bounding_box: empty box");
     scaling_init(c->sc, min_x, min_y, max_x, max_y);
     c->have_scaling = true;
-    // scaled coordinates of loaded maps are stale now
+    // scaled coordinates of loaded maps are stale now, and so is every result derived from them
+    c->ov.done = false;
+    c->ov.n_xsects = 0;
     for (auto& m : c->maps) {
       m.loaded = false;
       m.edge_order_valid = false;
@@ -615,6 +784,8 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
       c->use_cells = (int) value;
     } else if (n == "pip_park") {
       c->pip_park = value != 0;
+    } else if (n == "stage_timing") {
+      c->stage_timing = value != 0;
     } else if (n == "stats") {
       c->stats = value != 0;
     } else if (n == "keep_host_graph") {
@@ -640,6 +811,8 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
     m.edge_order_valid = false;
     m.bvh.built = false;
     m.grid.built = false;
+    c->ov.done = false;  // overlay results index the OLD map's edges and points
+    c->ov.n_xsects = 0;
     c->filter_useless = false;  // new data: let the occupancy filter prove itself again
     if (n_chains > 0) {
       RJB_REQUIRE(row_index[0] == 0 && row_index[n_chains] == n_points,
@@ -767,6 +940,41 @@ int rjb_lsi(rjb_ctx* c, int query_map_id, int mode, double xsect_factor,
   return rc;
 }
 
+int rjb_lsi_launch(rjb_ctx* c, int query_map_id, int mode, double xsect_factor) {
+  return guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    RJB_CUDA(cudaSetDevice(c->device));
+    c->lsi_pending.active = false;
+    lsi_enqueue(c, query_map_id, mode, xsect_factor);
+  });
+}
+
+int rjb_lsi_wait(rjb_ctx* c, const rjb_xsect** d_xsects, uint64_t* n_xsects, uint64_t* n_candidates) {
+  if (n_xsects) *n_xsects = 0;
+  if (d_xsects) *d_xsects = nullptr;
+  uint64_t needed = 0;
+  int rc = guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    RJB_CUDA(cudaSetDevice(c->device));
+    try {
+      needed = lsi_finish(c, n_candidates);
+    } catch (const Error& e) {
+      if (e.code == RJB_ERR_QUEUE_OVERFLOW) needed = (uint32_t) c->last_stats[0];
+      throw;
+    }
+    if (d_xsects) *d_xsects = c->xsects.p;
+  });
+  if (n_xsects) *n_xsects = needed;
+  return rc;
+}
+
+int rjb_last_launches(const rjb_ctx* c, uint32_t* out) {
+  return guarded([&] {
+    RJB_REQUIRE(c && out, "NULL argument");
+    *out = c->last_launches;
+  });
+}
+
 int rjb_pip(rjb_ctx* c, int query_map_id, int mode, const int64_t* d_points_xy, uint64_t n_points,
             const uint32_t** d_closest_eid, const int32_t** d_face_id, uint64_t* n_candidates) {
   return guarded([&] {
@@ -774,6 +982,7 @@ int rjb_pip(rjb_ctx* c, int query_map_id, int mode, const int64_t* d_points_xy, 
     RJB_CUDA(cudaSetDevice(c->device));
     check_map_id(query_map_id);
     const longlong2* pts = (const longlong2*) d_points_xy;
+    const bool user_points = pts != nullptr;
     if (!pts) {
       const DeviceMap& Qm = c->maps[query_map_id];
       RJB_REQUIRE(Qm.loaded, "rjb_pip: query map not loaded and no points given");
@@ -781,7 +990,7 @@ int rjb_pip(rjb_ctx* c, int query_map_id, int mode, const int64_t* d_points_xy, 
       n_points = Qm.n_points;
     }
     RJB_REQUIRE(n_points < 0xFFFFFFF0ull, "rjb_pip: too many points");
-    do_pip(c, query_map_id, mode, pts, (uint32_t) n_points, n_candidates);
+    do_pip(c, query_map_id, mode, pts, (uint32_t) n_points, n_candidates, user_points);
     if (d_closest_eid) *d_closest_eid = c->pip_eid.p;
     if (d_face_id) *d_face_id = c->pip_face.p;
   });
@@ -803,7 +1012,7 @@ int rjb_pip_host(rjb_ctx* c, int query_map_id, int mode, const double* h_xy, uin
       k_scale_points<<<div_up(n, 256), 256, 0, c->stream>>>(raw, n, c->sc.rx, c->sc.ry,
                                                             c->sc.deltax, c->sc.deltay, pts);
     }
-    do_pip(c, query_map_id, mode, pts, n, nullptr);
+    do_pip(c, query_map_id, mode, pts, n, nullptr, true);
     if (n && h_closest_eid)
       RJB_CUDA(cudaMemcpyAsync(h_closest_eid, c->pip_eid.p, (size_t) n * sizeof(uint32_t),
                                cudaMemcpyDeviceToHost, c->stream));
@@ -825,7 +1034,7 @@ int rjb_pip_host_scaled(rjb_ctx* c, int query_map_id, int mode, const int64_t* h
     if (n)
       RJB_CUDA(cudaMemcpyAsync(pts, h_points_xy, (size_t) n * sizeof(longlong2),
                                cudaMemcpyHostToDevice, c->stream));
-    do_pip(c, query_map_id, mode, pts, n, nullptr);
+    do_pip(c, query_map_id, mode, pts, n, nullptr, true);
     if (n && h_closest_eid)
       RJB_CUDA(cudaMemcpyAsync(h_closest_eid, c->pip_eid.p, (size_t) n * sizeof(uint32_t),
                                cudaMemcpyDeviceToHost, c->stream));
@@ -836,20 +1045,56 @@ int rjb_pip_host_scaled(rjb_ctx* c, int query_map_id, int mode, const int64_t* h
   });
 }
 
+// the events of the last query have completed (every query ends with a stream wait)
+static void resolve_timing(rjb_ctx* m) {
+  if (!m->timing_pending) return;
+  for (int k = 0; k < kTimedStages; k++) m->last_ms[k] = 0;
+  if (m->timing_layout == 2) {
+    // LBVH LSI without the per-kernel events: {filter + traversal, 0, exact + points, 0}
+    RJB_CUDA(cudaEventElapsedTime(&m->last_ms[0], m->ev[0], m->ev[2]));
+    RJB_CUDA(cudaEventElapsedTime(&m->last_ms[2], m->ev[2], m->ev[4]));
+    m->timing_layout = 1;
+  } else {
+    for (int k = 0; k < m->timing_pending; k++)
+      RJB_CUDA(cudaEventElapsedTime(&m->last_ms[k], m->ev[k], m->ev[k + 1]));
+  }
+  m->timing_pending = 0;
+}
+
 /* device times (ms) of the kernels of the last rjb_lsi / rjb_pip call:
- * out[0] = traversal / cell kernel, out[1] = intersection-point pass */
+ * out[0] = traversal / cell kernel (LBVH LSI: occupancy filter + tree walk),
+ * out[1] = exact pass (LBVH LSI: exact pass + point pass; grid / brute: point pass) */
 int rjb_last_kernel_ms(const rjb_ctx* c, double out[2]) {
   return guarded([&] {
     RJB_REQUIRE(c && out, "NULL argument");
     rjb_ctx* m = const_cast<rjb_ctx*>(c);
-    if (m->timing_pending) {  // the events have completed: every query ends with a stream wait
-      RJB_CUDA(cudaEventElapsedTime(&m->last_ms[0], m->ev[0], m->ev[1]));
-      m->last_ms[1] = 0;
-      if (m->timing_pending == 2) RJB_CUDA(cudaEventElapsedTime(&m->last_ms[1], m->ev[1], m->ev[2]));
-      m->timing_pending = 0;
+    resolve_timing(m);
+    if (c->timing_layout == 1) {
+      out[0] = (double) c->last_ms[0] + c->last_ms[1];
+      out[1] = (double) c->last_ms[2] + c->last_ms[3];
+    } else if (c->timing_layout == 3) {  // grid LSI: {cell filter, exact pass, point pass}
+      out[0] = (double) c->last_ms[0] + c->last_ms[1];
+      out[1] = c->last_ms[2];
+    } else if (c->timing_layout == 4) {  // PIP: {ordering, query kernel}
+      out[0] = c->last_ms[1];
+      out[1] = 0;
+    } else {
+      out[0] = c->last_ms[0];
+      out[1] = c->last_ms[1];
     }
-    out[0] = c->last_ms[0];
-    out[1] = c->last_ms[1];
+  });
+}
+
+/* per-kernel device times (ms) of the last query.  LBVH LSI: out = {k_lsi_filter,
+ * k_lsi_bvh (+ k_lsi_cells), k_lsi_exact, k_lsi_points}; any other query: {query kernel,
+ * point pass, 0, 0}.  *layout (optional) says which (1 = the four LBVH LSI stages). */
+int rjb_last_stage_ms(const rjb_ctx* c, double out[4], int* layout) {
+  return guarded([&] {
+    RJB_REQUIRE(c && out, "NULL argument");
+    rjb_ctx* m = const_cast<rjb_ctx*>(c);
+    resolve_timing(m);
+    for (int k = 0; k < kTimedStages; k++) out[k] = c->last_ms[k];
+    if (layout) *layout = c->timing_layout;
   });
 }
 
@@ -900,6 +1145,74 @@ int rjb_debug_sort_pairs(rjb_ctx* c, uint64_t* h_keys, uint32_t* h_vals, uint64_
     sort_pairs_u64_u32(ka, kb, va, vb, (uint32_t) n, begin_bit, end_bit, c->ord_sort, c->stream);
     RJB_CUDA(cudaMemcpyAsync(h_keys, kb, n * 8, cudaMemcpyDeviceToHost, c->stream));
     RJB_CUDA(cudaMemcpyAsync(h_vals, vb, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    RJB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+/* debug hooks: the exact arithmetic on the device over caller-supplied cases (rjb_debug.cuh) */
+int rjb_debug_intersect_batch(rjb_ctx* c, const int64_t* h_pts, uint64_t n, int mode, uint8_t* h_flags,
+                              int64_t* h_x, int64_t* h_y) {
+  return guarded([&] {
+    RJB_REQUIRE(c && (n == 0 || (h_pts && h_flags && h_x && h_y)), "NULL argument");
+    RJB_REQUIRE(mode == 0 || mode == 1, "mode must be 0 or 1");
+    RJB_CUDA(cudaSetDevice(c->device));
+    if (n == 0) return;
+    DBuf<long long> pts, x, y;
+    DBuf<unsigned char> fl;
+    pts.ensure(8 * n); x.ensure(n); y.ensure(n); fl.ensure(n);
+    RJB_CUDA(cudaMemcpyAsync(pts.p, h_pts, 8 * n * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    k_debug_intersect<<<div_up(n, 128), 128, 0, c->stream>>>(pts.p, n, mode, fl.p, x.p, y.p);
+    RJB_CUDA(cudaGetLastError());
+    RJB_CUDA(cudaMemcpyAsync(h_flags, fl.p, n, cudaMemcpyDeviceToHost, c->stream));
+    RJB_CUDA(cudaMemcpyAsync(h_x, x.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    RJB_CUDA(cudaMemcpyAsync(h_y, y.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    RJB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int rjb_debug_i128_batch(rjb_ctx* c, const uint64_t* h_v, const uint64_t* h_d, uint64_t n, double* h_cvt,
+                         double* h_div, int64_t* h_trunc) {
+  return guarded([&] {
+    RJB_REQUIRE(c && (n == 0 || (h_v && h_cvt)), "NULL argument");
+    RJB_REQUIRE(!h_d || (h_div && h_trunc), "NULL argument");
+    RJB_CUDA(cudaSetDevice(c->device));
+    if (n == 0) return;
+    DBuf<unsigned long long> v, d;
+    DBuf<double> cvt, dv;
+    DBuf<long long> tr;
+    v.ensure(2 * n); cvt.ensure(n);
+    RJB_CUDA(cudaMemcpyAsync(v.p, h_v, 16 * n, cudaMemcpyHostToDevice, c->stream));
+    if (h_d) {
+      d.ensure(2 * n); dv.ensure(n); tr.ensure(n);
+      RJB_CUDA(cudaMemcpyAsync(d.p, h_d, 16 * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    k_debug_i128<<<div_up(n, 256), 256, 0, c->stream>>>(v.p, h_d ? d.p : nullptr, n, cvt.p, dv.p, tr.p);
+    RJB_CUDA(cudaGetLastError());
+    RJB_CUDA(cudaMemcpyAsync(h_cvt, cvt.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (h_d) {
+      RJB_CUDA(cudaMemcpyAsync(h_div, dv.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+      RJB_CUDA(cudaMemcpyAsync(h_trunc, tr.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    RJB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int rjb_debug_pip_batch(rjb_ctx* c, const int64_t* h_edges, uint64_t n_edges, const int64_t* h_pts,
+                        uint64_t n, int query_map_id, uint32_t* h_out) {
+  return guarded([&] {
+    RJB_REQUIRE(c && (n == 0 || (h_pts && h_out)) && (n_edges == 0 || h_edges), "NULL argument");
+    RJB_REQUIRE(n_edges < 0xFFFFFFF0ull, "too many edges");
+    check_map_id(query_map_id);
+    RJB_CUDA(cudaSetDevice(c->device));
+    if (n == 0) return;
+    DBuf<long long> e, p;
+    DBuf<uint32_t> o;
+    e.ensure(4 * n_edges + 1); p.ensure(2 * n); o.ensure(n);
+    if (n_edges) RJB_CUDA(cudaMemcpyAsync(e.p, h_edges, 32 * n_edges, cudaMemcpyHostToDevice, c->stream));
+    RJB_CUDA(cudaMemcpyAsync(p.p, h_pts, 16 * n, cudaMemcpyHostToDevice, c->stream));
+    k_debug_pip<<<div_up(n, 128), 128, 0, c->stream>>>(e.p, (uint32_t) n_edges, p.p, n, query_map_id, o.p);
+    RJB_CUDA(cudaGetLastError());
+    RJB_CUDA(cudaMemcpyAsync(h_out, o.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
     RJB_CUDA(cudaStreamSynchronize(c->stream));
   });
 }

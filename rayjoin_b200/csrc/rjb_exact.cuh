@@ -269,6 +269,67 @@ static __host__ __device__ void lsi_point(const Seg& e1, const Seg& e2, long lon
   oy = lsi_point_axis(e1, e2, 1);
 }
 
+// ---- cell of the intersection point, as the reference's grid LSI computes it ----------
+// LSIGrid keeps a pair only in the cell of its intersection point (src/app/lsi_grid.h:62-66):
+// calculate_cell(gsize, scaling, xsect_x) with xsect_x the gcd-reduced, clamped
+// tcb::rational<__int128> (src/grid/cell.h:15-22).  `val - internal_min` is again a rational
+// (n' = num - imin * den over den), `* cell_scale` has no rational overload, so the rational
+// converts through operator double: cell = (int) (fl(fl(n') / fl(d')) * cell_scale).
+//
+// For an integer coordinate v the same function gives (int) ((double) (v - imin) * cell_scale).
+static RJB_HD int ref_cell(long long v, long long imin, double cell_scale) {
+  return (int) ((double) (v - imin) * cell_scale);
+}
+
+// Exact value V = X0 + rs / aden of the (clamped) point is known without the gcd (see
+// lsi_point_axis); the reference's three roundings move V * cell_scale by < 2^-36 cells and
+// the short-cut below by < 2^-37, so unless the product lies within 10^-6 of a cell boundary
+// every evaluation order truncates to the same cell.  Otherwise -- and for map-spanning edges,
+// whose 128-bit products wrap -- the reference's sequence is replayed literally.
+static __host__ __device__ int lsi_xsect_ref_cell(const Seg& e1, const Seg& e2, int axis, long long imin,
+                                                  double cell_scale) {
+  long long a1l, b1l, a2l, b2l;
+  edge_ab(e1, a1l, b1l);
+  edge_ab(e2, a2l, b2l);
+  const long long lo = axis == 0 ? min4ll(e1.x1, e1.x2, e2.x1, e2.x2) : min4ll(e1.y1, e1.y2, e2.y1, e2.y2);
+  const long long hi = axis == 0 ? max4ll(e1.x1, e1.x2, e2.x1, e2.x2) : max4ll(e1.y1, e1.y2, e2.y1, e2.y2);
+  const i128 a1 = a1l, b1 = b1l, a2 = a2l, b2 = b2l;
+  const i128 denom = (i128) ((u128) a1 * (u128) b2 - (u128) a2 * (u128) b1);
+  const long long lim = 1ll << 38;
+  if (a1l > -lim && a1l < lim && b1l < lim && a2l > -lim && a2l < lim && b2l < lim &&
+      lo >= -(1ll << 46) && hi <= (1ll << 46)) {
+    const i128 aden = iabs128(denom);
+    const i128 c2p = -((i128) (e2.x1 - e1.x1) * a2l + (i128) (e2.y1 - e1.y1) * b2l);
+    const i128 np = axis == 0 ? c2p * b1l : -c2p * a1l;
+    const long long q = (long long) rint((double) np / (double) denom);
+    const i128 r = np - (i128) q * denom;
+    long long X0 = (axis == 0 ? e1.x1 : e1.y1) + q;
+    i128 rs = denom < 0 ? -r : r;
+    while (rs < 0) { rs += aden; X0--; }
+    while (rs >= aden) { rs -= aden; X0++; }
+    if (X0 < lo) return ref_cell(lo, imin, cell_scale);
+    if (X0 > hi || (X0 == hi && rs != 0)) return ref_cell(hi, imin, cell_scale);
+    if (rs == 0) return ref_cell(X0, imin, cell_scale);
+    const double approx = ((double) (X0 - imin) + (double) rs / (double) aden) * cell_scale;
+    const double fr = approx - floor(approx);
+    if (fr > 1e-6 && fr < 1.0 - 1e-6) return (int) approx;
+  }
+  // the reference's own sequence
+  const i128 c1 = -(i128) e1.x1 * a1 - (i128) e1.y1 * b1;
+  const i128 c2 = -(i128) e2.x1 * a2 - (i128) e2.y1 * b2;
+  const i128 num = axis == 0 ? (i128) ((u128) c2 * (u128) b1 - (u128) c1 * (u128) b2)
+                             : (i128) ((u128) a2 * (u128) c1 - (u128) a1 * (u128) c2);
+  i128 rn, rd;
+  rat_make(num, denom, rn, rd);
+  if (rn < (i128) ((u128) (i128) lo * (u128) rd)) { rn = lo; rd = 1; }
+  if ((i128) ((u128) (i128) hi * (u128) rd) < rn) { rn = hi; rd = 1; }
+  // val - internal_min: rational{num * 1 - imin * den, den * 1}, simplified again
+  const i128 n1 = (i128) ((u128) rn - (u128) (i128) imin * (u128) rd);
+  i128 n2, d2;
+  rat_make(n1, rd, n2, d2);
+  return (int) (((double) n2 / (double) d2) * cell_scale);
+}
+
 // ---- PIP: closest edge above -----------------------------------------------
 // Update rule of src/algo/pip.h:27-96 == src/app/pip_lbvh.h:57-123.  Full ties
 // (same y*, same slope = coincident edges) are resolved like a scan in

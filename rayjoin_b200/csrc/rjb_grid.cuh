@@ -1,14 +1,25 @@
-// Uniform-grid variant (RayJoin's -mode=grid): the base map's edges are binned
-// into gsize x gsize cells (every cell the edge's bounding box touches, like
-// reference src/grid/uniform_grid.h:44-86), stored as CSR; LSI is
-// query-edge-centric, PIP walks the point's column upward.
+// Uniform-grid variant (RayJoin's -mode=grid).
 //
-// Replaces UniformGrid::AddMapToGrid (src/grid/uniform_grid.h:131-358),
-// LSIGrid::Query (src/app/lsi_grid.h:19-78,97-159: one thread per CELL doing
-// ne0 x ne1 tests -> 1.3 s load imbalance) and PIPGrid::Query
-// (src/app/pip_grid.h:21-77 + src/algo/pip.h:14-115).
-// The grid is only a filter; results come from the exact predicates, so they
-// equal the LBVH / brute-force results pair for pair.
+// Replaces UniformGrid::AddMapToGrid (reference: src/grid/uniform_grid.h:131-358: a dense
+// 12-byte Cell per grid cell, filled by two rounds of global atomics, 6 GB at 15000^2),
+// LSIGrid::Query (src/app/lsi_grid.h:19-78,97-159: one thread per CELL doing ne0 x ne1 tests
+// -> 1.3 s of load imbalance) and PIPGrid::Query (src/app/pip_grid.h:21-77 +
+// src/algo/pip.h:14-115).
+//
+// Index: SPARSE and built by sorting.  Every base edge is registered in every cell of the
+// cell-box of its end points (iterate_cell, uniform_grid.h:44-86) with the reference's own cell
+// function (cell.h:15-22, factor 0.999 and all); the (cell, edge) incidences are radix-sorted
+// by cell with the engine's onesweep and become a CSR over the OCCUPIED cells only.  A cell is
+// found through a bitmap (one bit per cell) and the rank of its word: id = rank[word] +
+// popcount(lower bits).  Cells are numbered column-major (bit = cx * stride + cy) so that the
+// PIP walk "next occupied cell above" is a scan of consecutive bits.  Items are the START
+// POINT index of the edge (eid + chain): the two vertices load without the eid -> chain ->
+// point chain.  Size: g^2 / 4 bytes (bitmap + ranks) + 4 B per occupied cell + 4 B per incidence.
+//
+// LSI semantics are the reference's grid semantics, not the LBVH's: the predicate is always
+// evaluated as intersect_test(map-0 edge, map-1 edge) whatever the query map is
+// (lsi_grid.h:62, "fixme: respect query map id" at :96), and a pair is kept only in the cell
+// of its intersection point (:64-67), i.e. iff that cell lies in the cell-boxes of both edges.
 #pragma once
 #include "rjb_exact.cuh"
 #include "rjb_lsi.cuh"
@@ -17,171 +28,523 @@
 namespace rjb {
 
 struct GridView {
-  const uint32_t* cell_begin;  // gsize*gsize + 1
-  const uint32_t* items;       // base eids
-  uint32_t gsize;
+  const uint32_t* bits;        // occupancy, column-major: bit (cx * gs + cy)
+  const uint32_t* rank;        // occupied cells before each bitmap word
+  const uint32_t* cell_begin;  // [n_occ + 1] CSR into items
+  const uint32_t* items;       // start point (eid + chain) of the base edges of a cell
+  uint32_t gsize, gs;          // cells per axis; column stride in bits (gsize rounded up to 32)
   long long imin;
+  double cell_scale;           // (double) gsize / internal_range * 0.999   (cell.h:19)
+  double inv_cell_scale;
 };
 
 struct Grid {
-  DBuf<uint32_t> cell_begin, items, cursor;
+  DBuf<uint32_t> bits, pop, rank, cell_begin, items, cnt, off, vals_a, big;
+  DBuf<uint64_t> keys_a, keys_b;
+  DBuf<unsigned long long> totals;
   ScanTemp scan_tmp;
-  uint32_t gsize = 0;
+  SortTemp sort_tmp;
+  uint32_t gsize = 0, gs = 0, n_occ = 0;
   uint64_t n_items = 0;
   long long imin = 0;
+  double cell_scale = 0;
   bool built = false;
+  uint32_t n_words() const { return gsize * (gs / 32); }
   GridView view() const {
     GridView v;
+    v.bits = bits.p;
+    v.rank = rank.p;
     v.cell_begin = cell_begin.p;
     v.items = items.p;
     v.gsize = gsize;
+    v.gs = gs;
     v.imin = imin;
+    v.cell_scale = cell_scale;
+    v.inv_cell_scale = cell_scale > 0 ? 1.0 / cell_scale : 0;
     return v;
   }
   size_t index_bytes() const {
-    return ((size_t) gsize * gsize + 1) * sizeof(uint32_t) + n_items * sizeof(uint32_t);
+    return 2 * (size_t) (n_words() + 1) * sizeof(uint32_t) + ((size_t) n_occ + 1) * sizeof(uint32_t) +
+           n_items * sizeof(uint32_t);
   }
 };
 
-// cell of an internal coordinate: floor((v - imin) * gsize / 2^47), monotone,
-// in [0, gsize - 1] for the whole 47-bit range
-static __device__ __forceinline__ int grid_cell(long long v, long long imin, uint32_t gsize) {
-  long long d = v - imin;
-  d = d < 0 ? 0 : (d > (1ll << 47) - 1 ? (1ll << 47) - 1 : d);  // points outside the box
-  return (int) (((unsigned long long) d * gsize) >> 47);
+// cell of a coordinate for FILTERING: the reference's function clamped into the grid (query
+// points may lie outside the bounding box of the maps); monotone
+static __device__ __forceinline__ int grid_cell(const GridView& g, long long v) {
+  const int c = ref_cell(v, g.imin, g.cell_scale);
+  return min(max(c, 0), (int) g.gsize - 1);
 }
 
-// smallest internal coordinate that lies in cell c (c may be gsize: upper end)
-static __device__ __forceinline__ long long grid_cell_lo(int c, long long imin, uint32_t gsize) {
-  unsigned long long t = (((unsigned long long) c << 47) + gsize - 1) / gsize;
-  return imin + (long long) t;
+struct CellBox {
+  int x0, x1, y0, y1;
+  __device__ __forceinline__ unsigned long long cells() const {
+    return (unsigned long long) (x1 - x0 + 1) * (unsigned long long) (y1 - y0 + 1);
+  }
+};
+
+static __device__ __forceinline__ CellBox edge_cell_box(const GridView& g, const longlong2& a, const longlong2& b) {
+  CellBox c;
+  c.x0 = grid_cell(g, min(a.x, b.x));
+  c.x1 = grid_cell(g, max(a.x, b.x));
+  c.y0 = grid_cell(g, min(a.y, b.y));
+  c.y1 = grid_cell(g, max(a.y, b.y));
+  return c;
 }
 
-template <bool kFill>
-__global__ void k_grid_bin(MapView B, GridView g, uint32_t* __restrict__ counts_or_cursor,
-                           uint32_t* __restrict__ items) {
-  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= B.n_edges) return;
-  Seg s = load_seg(B, e);
-  int cx0 = grid_cell(min(s.x1, s.x2), g.imin, g.gsize), cx1 = grid_cell(max(s.x1, s.x2), g.imin, g.gsize);
-  int cy0 = grid_cell(min(s.y1, s.y2), g.imin, g.gsize), cy1 = grid_cell(max(s.y1, s.y2), g.imin, g.gsize);
-  for (int cy = cy0; cy <= cy1; cy++)
-    for (int cx = cx0; cx <= cx1; cx++) {
-      size_t c = (size_t) cy * g.gsize + cx;
-      uint32_t pos = atomicAdd(&counts_or_cursor[c], 1u);
-      if (kFill) items[pos] = e;
+// occupied cell -> [begin, end) of its items
+static __device__ __forceinline__ bool grid_cell_range(const GridView& g, uint32_t bit, uint32_t& beg,
+                                                       uint32_t& end) {
+  const uint32_t w = __ldg(&g.bits[bit >> 5]);
+  if (!((w >> (bit & 31)) & 1u)) return false;
+  const uint32_t id = __ldg(&g.rank[bit >> 5]) + __popc(w & ((1u << (bit & 31)) - 1));
+  beg = __ldg(&g.cell_begin[id]);
+  end = __ldg(&g.cell_begin[id + 1]);
+  return true;
+}
+
+// ---- build ------------------------------------------------------------------------------
+// An edge that covers more than kGridBigCells cells is not walked by its thread: it goes to a
+// list that a CTA per edge works off (a map-spanning edge is g^2 incidences).
+constexpr uint32_t kGridBigCells = 256;
+
+// per START POINT: number of cells of the edge's cell-box (0 for the last point of a chain)
+__global__ void __launch_bounds__(256)
+k_grid_count(MapView B, GridView g, uint32_t* __restrict__ cnt, unsigned long long* __restrict__ totals) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long n = 0;
+  if (p < B.n_points) {
+    const bool last = (__ldg(&B.last_bits[p >> 5]) >> (p & 31)) & 1u;
+    if (!last) n = edge_cell_box(g, B.pts[p], B.pts[p + 1]).cells();
+    cnt[p] = (uint32_t) min(n, 0xFFFFFFFFull);
+  }
+  unsigned long long s = n;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(&totals[0], s);
+  if (n > kGridBigCells) atomicAdd(&totals[1], 1ull);
+}
+
+__global__ void __launch_bounds__(256)
+k_grid_emit(MapView B, GridView g, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off,
+            uint64_t* __restrict__ key, uint32_t* __restrict__ val, uint32_t* __restrict__ big_list,
+            unsigned long long* __restrict__ totals) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= B.n_points) return;
+  const uint32_t n = cnt[p];
+  if (n == 0) return;
+  if (n > kGridBigCells) {
+    big_list[atomicAdd(&totals[2], 1ull)] = p;
+    return;
+  }
+  const CellBox c = edge_cell_box(g, B.pts[p], B.pts[p + 1]);
+  uint32_t o = off[p];
+  for (int x = c.x0; x <= c.x1; x++)
+    for (int y = c.y0; y <= c.y1; y++) {
+      key[o] = (uint64_t) x * g.gs + y;
+      val[o] = p;
+      o++;
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_grid_emit_big(MapView B, GridView g, const uint32_t* __restrict__ off, const uint32_t* __restrict__ big_list,
+                const unsigned long long* __restrict__ totals, uint64_t* __restrict__ key,
+                uint32_t* __restrict__ val) {
+  const uint32_t n_big = (uint32_t) totals[2];
+  for (uint32_t i = blockIdx.x; i < n_big; i += gridDim.x) {
+    const uint32_t p = big_list[i];
+    const CellBox c = edge_cell_box(g, B.pts[p], B.pts[p + 1]);
+    const uint32_t ny = c.y1 - c.y0 + 1;
+    const uint32_t total = (uint32_t) c.cells();
+    const uint32_t o = off[p];
+    for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
+      key[o + t] = (uint64_t) (c.x0 + t / ny) * g.gs + (c.y0 + t % ny);
+      val[o + t] = p;
+    }
+  }
+}
+
+// sorted keys -> occupancy bits (the first item of every run sets its cell's bit)
+__global__ void k_grid_mark(const uint64_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ bits) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = key[i];
+  if (i == 0 || key[i - 1] != k) atomicOr(&bits[k >> 5], 1u << (k & 31));
+}
+
+__global__ void k_grid_popc(const uint32_t* __restrict__ bits, uint32_t n_words, uint32_t* __restrict__ pop) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < n_words) pop[w] = __popc(bits[w]);
+}
+
+__global__ void k_grid_cell_begin(const uint64_t* __restrict__ key, uint32_t n, const uint32_t* __restrict__ bits,
+                                  const uint32_t* __restrict__ rank, uint32_t n_words,
+                                  uint32_t* __restrict__ cell_begin) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = key[i];
+  if (i == 0 || key[i - 1] != k) {
+    const uint32_t id = rank[k >> 5] + __popc(bits[k >> 5] & ((1u << (k & 31)) - 1));
+    cell_begin[id] = i;
+  }
+  if (i == n - 1) cell_begin[rank[n_words]] = n;  // rank[n_words] = number of occupied cells
 }
 
 static inline void build_grid(Grid& g, const MapView& B, uint32_t gsize, long long imin,
-                              long long /*irange*/, cudaStream_t st) {
+                              long long irange, cudaStream_t st) {
   RJB_REQUIRE(gsize >= 1 && gsize <= 32768, "grid_size must be in 1..32768");
+  g.built = false;  // until the last call below has succeeded
   g.gsize = gsize;
+  g.gs = (gsize + 31u) & ~31u;
   g.imin = imin;
-  g.built = true;
+  g.cell_scale = (double) gsize / (double) irange * 0.999;  // src/grid/cell.h:19
   g.n_items = 0;
-  size_t ncell = (size_t) gsize * gsize;
-  RJB_REQUIRE(ncell < 0xFFFFFFF0ull, "grid too large");
-  uint32_t* begin = g.cell_begin.ensure(ncell + 1);
-  uint32_t* cursor = g.cursor.ensure(ncell + 1);
-  RJB_CUDA(cudaMemsetAsync(cursor, 0, (ncell + 1) * sizeof(uint32_t), st));
+  g.n_occ = 0;
+  const uint32_t n_words = g.n_words();
+  uint32_t* bits = g.bits.ensure(n_words + 1);
+  uint32_t* pop = g.pop.ensure(n_words + 1);
+  uint32_t* rank = g.rank.ensure(n_words + 1);
+  RJB_CUDA(cudaMemsetAsync(bits, 0, (n_words + 1) * sizeof(uint32_t), st));
+  unsigned long long* totals = g.totals.ensure(3);  // incidences, big edges, big-list cursor
+  RJB_CUDA(cudaMemsetAsync(totals, 0, 3 * sizeof(unsigned long long), st));
+  uint32_t* cnt = g.cnt.ensure(B.n_points + 1);
+  uint32_t* off = g.off.ensure(B.n_points + 1);
   GridView v = g.view();
-  if (B.n_edges) k_grid_bin<false><<<div_up(B.n_edges, 256), 256, 0, st>>>(B, v, cursor, nullptr);
-  exclusive_scan_u32(cursor, begin, (uint32_t) ncell, g.scan_tmp, st);
-  uint32_t total = 0;
-  RJB_CUDA(cudaMemcpyAsync(&total, begin + ncell, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  RJB_CUDA(cudaStreamSynchronize(st));
-  g.n_items = total;
-  uint32_t* items = g.items.ensure(total ? total : 1);
-  RJB_CUDA(cudaMemcpyAsync(cursor, begin, ncell * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-  v = g.view();
-  if (B.n_edges) k_grid_bin<true><<<div_up(B.n_edges, 256), 256, 0, st>>>(B, v, cursor, items);
-  RJB_CUDA(cudaGetLastError());
+  unsigned long long h_tot[2] = {0, 0};
+  if (B.n_points) {
+    k_grid_count<<<div_up(B.n_points, 256), 256, 0, st>>>(B, v, cnt, totals);
+    exclusive_scan_u32(cnt, off, B.n_points, g.scan_tmp, st);
+    RJB_CUDA(cudaMemcpyAsync(h_tot, totals, sizeof(h_tot), cudaMemcpyDeviceToHost, st));
+    RJB_CUDA(cudaStreamSynchronize(st));
+  }
+  // (the 32-bit scan above is only valid below 2^32; the 64-bit total says whether it is)
+  RJB_REQUIRE(h_tot[0] < (1ull << 30), "grid: more than 2^30 edge-cell incidences; lower -grid_size");
+  const uint32_t n = (uint32_t) h_tot[0];
+  g.n_items = n;
+  uint32_t* cbeg = g.cell_begin.ensure((size_t) std::min<uint64_t>(n, (uint64_t) n_words * 32) + 2);
+  uint32_t* items = g.items.ensure(n ? n : 1);
+  if (n) {
+    uint64_t* ka = g.keys_a.ensure(n);
+    uint64_t* kb = g.keys_b.ensure(n);
+    uint32_t* va = g.vals_a.ensure(n);
+    uint32_t* big = g.big.ensure(h_tot[1] ? h_tot[1] : 1);
+    k_grid_emit<<<div_up(B.n_points, 256), 256, 0, st>>>(B, v, cnt, off, ka, va, big, totals);
+    if (h_tot[1])
+      k_grid_emit_big<<<(unsigned) std::min<uint64_t>(h_tot[1], 4 * kNumSMs), 256, 0, st>>>(B, v, off, big, totals,
+                                                                                          ka, va);
+    int key_bits = 1;
+    while (key_bits < 40 && (((uint64_t) gsize * g.gs) >> key_bits)) key_bits++;
+    sort_pairs_u64_u32(ka, kb, va, items, n, 0, key_bits, g.sort_tmp, st);
+    k_grid_mark<<<div_up(n, 256), 256, 0, st>>>(kb, n, bits);
+    k_grid_popc<<<div_up(n_words, 256), 256, 0, st>>>(bits, n_words, pop);
+    exclusive_scan_u32(pop, rank, n_words, g.scan_tmp, st);
+    k_grid_cell_begin<<<div_up(n, 256), 256, 0, st>>>(kb, n, bits, rank, n_words, cbeg);
+    RJB_CUDA(cudaGetLastError());
+    RJB_CUDA(cudaMemcpyAsync(&g.n_occ, rank + n_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    RJB_CUDA(cudaStreamSynchronize(st));
+  } else {
+    RJB_CUDA(cudaMemsetAsync(rank, 0, (n_words + 1) * sizeof(uint32_t), st));
+    RJB_CUDA(cudaMemsetAsync(cbeg, 0, 2 * sizeof(uint32_t), st));
+    RJB_CUDA(cudaStreamSynchronize(st));
+  }
+  g.built = true;
 }
 
-// one thread per query edge; every (query, base) pair is examined in exactly
-// one cell: the cell of the lower-left corner of the intersection of the two
-// bounding boxes (both edges are registered there)
+// ---- LSI ----------------------------------------------------------------------------------
+// Pass 1 streams the query map (lane = start point, coalesced vertex loads) and emits one
+// work item (start point, cell) per OCCUPIED cell of the edge's cell-box: most query edges
+// fall into empty cells and end after one to four bitmap look-ups.  One atomic per warp.
+// Pass 2 resolves the work items densely (exact integer boxes, every pair in exactly one of
+// its common cells, intersect_test with every lane busy), pass 3 is the point pass of the
+// LBVH path.
+constexpr uint32_t kGridSmallCells = 16;
+
 __global__ void __launch_bounds__(256)
-k_lsi_grid(MapView Q, MapView B, GridView g, uint2* __restrict__ out, uint32_t cap,
-           unsigned int* counter, unsigned long long* n_cand) {
-  uint32_t qe = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long cand = 0;
-  if (qe < Q.n_edges) {
-    Seg q = load_seg(Q, qe);
-    long long qx0 = min(q.x1, q.x2), qx1 = max(q.x1, q.x2);
-    long long qy0 = min(q.y1, q.y2), qy1 = max(q.y1, q.y2);
-    int cx0 = grid_cell(qx0, g.imin, g.gsize), cx1 = grid_cell(qx1, g.imin, g.gsize);
-    int cy0 = grid_cell(qy0, g.imin, g.gsize), cy1 = grid_cell(qy1, g.imin, g.gsize);
-    for (int cy = cy0; cy <= cy1; cy++)
-      for (int cx = cx0; cx <= cx1; cx++) {
-        size_t c = (size_t) cy * g.gsize + cx;
-        uint32_t b = g.cell_begin[c], e = g.cell_begin[c + 1];
-        for (uint32_t k = b; k < e; k++) {
-          uint32_t be = g.items[k];
-          Seg s = load_seg(B, be);
-          long long bx0 = min(s.x1, s.x2), bx1 = max(s.x1, s.x2);
-          long long by0 = min(s.y1, s.y2), by1 = max(s.y1, s.y2);
-          if (bx1 < qx0 || qx1 < bx0 || by1 < qy0 || qy1 < by0) continue;
-          if (grid_cell(max(qx0, bx0), g.imin, g.gsize) != cx ||
-              grid_cell(max(qy0, by0), g.imin, g.gsize) != cy)
-            continue;
-          cand++;
-          if (lsi_intersect(q, s)) {
-            unsigned pos = atomicAdd(counter, 1u);
-            if (pos < cap) out[pos] = make_uint2(qe, be);
-          }
-        }
+k_grid_lsi_filter(MapView Q, GridView g, uint2* __restrict__ work, uint32_t work_cap, unsigned int* work_n,
+                  uint32_t* __restrict__ big_list, unsigned int* big_n) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (tile * 32 >= Q.n_points) return;
+  const QTile t = load_tile(Q, nullptr, Q.n_points, tile, lane);
+  CellBox c = {0, -1, 0, -1};
+  uint32_t hits = 0;  // bit k = k-th cell of the box (column by column) is occupied
+  bool big = false;
+  if (t.valid) {
+    c = edge_cell_box(g, t.a, t.b);
+    big = c.cells() > kGridSmallCells;
+    if (!big) {
+      const int ny = c.y1 - c.y0 + 1;
+      const int n = (int) c.cells();
+#pragma unroll 4
+      for (int k = 0; k < n; k++) {
+        const uint32_t bit = (uint32_t) (c.x0 + k / ny) * g.gs + (uint32_t) (c.y0 + k % ny);
+        if ((__ldg(&g.bits[bit >> 5]) >> (bit & 31)) & 1u) hits |= 1u << k;
       }
+    }
   }
-  if (n_cand) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
-    if ((threadIdx.x & 31) == 0 && cand) atomicAdd(n_cand, cand);
+  // long edges: a list of their own, resolved by a CTA each (k_grid_lsi_big)
+  const unsigned mb = __ballot_sync(0xffffffffu, big);
+  if (mb) {
+    unsigned base = 0;
+    const int leader = __ffs(mb) - 1;
+    if (lane == leader) base = atomicAdd(big_n, (unsigned) __popc(mb));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (big) big_list[base + __popc(mb & ((1u << lane) - 1))] = t.p;
+  }
+  const uint32_t cnt = __popc(hits);
+  const uint32_t inc = warp_incl_scan(cnt, lane);
+  const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+  if (total == 0) return;
+  unsigned base = 0;
+  if (lane == 31) base = atomicAdd(work_n, total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  uint32_t pos = base + inc - cnt;
+  const int ny = c.y1 - c.y0 + 1;
+  while (hits) {
+    const int k = __ffs(hits) - 1;
+    hits &= hits - 1;
+    if (pos < work_cap) work[pos] = make_uint2(t.p, (uint32_t) (c.x0 + k / ny) * g.gs + (uint32_t) (c.y0 + k % ny));
+    pos++;
   }
 }
 
-static inline void lsi_grid(const Grid& g, const MapView& Q, const MapView& B, uint2* out,
-                            uint32_t cap, unsigned int* counter, unsigned long long* n_cand,
-                            cudaStream_t st) {
-  k_lsi_grid<<<div_up(Q.n_edges, 256), 256, 0, st>>>(Q, B, g.view(), out, cap, counter, n_cand);
-}
-
-// one thread per point: walk the column upward from the cell of (py - 1) and
-// stop once the best hit is provably below the top of the visited cell
 __global__ void __launch_bounds__(256)
-k_pip_grid(const longlong2* __restrict__ pts, uint32_t n, MapView B, GridView g, int query_map_id,
-           uint32_t* __restrict__ out_eid, int32_t* __restrict__ out_face,
-           unsigned long long* n_cand) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+k_grid_lsi_big(MapView Q, GridView g, const uint32_t* __restrict__ big_list, const unsigned int* __restrict__ big_n,
+               uint2* __restrict__ work, uint32_t work_cap, unsigned int* work_n) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_big = *big_n;
+  for (uint32_t i = blockIdx.x; i < n_big; i += gridDim.x) {
+    const uint32_t p = big_list[i];
+    const CellBox c = edge_cell_box(g, Q.pts[p], Q.pts[p + 1]);
+    const uint32_t ny = c.y1 - c.y0 + 1;
+    const uint32_t total = (uint32_t) min(c.cells(), 0xFFFFFFFFull);
+    // block-uniform trip count (warp collectives inside)
+    for (uint32_t t0 = 0; t0 < total; t0 += blockDim.x) {
+      const uint32_t t = t0 + threadIdx.x;
+      uint32_t bit = 0;
+      bool hit = false;
+      if (t < total) {
+        bit = (uint32_t) (c.x0 + t / ny) * g.gs + (c.y0 + t % ny);
+        hit = (__ldg(&g.bits[bit >> 5]) >> (bit & 31)) & 1u;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m == 0) continue;
+      unsigned base = 0;
+      const int leader = __ffs(m) - 1;
+      if (lane == leader) base = atomicAdd(work_n, (unsigned) __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      const unsigned pos = base + __popc(m & ((1u << lane) - 1));
+      if (hit && pos < work_cap) work[pos] = make_uint2(p, bit);
+    }
+  }
+}
+
+// the pair (query edge, base edge) is examined in ONE of the cells both are registered in:
+// the min corner of the intersection of their cell-boxes
+static __device__ __forceinline__ bool grid_pair_here(const GridView& g, const Seg& q, const Seg& b, uint32_t bit) {
+  const int cx = max(grid_cell(g, min(q.x1, q.x2)), grid_cell(g, min(b.x1, b.x2)));
+  const int cy = max(grid_cell(g, min(q.y1, q.y2)), grid_cell(g, min(b.y1, b.y2)));
+  return (uint32_t) cx * g.gs + (uint32_t) cy == bit;
+}
+
+// reference rule (lsi_grid.h:64-67): kept iff the cell of the intersection point is a cell both
+// edges are registered in.  e0 = map-0 edge, e1 = map-1 edge.
+static __device__ __forceinline__ bool grid_owned(const GridView& g, const Seg& e0, const Seg& e1) {
+  const int cx = lsi_xsect_ref_cell(e0, e1, 0, g.imin, g.cell_scale);
+  const int cy = lsi_xsect_ref_cell(e0, e1, 1, g.imin, g.cell_scale);
+  auto lo = [&](long long a, long long b) { return ref_cell(min(a, b), g.imin, g.cell_scale); };
+  auto hi = [&](long long a, long long b) { return ref_cell(max(a, b), g.imin, g.cell_scale); };
+  return cx >= max(lo(e0.x1, e0.x2), lo(e1.x1, e1.x2)) && cx <= min(hi(e0.x1, e0.x2), hi(e1.x1, e1.x2)) &&
+         cy >= max(lo(e0.y1, e0.y2), lo(e1.y1, e1.y2)) && cy <= min(hi(e0.y1, e0.y2), hi(e1.y1, e1.y2));
+}
+
+// intersect_test(map-0 edge, map-1 edge) + the ownership rule for the lanes with `have`, hits
+// appended to the result queue as start-point index pairs (one atomic per warp)
+static __device__ __forceinline__ void grid_test_emit(const MapView& Q, const MapView& B, const GridView& g, int q,
+                                                      bool have, uint2 it, rjb_xsect* __restrict__ out,
+                                                      uint32_t cap, unsigned int* counter, int lane) {
+  bool found = false;
+  if (have) {
+    const longlong2 a = __ldg(&Q.pts[it.x]), b = __ldg(&Q.pts[it.x + 1]);
+    const longlong2 c = __ldg(&B.pts[it.y]), d = __ldg(&B.pts[it.y + 1]);
+    const Seg eq = {a.x, a.y, b.x, b.y}, eb = {c.x, c.y, d.x, d.y};
+    // always (map 0, map 1), whatever the query side is
+    const Seg& e0 = q == 0 ? eq : eb;
+    const Seg& e1 = q == 0 ? eb : eq;
+    found = lsi_intersect(e0, e1) && grid_owned(g, e0, e1);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, found);
+  if (m == 0) return;
+  unsigned base = 0;
+  const int leader = __ffs(m) - 1;
+  if (lane == leader) base = atomicAdd(counter, (unsigned) __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (found) {
+    const unsigned pos = base + __popc(m & ((1u << lane) - 1));
+    if (pos < cap) {
+      out[pos].eid[0] = it.x;  // point indices for now; the point pass turns them into eids
+      out[pos].eid[1] = it.y;
+    }
+  }
+}
+
+static __device__ __forceinline__ void grid_drain(const MapView& Q, const MapView& B, const GridView& g, int q,
+                                                  const uint2* list, unsigned n_list, rjb_xsect* __restrict__ out,
+                                                  uint32_t cap, unsigned int* counter) {
+  const int lane = threadIdx.x & 31;
+  for (unsigned t0 = threadIdx.x - lane; t0 < n_list; t0 += kExactThreads) {
+    const unsigned t = t0 + lane;
+    grid_test_emit(Q, B, g, q, t < n_list, t < n_list ? list[t] : make_uint2(0, 0), out, cap, counter, lane);
+  }
+}
+
+constexpr int kGridInLane = 8;  // items of a cell a lane walks itself; longer lists: the whole warp
+
+__global__ void __launch_bounds__(kExactThreads)
+k_grid_lsi_exact(MapView Q, MapView B, GridView g, int q, const uint2* __restrict__ work,
+                 const unsigned int* __restrict__ work_n_dev, uint32_t work_cap, rjb_xsect* __restrict__ out,
+                 uint32_t cap, unsigned int* counter, unsigned long long* n_cand) {
+  // < kExactThreads carried over + <= kGridInLane pushes per thread and round
+  __shared__ uint2 s_list[(kGridInLane + 1) * kExactThreads];
+  __shared__ unsigned s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const uint32_t n = min(*work_n_dev, work_cap);
+  const int lane = threadIdx.x & 31;
+  unsigned cand = 0;
+  // block-uniform trip count: every thread reaches the barriers
+  for (uint64_t i0 = (uint64_t) blockIdx.x * kExactThreads; i0 < n; i0 += (uint64_t) gridDim.x * kExactThreads) {
+    const uint64_t i = i0 + threadIdx.x;
+    uint32_t pq = 0, bit = 0, beg = 0, end = 0;
+    Seg eq = {0, 0, 0, 0};
+    if (i < n) {
+      const uint2 w = work[i];
+      pq = w.x;
+      bit = w.y;
+      grid_cell_range(g, bit, beg, end);
+      const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
+      eq = {a.x, a.y, b.x, b.y};
+    }
+    // the first kGridInLane items of the lane's own cell: item ids, then vertices, in flight together
+    uint32_t pb[kGridInLane];
+#pragma unroll
+    for (int k = 0; k < kGridInLane; k++) pb[k] = beg + k < end ? __ldg(&g.items[beg + k]) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < kGridInLane; k++) {
+      bool pass = false;
+      if (pb[k] != 0xFFFFFFFFu) {
+        const longlong2 c = __ldg(&B.pts[pb[k]]), d = __ldg(&B.pts[pb[k] + 1]);
+        const Seg eb = {c.x, c.y, d.x, d.y};
+        pass = seg_boxes_overlap(eq, eb) && grid_pair_here(g, eq, eb, bit);
+      }
+      exact_push(pass, make_uint2(pq, pb[k]), s_list, &s_n, lane, cand);
+    }
+    // longer lists (dense cells): one lane's cell at a time, the warp strides over its items and
+    // tests what passes the boxes at once
+    unsigned more = __ballot_sync(0xffffffffu, end - beg > (uint32_t) kGridInLane);
+    while (more) {
+      const int src = __ffs(more) - 1;
+      more &= more - 1;
+      const uint32_t b0 = __shfl_sync(0xffffffffu, beg, src) + kGridInLane, e0 = __shfl_sync(0xffffffffu, end, src);
+      const uint32_t spq = __shfl_sync(0xffffffffu, pq, src), sbit = __shfl_sync(0xffffffffu, bit, src);
+      const Seg sq = {__shfl_sync(0xffffffffu, eq.x1, src), __shfl_sync(0xffffffffu, eq.y1, src),
+                      __shfl_sync(0xffffffffu, eq.x2, src), __shfl_sync(0xffffffffu, eq.y2, src)};
+      for (uint32_t k0 = b0; k0 < e0; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        bool pass = false;
+        uint32_t p = 0;
+        if (k < e0) {
+          p = __ldg(&g.items[k]);
+          const longlong2 c = __ldg(&B.pts[p]), d = __ldg(&B.pts[p + 1]);
+          const Seg eb = {c.x, c.y, d.x, d.y};
+          pass = seg_boxes_overlap(sq, eb) && grid_pair_here(g, sq, eb, sbit);
+        }
+        cand += __popc(__ballot_sync(0xffffffffu, pass));
+        grid_test_emit(Q, B, g, q, pass, make_uint2(spq, p), out, cap, counter, lane);
+      }
+    }
+    __syncthreads();
+    const unsigned n_list = s_n;
+    if (n_list >= kExactThreads) {
+      grid_drain(Q, B, g, q, s_list, n_list, out, cap, counter);
+      __syncthreads();
+      if (threadIdx.x == 0) s_n = 0;
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  grid_drain(Q, B, g, q, s_list, s_n, out, cap, counter);
+  if (lane == 0 && cand) atomicAdd(n_cand, (unsigned long long) cand);
+}
+
+// ---- PIP ----------------------------------------------------------------------------------
+// One thread per point (points sorted by cell, so a warp walks one or two columns together):
+// from the cell of (py - 1) upward to the next OCCUPIED cell of the column -- a scan of
+// consecutive bitmap bits --, every edge registered there screened with integer tests (x range,
+// reaches up to py - 1) and put through the exact update rule, until the best hit provably lies
+// below everything not yet seen: an edge first registered above cell cy has ymin >= the lower
+// boundary of cell cy + 1, and y* carries < 2^-5 of rounding.  (Reference: src/app/pip_grid.h
+// walks cell by cell, empty or not, through a dense Cell array.)
+template <bool kPacked>
+__global__ void __launch_bounds__(256)
+k_pip_grid(const longlong2* __restrict__ pts, uint32_t n, const uint32_t* __restrict__ order, MapView B,
+           GridView g, int query_map_id, uint32_t* __restrict__ out_eid, int32_t* __restrict__ out_face,
+           uint2* __restrict__ out_packed, unsigned long long* n_cand) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long cand = 0;
-  if (i < n) {
-    longlong2 p = pts[i];
+  if (slot < n) {
+    const uint32_t i = order ? order[slot] : slot;
+    const longlong2 p = pts[i];
     PipBest best;
     pip_init(best);
-    int cx = grid_cell(p.x, g.imin, g.gsize);
-    for (int cy = grid_cell(p.y - 1, g.imin, g.gsize); cy < (int) g.gsize; cy++) {
-      size_t c = (size_t) cy * g.gsize + cx;
-      uint32_t b = g.cell_begin[c], e = g.cell_begin[c + 1];
-      for (uint32_t k = b; k < e; k++) {
-        uint32_t be = g.items[k];
-        cand++;
-        pip_update(best, query_map_id, p.x, p.y, load_seg(B, be), be);
+    const int cx = grid_cell(g, p.x);
+    int cy = grid_cell(g, p.y - 1);
+    const uint32_t col = (uint32_t) cx * g.gs;
+    const int gmax = (int) g.gsize;
+    while (cy < gmax) {
+      // next occupied cell at or above cy in this column
+      uint32_t bit = col + cy;
+      uint32_t w = __ldg(&g.bits[bit >> 5]) >> (bit & 31);
+      while (w == 0) {
+        bit = (bit | 31u) + 1;
+        if ((int) (bit - col) >= gmax) break;
+        w = __ldg(&g.bits[bit >> 5]);
       }
+      if (w == 0) break;
+      bit += __ffs(w) - 1;
+      cy = (int) (bit - col);
+      if (cy >= gmax) break;
       if (best.eid != RJB_NO_HIT) {
-        double top = (double) grid_cell_lo(cy + 1, g.imin, g.gsize) - 1.0;
-        if (best.y < top) break;
+        // everything in this and higher cells starts at or above the lower boundary of cell cy
+        const double low = (double) g.imin + floor((double) cy * g.inv_cell_scale) - 3.0;
+        if (best.y < low) break;
       }
+      uint32_t beg = 0, end = 0;
+      grid_cell_range(g, bit, beg, end);
+      for (uint32_t k = beg; k < end; k++) {
+        const uint32_t pb = __ldg(&g.items[k]);
+        const longlong2 a = __ldg(&B.pts[pb]), b = __ldg(&B.pts[pb + 1]);
+        if (min(a.x, b.x) <= p.x && p.x <= max(a.x, b.x) && max(a.y, b.y) >= p.y - 1) {
+          const Seg e = {a.x, a.y, b.x, b.y};
+          cand++;
+          pip_update(best, query_map_id, p.x, p.y, e, pb - __ldg(&B.point_chain[pb]));
+        }
+      }
+      cy++;
     }
-    out_eid[i] = best.eid;
-    if (out_face) {
-      int32_t face = RJB_EXTERIOR_FACE;
-      if (best.eid != RJB_NO_HIT) {
-        uint32_t ch = B.edge_chain[best.eid];
-        longlong2 a = B.pts[best.eid + ch], bb = B.pts[best.eid + ch + 1];
-        face = a.x < bb.x ? B.right[ch] : B.left[ch];
-      }
-      out_face[i] = face;
+    int32_t face = RJB_EXTERIOR_FACE;
+    if ((kPacked || out_face) && best.eid != RJB_NO_HIT) {
+      // get_face_id, src/map/map.h:79-87
+      const uint32_t ch = B.edge_chain[best.eid];
+      const longlong2 a = B.pts[best.eid + ch], bb = B.pts[best.eid + ch + 1];
+      face = a.x < bb.x ? B.right[ch] : B.left[ch];
+    }
+    if (kPacked) {
+      out_packed[i] = make_uint2(best.eid, (uint32_t) face);
+    } else {
+      out_eid[i] = best.eid;
+      if (out_face) out_face[i] = face;
     }
   }
   if (n_cand) {
@@ -189,13 +552,6 @@ k_pip_grid(const longlong2* __restrict__ pts, uint32_t n, MapView B, GridView g,
     for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
     if ((threadIdx.x & 31) == 0 && cand) atomicAdd(n_cand, cand);
   }
-}
-
-static inline void pip_grid(const Grid& g, const longlong2* pts, uint32_t n, const MapView& B,
-                            int query_map_id, uint32_t* out_eid, int32_t* out_face,
-                            unsigned long long* n_cand, cudaStream_t st) {
-  k_pip_grid<<<div_up(n, 256), 256, 0, st>>>(pts, n, B, g.view(), query_map_id, out_eid, out_face,
-                                             n_cand);
 }
 
 }  // namespace rjb

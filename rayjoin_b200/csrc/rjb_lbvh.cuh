@@ -283,26 +283,57 @@ __global__ void k_top_tree(const int4* __restrict__ node_box, const int2* __rest
 // edges: 4x fewer boxes, and the leaf box is what the traversal would test anyway.
 // (A warp-merged variant with __match_any_sync measured slower than plain atomics:
 // 71 vs 39 us for 1 M leaves.)
+//
+// Rows of a box are marked a bitmap WORD at a time (one atomicOr per 32 cells), and a
+// box of more than kOccBigWords words is not walked by its thread at all: it goes to a
+// list that k_occ_mark_big works off with one CTA per box, so a map-spanning edge costs
+// 512 K word operations spread over 256 threads instead of 16.7 M atomics in one thread.
+constexpr uint32_t kOccBigWords = 256;
+
+static __device__ __forceinline__ void occ_mark_row_words(uint32_t* __restrict__ occ, int y, int x0, int x1,
+                                                          int w) {
+  // word w of row y, cells [x0, x1] clipped to the word
+  const int lo = max(x0, 32 * w), hi = min(x1, 32 * w + 31);
+  const uint32_t m = (hi - lo == 31) ? 0xFFFFFFFFu : (((1u << (hi - lo + 1)) - 1) << (lo & 31));
+  uint32_t* p = &occ[(uint32_t) y * (kOccDim / 32) + w];
+  if ((*p & m) != m) atomicOr(p, m);  // mostly set already
+}
+
+// stats: [0] (leaf, cell) incidences, [1] cells of the largest box, [2] boxes on the big list
 __global__ void k_occ_mark(const int4* __restrict__ leaf_box, uint32_t n, uint32_t* __restrict__ occ,
-                           unsigned long long* __restrict__ n_incidences) {
+                           unsigned long long* __restrict__ stats, uint32_t* __restrict__ big_list) {
   uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long area = 0;
   if (l < n) {
     const int4 b = leaf_box[l];
     const int x0 = occ_cell(b.x), x1 = occ_cell(b.z), y0 = occ_cell(b.y), y1 = occ_cell(b.w);
     area = (unsigned long long) (x1 - x0 + 1) * (unsigned long long) (y1 - y0 + 1);
-    for (int y = y0; y <= y1; y++)
-      for (int x = x0; x <= x1; x++) {
-        const uint32_t bit = (uint32_t) y * kOccDim + x;
-        const uint32_t m = 1u << (bit & 31);
-        if (!(occ[bit >> 5] & m)) atomicOr(&occ[bit >> 5], m);  // mostly set already
-      }
+    const int w0 = x0 >> 5, w1 = x1 >> 5;
+    if ((uint32_t) (w1 - w0 + 1) * (uint32_t) (y1 - y0 + 1) > kOccBigWords) {
+      big_list[atomicAdd(&stats[2], 1ull)] = l;
+    } else {
+      for (int y = y0; y <= y1; y++)
+        for (int w = w0; w <= w1; w++) occ_mark_row_words(occ, y, x0, x1, w);
+    }
+    if (area > 1024) atomicMax(&stats[1], area);
   }
-  // (leaf, cell) incidences: the size of the cell directory (only when one is wanted)
-  if (n_incidences) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
-    if ((threadIdx.x & 31) == 0 && area) atomicAdd(n_incidences, area);
+  for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
+  if ((threadIdx.x & 31) == 0 && area) atomicAdd(&stats[0], area);
+}
+
+// one CTA per box of the big list
+__global__ void __launch_bounds__(256)
+k_occ_mark_big(const int4* __restrict__ leaf_box, const uint32_t* __restrict__ big_list,
+               const unsigned long long* __restrict__ stats, uint32_t* __restrict__ occ) {
+  const uint32_t n_big = (uint32_t) stats[2];
+  for (uint32_t i = blockIdx.x; i < n_big; i += gridDim.x) {
+    const int4 b = leaf_box[big_list[i]];
+    const int x0 = occ_cell(b.x), x1 = occ_cell(b.z), y0 = occ_cell(b.y), y1 = occ_cell(b.w);
+    const int w0 = x0 >> 5, nw = (x1 >> 5) - w0 + 1;
+    const uint32_t total = (uint32_t) nw * (uint32_t) (y1 - y0 + 1);
+    for (uint32_t t = threadIdx.x; t < total; t += blockDim.x)
+      occ_mark_row_words(occ, y0 + (int) (t / nw), x0, x1, w0 + (int) (t % nw));
   }
 }
 
@@ -350,11 +381,17 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
                               bool want_cells, cudaStream_t st) {
   RJB_REQUIRE(leaf_size >= 1 && leaf_size <= 8, "lbvh_leaf_size must be in 1..8");
   RJB_REQUIRE(m.n_chains < (1u << 28), "too many chains for the leaf record (2^28)");
+  // `built` stays false until the last call below has succeeded: a failed allocation or
+  // launch must not leave an index that passes the checks of rjb_lsi / rjb_pip
+  b.built = false;
+  b.have_cells = false;
   b.leaf_size = leaf_size;
-  b.built = true;
   b.n_leaves = 0;
   b.root_box = empty_box();
-  if (m.n_edges == 0) return;
+  if (m.n_edges == 0) {
+    b.built = true;
+    return;
+  }
   const int T = 256;
   uint32_t* cnt = b.chain_cnt.ensure(m.n_chains + 1);
   uint32_t* base = b.leaf_base.ensure(m.n_chains + 1);
@@ -397,13 +434,15 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
   const uint32_t occ_words = kOccWords;
   uint32_t* occ = b.occ.ensure(2 * occ_words);  // occ, then the dilated occ2
   RJB_CUDA(cudaMemsetAsync(occ, 0, occ_words * sizeof(uint32_t), st));
-  unsigned long long* inc = b.inc_counter.ensure(1);
-  RJB_CUDA(cudaMemsetAsync(inc, 0, sizeof(unsigned long long), st));
-  k_occ_mark<<<div_up(n, T), T, 0, st>>>(box_s, n, occ, want_cells ? inc : nullptr);
+  // [0] (leaf, cell) incidences, [1] cells of the largest box (> 1024 only), [2] big boxes
+  unsigned long long* inc = b.inc_counter.ensure(3);
+  RJB_CUDA(cudaMemsetAsync(inc, 0, 3 * sizeof(unsigned long long), st));
+  k_occ_mark<<<div_up(n, T), T, 0, st>>>(box_s, n, occ, inc, va /* free after the sort */);
+  k_occ_mark_big<<<kNumSMs, 256, 0, st>>>(box_s, va, inc, occ);
   k_occ_dilate<<<div_up(occ_words, T), T, 0, st>>>(occ, occ + occ_words);
   RJB_CUDA(cudaGetLastError());
   uint32_t n_occ = 0;
-  unsigned long long n_inc = 0;
+  unsigned long long n_inc = 0, max_area = 0;
   uint32_t* rank = nullptr;
   RJB_CUDA(cudaMemcpyAsync(&b.root_box, root_d, sizeof(int4), cudaMemcpyDeviceToHost, st));
   if (want_cells) {
@@ -414,6 +453,7 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
     exclusive_scan_u32(pop, rank, occ_words, b.scan_tmp, st);
     RJB_CUDA(cudaMemcpyAsync(&n_occ, rank + occ_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     RJB_CUDA(cudaMemcpyAsync(&n_inc, inc, sizeof(n_inc), cudaMemcpyDeviceToHost, st));
+    RJB_CUDA(cudaMemcpyAsync(&max_area, inc + 1, sizeof(max_area), cudaMemcpyDeviceToHost, st));
   }
   RJB_CUDA(cudaStreamSynchronize(st));
   // share of occupied cells (exact with the directory, else an upper estimate: a leaf
@@ -426,7 +466,8 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
   b.have_cells = false;
   b.n_occ_cells = n_occ;
   b.n_incidences = 0;
-  if (want_cells && b.occ_fraction < 0.25 && n_inc <= 8ull * n + 1024) {
+  // (k_cell_lists walks a box in one thread: no directory when some box spans > 1024 cells)
+  if (want_cells && b.occ_fraction < 0.25 && n_inc <= 8ull * n + 1024 && max_area <= 1024) {
     b.n_incidences = (uint32_t) n_inc;
     uint32_t* ccnt = b.cell_cnt.ensure(n_occ + 1);
     uint32_t* cbeg = b.cell_begin.ensure(n_occ + 1);
@@ -439,6 +480,7 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, long long
     RJB_CUDA(cudaGetLastError());
     b.have_cells = true;
   }
+  b.built = true;
 }
 
 }  // namespace rjb

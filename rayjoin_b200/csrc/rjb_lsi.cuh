@@ -196,7 +196,9 @@ constexpr int kFilterThreads = 256;
 constexpr int kFilterPerThread = 16;
 constexpr int kFilterCtaPoints = kFilterThreads * kFilterPerThread;
 
-// edge longer than a cell (rare): every cell of its box
+// edge longer than a cell (rare): every cell of its box, a bitmap word at a time.  A box of
+// more than 4096 words is kept without looking (the tree walk deals with it): the loop of
+// one thread stays bounded whatever the map contains.
 static __device__ __noinline__ bool occ_rect(const MapView& Q, const uint32_t* __restrict__ occ, uint32_t p,
                                              bool* within3) {
   const longlong2 a = __ldg(&Q.pts[p]), b = __ldg(&Q.pts[p + 1]);
@@ -205,10 +207,13 @@ static __device__ __noinline__ bool occ_rect(const MapView& Q, const uint32_t* _
   const uint32_t x1 = max(c1 & (kOccDim - 1), c2 & (kOccDim - 1));
   const uint32_t y0 = min(c1 >> kOccBits, c2 >> kOccBits), y1 = max(c1 >> kOccBits, c2 >> kOccBits);
   *within3 = x1 - x0 <= 2 && y1 - y0 <= 2;
+  const uint32_t w0 = x0 >> 5, w1 = x1 >> 5;
+  if ((w1 - w0 + 1) * (y1 - y0 + 1) > 4096u) return true;
   for (uint32_t y = y0; y <= y1; y++)
-    for (uint32_t x = x0; x <= x1; x++) {
-      const uint32_t bit = y * kOccDim + x;
-      if ((__ldg(&occ[bit >> 5]) >> (bit & 31)) & 1u) return true;
+    for (uint32_t w = w0; w <= w1; w++) {
+      const uint32_t lo = max(x0, 32 * w), hi = min(x1, 32 * w + 31);
+      const uint32_t m = (hi - lo == 31) ? 0xFFFFFFFFu : (((1u << (hi - lo + 1)) - 1) << (lo & 31));
+      if (__ldg(&occ[y * (kOccDim / 32) + w]) & m) return true;
     }
   return false;
 }
@@ -741,6 +746,7 @@ struct DeferItem {
   uint32_t i, pq, pb, axis;
 };
 
+// (Q = map of DeferItem::pq = the e1 side, B = map of pb = the e2 side)
 static __device__ __forceinline__ void points_flush(const MapView& Q, const MapView& B,
                                                     const DeferItem* list, unsigned n_list,
                                                     rjb_xsect* __restrict__ out) {
@@ -756,7 +762,7 @@ static __device__ __forceinline__ void points_flush(const MapView& Q, const MapV
 
 __global__ void __launch_bounds__(kPointsThreads)
 k_lsi_points(MapView Q, MapView B, int query_map_id, const unsigned int* __restrict__ counter,
-             uint32_t cap, rjb_xsect* __restrict__ out) {
+             uint32_t cap, rjb_xsect* __restrict__ out, bool base_first) {
   __shared__ DeferItem s_list[kDeferCap];
   __shared__ unsigned s_n;
   if (threadIdx.x == 0) s_n = 0;
@@ -771,13 +777,17 @@ k_lsi_points(MapView Q, MapView B, int query_map_id, const unsigned int* __restr
       const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
       const longlong2 c = __ldg(&B.pts[pb]), d = __ldg(&B.pts[pb + 1]);
       const uint32_t eq = pq - __ldg(&Q.point_chain[pq]), eb = pb - __ldg(&B.point_chain[pb]);
-      const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
+      // e1 = query edge (lsi_lbvh.h:71); grid mode with query map 1: e1 = the map-0 (base) edge
+      // (lsi_grid.h:62) -- the point is the same rational either way, the order is kept anyway
+      const Seg sq = {a.x, a.y, b.x, b.y}, sb = {c.x, c.y, d.x, d.y};
+      const Seg& e1 = base_first ? sb : sq;
+      const Seg& e2 = base_first ? sq : sb;
       bool dx = false, dy = false;
       rjb_xsect r;
       r.x = lsi_point_axis<true>(e1, e2, 0, &dx);
       r.y = lsi_point_axis<true>(e1, e2, 1, &dy);
-      if (dx) s_list[atomicAdd(&s_n, 1u)] = {i, pq, pb, 0u};
-      if (dy) s_list[atomicAdd(&s_n, 1u)] = {i, pq, pb, 1u};
+      if (dx) s_list[atomicAdd(&s_n, 1u)] = {i, base_first ? pb : pq, base_first ? pq : pb, 0u};
+      if (dy) s_list[atomicAdd(&s_n, 1u)] = {i, base_first ? pb : pq, base_first ? pq : pb, 1u};
       r.eid[0] = query_map_id == 0 ? eq : eb;
       r.eid[1] = query_map_id == 0 ? eb : eq;
       r.mid_point_polygon_id = RJB_DONTKNOW;
@@ -787,14 +797,14 @@ k_lsi_points(MapView Q, MapView B, int query_map_id, const unsigned int* __restr
     __syncthreads();  // records written, list complete for this round
     const unsigned n_list = s_n;
     if (n_list >= kPointsThreads) {
-      points_flush(Q, B, s_list, n_list, out);
+      points_flush(base_first ? B : Q, base_first ? Q : B, s_list, n_list, out);
       __syncthreads();
       if (threadIdx.x == 0) s_n = 0;
       __syncthreads();
     }
   }
   __syncthreads();
-  points_flush(Q, B, s_list, s_n, out);
+  points_flush(base_first ? B : Q, base_first ? Q : B, s_list, s_n, out);
 }
 
 // All |Q| x |B| pairs, no index: pins the exact arithmetic (RJB_MODE_BRUTE).

@@ -322,7 +322,10 @@ static void overlay_write(rjb_ctx* c, const char* path) {
                           cudaMemcpyDeviceToHost));
     // xs is sorted by eid[im]: CSR over the edges of this map
     std::vector<uint32_t> first(m.n_edges + 2, 0);
-    for (uint64_t i = 0; i < n; i++) first[xs[i].eid[im] + 1]++;
+    for (uint64_t i = 0; i < n; i++) {
+      RJB_REQUIRE(xs[i].eid[im] < m.n_edges, "rjb_overlay_write: result refers to an edge the map does not have");
+      first[xs[i].eid[im] + 1]++;
+    }
     for (uint32_t e = 0; e < m.n_edges; e++) first[e + 1] += first[e];
     for (uint32_t ic = 0; ic < m.n_chains; ic++) {
       uint32_t pb = m.h_row_index[ic], pe = m.h_row_index[ic + 1];

@@ -176,7 +176,7 @@ template <bool kStats, bool kPark>
 __global__ void __launch_bounds__(kLsiWarps * 32, 8)
 k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __restrict__ order,
           MapView B, BvhView bvh, int query_map_id, uint32_t* __restrict__ out_eid,
-          int32_t* __restrict__ out_face, unsigned long long* counters) {
+          int32_t* __restrict__ out_face, uint2* __restrict__ out_packed, unsigned long long* counters) {
   __shared__ int s_stack[kLsiWarps][kStackDepth];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* stack = s_stack[warp];
@@ -265,16 +265,20 @@ k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __r
   }
   if (kPark) pip_flush(B, bvh, L, query_map_id, cand);  // whatever is still parked
   if (L.valid) {
-    out_eid[pi] = L.best.eid;
-    if (out_face) {
-      int32_t face = RJB_EXTERIOR_FACE;
-      if (L.best.eid != RJB_NO_HIT) {
-        // get_face_id, src/map/map.h:79-87
-        uint32_t c = B.edge_chain[L.best.eid];
-        longlong2 a = B.pts[L.best.eid + c], b = B.pts[L.best.eid + c + 1];
-        face = a.x < b.x ? B.right[c] : B.left[c];
-      }
-      out_face[pi] = face;
+    int32_t face = RJB_EXTERIOR_FACE;
+    if ((out_face || out_packed) && L.best.eid != RJB_NO_HIT) {
+      // get_face_id, src/map/map.h:79-87
+      uint32_t c = B.edge_chain[L.best.eid];
+      longlong2 a = B.pts[L.best.eid + c], b = B.pts[L.best.eid + c + 1];
+      face = a.x < b.x ? B.right[c] : B.left[c];
+    }
+    if (out_packed) {
+      // ordered queries: ONE scattered 8-byte store per point (k_pip_split separates the
+      // two result arrays afterwards with coalesced accesses) instead of two 4-byte ones
+      out_packed[pi] = make_uint2(L.best.eid, (uint32_t) face);
+    } else {
+      out_eid[pi] = L.best.eid;
+      if (out_face) out_face[pi] = face;
     }
   }
 #pragma unroll
@@ -290,6 +294,15 @@ k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __r
       atomicMax(counters + 7, (unsigned long long) st.maxsp);
     }
   }
+}
+
+__global__ void k_pip_split(const uint2* __restrict__ packed, uint32_t n, uint32_t* __restrict__ out_eid,
+                            int32_t* __restrict__ out_face) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2 v = packed[i];
+  out_eid[i] = v.x;
+  out_face[i] = (int32_t) v.y;
 }
 
 // all points x all edges (RJB_MODE_BRUTE): pins the PIP arithmetic

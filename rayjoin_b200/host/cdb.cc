@@ -375,6 +375,17 @@ int read_bin(const char* path, GraphOwner* o) {
   bool ok = rd(f, magic) && magic == 0xabcdabcdull && rd(f, n_chains) && rd(f, n_row) &&
             rd(f, n_points);
   if (ok) {
+    // the counts come straight from the file: check them against each other and against the
+    // file size before any vector is sized from them (a truncated or corrupt cache must give
+    // RJB_ERR_IO, not std::bad_alloc)
+    struct stat sb;
+    ok = fstat(fileno(f), &sb) == 0;
+    const uint64_t lim = 1ull << 40;
+    ok = ok && n_chains < lim && n_row < lim && n_points < lim;
+    ok = ok && n_row == (n_points ? n_chains + 1 : 0) && n_points < 0xFFFFFFF0ull;
+    ok = ok && (uint64_t) sb.st_size == 8 * 4 + n_chains * 40 + n_row * 4 + n_points * 16 + 4 * 8 + 8;
+  }
+  if (ok) {
     o->chain_id.resize(n_chains);
     o->first_point.resize(n_chains);
     o->last_point.resize(n_chains);
@@ -395,32 +406,36 @@ int read_bin(const char* path, GraphOwner* o) {
   return RJB_OK;
 }
 
+// no exception leaves the C ABI: allocation failures while parsing become RJB_ERR_IO
+template <typename F>
+int read_guarded(const char* path, rjb_graph* out, F&& reader) {
+  if (!path || !out) return RJB_ERR_INVALID;
+  GraphOwner* o = nullptr;
+  try {
+    o = new GraphOwner();
+    int rc = reader(path, o);
+    if (rc != RJB_OK) {
+      delete o;
+      return rc;
+    }
+    publish(o, out);
+    return RJB_OK;
+  } catch (const std::exception& e) {
+    delete o;
+    return fail(std::string("Cannot load ") + path + ": " + e.what());
+  }
+}
+
 }  // namespace
 
 extern "C" {
 
 int rjb_graph_read_text(const char* path, rjb_graph* out) {
-  if (!path || !out) return RJB_ERR_INVALID;
-  GraphOwner* o = new GraphOwner();
-  int rc = read_text(path, o);
-  if (rc != RJB_OK) {
-    delete o;
-    return rc;
-  }
-  publish(o, out);
-  return RJB_OK;
+  return read_guarded(path, out, [](const char* p, GraphOwner* o) { return read_text(p, o); });
 }
 
 int rjb_graph_read_bin(const char* path, rjb_graph* out) {
-  if (!path || !out) return RJB_ERR_INVALID;
-  GraphOwner* o = new GraphOwner();
-  int rc = read_bin(path, o);
-  if (rc != RJB_OK) {
-    delete o;
-    return rc;
-  }
-  publish(o, out);
-  return RJB_OK;
+  return read_guarded(path, out, [](const char* p, GraphOwner* o) { return read_bin(p, o); });
 }
 
 int rjb_graph_write_bin(const rjb_graph* g, const char* path) {
@@ -452,8 +467,7 @@ int rjb_graph_write_bin(const rjb_graph* g, const char* path) {
   return ok ? RJB_OK : fail(std::string("Write failed: ") + path);
 }
 
-int rjb_graph_load(const char* path, const char* serialize_prefix, rjb_graph* out) {
-  if (!path || !out) return RJB_ERR_INVALID;
+static int graph_load(const char* path, const char* serialize_prefix, rjb_graph* out) {
   std::string prefix = serialize_prefix ? serialize_prefix : "";
   std::string escaped(path);
   for (char& ch : escaped)
@@ -474,6 +488,15 @@ int rjb_graph_load(const char* path, const char* serialize_prefix, rjb_graph* ou
   if (rc != RJB_OK) return rc;
   if (!prefix.empty() && access(prefix.c_str(), W_OK) == 0) rjb_graph_write_bin(out, ser.c_str());
   return RJB_OK;
+}
+
+int rjb_graph_load(const char* path, const char* serialize_prefix, rjb_graph* out) {
+  if (!path || !out) return RJB_ERR_INVALID;
+  try {
+    return graph_load(path, serialize_prefix, out);
+  } catch (const std::exception& e) {
+    return fail(std::string("Cannot load ") + path + ": " + e.what());
+  }
 }
 
 void rjb_graph_free(rjb_graph* g) {

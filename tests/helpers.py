@@ -82,6 +82,11 @@ class OracleMaps:
             return self.O.lsi_brute(self.pts[q], self.p1[q], self.pts[b], self.p1[b])
         return self.O.lsi_grid(self.pts[q], self.p1[q], self.pts[b], self.p1[b], self.sc)
 
+    def lsi_refgrid(self, q, gsize, brute=False):
+        """the reference's -mode=grid pair set, ordered like sort_xsects(xs, q)"""
+        return self.O.lsi_refgrid(self.pts[0], self.p1[0], self.pts[1], self.p1[1], self.sc, gsize,
+                                  sort_map=q, brute=brute)
+
     def pip(self, q, pts, brute=False):
         b = 1 - q
         if brute:
@@ -99,3 +104,35 @@ def sort_xsects(xs, q):
     eq, eb = xs["eid"][:, q].astype(np.int64), xs["eid"][:, 1 - q].astype(np.int64)
     o = np.lexsort((eb, eq))
     return eq[o].astype(np.uint32), eb[o].astype(np.uint32), xs["x"][o], xs["y"][o]
+
+
+def i128_kat(n_random=200000, seed=99):
+    """Known-answer inputs for (double)(__int128): magnitudes just above 2^53, 2^64 and 2^96,
+    exact ties between two doubles (with even and odd mantissas), ties +-1, powers of two
+    +-1, and random values of every bit length.  Returns (python ints, (n, 2) uint64 words)."""
+    rng = np.random.default_rng(seed)
+    vals = [0, 1, -1, 2**53, 2**53 + 1, 2**53 + 2, 2**53 + 3, -(2**53 + 1), 2**64, 2**64 + 1, 2**64 - 1,
+            2**96, 2**96 + 1, 2**96 - 1, 2**127 - 1, -(2**127), -(2**127) + 1, 2**63, -(2**63), 2**63 - 1]
+    for k in range(1, 75):           # v needs 53 + k bits
+        half = 1 << (k - 1)
+        for m in rng.integers(2**52, 2**53, size=40).tolist():
+            for mm in (m, m | 1, m & ~1):
+                base = mm << k
+                for d in (0, half - 1, half, half + 1, (1 << k) - 1):
+                    if d < 0 or base + d >= 2**127:
+                        continue
+                    vals.append(base + d)
+                    vals.append(-(base + d))
+    for b in (53, 54, 55, 63, 64, 65, 95, 96, 97, 126):
+        for d in range(-3, 4):
+            vals.append(2**b + d)
+            vals.append(-(2**b + d))
+    bits = rng.integers(1, 127, size=n_random)
+    hi = rng.integers(0, 2**62, size=n_random).tolist()
+    lo = rng.integers(0, 2**62, size=n_random).tolist()
+    sg = rng.integers(0, 2, size=n_random).tolist()
+    for b, h, l, s in zip(bits.tolist(), hi, lo, sg):
+        v = ((h << 62) | l) & ((1 << b) - 1) | (1 << (b - 1))
+        vals.append(-v if s else v)
+    words = np.array([[(v & (2**64 - 1)), ((v >> 64) & (2**64 - 1))] for v in vals], dtype=np.uint64)
+    return vals, words

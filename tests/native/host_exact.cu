@@ -36,6 +36,20 @@ void hx_intersect_batch(const long long* pts, unsigned long long n, int mode, un
   if (n_deferred) *n_deferred = nd;
 }
 
+// cell of the intersection point the way the grid LSI kernel computes it (lsi_xsect_ref_cell:
+// gcd-free short-cut with the reference's literal sequence as the fall-back)
+void hx_xsect_ref_cells(const long long* pts, unsigned long long n, long long imin, double cell_scale,
+                        int* cx, int* cy) {
+  for (unsigned long long i = 0; i < n; i++) {
+    const long long* p = pts + 8 * i;
+    const Seg e1 = {p[0], p[1], p[2], p[3]}, e2 = {p[4], p[5], p[6], p[7]};
+    cx[i] = cy[i] = 0;
+    if (!lsi_intersect(e1, e2)) continue;
+    cx[i] = lsi_xsect_ref_cell(e1, e2, 0, imin, cell_scale);
+    cy[i] = lsi_xsect_ref_cell(e1, e2, 1, imin, cell_scale);
+  }
+}
+
 // occupancy cell code of a vertex and descriptor of an edge (what k_load_points writes and
 // k_lsi_filter reads)
 unsigned hx_occ_code(long long x, long long y) { return occ_code(x, y); }

@@ -164,3 +164,31 @@ def test_pip_update_rule_matches_oracle(hx, oracle, q):
         hx.hx_pip_batch(p(edges), C.c_uint64(len(edges)), p(pts), C.c_uint64(len(pts)), C.c_int(q), p(got))
         assert np.array_equal(got, want), name
         assert (got != 0xFFFFFFFF).any()
+
+
+@pytest.mark.parametrize("gsize", [64, 2048, 15000, 32768])
+def test_xsect_cell_shortcut_matches_reference_sequence(hx, oracle, gsize):
+    """Grid LSI keeps a pair only in the cell of its intersection point (src/app/lsi_grid.h:62-67,
+    src/grid/cell.h:15-22).  The kernel decides the cell without the gcd unless the point lies
+    within 1e-6 of a cell boundary; the oracle replays the reference's rational -> double
+    sequence literally (including the 128-bit wrap-around for long edges)."""
+    sc = oracle.scaling_init(-179.15, -14.55, 179.78, 71.39)
+    cs = float(gsize) / float(sc.irange) * 0.999
+    rng = np.random.default_rng(gsize)
+    sets = [crossing(rng, 60000, b) for b in (4, 12, 20, 28, 33, 36, 37, 38, 41, 44)]
+    # points ON cell boundaries: lattice of multiples of the cell width (integer crossings)
+    w = int(1.0 / cs) + 1
+    base = rng.integers(-2**45 // w, 2**45 // w, size=(40000, 1, 2)) * w
+    d = rng.integers(1, 2**10, size=(40000, 2, 2))
+    e = np.concatenate([base - d[:, :1] * [[1, 0]], base + d[:, :1] * [[1, 0]],
+                        base - d[:, 1:] * [[0, 1]], base + d[:, 1:] * [[0, 1]]], axis=1).reshape(-1, 8)
+    sets.append(e)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for pts in sets:
+        pts = np.ascontiguousarray(pts, np.int64)
+        hit, cx, cy, owned = oracle.refgrid_cells(pts, sc, gsize)
+        gx, gy = np.zeros(len(pts), np.int32), np.zeros(len(pts), np.int32)
+        hx.hx_xsect_ref_cells(p(pts), C.c_uint64(len(pts)), C.c_longlong(sc.imin), C.c_double(cs), p(gx), p(gy))
+        m = hit == 1
+        assert m.sum() > 1000
+        assert np.array_equal(gx[m], cx[m]) and np.array_equal(gy[m], cy[m])

@@ -30,7 +30,7 @@ def test_overlay_matches_oracle(rjb, name, mode, tmp_path):
         B = synth.voronoi_map(60, 1200, synth.BRAZIL_BBOX, seed=22)
         if name == "shared":
             B = synth.share_chains(A, B, frac=0.3)
-    oo = OverlayOracle([A, B]).run()
+    oo = OverlayOracle([A, B], grid_size=64 if mode == "grid" else None).run()
     ctx = rjb.Context([A, B])
     ov = rjb.MapOverlay(ctx, mode, grid_size=64, xsect_factor=4.0)
     ov.Run()

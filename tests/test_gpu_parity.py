@@ -50,7 +50,10 @@ def test_lsi_pair_set_and_points(rjb, loaded, name, mode, q):
     lsi.Init(4.0)
     n = lsi.Query(q)
     got = sort_xsects(lsi.get_xsects(), q)
-    want = om.lsi(q)
+    # grid mode has the reference's GRID semantics (src/app/lsi_grid.h:62-67): predicate
+    # evaluated as (map-0 edge, map-1 edge) whatever the query side, pair kept iff the cell of
+    # its intersection point holds both edges; lbvh / brute: e1 = query edge, no cell rule
+    want = om.lsi_refgrid(q, 64) if mode == "grid" else om.lsi(q)
     assert n == len(want[0])
     for g, w, what in zip(got, want, ("eid_query", "eid_base", "x", "y")):
         assert np.array_equal(g, w), what
@@ -160,10 +163,10 @@ def test_chunked_upload_matches_single_chunk(rjb, oracle):
             assert lsi.Query(1) == len(want[0])
             for g, w in zip(sort_xsects(lsi.get_xsects(), 1), want):
                 assert np.array_equal(g, w)
-            ctx.build_index(0, "grid", grid_size=64)  # the grid path reads edge_chain
+            ctx.build_index(0, "grid", grid_size=64)  # the grid path reads last_bits / point_chain
             lsi = rjb.LSI(ctx, "grid")
             lsi.Init(4.0)
-            assert lsi.Query(1) == len(want[0])
+            assert lsi.Query(1) == len(om.lsi_refgrid(1, 64)[0])
             pip = rjb.PIP(ctx, "lbvh")
             pip.Query(1)
             assert np.array_equal(pip.get_closest_eids(), om.pip(1, om.pts[1]))

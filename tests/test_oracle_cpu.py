@@ -91,3 +91,13 @@ def test_pip_rule_hand_cases(oracle):
     # a point ON the horizontal edge: diff == 0 -> -a/+a == 0 -> -b/+b decides:
     # q == 0 perturbs the point below the edge (hit), q == 1 above it (next edge up)
     assert e0[1] == 0 and e1[1] == 1
+
+
+def test_oracle_int128_to_double_is_correctly_rounded(oracle):
+    """SURVEY section 9 Q2, host half: libgcc's __floattidf (what the oracle and the reference's
+    host code use) against Python's correctly rounded int -> float on the KAT the device test
+    (tests/test_gpu_device_arith.py) runs through the sm_100a conversion sequence."""
+    from helpers import i128_kat
+    vals, words = i128_kat(n_random=100000)
+    want = np.array([float(v) for v in vals])
+    assert np.array_equal(oracle.i128_to_double(words).view(np.uint64), want.view(np.uint64))
