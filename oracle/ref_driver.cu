@@ -14,6 +14,8 @@
  *
  *   ref_exec lsi|pip|overlay lbvh|grid MAP0 MAP1 [-grid_size N] [-xsect_factor F]
  *            [-warmup W] [-repeat K] [-dump FILE] [-output FILE] [-v]
+ *   ref_exec lsi|pip rjb|rjbgrid MAP0 MAP1 ...   the same driver loop calling librjb200 through
+ *            LSIRJB / PIPRJB (oracle/rjb_binding.h): the binding, compiled and run
  *   MAPx: a RayJoin .bin graph (planar_graph.h:128-167) or a CDB text file.
  */
 #include <array>
@@ -47,6 +49,8 @@ int verbose = 0;
 #include "app/pip_lbvh.h"
 #include "map/planar_graph.h"
 #include "tree/primtive.h"
+// the reference-side binding of librjb200, driven like any other backend
+#include "rjb_binding.h"
 
 using namespace rayjoin;
 using context_t = Context<coord_t, coefficient_t>;
@@ -102,7 +106,15 @@ static int run_lsi(const Args& a) {
   std::shared_ptr<LSI<context_t>> lsi;
   std::shared_ptr<bvh_t> bvh;
   double t_init0 = now_ms(), t_build0, t_build1;
-  if (a.mode == "grid") {
+  if (a.mode == "rjb" || a.mode == "rjbgrid") {
+    auto p = std::make_shared<LSIRJB<context_t>>(ctx, a.mode == "rjb" ? RJB_MODE_LBVH : RJB_MODE_GRID,
+                                                  a.grid_size);
+    p->Init(queue_cap);
+    t_build0 = now_ms();
+    p->BuildIndex(base_map_id);
+    t_build1 = now_ms();
+    lsi = p;
+  } else if (a.mode == "grid") {
     auto grid = std::make_shared<UniformGrid>(a.grid_size);
     auto p = std::make_shared<LSIGrid<context_t>>(ctx, grid);
     QueryConfigGrid qc;
@@ -171,7 +183,16 @@ static int run_pip(const Args& a) {
   std::shared_ptr<bvh_t> bvh;
   double t_build0, t_build1;
   std::function<void()> query;
-  if (a.mode == "grid") {
+  if (a.mode == "rjb" || a.mode == "rjbgrid") {
+    auto p = std::make_shared<PIPRJB<context_t>>(ctx, a.mode == "rjb" ? RJB_MODE_LBVH : RJB_MODE_GRID,
+                                                  a.grid_size);
+    p->Init(query_points.size());
+    t_build0 = now_ms();
+    p->BuildIndex(base_map_id);
+    t_build1 = now_ms();
+    query = [=, &stream]() mutable { p->Query(stream, query_map_id, d_query_points); };
+    pip = p;
+  } else if (a.mode == "grid") {
     auto grid = std::make_shared<UniformGrid>(a.grid_size);
     auto p = std::make_shared<PIPGrid<context_t>>(ctx, grid);
     p->Init(query_points.size());
@@ -292,7 +313,11 @@ int main(int argc, char** argv) {
     else if (f == "-v") rjb_glog_shim::verbose = 1;
     else { fprintf(stderr, "unknown flag %s\n", f.c_str()); return 2; }
   }
-  if (a.mode != "grid" && a.mode != "lbvh") { fprintf(stderr, "mode must be grid|lbvh\n"); return 2; }
+  const bool rjb_mode = a.mode == "rjb" || a.mode == "rjbgrid";
+  if (a.mode != "grid" && a.mode != "lbvh" && !(rjb_mode && a.query != "overlay")) {
+    fprintf(stderr, "mode must be grid|lbvh (lsi / pip also: rjb|rjbgrid)\n");
+    return 2;
+  }
   try {
     if (a.query == "lsi") return run_lsi(a);
     if (a.query == "pip") return run_pip(a);

@@ -311,7 +311,7 @@ static void ensure_load_pipeline(rjb_ctx* c) {
 }
 
 static void ensure_events(rjb_ctx* c) {
-  if (!c->h_counters) RJB_CUDA(cudaHostAlloc((void**) &c->h_counters, 16 * sizeof(unsigned long long), cudaHostAllocDefault));
+  if (!c->h_counters) RJB_CUDA(cudaHostAlloc((void**) &c->h_counters, 128 * sizeof(unsigned long long), cudaHostAllocDefault));
   for (int i = 0; i <= kTimedStages; i++)
     if (!c->ev[i]) RJB_CUDA(cudaEventCreate(&c->ev[i]));
   for (int i = 0; i < 2; i++)
@@ -361,7 +361,7 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
   // counters: [0] results, [1] candidates (= exact-predicate evaluations),
   // [2..7] traversal statistics
   // [8], [9]: {filter survivors, (query, leaf) pairs, long survivors} as 32-bit counters
-  unsigned long long* ctr = c->counters.ensure(10);
+  unsigned long long* ctr = c->counters.ensure(128);
   ensure_events(c);
   MapView Q = Qm.view(), B = Bm.view();
   LsiPending& P = c->lsi_pending;
@@ -613,9 +613,11 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
   RJB_REQUIRE(mode == RJB_MODE_LBVH || mode == RJB_MODE_GRID || mode == RJB_MODE_BRUTE, "rjb_pip: unknown mode");
   uint32_t* eid = c->pip_eid.ensure(n ? n : 1);
   int32_t* face = c->pip_face.ensure(n ? n : 1);
-  unsigned long long* ctr = c->counters.ensure(10);
+  // [0..7] statistics, [16 .. 16 + kCtrSlots) partial candidate counts
+  constexpr int kPipCtrs = 16 + kCtrSlots;
+  unsigned long long* ctr = c->counters.ensure(kPipCtrs);
   ensure_events(c);
-  RJB_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
+  RJB_CUDA(cudaMemsetAsync(ctr, 0, kPipCtrs * sizeof(unsigned long long), c->stream));
   MapView B = Bm.view();
   if (mode == RJB_MODE_LBVH && !Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no LBVH on the base map");
   if (mode == RJB_MODE_GRID && !Bm.grid.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no grid on the base map");
@@ -661,9 +663,9 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
     } else if (mode == RJB_MODE_GRID) {
       const GridView gv = Bm.grid.view();
       if (packed)
-        k_pip_grid<true><<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, order, B, gv, q, eid, face, packed, ctr + 1);
+        k_pip_grid<true><<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, order, B, gv, q, eid, face, packed, ctr + 16);
       else
-        k_pip_grid<false><<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, order, B, gv, q, eid, face, nullptr, ctr + 1);
+        k_pip_grid<false><<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, order, B, gv, q, eid, face, nullptr, ctr + 16);
     } else {
       k_pip_brute<<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, B, q, eid, face);
     }
@@ -675,9 +677,11 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
   }
   RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
   RJB_CUDA(cudaGetLastError());
-  RJB_CUDA(cudaMemcpyAsync(c->h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  RJB_CUDA(cudaMemcpyAsync(c->h_counters, ctr, kPipCtrs * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                           c->stream));
   RJB_CUDA(cudaStreamSynchronize(c->stream));
   memcpy(c->last_stats, c->h_counters, 8 * sizeof(unsigned long long));
+  for (int k = 0; k < kCtrSlots; k++) c->last_stats[1] += c->h_counters[16 + k];
   c->last_launches = launches;
   c->timing_pending = 2;
   c->timing_layout = 4;  // {ordering of the points, query kernel (+ result split)}

@@ -547,10 +547,10 @@ k_pip_grid(const longlong2* __restrict__ pts, uint32_t n, const uint32_t* __rest
       if (out_face) out_face[i] = face;
     }
   }
-  if (n_cand) {
+  if (n_cand) {  // kCtrSlots slots, summed on the host
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
-    if ((threadIdx.x & 31) == 0 && cand) atomicAdd(n_cand, cand);
+    if ((threadIdx.x & 31) == 0 && cand) atomicAdd(n_cand + (blockIdx.x & (kCtrSlots - 1)), cand);
   }
 }
 

@@ -284,7 +284,7 @@ k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __r
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
   if (lane == 0) {
-    if (cand) atomicAdd(counters + 1, cand);
+    if (cand) atomicAdd(counters + 16 + (blockIdx.x & (kCtrSlots - 1)), cand);  // spread, summed on the host
     if (kStats) {
       atomicAdd(counters + 2, (unsigned long long) st.nodes);
       atomicAdd(counters + 3, (unsigned long long) st.leaves);
