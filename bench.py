@@ -437,7 +437,7 @@ def main():
     ap.add_argument("--stage-timing", type=int, default=1, help="CUDA event after every kernel of the query")
     ap.add_argument("--legs", default="", help="lsi,pip,overlay (default: all at N = 1, lsi at N > 1)")
     ap.add_argument("--pip-modes", default="lbvh,grid")
-    ap.add_argument("--pip-grid-size", type=int, default=4096)
+    ap.add_argument("--pip-grid-size", type=int, default=16384)
     ap.add_argument("--pip-check", type=int, default=10_000_000, help="points checked against the oracle (-1: all)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -126,6 +126,12 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
 
 /* tuning knobs that have no RayJoin flag (defaults are fine):
  *   "lbvh_leaf_size"  edges per LBVH leaf, 1..8 (default 4)
+ *   "lbvh_ag"         1 = adaptive leaf grouping: leaves are runs of consecutive chain edges
+ *                     merged by RayJoin's Adaptive Grouping rule (-ag, src/rt/primitive.h:120-260:
+ *                     neighbours merge while area(merged) / max(area) < enlarge), 0 (default) =
+ *                     fixed runs of lbvh_leaf_size edges.  Set it before rjb_build_index.
+ *   "lbvh_ag_iter"    merge rounds (-ag_iter, default 5; leaves hold <= 8 edges: 3 take effect)
+ *   "lbvh_enlarge_x1000"  the area limit times 1000 (-enlarge, default 5.0 -> 5000)
  *   "sort_queries"    visit queries in Morton order: 1 on, 0 off, -1 auto (default:
  *                     LSI query edges are ordered when the query map averages
  *                     < 32 edges per chain; points only on request)

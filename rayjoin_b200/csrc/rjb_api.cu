@@ -100,6 +100,9 @@ struct rjb_ctx {
   rjb_scaling sc;
   DeviceMap maps[2];
   int leaf_size = 4;
+  // adaptive leaf grouping (RayJoin's -ag / -ag_iter / -enlarge, src/rt/primitive.h:120-260)
+  int ag = 0, ag_iter = 5;
+  float ag_enlarge = 5.0f;
   int sort_queries = -1;  // -1 auto: Morton-order query EDGES when the chains are short
   bool filter_useless = false;  // the occupancy filter kept > 50 % last time: skip it
   int stats = 0;  // collect traversal statistics (slower)
@@ -325,7 +328,8 @@ static void do_build_index(rjb_ctx* c, int map_id, int mode, uint32_t grid_size,
   ensure_events(c);
   RJB_CUDA(cudaEventRecord(c->bev[0], c->stream));
   if (mode == RJB_MODE_LBVH) {
-    build_lbvh(m.bvh, m.view(), c->leaf_size, c->sc.internal_min, c->use_cells > 0, c->stream);
+    build_lbvh(m.bvh, m.view(), c->leaf_size, c->ag ? c->ag_iter : 0, c->ag_enlarge, c->sc.internal_min,
+               c->use_cells > 0, c->stream);
   } else if (mode == RJB_MODE_GRID) {
     build_grid(m.grid, m.view(), grid_size, c->sc.internal_min, c->sc.internal_range, c->stream);
   } else if (mode == RJB_MODE_BRUTE) {
@@ -598,7 +602,7 @@ __global__ void k_query_keys_points_grid(const longlong2* __restrict__ pts, uint
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const longlong2 p = pts[i];
-  key[i] = (uint64_t) grid_cell(g, p.x) * g.gs + (uint64_t) grid_cell(g, p.y - 1);
+  key[i] = (uint64_t) grid_cx(g, p.x) * g.gs + (uint64_t) grid_cy(g, p.y - 1);
   val[i] = i;
 }
 
@@ -635,7 +639,7 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
       const GridView gv = Bm.grid.view();
       k_query_keys_points_grid<<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, gv, ka, va);
       int bits = 1;
-      while (bits < 40 && (((uint64_t) gv.gsize * gv.gs) >> bits)) bits++;
+      while (bits < 40 && (((uint64_t) gv.gx * gv.gs) >> bits)) bits++;
       // the low (row) bits beyond 24 key bits buy nothing: three radix passes at most
       const int lo = bits > 24 ? bits - 24 : 0;
       sort_pairs_u64_u32(ka, kb, va, vb, n, lo, bits, c->ord_sort, c->stream);
@@ -776,6 +780,14 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
     if (n == "lbvh_leaf_size") {
       RJB_REQUIRE(value >= 1 && value <= 8, "lbvh_leaf_size must be in 1..8");
       c->leaf_size = (int) value;
+    } else if (n == "lbvh_ag") {
+      c->ag = value != 0;
+    } else if (n == "lbvh_ag_iter") {
+      RJB_REQUIRE(value >= 1 && value <= 64, "lbvh_ag_iter must be in 1..64");
+      c->ag_iter = (int) value;
+    } else if (n == "lbvh_enlarge_x1000") {
+      RJB_REQUIRE(value >= 1000 && value <= 1000000000ll, "lbvh_enlarge_x1000 must be >= 1000");
+      c->ag_enlarge = (float) value / 1000.0f;
     } else if (n == "sort_queries") {
       c->sort_queries = (int) value;
     } else if (n == "lsi_filter") {

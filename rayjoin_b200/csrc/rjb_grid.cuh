@@ -27,29 +27,41 @@
 
 namespace rjb {
 
+// The cells of the INDEX are not the reference's square cells: the same number of them
+// (-grid_size squared) is laid out as 4 x as many columns of a quarter of the rows.  PIP walks a
+// column upward, and in a narrow column nearly every edge met spans the whole column, so the
+// first occupied cell above the point almost always holds the answer (square cells of one edge
+// length: 16 occupied cells and 53 screened edges per point on the 28 M-edge map, most of them
+// edges that run alongside the column without covering px).  The index is only a filter; the
+// reference's square cells enter where they define the RESULT: the ownership rule of the grid
+// LSI (grid_owned) is evaluated arithmetically with ref_scale, whatever cells the index has.
 struct GridView {
   const uint32_t* bits;        // occupancy, column-major: bit (cx * gs + cy)
   const uint32_t* rank;        // occupied cells before each bitmap word
   const uint32_t* cell_begin;  // [n_occ + 1] CSR into items
-  const uint32_t* items;       // start point (eid + chain) of the base edges of a cell
-  uint32_t gsize, gs;          // cells per axis; column stride in bits (gsize rounded up to 32)
+  const uint2* items;          // per incidence: {start point (eid + chain) of the base edge,
+                               //  its box relative to the cell in 1/128 steps (grid_qbox)}
+  uint32_t gx, gy, gs;         // columns, rows; column stride in bits (gy rounded up to 32)
+  uint32_t gsize;              // the caller's -grid_size (reference cells: gsize x gsize)
   long long imin;
-  double cell_scale;           // (double) gsize / internal_range * 0.999   (cell.h:19)
-  double inv_cell_scale;
+  double sx, sy;               // index cells: (double) gx / internal_range * 0.999, likewise gy
+  double inv_sy;
+  double ref_scale;            // (double) gsize / internal_range * 0.999   (cell.h:19)
 };
 
 struct Grid {
-  DBuf<uint32_t> bits, pop, rank, cell_begin, items, cnt, off, vals_a, big;
+  DBuf<uint32_t> bits, pop, rank, cell_begin, cnt, off, vals_a, vals_b, big;
+  DBuf<uint2> items;
   DBuf<uint64_t> keys_a, keys_b;
   DBuf<unsigned long long> totals;
   ScanTemp scan_tmp;
   SortTemp sort_tmp;
-  uint32_t gsize = 0, gs = 0, n_occ = 0;
+  uint32_t gsize = 0, gx = 0, gy = 0, gs = 0, n_occ = 0;
   uint64_t n_items = 0;
   long long imin = 0;
-  double cell_scale = 0;
+  double sx = 0, sy = 0, ref_scale = 0;
   bool built = false;
-  uint32_t n_words() const { return gsize * (gs / 32); }
+  uint32_t n_words() const { return gx * (gs / 32); }
   GridView view() const {
     GridView v;
     v.bits = bits.p;
@@ -57,23 +69,67 @@ struct Grid {
     v.cell_begin = cell_begin.p;
     v.items = items.p;
     v.gsize = gsize;
+    v.gx = gx;
+    v.gy = gy;
     v.gs = gs;
     v.imin = imin;
-    v.cell_scale = cell_scale;
-    v.inv_cell_scale = cell_scale > 0 ? 1.0 / cell_scale : 0;
+    v.sx = sx;
+    v.sy = sy;
+    v.inv_sy = sy > 0 ? 1.0 / sy : 0;
+    v.ref_scale = ref_scale;
     return v;
   }
   size_t index_bytes() const {
     return 2 * (size_t) (n_words() + 1) * sizeof(uint32_t) + ((size_t) n_occ + 1) * sizeof(uint32_t) +
-           n_items * sizeof(uint32_t);
+           n_items * sizeof(uint2);
   }
 };
 
 // cell of a coordinate for FILTERING: the reference's function clamped into the grid (query
 // points may lie outside the bounding box of the maps); monotone
-static __device__ __forceinline__ int grid_cell(const GridView& g, long long v) {
-  const int c = ref_cell(v, g.imin, g.cell_scale);
-  return min(max(c, 0), (int) g.gsize - 1);
+static __device__ __forceinline__ int grid_cx(const GridView& g, long long v) {
+  return min(max(ref_cell(v, g.imin, g.sx), 0), (int) g.gx - 1);
+}
+static __device__ __forceinline__ int grid_cy(const GridView& g, long long v) {
+  return min(max(ref_cell(v, g.imin, g.sy), 0), (int) g.gy - 1);
+}
+
+// Position of a coordinate inside cell c of its axis in 1/128 steps, clamped to [0, 127]:
+// monotone in v (every floating-point step is), so v1 <= v2 implies grid_q(v1) <= grid_q(v2) and
+// comparisons of these numbers are CONSERVATIVE stand-ins for comparisons of the coordinates.
+constexpr int kGridQ = 128;   // steps per cell row (y)
+constexpr int kGridQX = 64;   // steps per cell column (x)
+
+static __device__ __forceinline__ uint32_t grid_q(long long v, long long imin, double scale, int c, int steps) {
+  const double t = ((double) (v - imin) * scale - (double) c) * (double) steps;
+  return (uint32_t) min(max((int) floor(t), 0), steps - 1);
+}
+static __device__ __forceinline__ uint32_t grid_qx(const GridView& g, long long v, int c) {
+  return grid_q(v, g.imin, g.sx, c, kGridQX);
+}
+static __device__ __forceinline__ uint32_t grid_qy(const GridView& g, long long v, int c) {
+  return grid_q(v, g.imin, g.sy, c, kGridQ);
+}
+
+// Box of an edge as seen from cell (cx, cy), 32 bits:
+//   bits  0.. 5  qx0   x range inside the cell's column in 1/64 steps (clamped)
+//   bits  6..11  qx1
+//   bit  12      the edge starts LEFT of the column  (so xmin < px for every px in the column)
+//   bit  13      the edge ends RIGHT of the column
+//   bits 14..20  qy0   ymin inside the cell (0 when the edge starts below it)
+//   bits 21..27  qy1   ymax inside ITS cell, which is cell cy + dy
+//   bits 28..31  dy    rows between this cell and the cell of ymax (15 = that many or more)
+// The PIP walk screens and bounds an edge with this word alone; the vertices are loaded
+// afterwards, and only for the edges that pass.
+static __device__ __forceinline__ uint32_t grid_qbox(const GridView& g, const longlong2& a, const longlong2& b,
+                                                     int cx, int cy) {
+  const long long ymax = max(a.y, b.y);
+  const int cy1 = grid_cy(g, ymax);
+  const uint32_t dy = (uint32_t) min(max(cy1 - cy, 0), 15);
+  const long long xmin = min(a.x, b.x), xmax = max(a.x, b.x);
+  const uint32_t xl = grid_cx(g, xmin) < cx ? 1u : 0u, xr = grid_cx(g, xmax) > cx ? 1u : 0u;
+  return grid_qx(g, xmin, cx) | (grid_qx(g, xmax, cx) << 6) | (xl << 12) | (xr << 13) |
+         (grid_qy(g, min(a.y, b.y), cy) << 14) | (grid_qy(g, ymax, cy1) << 21) | (dy << 28);
 }
 
 struct CellBox {
@@ -85,10 +141,10 @@ struct CellBox {
 
 static __device__ __forceinline__ CellBox edge_cell_box(const GridView& g, const longlong2& a, const longlong2& b) {
   CellBox c;
-  c.x0 = grid_cell(g, min(a.x, b.x));
-  c.x1 = grid_cell(g, max(a.x, b.x));
-  c.y0 = grid_cell(g, min(a.y, b.y));
-  c.y1 = grid_cell(g, max(a.y, b.y));
+  c.x0 = grid_cx(g, min(a.x, b.x));
+  c.x1 = grid_cx(g, max(a.x, b.x));
+  c.y0 = grid_cy(g, min(a.y, b.y));
+  c.y1 = grid_cy(g, max(a.y, b.y));
   return c;
 }
 
@@ -191,14 +247,28 @@ __global__ void k_grid_cell_begin(const uint64_t* __restrict__ key, uint32_t n, 
   if (i == n - 1) cell_begin[rank[n_words]] = n;  // rank[n_words] = number of occupied cells
 }
 
+__global__ void k_grid_items(MapView B, GridView g, const uint64_t* __restrict__ key, const uint32_t* __restrict__ p_sorted,
+                             uint32_t n, uint2* __restrict__ items) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = key[i];
+  const uint32_t p = p_sorted[i];
+  items[i] = make_uint2(p, grid_qbox(g, B.pts[p], B.pts[p + 1], (int) (k / g.gs), (int) (k % g.gs)));
+}
+
 static inline void build_grid(Grid& g, const MapView& B, uint32_t gsize, long long imin,
                               long long irange, cudaStream_t st) {
   RJB_REQUIRE(gsize >= 1 && gsize <= 32768, "grid_size must be in 1..32768");
   g.built = false;  // until the last call below has succeeded
   g.gsize = gsize;
-  g.gs = (gsize + 31u) & ~31u;
+  // the same number of cells as the reference's gsize x gsize, 4 x the columns, 1/4 of the rows
+  g.gx = gsize >= 4 ? std::min(gsize * 4u, 65536u) : gsize;
+  g.gy = std::max(1u, (uint32_t) (((uint64_t) gsize * gsize + g.gx - 1) / g.gx));
+  g.gs = (g.gy + 31u) & ~31u;
   g.imin = imin;
-  g.cell_scale = (double) gsize / (double) irange * 0.999;  // src/grid/cell.h:19
+  g.ref_scale = (double) gsize / (double) irange * 0.999;  // src/grid/cell.h:19
+  g.sx = (double) g.gx / (double) irange * 0.999;
+  g.sy = (double) g.gy / (double) irange * 0.999;
   g.n_items = 0;
   g.n_occ = 0;
   const uint32_t n_words = g.n_words();
@@ -223,19 +293,21 @@ static inline void build_grid(Grid& g, const MapView& B, uint32_t gsize, long lo
   const uint32_t n = (uint32_t) h_tot[0];
   g.n_items = n;
   uint32_t* cbeg = g.cell_begin.ensure((size_t) std::min<uint64_t>(n, (uint64_t) n_words * 32) + 2);
-  uint32_t* items = g.items.ensure(n ? n : 1);
+  uint2* items = g.items.ensure(n ? n : 1);
   if (n) {
     uint64_t* ka = g.keys_a.ensure(n);
     uint64_t* kb = g.keys_b.ensure(n);
     uint32_t* va = g.vals_a.ensure(n);
+    uint32_t* vb = g.vals_b.ensure(n);
     uint32_t* big = g.big.ensure(h_tot[1] ? h_tot[1] : 1);
     k_grid_emit<<<div_up(B.n_points, 256), 256, 0, st>>>(B, v, cnt, off, ka, va, big, totals);
     if (h_tot[1])
       k_grid_emit_big<<<(unsigned) std::min<uint64_t>(h_tot[1], 4 * kNumSMs), 256, 0, st>>>(B, v, off, big, totals,
                                                                                           ka, va);
     int key_bits = 1;
-    while (key_bits < 40 && (((uint64_t) gsize * g.gs) >> key_bits)) key_bits++;
-    sort_pairs_u64_u32(ka, kb, va, items, n, 0, key_bits, g.sort_tmp, st);
+    while (key_bits < 40 && (((uint64_t) g.gx * g.gs) >> key_bits)) key_bits++;
+    sort_pairs_u64_u32(ka, kb, va, vb, n, 0, key_bits, g.sort_tmp, st);
+    k_grid_items<<<div_up(n, 256), 256, 0, st>>>(B, g.view(), kb, vb, n, items);
     k_grid_mark<<<div_up(n, 256), 256, 0, st>>>(kb, n, bits);
     k_grid_popc<<<div_up(n_words, 256), 256, 0, st>>>(bits, n_words, pop);
     exclusive_scan_u32(pop, rank, n_words, g.scan_tmp, st);
@@ -343,18 +415,19 @@ k_grid_lsi_big(MapView Q, GridView g, const uint32_t* __restrict__ big_list, con
 // the pair (query edge, base edge) is examined in ONE of the cells both are registered in:
 // the min corner of the intersection of their cell-boxes
 static __device__ __forceinline__ bool grid_pair_here(const GridView& g, const Seg& q, const Seg& b, uint32_t bit) {
-  const int cx = max(grid_cell(g, min(q.x1, q.x2)), grid_cell(g, min(b.x1, b.x2)));
-  const int cy = max(grid_cell(g, min(q.y1, q.y2)), grid_cell(g, min(b.y1, b.y2)));
+  const int cx = max(grid_cx(g, min(q.x1, q.x2)), grid_cx(g, min(b.x1, b.x2)));
+  const int cy = max(grid_cy(g, min(q.y1, q.y2)), grid_cy(g, min(b.y1, b.y2)));
   return (uint32_t) cx * g.gs + (uint32_t) cy == bit;
 }
 
 // reference rule (lsi_grid.h:64-67): kept iff the cell of the intersection point is a cell both
 // edges are registered in.  e0 = map-0 edge, e1 = map-1 edge.
 static __device__ __forceinline__ bool grid_owned(const GridView& g, const Seg& e0, const Seg& e1) {
-  const int cx = lsi_xsect_ref_cell(e0, e1, 0, g.imin, g.cell_scale);
-  const int cy = lsi_xsect_ref_cell(e0, e1, 1, g.imin, g.cell_scale);
-  auto lo = [&](long long a, long long b) { return ref_cell(min(a, b), g.imin, g.cell_scale); };
-  auto hi = [&](long long a, long long b) { return ref_cell(max(a, b), g.imin, g.cell_scale); };
+  // the REFERENCE's square cells (gsize x gsize), not the cells of the index
+  const int cx = lsi_xsect_ref_cell(e0, e1, 0, g.imin, g.ref_scale);
+  const int cy = lsi_xsect_ref_cell(e0, e1, 1, g.imin, g.ref_scale);
+  auto lo = [&](long long a, long long b) { return ref_cell(min(a, b), g.imin, g.ref_scale); };
+  auto hi = [&](long long a, long long b) { return ref_cell(max(a, b), g.imin, g.ref_scale); };
   return cx >= max(lo(e0.x1, e0.x2), lo(e1.x1, e1.x2)) && cx <= min(hi(e0.x1, e0.x2), hi(e1.x1, e1.x2)) &&
          cy >= max(lo(e0.y1, e0.y2), lo(e1.y1, e1.y2)) && cy <= min(hi(e0.y1, e0.y2), hi(e1.y1, e1.y2));
 }
@@ -429,7 +502,7 @@ k_grid_lsi_exact(MapView Q, MapView B, GridView g, int q, const uint2* __restric
     // the first kGridInLane items of the lane's own cell: item ids, then vertices, in flight together
     uint32_t pb[kGridInLane];
 #pragma unroll
-    for (int k = 0; k < kGridInLane; k++) pb[k] = beg + k < end ? __ldg(&g.items[beg + k]) : 0xFFFFFFFFu;
+    for (int k = 0; k < kGridInLane; k++) pb[k] = beg + k < end ? __ldg(&g.items[beg + k].x) : 0xFFFFFFFFu;
 #pragma unroll
     for (int k = 0; k < kGridInLane; k++) {
       bool pass = false;
@@ -455,7 +528,7 @@ k_grid_lsi_exact(MapView Q, MapView B, GridView g, int q, const uint2* __restric
         bool pass = false;
         uint32_t p = 0;
         if (k < e0) {
-          p = __ldg(&g.items[k]);
+          p = __ldg(&g.items[k].x);
           const longlong2 c = __ldg(&B.pts[p]), d = __ldg(&B.pts[p + 1]);
           const Seg eb = {c.x, c.y, d.x, d.y};
           pass = seg_boxes_overlap(sq, eb) && grid_pair_here(g, sq, eb, sbit);
@@ -479,13 +552,50 @@ k_grid_lsi_exact(MapView Q, MapView B, GridView g, int q, const uint2* __restric
 }
 
 // ---- PIP ----------------------------------------------------------------------------------
-// One thread per point (points sorted by cell, so a warp walks one or two columns together):
-// from the cell of (py - 1) upward to the next OCCUPIED cell of the column -- a scan of
-// consecutive bitmap bits --, every edge registered there screened with integer tests (x range,
-// reaches up to py - 1) and put through the exact update rule, until the best hit provably lies
-// below everything not yet seen: an edge first registered above cell cy has ymin >= the lower
-// boundary of cell cy + 1, and y* carries < 2^-5 of rounding.  (Reference: src/app/pip_grid.h
-// walks cell by cell, empty or not, through a dense Cell array.)
+// One thread per point (points sorted by cell, so a warp works in one or two columns), walking
+// the column upward from the cell of (py - 1): the next OCCUPIED cell is a scan of consecutive
+// bitmap bits, an edge first registered above cell cy has ymin >= the lower boundary of cell
+// cy, and y* carries < 2^-5 of rounding, so the walk ends once the best hit lies provably below
+// everything not yet seen.  (Reference: src/app/pip_grid.h walks cell by cell, empty or not,
+// through a dense Cell array.)
+//
+// The WALK runs on the 32-bit boxes of the item records alone (grid_qbox) and the exact update
+// rule runs afterwards, converged.  While walking, a lane screens the edges of its cells -- x
+// range contains px, reaches up to py - 1, both in 1/128 steps of the cell, conservative -- and
+// only NOTES the ones that pass in a four-entry register queue: no vertex is loaded, nothing
+// wider than 32 bits is compared.  The walk needs no exact crossing to know when to stop: an
+// edge with px strictly inside its x range that starts above py + 1 is certainly accepted by the
+// rule and crosses at or below its ymax, so U = min(ymax) over such edges (in 1/128 cell rows,
+// rounded up) bounds the best crossing from above, and the walk ends at the first occupied cell
+// that lies wholly above U.  Then all lanes put their noted edges through the rule together
+// (any order: the rule's tie-breaks make it order independent).
+// ncu history (20 M points, g = 8192): rule evaluated where the screen passed, every lane in a
+// cell of its own: 5.0 of 32 threads active per instruction, 176 warp instructions per point;
+// rule deferred, vertices screened in the walk: 9.1 threads, 105 per point.
+struct PipCandQueue {
+  uint32_t c0, c1, c2, c3;
+  int n;
+  __device__ __forceinline__ void push(uint32_t v) {
+    c3 = c2; c2 = c1; c1 = c0; c0 = v;
+    n++;
+  }
+  __device__ __forceinline__ uint32_t pop() {
+    const uint32_t v = c0;
+    c0 = c1; c1 = c2; c2 = c3;
+    n--;
+    return v;
+  }
+};
+
+// best_pb: start point of the best edge so far (its chain is best_pb - best.eid)
+static __device__ __forceinline__ void pip_eval(const MapView& B, PipBest& best, uint32_t& best_pb, int q,
+                                                const longlong2& p, uint32_t pb, unsigned long long& cand) {
+  const longlong2 a = __ldg(&B.pts[pb]), b = __ldg(&B.pts[pb + 1]);
+  const Seg e = {a.x, a.y, b.x, b.y};
+  cand++;
+  if (pip_update(best, q, p.x, p.y, e, pb - __ldg(&B.point_chain[pb]))) best_pb = pb;
+}
+
 template <bool kPacked>
 __global__ void __launch_bounds__(256)
 k_pip_grid(const longlong2* __restrict__ pts, uint32_t n, const uint32_t* __restrict__ order, MapView B,
@@ -493,15 +603,30 @@ k_pip_grid(const longlong2* __restrict__ pts, uint32_t n, const uint32_t* __rest
            uint2* __restrict__ out_packed, unsigned long long* n_cand) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long cand = 0;
-  if (slot < n) {
-    const uint32_t i = order ? order[slot] : slot;
-    const longlong2 p = pts[i];
-    PipBest best;
-    pip_init(best);
-    const int cx = grid_cell(g, p.x);
-    int cy = grid_cell(g, p.y - 1);
-    const uint32_t col = (uint32_t) cx * g.gs;
-    const int gmax = (int) g.gsize;
+  const bool valid = slot < n;
+  uint32_t i = 0;
+  longlong2 p = make_longlong2(0, 0);
+  if (valid) {
+    i = order ? order[slot] : slot;
+    p = pts[i];
+  }
+  PipBest best;
+  pip_init(best);
+  uint32_t best_pb = 0;
+  const int gmax = (int) g.gy;
+  const int cxp = grid_cx(g, p.x);
+  const uint32_t col = (uint32_t) cxp * g.gs;
+  const uint32_t qpx = grid_qx(g, p.x, cxp);
+  int cy = grid_cy(g, p.y - 1);
+  PipCandQueue Q = {0, 0, 0, 0, 0};
+  if (valid) {
+    // 1/128 cell rows: row of cell c = c * 128.  (py + 1, rounded up to the next step, must lie
+    // BELOW the start of an edge for the edge to count as certainly above the point.)
+    const int cy_lo = grid_cy(g, p.y + 1);
+    const uint32_t y_above = (uint32_t) cy_lo * kGridQ + grid_qy(g, p.y + 1, cy_lo);
+    uint32_t U = 0xFFFFFF00u;  // upper bound of the best crossing (none yet; U + 1 must not wrap)
+    const uint32_t qpy = grid_qy(g, p.y - 1, cy);
+    const int cy_start = cy;
     while (cy < gmax) {
       // next occupied cell at or above cy in this column
       uint32_t bit = col + cy;
@@ -515,30 +640,42 @@ k_pip_grid(const longlong2* __restrict__ pts, uint32_t n, const uint32_t* __rest
       bit += __ffs(w) - 1;
       cy = (int) (bit - col);
       if (cy >= gmax) break;
-      if (best.eid != RJB_NO_HIT) {
-        // everything in this and higher cells starts at or above the lower boundary of cell cy
-        const double low = (double) g.imin + floor((double) cy * g.inv_cell_scale) - 3.0;
-        if (best.y < low) break;
-      }
+      // every edge first met in this or a higher cell starts at or above row cy * 128; one step
+      // of slack covers the +-3 units between the rows of the cell function and the rounding of y*
+      if ((uint32_t) cy * kGridQ > U + 1) break;
       uint32_t beg = 0, end = 0;
       grid_cell_range(g, bit, beg, end);
+      const uint32_t row0 = (uint32_t) cy * kGridQ;
+      const uint32_t qy_min = cy == cy_start ? qpy : 0u;  // higher cells lie above py - 1 anyway
       for (uint32_t k = beg; k < end; k++) {
-        const uint32_t pb = __ldg(&g.items[k]);
-        const longlong2 a = __ldg(&B.pts[pb]), b = __ldg(&B.pts[pb + 1]);
-        if (min(a.x, b.x) <= p.x && p.x <= max(a.x, b.x) && max(a.y, b.y) >= p.y - 1) {
-          const Seg e = {a.x, a.y, b.x, b.y};
-          cand++;
-          pip_update(best, query_map_id, p.x, p.y, e, pb - __ldg(&B.point_chain[pb]));
-        }
+        const uint2 it = __ldg(&g.items[k]);
+        const uint32_t qx0 = it.y & 63u, qx1 = (it.y >> 6) & 63u, qy0 = (it.y >> 14) & 127u;
+        const uint32_t qy1 = (it.y >> 21) & 127u, dy = it.y >> 28;
+        if (qx0 > qpx || qx1 < qpx || (dy == 0 && qy1 < qy_min)) continue;
+        // certainly above the point, crossing at or below the end of step qy1 of row cy + dy.
+        // (qy0 == 0 may mean "starts below this cell": such an edge was judged in the cell of its
+        // ymin, or starts below the walk altogether; it is not judged again.)
+        const bool x_strict = (((it.y >> 12) & 1u) || qx0 < qpx) && (((it.y >> 13) & 1u) || qpx < qx1);
+        if (x_strict && qy0 > 0 && row0 + qy0 > y_above && dy < 15) U = min(U, row0 + dy * kGridQ + qy1 + 1);
+        // an edge spanning several cells is met again: keep it once
+        if (Q.n > 0 && (Q.c0 == it.x || (Q.n > 1 && Q.c1 == it.x))) continue;
+        if (Q.n == 4) pip_eval(B, best, best_pb, query_map_id, p, Q.c3, cand), Q.n = 3;  // queue full (rare)
+        Q.push(it.x);
       }
       cy++;
     }
+  }
+  // the exact update rule, converged: first every lane's first noted edge, then the second ...
+  while (__any_sync(0xffffffffu, Q.n > 0)) {
+    if (Q.n > 0) pip_eval(B, best, best_pb, query_map_id, p, Q.pop(), cand);
+  }
+  if (valid) {
     int32_t face = RJB_EXTERIOR_FACE;
     if ((kPacked || out_face) && best.eid != RJB_NO_HIT) {
-      // get_face_id, src/map/map.h:79-87
-      const uint32_t ch = B.edge_chain[best.eid];
-      const longlong2 a = B.pts[best.eid + ch], bb = B.pts[best.eid + ch + 1];
-      face = a.x < bb.x ? B.right[ch] : B.left[ch];
+      // get_face_id, src/map/map.h:79-87 (chain = start point - eid)
+      const uint32_t ch = best_pb - best.eid;
+      const longlong2 a = __ldg(&B.pts[best_pb]), bb = __ldg(&B.pts[best_pb + 1]);
+      face = a.x < bb.x ? __ldg(&B.right[ch]) : __ldg(&B.left[ch]);
     }
     if (kPacked) {
       out_packed[i] = make_uint2(best.eid, (uint32_t) face);

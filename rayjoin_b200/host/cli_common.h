@@ -26,7 +26,8 @@ struct Flags {
       {"ag", "1"},        {"ag_iter", "5"},     {"win", "32"},        {"enlarge", "5"},
       {"sample_map_id", "-1"}, {"sample", ""},  {"query", ""},        {"sample_rate", "1"},
       {"seed", "0"},      {"gen_t", "0.1"},     {"gen_n", "10000"},   {"histo", "false"},
-      {"profile", "false"}, {"v", "0"},         {"device", "0"},      {"lbvh_leaf_size", "4"}};
+      {"profile", "false"}, {"v", "0"},         {"device", "0"},      {"lbvh_leaf_size", "4"},
+      {"lbvh_ag", "-1"}};
   static bool is_bool(const std::string& n) {
     return n == "box" || n == "check" || n == "fau" || n == "histo" || n == "profile";
   }
@@ -107,6 +108,24 @@ inline int parse_mode(const std::string& mode) {
   }
   die("Illegal mode: " + mode);
   return -1;
+}
+
+// Leaf shape of the LBVH.  RayJoin's Adaptive Grouping flags (-ag -ag_iter -enlarge,
+// src/flags.cc:20-24) belong to its RT backend (src/run_query.cu:237-271); -mode=rt runs the
+// CUDA BVH traversal here, so there they size the LBVH leaves with the same merge rule.
+// -mode=lbvh keeps fixed runs of -lbvh_leaf_size edges unless -lbvh_ag=1 asks for grouping.
+inline void set_leaf_options(rjb_ctx* ctx, const Flags& f) {
+  ok(rjb_set_option(ctx, "lbvh_leaf_size", f.i("lbvh_leaf_size")), "rjb_set_option");
+  int ag = f.i("lbvh_ag");
+  if (ag < 0) ag = f.s("mode") == "rt" ? f.i("ag") : 0;
+  ok(rjb_set_option(ctx, "lbvh_ag", ag), "rjb_set_option");
+  if (ag) {
+    ok(rjb_set_option(ctx, "lbvh_ag_iter", std::max(1, f.i("ag_iter"))), "rjb_set_option");
+    ok(rjb_set_option(ctx, "lbvh_enlarge_x1000", (long long) (std::max(1.0, f.d("enlarge")) * 1000.0)),
+       "rjb_set_option");
+    std::cerr << "Adaptive leaf grouping: enlarge limit " << f.d("enlarge") << " max iter " << f.i("ag_iter")
+              << std::endl;
+  }
 }
 
 inline void load_graph(const std::string& path, const std::string& prefix, rjb_graph* g) {

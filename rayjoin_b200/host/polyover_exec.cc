@@ -29,7 +29,7 @@ int main(int argc, char** argv) {
   int mode = parse_mode(f.s("mode"));
   rjb_ctx* ctx = nullptr;
   ok(rjb_create(f.i("device"), &ctx), "rjb_create");
-  ok(rjb_set_option(ctx, "lbvh_leaf_size", f.i("lbvh_leaf_size")), "rjb_set_option");
+  set_leaf_options(ctx, f);
   tm.next("Load Data");
   set_maps(ctx, &g0, &g1);
   tm.next("Overlay (device)");

@@ -92,7 +92,7 @@ static int run_lsi(const Flags& f) {
   int mode = parse_mode(f.s("mode"));
   rjb_ctx* ctx = nullptr;
   ok(rjb_create(f.i("device"), &ctx), "rjb_create");
-  ok(rjb_set_option(ctx, "lbvh_leaf_size", f.i("lbvh_leaf_size")), "rjb_set_option");
+  set_leaf_options(ctx, f);
   tm.next("Load Data");
   if (generated) {
     // the context is built on the base map alone (run_query.cu:184-186): its box scales both
@@ -159,6 +159,7 @@ static int run_pip(const Flags& f) {
   int mode = parse_mode(f.s("mode"));
   rjb_ctx* ctx = nullptr;
   ok(rjb_create(f.i("device"), &ctx), "rjb_create");
+  set_leaf_options(ctx, f);
   std::vector<uint32_t> eids;
   std::vector<int64_t> gen_pts;
   bool generated = f.s("poly2").empty();

@@ -78,6 +78,45 @@ def test_lsi_lbvh_leaf_sizes_and_sorted_queries(rjb, loaded, leaf):
         ctx.set_option("sort_queries", 0)
 
 
+@pytest.mark.parametrize("enlarge,iters", [(5.0, 5), (3.5, 2), (1.5, 1), (1000.0, 3)])
+@pytest.mark.parametrize("name", ["voronoi", "shared", "lattice", "soup"])
+def test_adaptive_leaf_grouping(rjb, loaded, name, enlarge, iters):
+    """Options lbvh_ag / lbvh_ag_iter / lbvh_enlarge_x1000 (RayJoin's -ag -ag_iter -enlarge,
+    src/rt/primitive.h:120-260): leaves are merged runs of consecutive chain edges.  The
+    grouping changes the index, never the result; a huge limit merges everything a block holds,
+    a limit near 1 merges next to nothing."""
+    ctx, om = loaded(name)
+    try:
+        ctx.set_option("lbvh_leaf_size", 1)
+        ctx.build_index(0, "lbvh")
+        n_edges_as_leaves = ctx.index_info(0, "lbvh")["units"]
+        ctx.set_option("lbvh_ag", 1)
+        ctx.set_option("lbvh_ag_iter", iters)
+        ctx.set_option("lbvh_enlarge_x1000", int(enlarge * 1000))
+        for q in (1, 0):
+            ctx.build_index(1 - q, "lbvh")
+            lsi = rjb.LSI(ctx, "lbvh")
+            lsi.Init(4.0)
+            n = lsi.Query(q)
+            want = om.lsi(q)
+            assert n == len(want[0])
+            for g, w in zip(sort_xsects(lsi.get_xsects(), q), want):
+                assert np.array_equal(g, w)
+            pip = rjb.PIP(ctx, "lbvh")
+            pip.Query(q)
+            assert np.array_equal(pip.get_closest_eids(), om.pip(q, om.pts[q]))
+        ctx.build_index(0, "lbvh")
+        leaves = ctx.index_info(0, "lbvh")["units"]
+        assert leaves <= n_edges_as_leaves
+        if enlarge >= 1000:  # everything inside a block of 2^iters edges merges
+            assert leaves <= n_edges_as_leaves // 2 + ctx.map_info(0)["chains"] * 4
+        if name == "voronoi" and enlarge == 5.0:
+            assert leaves < 0.6 * n_edges_as_leaves
+    finally:
+        ctx.set_option("lbvh_ag", 0)
+        ctx.set_option("lbvh_leaf_size", 4)
+
+
 @pytest.mark.parametrize("q", [1, 0])
 @pytest.mark.parametrize("name", DATASETS + ["dense"])
 def test_lsi_cell_directory_path(rjb, loaded, name, q):
