@@ -17,8 +17,7 @@ rjb_xsect results, every step.
 Multi-GPU: R and its LBVH are replicated, S is sharded.  Default = weak scaling (rank r
 owns its own 9M-edge S, seed 2 + r); the line also carries a strong-scaling leg (ONE
 9M-edge S cut by whole chains over the ranks, rayjoin_b200.dist.shard_graph).  NCCL
-carries only the per-step count all-gather, issued on a side stream while the next
-step runs.  Prints ONE JSON line on rank 0.
+carries only the count all-gather (one per timed region).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import gc
@@ -483,7 +482,6 @@ def main():
         % (rank, time.time() - t0, R.n_edges, R.n_chains, S.n_edges, S.n_chains, n_cores))
 
     stream = torch.cuda.Stream(device=dev)
-    side = torch.cuda.Stream(device=dev)  # count exchange: off the critical path of the queries
     ctx = RJ.Context(device=local_rank, stream=stream.cuda_stream)
     ctx.set_option("keep_host_graph", 0)
     ctx.set_option("lbvh_leaf_size", args.leaf_size)
@@ -512,35 +510,41 @@ def main():
     lsi.Init(XSECT_FACTOR)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    # the only data-path collective: the per-rank {result, candidate} counts of a step, one
-    # NCCL all-gather of 16 B per rank, issued on the side stream right after the step's
-    # wait -- it travels while the next step's kernels run, only the last one is exposed
-    counts_host = torch.zeros((max(args.steps, args.warmup, 1) + 4, 2), dtype=torch.int64).pin_memory()
+    # the only data-path collective: the per-rank {result, candidate} counts of the steps of a
+    # timed region, ONE NCCL all-gather of 16 B per step and rank after the last step (nothing
+    # in a query depends on another rank's counts; a small all-gather costs 0.1-0.2 ms of latency,
+    # more than a whole step, so it is not issued per step).  Fixed shape: NCCL sets its
+    # connections up lazily on the first use of a shape, which the warm-up absorbs.
+    n_rows = max(args.steps, args.warmup, 1)
+    counts_host = torch.zeros((n_rows, 2), dtype=torch.int64).pin_memory()
     counts_dev = torch.zeros_like(counts_host, device=dev)
-    counts_all = torch.zeros((counts_host.shape[0], world, 2), dtype=torch.int64, device=dev)
+    counts_all = torch.zeros((world, n_rows, 2), dtype=torch.int64, device=dev)
 
-    def exchange(i, n, cand):
+    def exchange(rows):
         if world == 1:
             return
-        counts_host[i, 0], counts_host[i, 1] = n, cand
-        with torch.cuda.stream(side):
-            counts_dev[i].copy_(counts_host[i], non_blocking=True)
-            dist.all_gather_into_tensor(counts_all[i], counts_dev[i])
+        counts_host.zero_()
+        counts_host[:len(rows)] = torch.tensor(rows[-n_rows:], dtype=torch.int64)
+        with torch.cuda.stream(stream):
+            counts_dev.copy_(counts_host, non_blocking=True)
+            dist.all_gather_into_tensor(counts_all, counts_dev)
 
     def timed_steps(n_steps, n_warm):
-        """-> (per-step device ms, drain ms of the last count exchange, per-kernel ms, pairs, cand)"""
+        """-> (per-step device ms, ms of the count exchange, per-kernel ms, pairs, cand)"""
+        rows = []
         for i in range(n_warm):
             lsi.Launch(1)
-            n = lsi.Wait()
-            exchange(i, n, lsi.n_candidates)
+            rows.append((lsi.Wait(), lsi.n_candidates))
+            if i < 2:
+                exchange(rows)  # twice: connection set-up, then the steady state
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
               for _ in range(n_steps)]
-        fin = torch.cuda.Event(enable_timing=True)
-        stage = []
+        xch = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        stage, rows = [], []
         n = 0
         gc.disable()  # a collection inside a 0.16 ms step shows up as a 5x outlier
         for i in range(n_steps):
@@ -550,13 +554,16 @@ def main():
                 lsi.Launch(1)     # the whole query is enqueued ...
                 ev[i][1].record(stream)
             n = lsi.Wait()        # ... and completed; the events bracket its device time
-            exchange(i, n, lsi.n_candidates)
+            rows.append((n, lsi.n_candidates))
             stage.append(ctx.last_stage_ms()[0])
-        fin.record(side)
+        with torch.cuda.stream(stream):
+            xch[0].record(stream)
+            exchange(rows)
+            xch[1].record(stream)
         torch.cuda.synchronize()
         gc.enable()
         step_ms = [a.elapsed_time(b) for a, b in ev]
-        drain = max(0.0, ev[-1][1].elapsed_time(fin)) if world > 1 else 0.0
+        drain = xch[0].elapsed_time(xch[1]) if world > 1 else 0.0
         return step_ms, drain, np.mean(np.asarray(stage), axis=0), n, lsi.n_candidates
 
     sampler = ClockSampler(local_rank)
@@ -566,7 +573,7 @@ def main():
     total_ms = sum(step_ms) + drain_ms
     launches = ctx.last_launches()
     lst = ctx.last_stats()
-    log("[rank %d] step ms min/median/max %.4f/%.4f/%.4f, exposed count exchange %.4f ms"
+    log("[rank %d] step ms min/median/max %.4f/%.4f/%.4f, count exchange %.4f ms"
         % (rank, min(step_ms), float(np.median(step_ms)), max(step_ms), drain_ms))
 
     # ---- end to end through the synchronous C ABI from pinned host buffers ---------
@@ -590,6 +597,7 @@ def main():
         torch.cuda.synchronize()
         return (time.perf_counter() - t) * 1e3, n
     e2e_total_ms, _ = e2e_run(hb_S, args.steps)
+    weak_result = out_np[:n_pairs].copy()  # checked against the oracle below
     clocks = sampler.summary()
 
     times = torch.tensor([total_ms, e2e_total_ms, max(step_ms), float(np.median(step_ms))], dtype=torch.float64, device=dev)
@@ -669,12 +677,12 @@ def main():
             "config": cfg,
             "engine": {"mode": args.mode, "lbvh_leaf_size": args.leaf_size, "sort_queries": args.sort_queries,
                        "timing": "CUDA events on the launch stream around the enqueued query (rjb_lsi_launch); "
-                                 "max over ranks of the sum of the K step times + the exposed part of the last "
-                                 "count exchange",
+                                 "max over ranks of the sum of the K step times + the count exchange",
                        "l2": "256 MiB flush write between timed iterations; inputs (S descriptors + survivors' "
                              "vertices + index, ~150 MB) also exceed L2",
-                       "sharding": "R + index replicated, S sharded per rank (seed 2+rank); NCCL: one 16 B "
-                                   "all-gather of the step's counts per step on a side stream",
+                       "sharding": "R + index replicated, S sharded per rank (seed 2+rank); NCCL: one all-gather "
+                                   "of the per-step counts (16 B per step and rank) per timed region, its "
+                                   "CUDA-event time added to the K step times",
                        "host_cores_per_rank": n_cores},
             "join_ms": ms_per_step, "result_pairs": int(all_pairs),
             "candidate_pairs": int(all_cand),
@@ -683,7 +691,7 @@ def main():
             "index_units": int(idx["units"]),
             "kernel_ms": {r["kernel"]: r["ms"] for r in rk},
             "step_ms": {"median_worst_rank": worst_median, "max_worst_rank": worst_step,
-                        "exposed_count_exchange": drain_ms},
+                        "count_exchange": drain_ms},
             "e2e": {"value": all_edges / (e2e_ms / 1e3 / args.steps), "unit": "query_edges/s",
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
@@ -713,7 +721,7 @@ def main():
             if not args.no_check:
                 sys.path.insert(0, os.path.join(ROOT, "tests"))
                 from helpers import sort_xsects
-                got = sort_xsects(out_np[:n_pairs].copy(), 1)
+                got = sort_xsects(weak_result, 1)
                 ok = n_pairs == n_ref and all(np.array_equal(g, w) for g, w in zip(got, res[:4]))
                 line["parity_vs_oracle"] = "bit-exact" if ok else "MISMATCH"
                 if not ok:

@@ -126,6 +126,10 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
 
 /* tuning knobs that have no RayJoin flag (defaults are fine):
  *   "lbvh_leaf_size"  edges per LBVH leaf, 1..8 (default 4)
+ *   "lsi_window_begin", "lsi_window_end"  rjb_lsi queries only the edges that START at points
+ *                     [begin, end) of the query map (0, 0 = the whole map, the default): a
+ *                     multi-GPU driver keeps both maps whole on every rank and gives each rank
+ *                     a window (whole chains) of the query side; edge ids stay global
  *   "lbvh_ag"         1 = adaptive leaf grouping: leaves are runs of consecutive chain edges
  *                     merged by RayJoin's Adaptive Grouping rule (-ag, src/rt/primitive.h:120-260:
  *                     neighbours merge while area(merged) / max(area) < enlarge), 0 (default) =
@@ -218,6 +222,14 @@ int rjb_overlay_finish(rjb_ctx* ctx, int mode, uint32_t grid_size,
                        const uint32_t* h_closest_eid0, const int32_t* h_point_in_polygon0,
                        const uint32_t* h_closest_eid1, const int32_t* h_point_in_polygon1,
                        double* phase_ms);
+/* The same with the gathered arrays in DEVICE memory (what a grouped ncclSend / ncclRecv
+ * leaves on the finishing rank: no host staging).  When the context already holds the indexes of
+ * this mode -- the finishing rank took part in the sharded phases -- they are reused.          */
+int rjb_overlay_finish_device(rjb_ctx* ctx, int mode, uint32_t grid_size,
+                              const rjb_xsect* d_xsects, uint64_t n_xsects,
+                              const uint32_t* d_closest_eid0, const int32_t* d_point_in_polygon0,
+                              const uint32_t* d_closest_eid1, const int32_t* d_point_in_polygon1,
+                              double* phase_ms);
 /* results of the last rjb_overlay_run, device pointers:
  *  xsects sorted by eid[im] and along the edge, with mid_point_polygon_id
  *  (xsect_edges_sorted_[im]); closest_eid / point_in_polygon per vertex of
@@ -261,6 +273,11 @@ int rjb_index_info(const rjb_ctx* ctx, int map_id, int mode, uint64_t out[4]);
  * bits [begin_bit, end_bit), stable; arrays are sorted in place                 */
 int rjb_debug_sort_pairs(rjb_ctx* ctx, uint64_t* h_keys, uint32_t* h_vals,
                          uint64_t n, int begin_bit, int end_bit);
+
+/* the packed-pair onesweep every path of the engine sorts with (rjb_sort.cuh): 64-bit words =
+ * 32-bit key << 32 | 32-bit payload, sorted in place, stably, by bits [begin_bit, end_bit) of the
+ * KEY (0 <= begin_bit < end_bit <= 32)                                                       */
+int rjb_debug_sort_packed(rjb_ctx* ctx, uint64_t* h_words, uint64_t n, int begin_bit, int end_bit);
 
 /* test hooks: the exact arithmetic of the query kernels (the same device functions) over
  * caller-supplied HOST arrays, so that the golden vectors of the reference's

@@ -23,8 +23,8 @@ EXPORTS = [
     "rjb_set_bounding_box", "rjb_get_scaling", "rjb_set_map", "rjb_map_info",
     "rjb_map_device_views", "rjb_build_index", "rjb_set_option", "rjb_lsi", "rjb_lsi_launch", "rjb_lsi_wait",
     "rjb_last_launches", "rjb_pip",
-    "rjb_pip_host", "rjb_pip_host_scaled", "rjb_overlay_run", "rjb_overlay_finish", "rjb_overlay_results", "rjb_overlay_write",
-    "rjb_debug_sort_pairs", "rjb_debug_intersect_batch", "rjb_debug_i128_batch", "rjb_debug_pip_batch",
+    "rjb_pip_host", "rjb_pip_host_scaled", "rjb_overlay_run", "rjb_overlay_finish", "rjb_overlay_finish_device", "rjb_overlay_results", "rjb_overlay_write",
+    "rjb_debug_sort_pairs", "rjb_debug_sort_packed", "rjb_debug_intersect_batch", "rjb_debug_i128_batch", "rjb_debug_pip_batch",
     "rjb_last_kernel_ms", "rjb_last_stage_ms", "rjb_last_stats", "rjb_index_info", "rjb_copy_to_host", "rjb_sync",
     "rjb_graph_load", "rjb_graph_read_text", "rjb_graph_read_bin", "rjb_graph_write_bin",
     "rjb_graph_free",
@@ -328,6 +328,12 @@ class Context:
                                              C.c_int(begin_bit), C.c_int(end_bit)))
         return keys, vals
 
+    def debug_sort_packed(self, words, begin_bit=0, end_bit=32):
+        words = np.ascontiguousarray(words, dtype=np.uint64).copy()
+        _check(self.lib.rjb_debug_sort_packed(self._h, _ptr(words), C.c_uint64(len(words)),
+                                              C.c_int(begin_bit), C.c_int(end_bit)))
+        return words
+
     def last_stats(self):
         out = (C.c_uint64 * 8)()
         _check(self.lib.rjb_last_stats(self._h, out))
@@ -489,6 +495,17 @@ class MapOverlay:
         _check(self.ctx.lib.rjb_overlay_finish(
             self.ctx._h, C.c_int(MODES.get(self.mode, self.mode)), C.c_uint32(self.grid_size),
             _ptr(xs), C.c_uint64(len(xs)), _ptr(ce[0]), _ptr(pf[0]), _ptr(ce[1]), _ptr(pf[1]), ms))
+        self.phase_ms = dict(zip(("build", "lsi", "pip0", "pip1", "polygons", "total"), ms))
+        return self.phase_ms
+
+    def FinishDevice(self, d_xsects, n_xsects, d_closest_eids, d_point_in_polygon):
+        """Finish with the gathered arrays in device memory (raw pointers, e.g. torch data_ptr())."""
+        ms = (C.c_double * 6)()
+        _check(self.ctx.lib.rjb_overlay_finish_device(
+            self.ctx._h, C.c_int(MODES.get(self.mode, self.mode)), C.c_uint32(self.grid_size),
+            C.c_void_p(d_xsects), C.c_uint64(n_xsects), C.c_void_p(d_closest_eids[0]),
+            C.c_void_p(d_point_in_polygon[0]), C.c_void_p(d_closest_eids[1]),
+            C.c_void_p(d_point_in_polygon[1]), ms))
         self.phase_ms = dict(zip(("build", "lsi", "pip0", "pip1", "polygons", "total"), ms))
         return self.phase_ms
 

@@ -122,7 +122,11 @@ struct rjb_ctx {
   uint32_t load_chunk = kLoadChunkPoints;  // points per upload chunk (option load_chunk_points)
   int use_cells = 0;      // LSI: cell directory for the filter's survivors (experimental, off)
   size_t cand_cap = 0;
-  size_t grid_work_cap = 0;  // grid LSI: capacity of the (query edge, cell) work list
+  size_t grid_work_cap = 0;
+  // query window of rjb_lsi: only the query edges starting at points [win_begin, win_end) of the
+  // query map (options lsi_window_begin / lsi_window_end; 0, 0 = the whole map).  A multi-GPU
+  // driver keeps both maps whole on every rank and gives each rank a window of the query side.
+  uint32_t win_begin = 0, win_end = 0;  // grid LSI: capacity of the (query edge, cell) work list
   DBuf<rjb_xsect> xsects;
   DBuf<unsigned long long> counters;  // [0] = queue counter (low 32 bits), [1] = candidates
   // PIP results
@@ -232,22 +236,28 @@ __global__ void k_scale_points(const double2* __restrict__ in, uint32_t n, doubl
   out[i] = o;
 }
 
-__global__ void k_query_keys_edges(MapView Q, long long imin, uint64_t* __restrict__ key,
-                                   uint32_t* __restrict__ val) {
+// Sort keys travel packed with their payload: key (the top 32 Morton bits) in the high half of a
+// 64-bit word, payload in the low half (sort_packed, rjb_sort.cuh).
+__global__ void k_query_keys_edges(MapView Q, long long imin, uint64_t* __restrict__ packed) {
   uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= Q.n_edges) return;
   Seg s = load_seg(Q, e);
-  key[e] = morton64(s.x1 + ((s.x2 - s.x1) >> 1), s.y1 + ((s.y2 - s.y1) >> 1), imin);
-  val[e] = e + Q.edge_chain[e];  // the edge's start point: what the traversal consumes
+  const uint64_t key = morton64(s.x1 + ((s.x2 - s.x1) >> 1), s.y1 + ((s.y2 - s.y1) >> 1), imin);
+  // payload: the edge's start point, what the traversal consumes
+  packed[e] = (key & 0xFFFFFFFF00000000ull) | (uint64_t) (e + Q.edge_chain[e]);
 }
 
 __global__ void k_query_keys_points(const longlong2* __restrict__ pts, uint32_t n, long long imin,
-                                    uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+                                    uint64_t* __restrict__ packed) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   longlong2 p = pts[i];
-  key[i] = morton64(p.x, p.y, imin);
-  val[i] = i;
+  packed[i] = (morton64(p.x, p.y, imin) & 0xFFFFFFFF00000000ull) | (uint64_t) i;
+}
+
+__global__ void k_unpack_low(const uint64_t* __restrict__ packed, uint32_t n, uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t) packed[i];
 }
 
 static void scaling_init(rjb_scaling& s, double bminx, double bminy, double bmaxx, double bmaxy) {
@@ -283,14 +293,13 @@ static const uint32_t* query_order_edges(rjb_ctx* c, DeviceMap& Qm, const MapVie
   uint32_t n = Q.n_edges;
   uint64_t* ka = c->ord_keys_a.ensure(n);
   uint64_t* kb = c->ord_keys_b.ensure(n);
-  uint32_t* va = c->ord_vals_a.ensure(n);
-  uint32_t* vb = c->ord_vals_b.ensure(n);
-  k_query_keys_edges<<<div_up(n, 256), 256, 0, c->stream>>>(Q, c->sc.internal_min, ka, va);
-  sort_pairs_u64_u32(ka, kb, va, vb, n, 40, 64, c->ord_sort, c->stream);
+  k_query_keys_edges<<<div_up(n, 256), 256, 0, c->stream>>>(Q, c->sc.internal_min, ka);
+  // only coherence is needed: the top 24 Morton bits (4096 x 4096 cells) = 3 radix passes
+  const uint64_t* sorted = sort_packed(ka, kb, n, 8, 32, c->ord_sort, c->stream);
   // the order belongs to the map, not to the query: keep it (the scratch buffers are
   // shared with the point ordering of PIP)
   uint32_t* keep = Qm.edge_order.ensure(n);
-  RJB_CUDA(cudaMemcpyAsync(keep, vb, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+  k_unpack_low<<<div_up(n, 256), 256, 0, c->stream>>>(sorted, n, keep);
   Qm.edge_order_valid = true;
   return keep;
 }
@@ -376,7 +385,16 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
   P.xsect_factor = xsect_factor;
   P.cap = cap;
   P.attempt = attempt;
-  const bool nonempty = Q.n_edges > 0 && B.n_edges > 0;
+  // query window (start points); the whole map unless a window is set
+  uint32_t p_lo = 0, p_hi = Q.n_points;
+  if (c->win_end > 0) {
+    RJB_REQUIRE(c->win_begin <= c->win_end && c->win_end <= Q.n_points, "rjb_lsi: query window outside the map");
+    RJB_REQUIRE(mode != RJB_MODE_BRUTE, "rjb_lsi: the brute-force mode takes no query window");
+    p_lo = c->win_begin;
+    p_hi = c->win_end;
+  }
+  const bool windowed = p_lo != 0 || p_hi != Q.n_points;
+  const bool nonempty = Q.n_edges > 0 && B.n_edges > 0 && p_hi > p_lo;
   if (mode == RJB_MODE_LBVH && !Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no LBVH on the base map");
   if (mode == RJB_MODE_GRID && nonempty && !Bm.grid.built)
     throw Error(RJB_ERR_NO_INDEX, "rjb_lsi: no grid on the base map");
@@ -384,7 +402,7 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     // traversal -> candidate pairs (exact integer boxes overlap) -> dense exact pass.
     // The candidate buffer is internal: it grows and the query is repeated if it was too small.
     if (c->cand_cap < (size_t) cap + 65536) c->cand_cap = 2 * (size_t) cap + 65536;
-    const uint32_t* order = query_order_edges(c, Qm, Q);
+    const uint32_t* order = windowed ? nullptr : query_order_edges(c, Qm, Q);  // (a window walks in map order)
     // occupancy pre-filter: worthwhile when the base map covers a small part of the
     // plane; it replaces the Morton order (survivors come out in map order)
     const bool filter = !order && (c->use_filter == 1 || (c->use_filter < 0 && Bm.bvh.occ_fraction < 0.25 &&
@@ -403,14 +421,16 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     // query slots: point indices (edge = slot, slot + 1), or a list of start points
     // (Morton-sorted edges, or the survivors of the occupancy filter, whose count
     // stays on the device)
-    uint32_t n_slots = order ? Q.n_edges : Q.n_points;
+    uint32_t n_slots = order ? Q.n_edges : p_hi;
+    uint32_t slot_lo = order ? 0u : p_lo;  // plain slots: the window's first start point
     const uint32_t* slots = order;
     const unsigned int* n_slots_dev = nullptr;
     if (filter) {
-      k_lsi_filter<<<div_up(Q.n_points, kFilterCtaPoints), kFilterThreads, 0, c->stream>>>(
-          Q, Bm.bvh.occ.p, surv, surv_n, long_list, surv_n + 2);
+      k_lsi_filter<<<div_up(p_hi - (p_lo & ~31u), kFilterCtaPoints), kFilterThreads, 0, c->stream>>>(
+          Q, p_lo, p_hi, Bm.bvh.occ.p, surv, surv_n, long_list, surv_n + 2);
       slots = surv;
       n_slots_dev = surv_n;
+      slot_lo = 0;
       // grid for the worst case; warps beyond the survivor count exit at once
       n_slots = c->last_survivors ? min(Q.n_points, c->last_survivors + c->last_survivors / 4 + 4096) : Q.n_points;
     }
@@ -421,20 +441,21 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
                                                                 surv_n + 1);
       slots = long_list;
       n_slots_dev = surv_n + 2;
+      slot_lo = 0;
       n_slots = c->last_long ? min(Q.n_points, c->last_long + c->last_long / 4 + 1024) : 0;
     }
     // the long-edge list comes from all over the map: two queries per warp while it is short
     const uint32_t spw = cells && n_slots <= 16384 ? 2 : 32;
-    unsigned tiles = div_up(n_slots, spw);
+    unsigned tiles = div_up(n_slots, spw) - (slots ? 0u : slot_lo / 32);
     unsigned blocks = div_up(tiles, kLsiWarps);
     if (blocks == 0) {
       // nothing to walk (no long edges last time; a non-empty list triggers the retry in lsi_finish)
     } else if (c->stats)
       k_lsi_bvh<true><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-          Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
+          Q, B, Bm.bvh.view(), slots, n_slots, slot_lo, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
     else
       k_lsi_bvh<false><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-          Q, B, Bm.bvh.view(), slots, n_slots, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
+          Q, B, Bm.bvh.view(), slots, n_slots, slot_lo, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
     RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
     k_lsi_exact<<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
                                                    xs, cap, (unsigned int*) ctr, ctr + 1);
@@ -463,7 +484,8 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     const GridView gv = Bm.grid.view();
     RJB_CUDA(cudaMemsetAsync(ctr, 0, 10 * sizeof(unsigned long long), c->stream));
     RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    k_grid_lsi_filter<<<div_up(Q.n_points, 256), 256, 0, c->stream>>>(Q, gv, work, wcap, wn, big, wn + 2);
+    k_grid_lsi_filter<<<div_up(p_hi - (p_lo & ~31u), 256), 256, 0, c->stream>>>(Q, p_lo, p_hi, gv, work, wcap, wn, big,
+                                                                               wn + 2);
     k_grid_lsi_big<<<kNumSMs, 256, 0, c->stream>>>(Q, gv, big, wn + 2, work, wcap, wn);
     RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
     k_grid_lsi_exact<<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, gv, q, work, wn, wcap, xs, cap,
@@ -598,12 +620,12 @@ static uint64_t do_lsi(rjb_ctx* c, int q, int mode, double xsect_factor, uint64_
 // Morton order (LBVH) or its grid cell in the grid's own column-major numbering (grid: a warp
 // then walks one column together).  Only coherence is needed, not a total order.
 __global__ void k_query_keys_points_grid(const longlong2* __restrict__ pts, uint32_t n, GridView g,
-                                         uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+                                         uint64_t* __restrict__ packed) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const longlong2 p = pts[i];
-  key[i] = (uint64_t) grid_cx(g, p.x) * g.gs + (uint64_t) grid_cy(g, p.y - 1);
-  val[i] = i;
+  const uint64_t key = (uint64_t) grid_cx(g, p.x) * g.gs + (uint64_t) grid_cy(g, p.y - 1);  // < 2^32
+  packed[i] = (key << 32) | (uint64_t) i;
 }
 
 // `user_points`: the caller handed its own points (not the vertices of a map, which are
@@ -627,30 +649,28 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
   if (mode == RJB_MODE_GRID && !Bm.grid.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no grid on the base map");
   unsigned launches = 0;
   RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
-  const uint32_t* order = nullptr;
+  const uint64_t* order = nullptr;  // packed: the point index is the low half of each word
   const bool sort = n > 0 && mode != RJB_MODE_BRUTE && B.n_edges > 0 &&
                     (c->sort_queries > 0 || (c->sort_queries < 0 && user_points && n >= 65536));
   if (sort) {
     uint64_t* ka = c->ord_keys_a.ensure(n);
     uint64_t* kb = c->ord_keys_b.ensure(n);
-    uint32_t* va = c->ord_vals_a.ensure(n);
-    uint32_t* vb = c->ord_vals_b.ensure(n);
     if (mode == RJB_MODE_GRID) {
       const GridView gv = Bm.grid.view();
-      k_query_keys_points_grid<<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, gv, ka, va);
+      RJB_REQUIRE((uint64_t) gv.gx * gv.gs <= (1ull << 32), "grid too large to order the points by cell");
+      k_query_keys_points_grid<<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, gv, ka);
       int bits = 1;
-      while (bits < 40 && (((uint64_t) gv.gx * gv.gs) >> bits)) bits++;
+      while (bits < 32 && (((uint64_t) gv.gx * gv.gs) >> bits)) bits++;
       // the low (row) bits beyond 24 key bits buy nothing: three radix passes at most
       const int lo = bits > 24 ? bits - 24 : 0;
-      sort_pairs_u64_u32(ka, kb, va, vb, n, lo, bits, c->ord_sort, c->stream);
-      launches += 2 + (bits - lo + 7) / 8 + 1;
+      order = sort_packed(ka, kb, n, lo, bits, c->ord_sort, c->stream);
+      launches += 3 + (bits - lo + 7) / 8;
     } else {
-      k_query_keys_points<<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, c->sc.internal_min, ka, va);
+      k_query_keys_points<<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, c->sc.internal_min, ka);
       // the top 24 Morton bits (4096 x 4096 cells) = 3 radix passes instead of 8
-      sort_pairs_u64_u32(ka, kb, va, vb, n, 40, 64, c->ord_sort, c->stream);
-      launches += 2 + 3 + 1;
+      order = sort_packed(ka, kb, n, 8, 32, c->ord_sort, c->stream);
+      launches += 3 + 3;
     }
-    order = vb;
   }
   RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
   // ordered queries write their results through ONE scattered 8-byte store per point
@@ -780,6 +800,12 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
     if (n == "lbvh_leaf_size") {
       RJB_REQUIRE(value >= 1 && value <= 8, "lbvh_leaf_size must be in 1..8");
       c->leaf_size = (int) value;
+    } else if (n == "lsi_window_begin") {
+      RJB_REQUIRE(value >= 0 && value < 0xFFFFFFF0ll, "lsi_window_begin out of range");
+      c->win_begin = (uint32_t) value;
+    } else if (n == "lsi_window_end") {
+      RJB_REQUIRE(value >= 0 && value < 0xFFFFFFF0ll, "lsi_window_end out of range");
+      c->win_end = (uint32_t) value;
     } else if (n == "lbvh_ag") {
       c->ag = value != 0;
     } else if (n == "lbvh_ag_iter") {
@@ -1233,6 +1259,23 @@ int rjb_debug_pip_batch(rjb_ctx* c, const int64_t* h_edges, uint64_t n_edges, co
   });
 }
 
+/* the packed-pair sort every path of the engine uses: words = (key << 32 | payload), sorted in
+ * place (stable) by key bits [begin_bit, end_bit) of the 32-bit key */
+int rjb_debug_sort_packed(rjb_ctx* c, uint64_t* h_words, uint64_t n, int begin_bit, int end_bit) {
+  return guarded([&] {
+    RJB_REQUIRE(c && (n == 0 || h_words), "NULL argument");
+    RJB_REQUIRE(n < (1u << 30), "too many pairs");
+    RJB_CUDA(cudaSetDevice(c->device));
+    if (n == 0) return;
+    uint64_t* ka = c->ord_keys_a.ensure(n);
+    uint64_t* kb = c->ord_keys_b.ensure(n);
+    RJB_CUDA(cudaMemcpyAsync(ka, h_words, n * 8, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t* sorted = sort_packed(ka, kb, (uint32_t) n, begin_bit, end_bit, c->ord_sort, c->stream);
+    RJB_CUDA(cudaMemcpyAsync(h_words, sorted, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    RJB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
 int rjb_overlay_run(rjb_ctx* c, int mode, uint32_t grid_size, double xsect_factor,
                     double* phase_ms) {
   return guarded([&] {
@@ -1259,6 +1302,28 @@ int rjb_overlay_finish(rjb_ctx* c, int mode, uint32_t grid_size, const rjb_xsect
     imp.h_closest_eid[1] = h_closest_eid1;
     imp.h_point_in_polygon[0] = h_point_in_polygon0;
     imp.h_point_in_polygon[1] = h_point_in_polygon1;
+    overlay_run(c, mode, grid_size, 0.0, phase_ms, &imp);
+  });
+}
+
+int rjb_overlay_finish_device(rjb_ctx* c, int mode, uint32_t grid_size, const rjb_xsect* d_xsects,
+                              uint64_t n_xsects, const uint32_t* d_closest_eid0,
+                              const int32_t* d_point_in_polygon0, const uint32_t* d_closest_eid1,
+                              const int32_t* d_point_in_polygon1, double* phase_ms) {
+  return guarded([&] {
+    RJB_REQUIRE(c, "ctx is NULL");
+    RJB_REQUIRE(n_xsects == 0 || d_xsects, "rjb_overlay_finish_device: NULL xsects");
+    RJB_REQUIRE(d_closest_eid0 && d_point_in_polygon0 && d_closest_eid1 && d_point_in_polygon1,
+                "rjb_overlay_finish_device: NULL vertex-location arrays");
+    RJB_CUDA(cudaSetDevice(c->device));
+    OverlayImport imp;
+    imp.device = true;
+    imp.h_xsects = d_xsects;
+    imp.n_xsects = n_xsects;
+    imp.h_closest_eid[0] = d_closest_eid0;
+    imp.h_closest_eid[1] = d_closest_eid1;
+    imp.h_point_in_polygon[0] = d_point_in_polygon0;
+    imp.h_point_in_polygon[1] = d_point_in_polygon1;
     overlay_run(c, mode, grid_size, 0.0, phase_ms, &imp);
   });
 }

@@ -50,7 +50,7 @@ struct GridView {
 };
 
 struct Grid {
-  DBuf<uint32_t> bits, pop, rank, cell_begin, cnt, off, vals_a, vals_b, big;
+  DBuf<uint32_t> bits, pop, rank, cell_begin, cnt, off, big;
   DBuf<uint2> items;
   DBuf<uint64_t> keys_a, keys_b;
   DBuf<unsigned long long> totals;
@@ -183,7 +183,7 @@ k_grid_count(MapView B, GridView g, uint32_t* __restrict__ cnt, unsigned long lo
 
 __global__ void __launch_bounds__(256)
 k_grid_emit(MapView B, GridView g, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off,
-            uint64_t* __restrict__ key, uint32_t* __restrict__ val, uint32_t* __restrict__ big_list,
+            uint64_t* __restrict__ key, uint32_t* __restrict__ big_list,
             unsigned long long* __restrict__ totals) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= B.n_points) return;
@@ -197,16 +197,14 @@ k_grid_emit(MapView B, GridView g, const uint32_t* __restrict__ cnt, const uint3
   uint32_t o = off[p];
   for (int x = c.x0; x <= c.x1; x++)
     for (int y = c.y0; y <= c.y1; y++) {
-      key[o] = (uint64_t) x * g.gs + y;
-      val[o] = p;
+      key[o] = (((uint64_t) x * g.gs + y) << 32) | p;  // packed (cell, start point)
       o++;
     }
 }
 
 __global__ void __launch_bounds__(256)
 k_grid_emit_big(MapView B, GridView g, const uint32_t* __restrict__ off, const uint32_t* __restrict__ big_list,
-                const unsigned long long* __restrict__ totals, uint64_t* __restrict__ key,
-                uint32_t* __restrict__ val) {
+                const unsigned long long* __restrict__ totals, uint64_t* __restrict__ key) {
   const uint32_t n_big = (uint32_t) totals[2];
   for (uint32_t i = blockIdx.x; i < n_big; i += gridDim.x) {
     const uint32_t p = big_list[i];
@@ -215,8 +213,7 @@ k_grid_emit_big(MapView B, GridView g, const uint32_t* __restrict__ off, const u
     const uint32_t total = (uint32_t) c.cells();
     const uint32_t o = off[p];
     for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
-      key[o + t] = (uint64_t) (c.x0 + t / ny) * g.gs + (c.y0 + t % ny);
-      val[o + t] = p;
+      key[o + t] = (((uint64_t) (c.x0 + t / ny) * g.gs + (c.y0 + t % ny)) << 32) | p;
     }
   }
 }
@@ -225,8 +222,8 @@ k_grid_emit_big(MapView B, GridView g, const uint32_t* __restrict__ off, const u
 __global__ void k_grid_mark(const uint64_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ bits) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t k = key[i];
-  if (i == 0 || key[i - 1] != k) atomicOr(&bits[k >> 5], 1u << (k & 31));
+  const uint32_t k = (uint32_t) (key[i] >> 32);
+  if (i == 0 || (uint32_t) (key[i - 1] >> 32) != k) atomicOr(&bits[k >> 5], 1u << (k & 31));
 }
 
 __global__ void k_grid_popc(const uint32_t* __restrict__ bits, uint32_t n_words, uint32_t* __restrict__ pop) {
@@ -239,20 +236,20 @@ __global__ void k_grid_cell_begin(const uint64_t* __restrict__ key, uint32_t n, 
                                   uint32_t* __restrict__ cell_begin) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t k = key[i];
-  if (i == 0 || key[i - 1] != k) {
+  const uint32_t k = (uint32_t) (key[i] >> 32);
+  if (i == 0 || (uint32_t) (key[i - 1] >> 32) != k) {
     const uint32_t id = rank[k >> 5] + __popc(bits[k >> 5] & ((1u << (k & 31)) - 1));
     cell_begin[id] = i;
   }
   if (i == n - 1) cell_begin[rank[n_words]] = n;  // rank[n_words] = number of occupied cells
 }
 
-__global__ void k_grid_items(MapView B, GridView g, const uint64_t* __restrict__ key, const uint32_t* __restrict__ p_sorted,
-                             uint32_t n, uint2* __restrict__ items) {
+__global__ void k_grid_items(MapView B, GridView g, const uint64_t* __restrict__ key, uint32_t n,
+                             uint2* __restrict__ items) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t k = key[i];
-  const uint32_t p = p_sorted[i];
+  const uint32_t k = (uint32_t) (key[i] >> 32);
+  const uint32_t p = (uint32_t) key[i];
   items[i] = make_uint2(p, grid_qbox(g, B.pts[p], B.pts[p + 1], (int) (k / g.gs), (int) (k % g.gs)));
 }
 
@@ -296,18 +293,15 @@ static inline void build_grid(Grid& g, const MapView& B, uint32_t gsize, long lo
   uint2* items = g.items.ensure(n ? n : 1);
   if (n) {
     uint64_t* ka = g.keys_a.ensure(n);
-    uint64_t* kb = g.keys_b.ensure(n);
-    uint32_t* va = g.vals_a.ensure(n);
-    uint32_t* vb = g.vals_b.ensure(n);
+    g.keys_b.ensure(n);
     uint32_t* big = g.big.ensure(h_tot[1] ? h_tot[1] : 1);
-    k_grid_emit<<<div_up(B.n_points, 256), 256, 0, st>>>(B, v, cnt, off, ka, va, big, totals);
+    k_grid_emit<<<div_up(B.n_points, 256), 256, 0, st>>>(B, v, cnt, off, ka, big, totals);
     if (h_tot[1])
-      k_grid_emit_big<<<(unsigned) std::min<uint64_t>(h_tot[1], 4 * kNumSMs), 256, 0, st>>>(B, v, off, big, totals,
-                                                                                          ka, va);
+      k_grid_emit_big<<<(unsigned) std::min<uint64_t>(h_tot[1], 4 * kNumSMs), 256, 0, st>>>(B, v, off, big, totals, ka);
     int key_bits = 1;
-    while (key_bits < 40 && (((uint64_t) g.gx * g.gs) >> key_bits)) key_bits++;
-    sort_pairs_u64_u32(ka, kb, va, vb, n, 0, key_bits, g.sort_tmp, st);
-    k_grid_items<<<div_up(n, 256), 256, 0, st>>>(B, g.view(), kb, vb, n, items);
+    while (key_bits < 32 && (((uint64_t) g.gx * g.gs) >> key_bits)) key_bits++;
+    const uint64_t* kb = sort_packed(ka, g.keys_b.p, n, 0, key_bits, g.sort_tmp, st);
+    k_grid_items<<<div_up(n, 256), 256, 0, st>>>(B, g.view(), kb, n, items);
     k_grid_mark<<<div_up(n, 256), 256, 0, st>>>(kb, n, bits);
     k_grid_popc<<<div_up(n_words, 256), 256, 0, st>>>(bits, n_words, pop);
     exclusive_scan_u32(pop, rank, n_words, g.scan_tmp, st);
@@ -333,12 +327,12 @@ static inline void build_grid(Grid& g, const MapView& B, uint32_t gsize, long lo
 constexpr uint32_t kGridSmallCells = 16;
 
 __global__ void __launch_bounds__(256)
-k_grid_lsi_filter(MapView Q, GridView g, uint2* __restrict__ work, uint32_t work_cap, unsigned int* work_n,
-                  uint32_t* __restrict__ big_list, unsigned int* big_n) {
+k_grid_lsi_filter(MapView Q, uint32_t p_lo, uint32_t p_hi, GridView g, uint2* __restrict__ work,
+                  uint32_t work_cap, unsigned int* work_n, uint32_t* __restrict__ big_list, unsigned int* big_n) {
   const int lane = threadIdx.x & 31;
-  const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (tile * 32 >= Q.n_points) return;
-  const QTile t = load_tile(Q, nullptr, Q.n_points, tile, lane);
+  const uint32_t tile = p_lo / 32 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (tile * 32 >= p_hi) return;
+  const QTile t = load_tile(Q, nullptr, p_hi, tile, lane, 32, p_lo);  // query window [p_lo, p_hi)
   CellBox c = {0, -1, 0, -1};
   uint32_t hits = 0;  // bit k = k-th cell of the box (column by column) is occupied
   bool big = false;
@@ -598,7 +592,7 @@ static __device__ __forceinline__ void pip_eval(const MapView& B, PipBest& best,
 
 template <bool kPacked>
 __global__ void __launch_bounds__(256)
-k_pip_grid(const longlong2* __restrict__ pts, uint32_t n, const uint32_t* __restrict__ order, MapView B,
+k_pip_grid(const longlong2* __restrict__ pts, uint32_t n, const uint64_t* __restrict__ order, MapView B,
            GridView g, int query_map_id, uint32_t* __restrict__ out_eid, int32_t* __restrict__ out_face,
            uint2* __restrict__ out_packed, unsigned long long* n_cand) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -607,7 +601,7 @@ k_pip_grid(const longlong2* __restrict__ pts, uint32_t n, const uint32_t* __rest
   uint32_t i = 0;
   longlong2 p = make_longlong2(0, 0);
   if (valid) {
-    i = order ? order[slot] : slot;
+    i = order ? (uint32_t) order[slot] : slot;  // packed (key, point index) words
     p = pts[i];
   }
   PipBest best;

@@ -96,8 +96,7 @@ static __device__ __forceinline__ uint64_t morton64(long long x, long long y, lo
 // one thread per leaf: locate the chain, emit {record, quantised box, key}
 __global__ void k_leaf_fill(MapView m, const uint32_t* __restrict__ leaf_base, uint32_t n_leaves,
                             int G, long long imin, uint2* __restrict__ rec,
-                            int4* __restrict__ box, uint64_t* __restrict__ key,
-                            uint32_t* __restrict__ val) {
+                            int4* __restrict__ box, uint64_t* __restrict__ key) {
   uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= n_leaves) return;
   // chain c with leaf_base[c] <= l < leaf_base[c+1]
@@ -125,8 +124,8 @@ __global__ void k_leaf_fill(MapView m, const uint32_t* __restrict__ leaf_base, u
   // 32 significant key bits (cells of 2^-16 of the range per axis, about one edge
   // length on a 10 M-edge map) = 4 radix passes;
   // the low bits are cleared so that the sorted keys stay monotone for Karras' delta()
-  key[l] = morton64(xmin + ((xmax - xmin) >> 1), ymin + ((ymax - ymin) >> 1), imin) & ~((1ull << kMortonDrop) - 1);
-  val[l] = l;
+  // (packed with the leaf id in the cleared low half: sort_packed, rjb_sort.cuh)
+  key[l] = (morton64(xmin + ((xmax - xmin) >> 1), ymin + ((ymax - ymin) >> 1), imin) & ~((1ull << kMortonDrop) - 1)) | l;
 }
 
 // ---- adaptive leaf grouping ---------------------------------------------------------------
@@ -229,7 +228,7 @@ __global__ void k_ag_group(MapView m, const uint32_t* __restrict__ block_base, u
 __global__ void k_leaf_fill_ag(MapView m, const uint32_t* __restrict__ block_base, uint32_t n_blocks,
                                const uint32_t* __restrict__ packed, const uint32_t* __restrict__ leaf_off,
                                long long imin, uint2* __restrict__ rec, int4* __restrict__ box,
-                               uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+                               uint64_t* __restrict__ key) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_blocks) return;
   uint32_t c, p0, ne;
@@ -247,18 +246,17 @@ __global__ void k_leaf_fill_ag(MapView m, const uint32_t* __restrict__ block_bas
     }
     rec[l] = make_uint2(p1 - c, (cntg << 28) | c);
     box[l] = make_int4(quant(xmin), quant(ymin), quant(xmax), quant(ymax));
-    key[l] = morton64(xmin + ((xmax - xmin) >> 1), ymin + ((ymax - ymin) >> 1), imin) & ~((1ull << kMortonDrop) - 1);
-    val[l] = l;
+    key[l] = (morton64(xmin + ((xmax - xmin) >> 1), ymin + ((ymax - ymin) >> 1), imin) & ~((1ull << kMortonDrop) - 1)) | l;
     p1 += cntg;
   }
 }
 
-__global__ void k_leaf_gather(const uint32_t* __restrict__ order, uint32_t n,
+__global__ void k_leaf_gather(const uint64_t* __restrict__ sorted, uint32_t n,
                               const uint2* __restrict__ rec_u, const int4* __restrict__ box_u,
                               uint2* __restrict__ rec_s, int4* __restrict__ box_s) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t j = order[i];
+  uint32_t j = (uint32_t) sorted[i];  // packed (key, leaf id)
   rec_s[i] = rec_u[j];
   box_s[i] = box_u[j];
 }
@@ -266,7 +264,8 @@ __global__ void k_leaf_gather(const uint32_t* __restrict__ order, uint32_t n,
 // Karras 2012: common-prefix length of sorted keys i and j, index tie-break
 static __device__ __forceinline__ int delta(const uint64_t* __restrict__ key, uint32_t n, int i, int j) {
   if (j < 0 || j >= (int) n) return -1;
-  uint64_t a = key[i], b = key[j];
+  // packed words: the key is the high half
+  uint64_t a = key[i] & 0xFFFFFFFF00000000ull, b = key[j] & 0xFFFFFFFF00000000ull;
   if (a == b) return 64 + __clz((uint32_t) i ^ (uint32_t) j);
   return __clzll((long long) (a ^ b));
 }
@@ -549,8 +548,7 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, int ag_it
   int4* box_s = b.leaf_box_s.ensure(n);
   uint64_t* ka = b.keys_a.ensure(n);
   uint64_t* kb = b.keys_b.ensure(n);
-  uint32_t* va = b.vals_a.ensure(n);
-  uint32_t* vb = b.vals_b.ensure(n);
+  uint32_t* va = b.vals_a.ensure(n);  // scratch of k_occ_mark (big-box list)
   uint2* rec_s = b.leaf_rec.ensure(n);
   int4* nbox = b.node_box.ensure(2 * (size_t) n_int);
   int2* nchild = b.node_child.ensure(n_int);
@@ -558,16 +556,16 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, int ag_it
   int4* root_d = b.root_box_d.ensure(1);
 
   if (ag)
-    k_leaf_fill_ag<<<div_up(n_blocks, T), T, 0, st>>>(m, base, n_blocks, ag_packed, ag_off, imin, rec_u, box_u, ka, va);
+    k_leaf_fill_ag<<<div_up(n_blocks, T), T, 0, st>>>(m, base, n_blocks, ag_packed, ag_off, imin, rec_u, box_u, ka);
   else
-    k_leaf_fill<<<div_up(n, T), T, 0, st>>>(m, base, n, leaf_size, imin, rec_u, box_u, ka, va);
-  sort_pairs_u64_u32(ka, kb, va, vb, n, kMortonDrop, 64, b.sort_tmp, st);
-  k_leaf_gather<<<div_up(n, T), T, 0, st>>>(vb, n, rec_u, box_u, rec_s, box_s);
+    k_leaf_fill<<<div_up(n, T), T, 0, st>>>(m, base, n, leaf_size, imin, rec_u, box_u, ka);
+  const uint64_t* sorted = sort_packed(ka, kb, n, 0, 64 - kMortonDrop, b.sort_tmp, st);
+  k_leaf_gather<<<div_up(n, T), T, 0, st>>>(sorted, n, rec_u, box_u, rec_s, box_s);
   if (n == 1) {
     k_single_leaf_root<<<1, 1, 0, st>>>(box_s, nbox, nchild, root_d);
   } else {
     k_refit_init<<<div_up(n_int, T), T, 0, st>>>(nbox, n_int);
-    k_karras<<<div_up(n - 1, T), T, 0, st>>>(kb, n, nchild, parent);
+    k_karras<<<div_up(n - 1, T), T, 0, st>>>(sorted, n, nchild, parent);
     k_refit<<<div_up(n, T), T, 0, st>>>(box_s, n, nchild, parent, nbox, root_d);
   }
   b.top_levels = n >= (1u << 18) ? 4 : 3;

@@ -151,9 +151,10 @@ struct QTile {
   bool valid;
 };
 
+// (p_lo: plain slots only -- start points below it are outside the query window)
 static __device__ __forceinline__ QTile load_tile(const MapView& Q, const uint32_t* __restrict__ order,
                                                   uint32_t n_slots, uint32_t tile, int lane,
-                                                  uint32_t spw = 32) {
+                                                  uint32_t spw = 32, uint32_t p_lo = 0) {
   QTile t;
   t.a = make_longlong2(0, 0);
   t.b = make_longlong2(0, 0);
@@ -167,7 +168,7 @@ static __device__ __forceinline__ QTile load_tile(const MapView& Q, const uint32
     t.p = slot;
     if (tile * 32 < n_slots) {
       const uint32_t w = __ldg(&Q.last_bits[tile]);  // warp-uniform
-      t.valid = t.valid && !((w >> lane) & 1u);
+      t.valid = t.valid && !((w >> lane) & 1u) && slot >= p_lo;
     }
   }
   if (t.valid) {
@@ -225,14 +226,16 @@ static __device__ __noinline__ bool occ_rect(const MapView& Q, const uint32_t* _
 // atomic per warp the runs of concurrently running warps from all over the map
 // interleave, and every traversal warp has to follow up to 32 separate clusters.)
 __global__ void __launch_bounds__(kFilterThreads)
-k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__ survivors,
-             unsigned int* counter, uint32_t* __restrict__ long_list, unsigned int* long_counter) {
+k_lsi_filter(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __restrict__ occ,
+             uint32_t* __restrict__ survivors, unsigned int* counter, uint32_t* __restrict__ long_list,
+             unsigned int* long_counter) {
   constexpr int kWarps = kFilterThreads / 32;
   __shared__ unsigned s_wsum[kWarps];
   __shared__ unsigned s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // point of (round e, lane) = w0 + 32 * e + lane
-  const uint32_t w0 = blockIdx.x * kFilterCtaPoints + warp * (32 * kFilterPerThread);
+  // point of (round e, lane) = w0 + 32 * e + lane; only start points in the query window
+  // [p_lo, p_hi) are looked at (a shard of the query map; the whole map by default)
+  const uint32_t w0 = (p_lo & ~31u) + blockIdx.x * kFilterCtaPoints + warp * (32 * kFilterPerThread);
   // stage 1: the descriptors (edge_desc is padded with "no edge" up to a multiple of 16;
   // beyond that the index is clamped and the value ignored)
   uint32_t d[kFilterPerThread];
@@ -240,7 +243,7 @@ k_lsi_filter(MapView Q, const uint32_t* __restrict__ occ, uint32_t* __restrict__
   for (int e = 0; e < kFilterPerThread; e++) {
     const uint32_t p = w0 + 32 * e + lane;
     d[e] = __ldg(&Q.edge_desc[min(p, Q.n_points)]);
-    if (p >= Q.n_points) d[e] = kDescNone << 24;
+    if (p >= p_hi || p < p_lo) d[e] = kDescNone << 24;
   }
   // stage 2: one look-up per edge; class bit 0 selects occ2 (kDescNone / kDescBig read a
   // valid word too and ignore it)
@@ -478,7 +481,7 @@ static __device__ __forceinline__ void prefetch_node(const BvhView& bvh, int nod
 template <bool kStats>
 __global__ void __launch_bounds__(kLsiWarps * 32)
 k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order, uint32_t n_slots,
-          const unsigned int* __restrict__ n_slots_dev, uint32_t spw,
+          uint32_t p_lo, const unsigned int* __restrict__ n_slots_dev, uint32_t spw,
           uint2* __restrict__ out, uint32_t cap, unsigned int* counter,
           unsigned long long* stats) {
   __shared__ int s_stack[kLsiWarps][kStackDepth];
@@ -490,13 +493,14 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
   // spw = query slots per warp: 32, or fewer for a list of queries from all over the map
   // (the long edges the cell directory leaves over): a warp follows the clusters of its
   // queries one after the other, and 32 unrelated queries are 32 clusters
+  // plain slots (no list): n_slots = end of the query window, p_lo = its begin
   const uint32_t n_tiles = (n_slots + spw - 1) / spw;
-  const uint32_t tile = blockIdx.x * kLsiWarps + warp;
+  const uint32_t tile = (order ? 0u : p_lo / 32) + blockIdx.x * kLsiWarps + warp;
   TravStats st = {0, 0, 0, 0, 0};
   const int4 kNeutral = empty_box();
   const int4 kEmpty = empty_box();
   if (tile >= n_tiles) return;
-  const QTile cur = load_tile(Q, order, n_slots, tile, lane, spw);
+  const QTile cur = load_tile(Q, order, n_slots, tile, lane, spw, order ? 0u : p_lo);
   const bool valid = cur.valid;
   const uint32_t qe = cur.p;
   const Seg q = {cur.a.x, cur.a.y, cur.b.x, cur.b.y};

@@ -19,23 +19,21 @@
 
 namespace rjb {
 
-// key = eid[im] (high 32 bits) | queue position (low 32 bits)
-__global__ void k_ov_keys(const rjb_xsect* __restrict__ xs, uint32_t n, int im,
-                          uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+// packed word: eid[im] (high 32 bits) | queue position (low 32 bits)
+__global__ void k_ov_keys(const rjb_xsect* __restrict__ xs, uint32_t n, int im, uint64_t* __restrict__ key) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  key[i] = ((uint64_t) xs[i].eid[im] << 32);
-  val[i] = i;
+  key[i] = ((uint64_t) xs[i].eid[im] << 32) | i;
 }
 
-__global__ void k_ov_gather(const rjb_xsect* __restrict__ xs, const uint32_t* __restrict__ order,
+__global__ void k_ov_gather(const rjb_xsect* __restrict__ xs, const uint64_t* __restrict__ order,
                             uint32_t n, int im, rjb_xsect* __restrict__ out,
                             uint32_t* __restrict__ seg_flag) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  rjb_xsect x = xs[order[i]];
+  rjb_xsect x = xs[(uint32_t) order[i]];
   out[i] = x;
-  uint32_t prev = i ? xs[order[i - 1]].eid[im] : 0xFFFFFFFFu;
+  uint32_t prev = i ? (uint32_t) (order[i - 1] >> 32) : 0xFFFFFFFFu;
   seg_flag[i] = (i == 0 || prev != x.eid[im]) ? 1u : 0u;
 }
 
@@ -103,6 +101,7 @@ __global__ void k_ov_fill_mid_faces(rjb_xsect* __restrict__ xs, const uint32_t* 
 // sharded over the ranks and gathered on one) handed to overlay_run instead of
 // running IntersectEdge / LocateVerticesInOtherMap here.
 struct OverlayImport {
+  bool device = false;  // the arrays below are DEVICE pointers (gathered over NCCL), else host
   const rjb_xsect* h_xsects = nullptr;
   uint64_t n_xsects = 0;
   const uint32_t* h_closest_eid[2] = {nullptr, nullptr};
@@ -121,25 +120,29 @@ static void overlay_run(rjb_ctx* c, int mode, uint32_t grid_size, double xsect_f
   for (auto& e : ev) RJB_CUDA(cudaEventCreate(&e));
   auto mark = [&](int i) { RJB_CUDA(cudaEventRecord(ev[i], st)); };
   mark(0);
-  // BuildIndex: one index per map, both directions are queried
-  for (int im = 0; im < 2; im++) do_build_index(c, im, mode, grid_size, nullptr);
+  // BuildIndex: one index per map, both directions are queried.  (The multi-GPU finish on a
+  // rank that ran the sharded phases reuses its resident maps and the indexes built for them.)
+  for (int im = 0; im < 2; im++) {
+    DeviceMap& m = c->maps[im];
+    const bool have = mode == RJB_MODE_LBVH ? m.bvh.built
+                                            : (mode == RJB_MODE_GRID ? m.grid.built && m.grid.gsize == grid_size : true);
+    if (!(imp && have)) do_build_index(c, im, mode, grid_size, nullptr);
+  }
   mark(1);
   uint64_t n = 0;
   if (imp) {
     // gathered results of the sharded phases
     n = imp->n_xsects;
     rjb_xsect* xs = c->xsects.ensure(n ? n : 1);
-    if (n)
-      RJB_CUDA(cudaMemcpyAsync(xs, imp->h_xsects, n * sizeof(rjb_xsect), cudaMemcpyHostToDevice, st));
+    const cudaMemcpyKind kind = imp->device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (n) RJB_CUDA(cudaMemcpyAsync(xs, imp->h_xsects, n * sizeof(rjb_xsect), kind, st));
     mark(2);
     for (int im = 0; im < 2; im++) {
       DeviceMap& Qm = c->maps[im];
       uint32_t* ce = ov.closest_eid[im].ensure(Qm.n_points ? Qm.n_points : 1);
       int32_t* pf = ov.point_in_polygon[im].ensure(Qm.n_points ? Qm.n_points : 1);
-      RJB_CUDA(cudaMemcpyAsync(ce, imp->h_closest_eid[im], Qm.n_points * sizeof(uint32_t),
-                               cudaMemcpyHostToDevice, st));
-      RJB_CUDA(cudaMemcpyAsync(pf, imp->h_point_in_polygon[im], Qm.n_points * sizeof(int32_t),
-                               cudaMemcpyHostToDevice, st));
+      RJB_CUDA(cudaMemcpyAsync(ce, imp->h_closest_eid[im], Qm.n_points * sizeof(uint32_t), kind, st));
+      RJB_CUDA(cudaMemcpyAsync(pf, imp->h_point_in_polygon[im], Qm.n_points * sizeof(int32_t), kind, st));
       mark(3 + im);
     }
   } else {
@@ -168,13 +171,11 @@ static void overlay_run(rjb_ctx* c, int mode, uint32_t grid_size, double xsect_f
     uint32_t n32 = (uint32_t) n;
     uint64_t* ka = ov.keys_a.ensure(n);
     uint64_t* kb = ov.keys_b.ensure(n);
-    uint32_t* va = ov.vals_a.ensure(n);
-    uint32_t* vb = ov.vals_b.ensure(n);
     uint32_t* flag = ov.seg_flag.ensure(n + 1);
     uint32_t* scan = ov.seg_scan.ensure(n + 1);
-    k_ov_keys<<<div_up(n, 256), 256, 0, st>>>(c->xsects.p, n32, im, ka, va);
-    sort_pairs_u64_u32(ka, kb, va, vb, n32, 32, 64, ov.sort_tmp, st);
-    k_ov_gather<<<div_up(n, 256), 256, 0, st>>>(c->xsects.p, vb, n32, im, sorted, flag);
+    k_ov_keys<<<div_up(n, 256), 256, 0, st>>>(c->xsects.p, n32, im, ka);
+    const uint64_t* order = sort_packed(ka, kb, n32, 0, 32, ov.sort_tmp, st);
+    k_ov_gather<<<div_up(n, 256), 256, 0, st>>>(c->xsects.p, order, n32, im, sorted, flag);
     exclusive_scan_u32(flag, scan, n32, ov.scan_tmp, st);
     uint32_t n_segs = 0;
     RJB_CUDA(cudaMemcpyAsync(&n_segs, scan + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

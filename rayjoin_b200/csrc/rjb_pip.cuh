@@ -174,7 +174,7 @@ static __device__ __forceinline__ int lowest_slot(unsigned m, int ymin, int lane
 
 template <bool kStats, bool kPark>
 __global__ void __launch_bounds__(kLsiWarps * 32, 8)
-k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __restrict__ order,
+k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint64_t* __restrict__ order,
           MapView B, BvhView bvh, int query_map_id, uint32_t* __restrict__ out_eid,
           int32_t* __restrict__ out_face, uint2* __restrict__ out_packed, unsigned long long* counters) {
   __shared__ int s_stack[kLsiWarps][kStackDepth];
@@ -188,7 +188,7 @@ k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint32_t* __r
   L.y_hi = 0x7fffffff;
   uint32_t pi = 0;
   if (L.valid) {
-    pi = order ? order[slot] : slot;
+    pi = order ? (uint32_t) order[slot] : slot;  // packed (key, point index) words
     const longlong2 p = pts[pi];
     L.px = p.x;
     L.py = p.y;

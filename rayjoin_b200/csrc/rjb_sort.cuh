@@ -185,6 +185,120 @@ k_sort_onesweep(const uint64_t* __restrict__ k_in, uint64_t* __restrict__ k_out,
   }
 }
 
+// ---- packed pairs -------------------------------------------------------------------------
+// Every sort of the engine has a key of at most 32 significant bits (Morton prefixes, grid cell
+// ids, edge ids) and a 32-bit payload, so the pair travels as ONE 64-bit word, key in the high
+// half: a pass moves 8 bytes per element each way instead of 12 through two arrays, the tile is
+// one shared-memory array, and a tile holds 4096 pairs (16 per thread) so that the runs a tile
+// writes per digit are twice as long.  Same structure as k_sort_onesweep above (warp-level
+// multi-split, decoupled look-back, digit-contiguous write-out); stable.
+constexpr int kSortPItems = 16;
+constexpr int kSortPTile = kSortThreads * kSortPItems;  // 4096 words per tile
+
+__global__ void __launch_bounds__(kSortThreads)
+k_sort_onesweep_packed(const uint64_t* __restrict__ w_in, uint64_t* __restrict__ w_out, uint32_t n, int shift,
+                       uint32_t mask, const uint32_t* __restrict__ digit_base /* [256] exclusive */,
+                       volatile uint32_t* tile_state /* [n_tiles][256], zeroed */,
+                       unsigned int* ticket /* zeroed */) {
+  __shared__ uint64_t s_words[kSortPTile];
+  __shared__ uint32_t s_wcount[kSortWarps][256];  // per-warp digit counts -> exclusive offsets
+  __shared__ uint32_t s_start[256];               // tile-local start of each digit
+  __shared__ uint32_t s_gbase[256];               // global position of the tile's first word of a digit
+  __shared__ uint32_t s_wtot[kSortWarps];
+  __shared__ unsigned int s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&s_wcount[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t tile_begin = tile * kSortPTile;
+  const uint32_t tile_n = min((uint32_t) kSortPTile, n - tile_begin);
+
+  // all loads first (16 independent 8-byte loads per thread in flight), then the ranking
+  uint64_t word[kSortPItems];
+  uint16_t rank[kSortPItems];
+#pragma unroll
+  for (int r = 0; r < kSortPItems; r++) {
+    const uint32_t local = warp * (32 * kSortPItems) + r * 32 + lane;
+    word[r] = local < tile_n ? __ldg(&w_in[tile_begin + local]) : ~0ull;
+  }
+#pragma unroll
+  for (int r = 0; r < kSortPItems; r++) {
+    const uint32_t local = warp * (32 * kSortPItems) + r * 32 + lane;
+    // padding words get digit 255 and sit after every real word of that digit because they
+    // are the last items of the last warps
+    const uint32_t d = local < tile_n ? ((uint32_t) (word[r] >> shift) & mask) : 255u;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader) {
+      base = s_wcount[warp][d];
+      s_wcount[warp][d] = base + __popc(peers);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    rank[r] = (uint16_t) (base + __popc(peers & ((1u << lane) - 1)));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // thread d: exclusive prefix of digit d over the warps, tile count of digit d
+  const uint32_t d_own = threadIdx.x;  // kSortThreads == 256 digits
+  uint32_t count = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; w++) {
+    const uint32_t c = s_wcount[w][d_own];
+    s_wcount[w][d_own] = count;
+    count += c;
+  }
+  uint32_t real = count;
+  if (d_own == 255) real = count - (kSortPTile - tile_n);  // minus the padding
+  volatile uint32_t* my_state = tile_state + (size_t) tile * 256;
+  if (tile == 0) my_state[d_own] = kFlagInclusive | real;
+  else my_state[d_own] = kFlagAggregate | real;
+  __threadfence();
+  uint32_t incl = count;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_wtot[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; w++)
+    if (w < warp) woff += s_wtot[w];
+  s_start[d_own] = woff + incl - count;
+  uint32_t excl = 0;
+  if (tile > 0) {
+    int j = (int) tile - 1;
+    while (true) {
+      const uint32_t st = tile_state[(size_t) j * 256 + d_own];
+      const uint32_t flag = st & ~kValueMask;
+      if (flag == 0) continue;  // predecessor not there yet (it holds an earlier ticket)
+      excl += st & kValueMask;
+      if (flag == kFlagInclusive) break;
+      j--;
+    }
+    my_state[d_own] = kFlagInclusive | (excl + real);
+  }
+  s_gbase[d_own] = digit_base[d_own] + excl;
+  __syncthreads();
+
+#pragma unroll
+  for (int r = 0; r < kSortPItems; r++) {
+    const uint32_t local = warp * (32 * kSortPItems) + r * 32 + lane;
+    const uint32_t d = local < tile_n ? ((uint32_t) (word[r] >> shift) & mask) : 255u;
+    s_words[s_start[d] + s_wcount[warp][d] + rank[r]] = word[r];
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < tile_n; i += kSortThreads) {
+    const uint64_t w = s_words[i];
+    const uint32_t d = (uint32_t) (w >> shift) & mask;
+    w_out[s_gbase[d] + (i - s_start[d])] = w;
+  }
+}
+
 struct SortTemp {
   DBuf<uint8_t> hist, state, ticket;
 };
@@ -228,6 +342,37 @@ static inline void sort_pairs_u64_u32(uint64_t* k_in, uint64_t* k_out, uint32_t*
     RJB_CUDA(cudaMemcpyAsync(k_out, ks, (size_t) n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     RJB_CUDA(cudaMemcpyAsync(v_out, vs, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   }
+}
+
+// Sorts packed words (key in the high 32 bits, payload in the low 32) by key bits
+// [begin_bit, end_bit) of the KEY.  `a` holds the input; `b` is scratch of the same size.
+// Returns the buffer that holds the result (a or b): no final copy.
+static inline uint64_t* sort_packed(uint64_t* a, uint64_t* b, uint32_t n, int begin_bit, int end_bit,
+                                    SortTemp& tmp, cudaStream_t st) {
+  if (n == 0) return a;
+  RJB_REQUIRE(n < (1u << 30), "sort: at most 2^30 - 1 pairs");
+  RJB_REQUIRE(begin_bit >= 0 && end_bit <= 32 && begin_bit < end_bit, "sort: bad key bit range");
+  const int n_passes = (end_bit - begin_bit + 7) / 8;
+  const uint32_t n_tiles = div_up(n, kSortPTile);
+  uint32_t* hist = (uint32_t*) tmp.hist.ensure(kSortMaxPasses * 256 * sizeof(uint32_t));
+  uint32_t* state = (uint32_t*) tmp.state.ensure((size_t) n_passes * n_tiles * 256 * sizeof(uint32_t));
+  unsigned int* ticket = (unsigned int*) tmp.ticket.ensure(kSortMaxPasses * sizeof(unsigned int));
+  RJB_CUDA(cudaMemsetAsync(hist, 0, kSortMaxPasses * 256 * sizeof(uint32_t), st));
+  RJB_CUDA(cudaMemsetAsync(state, 0, (size_t) n_passes * n_tiles * 256 * sizeof(uint32_t), st));
+  RJB_CUDA(cudaMemsetAsync(ticket, 0, kSortMaxPasses * sizeof(unsigned int), st));
+  const unsigned hb = min(div_up(n, kSortThreads * 16), (unsigned) (kNumSMs * 8));
+  k_sort_histogram<<<hb, kSortThreads, 0, st>>>(a, n, 32 + begin_bit, 32 + end_bit, n_passes, hist);
+  k_sort_scan_hist<<<1, 256, 0, st>>>(hist, n_passes);
+  uint64_t* src = a;
+  uint64_t* dst = b;
+  for (int p = 0; p < n_passes; p++) {
+    const uint32_t mask = (1u << std::min(8, end_bit - (begin_bit + 8 * p))) - 1;
+    k_sort_onesweep_packed<<<n_tiles, kSortThreads, 0, st>>>(src, dst, n, 32 + begin_bit + 8 * p, mask, hist + p * 256,
+                                                             state + (size_t) p * n_tiles * 256, ticket + p);
+    std::swap(src, dst);
+  }
+  RJB_CUDA(cudaGetLastError());
+  return src;  // written last
 }
 
 }  // namespace rjb

@@ -88,59 +88,133 @@ def gather_array(dist, local, counts, device, dst=0):
                            for r in range(world)])
 
 
+class _DevBytes:
+    """A device allocation owned by the engine, as a zero-copy uint8 torch view."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def device_view(ptr, nbytes, torch_device):
+    import torch
+    if nbytes == 0:
+        return torch.empty(0, dtype=torch.uint8, device=torch_device)
+    return torch.as_tensor(_DevBytes(ptr, nbytes), device=torch_device)
+
+
+def gather_bytes(dist, local, nbytes_per_rank, dst=0):
+    """Variable-length gather of uint8 tensors to `dst` as ONE batch of point-to-point
+    operations (NCCL: a grouped ncclSend / ncclRecv, device memory to device memory; gloo: the
+    same calls on host tensors).  -> concatenation in rank order on dst, None elsewhere."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = [int(x) for x in nbytes_per_rank]
+    if rank != dst:
+        if sizes[rank]:
+            for r in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), dst)]):
+                r.wait()
+        return None
+    out = torch.empty(sum(sizes), dtype=torch.uint8, device=local.device)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    ops = [dist.P2POp(dist.irecv, out[offs[r]:offs[r + 1]], r) for r in range(world) if r != dst and sizes[r]]
+    out[offs[dst]:offs[dst + 1]].copy_(local)
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    return out
+
+
 def distributed_overlay(dist, graphs, mode="lbvh", grid_size=2048, xsect_factor=0.5, device=0,
                         torch_device=None, output=None, bbox=None):
-    """Polygon overlay of graphs[0] x graphs[1] over all ranks of `dist` (one process
-    per GPU).  Every rank holds two contexts -- (shard of map 0, full map 1) for
-    IntersectEdge(0) and the location of map 0's vertices, (full map 0, shard of map 1)
-    for the location of map 1's vertices -- so the base side and its index are always
-    complete and replicated while the query side is sharded by whole chains.  Counts go
-    through an all-gather, the results through padded gathers to rank 0, which imports
-    them (rjb_overlay_finish), runs ComputeOutputPolygons and writes the chains.
+    """Polygon overlay of graphs[0] x graphs[1] over all ranks of `dist` (one process per GPU;
+    BASELINE.json configs[3]).  Every rank holds ONE context with both maps whole and both
+    indexes (the build is cheaper than any broadcast); the query side of each phase is cut by
+    whole chains: rank r runs IntersectEdge(0) on its window of map 0 (option lsi_window_*; edge
+    ids stay global) and locates its range of the vertices of both maps.  NCCL carries the
+    count all-gather and one grouped send / recv per result array into device memory of rank 0,
+    which hands the device pointers to rjb_overlay_finish_device -- its resident maps and
+    indexes are reused -- runs ComputeOutputPolygons and writes the chains.  With a host
+    (gloo) group the same protocol runs on host copies.
     Returns (MapOverlay on rank 0 | None, phase dict)."""
     import time
     import torch
     from . import capi, synth
     world, rank = dist.get_world_size(), dist.get_rank()
     tdev = torch_device if torch_device is not None else torch.device("cuda", device)
+    on_device = tdev.type == "cuda"
     bbox = bbox or synth.union_bbox(*graphs)
     t0 = time.perf_counter()
-    sh0, eoff0, poff0 = shard_graph(graphs[0], rank, world)
-    sh1, eoff1, poff1 = shard_graph(graphs[1], rank, world)
-    ctx_a = capi.Context([sh0, graphs[1]], device=device, bbox=bbox)
-    ctx_b = capi.Context([graphs[0], sh1], device=device, bbox=bbox)
-    ctx_a.build_index(1, mode, grid_size)
-    ctx_b.build_index(0, mode, grid_size)
-    t1 = time.perf_counter()
-    lsi = capi.LSI(ctx_a, mode)
-    lsi.Init(xsect_factor)
-    n = lsi.Query(0)
-    xs = lsi.get_xsects()
-    pip_a = capi.PIP(ctx_a, mode)
-    pip_a.Query(0)
-    e0, f0 = pip_a.get_closest_eids(), pip_a.get_face_ids()
-    pip_b = capi.PIP(ctx_b, mode)
-    pip_b.Query(1)
-    e1, f1 = pip_b.get_closest_eids(), pip_b.get_face_ids()
-    t2 = time.perf_counter()
-    counts = allgather_counts(dist, [n, sh0.n_points, sh1.n_points], tdev)
-    all_xs = gather_xsects(dist, xs, counts[:, 0], eoff0, 0, tdev)
-    g_e0 = gather_array(dist, e0, counts[:, 1], tdev)
-    g_f0 = gather_array(dist, f0, counts[:, 1], tdev)
-    g_e1 = gather_array(dist, e1, counts[:, 2], tdev)
-    g_f1 = gather_array(dist, f1, counts[:, 2], tdev)
-    t3 = time.perf_counter()
-    ctx_a.close()
-    ctx_b.close()
-    phases = {"load_build_s": t1 - t0, "sharded_queries_s": t2 - t1, "gather_s": t3 - t2,
-              "n_xsects_local": int(n)}
-    if rank != 0:
-        return None, phases
     ctx = capi.Context(list(graphs), device=device, bbox=bbox)
+    ctx.set_option("sort_queries", 0)  # map vertices are coherent along their chains
+    for im in range(2):
+        ctx.build_index(im, mode, grid_size)
+    # windows of this rank: whole chains -> point ranges of map 0 and map 1
+    win = []
+    for g in graphs:
+        c0, c1 = shard_bounds(g, world)[rank]
+        row = g.row_index.astype(np.int64)
+        win.append((int(row[c0]), int(row[c1])) if g.n_chains else (0, 0))
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    t1 = time.perf_counter()
+
+    def view(ptr, nbytes):
+        # results live in buffers of the context that the next query reuses: take a copy
+        if on_device:
+            return device_view(ptr, nbytes, tdev).clone()
+        out = np.empty(nbytes, np.uint8)
+        ctx.copy_to_host(ptr, out)
+        return torch.from_numpy(out)
+
+    lsi = capi.LSI(ctx, mode)
+    lsi.Init(xsect_factor)
+    ctx.set_option("lsi_window_begin", win[0][0])
+    ctx.set_option("lsi_window_end", win[0][1])
+    n = lsi.Query(0) if win[0][1] > win[0][0] else 0
+    ctx.set_option("lsi_window_begin", 0)
+    ctx.set_option("lsi_window_end", 0)
+    xs = view(lsi._res[0], 32 * n) if n else torch.empty(0, dtype=torch.uint8, device=tdev)
+    loc = []
+    for im in range(2):
+        p0, p1 = win[im]
+        if p1 > p0:
+            de, df, _ = ctx.pip_device(im, mode, ctx.map_points_device_ptr(im) + 16 * p0, p1 - p0)
+            loc.append((view(de, 4 * (p1 - p0)), view(df, 4 * (p1 - p0))))
+        else:
+            e = torch.empty(0, dtype=torch.uint8, device=tdev)
+            loc.append((e, e.clone()))
+    if on_device:
+        torch.cuda.synchronize(tdev)
+    t2 = time.perf_counter()
+    counts = allgather_counts(dist, [n, win[0][1] - win[0][0], win[1][1] - win[1][0]], tdev)
+    g_xs = gather_bytes(dist, xs, counts[:, 0] * 32)
+    g_loc = [(gather_bytes(dist, loc[im][0], counts[:, 1 + im] * 4),
+              gather_bytes(dist, loc[im][1], counts[:, 1 + im] * 4)) for im in range(2)]
+    if on_device:
+        torch.cuda.synchronize(tdev)
+    t3 = time.perf_counter()
+    phases = {"load_build_s": t1 - t0, "sharded_queries_s": t2 - t1, "gather_s": t3 - t2,
+              "n_xsects_local": int(n), "collective": "nccl grouped send/recv (device)" if on_device
+              else "host point-to-point (gloo)"}
+    if rank != 0:
+        ctx.close()
+        return None, phases
+    n_all = int(counts[:, 0].sum())
     ov = capi.MapOverlay(ctx, mode, grid_size, xsect_factor)
-    ov.Finish(all_xs, [g_e0, g_e1], [g_f0, g_f1])
+    if on_device:
+        ov.FinishDevice(g_xs.data_ptr(), n_all, [g_loc[0][0].data_ptr(), g_loc[1][0].data_ptr()],
+                        [g_loc[0][1].data_ptr(), g_loc[1][1].data_ptr()])
+    else:
+        ov.Finish(g_xs.numpy().view(XSECT_DTYPE),
+                  [g_loc[0][0].numpy().view(np.uint32), g_loc[1][0].numpy().view(np.uint32)],
+                  [g_loc[0][1].numpy().view(np.int32), g_loc[1][1].numpy().view(np.int32)])
+    phases["finish_device_ms"] = dict(ov.phase_ms)
+    t4 = time.perf_counter()
     if output:
         ov.WriteResult(output)
-    phases["finish_s"] = time.perf_counter() - t3
-    phases["n_xsects"] = int(len(all_xs))
+    phases["finish_s"] = t4 - t3
+    phases["write_s"] = time.perf_counter() - t4
+    phases["n_xsects"] = n_all
     return ov, phases

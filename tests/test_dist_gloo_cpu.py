@@ -79,3 +79,38 @@ def test_shard_bounds_cover_and_balance():
             if sh.n_chains:
                 assert sh.row_index[0] == 0 and sh.row_index[-1] == sh.n_points
         assert total_e == S.n_edges and total_p == S.n_points
+
+
+def _gather_worker(rank, world, port, out_path):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from rayjoin_b200 import dist as rd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sizes = [(7 * r) % 5 * 1000 + (0 if r == 1 else 13) for r in range(world)]  # rank 1 sends nothing
+    sizes[1] = 0
+    local = torch.full((sizes[rank],), rank + 1, dtype=torch.uint8)
+    counts = rd.allgather_counts(dist, [sizes[rank]], torch.device("cpu"))[:, 0]
+    assert counts.tolist() == sizes
+    out = rd.gather_bytes(dist, local, counts)
+    if rank == 0:
+        np.save(out_path, out.numpy())
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_variable_length_gather(world, tmp_path):
+    """gather_bytes: the grouped point-to-point gather of the overlay results (ragged, with an
+    empty contribution) -- on NCCL the same calls move device memory."""
+    out = str(tmp_path / "g.npy")
+    mp.spawn(_gather_worker, args=(world, 29700 + world + (os.getpid() % 200), out), nprocs=world, join=True)
+    got = np.load(out)
+    sizes = [(7 * r) % 5 * 1000 + 13 for r in range(world)]
+    sizes[1] = 0
+    want = np.concatenate([np.full(sizes[r], r + 1, np.uint8) for r in range(world)])
+    assert np.array_equal(got, want)

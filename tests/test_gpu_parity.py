@@ -152,6 +152,42 @@ def test_lsi_cell_directory_path(rjb, loaded, name, q):
     assert counts[0] == counts[1]
 
 
+@pytest.mark.parametrize("mode,flt", [("lbvh", 1), ("lbvh", 0), ("grid", 0)])
+@pytest.mark.parametrize("name", ["voronoi", "shared", "soup"])
+def test_lsi_query_window(rjb, loaded, name, mode, flt):
+    """Options lsi_window_begin / lsi_window_end: the query edges starting in a window of the
+    query map's points (what one rank of the multi-GPU overlay runs).  Windows that tile the map
+    -- cut at arbitrary points, not multiples of 32 -- add up to the whole result, ids global."""
+    ctx, om = loaded(name)
+    q = 1
+    n_pts = ctx.map_info(q)["points"]
+    cuts = [0, n_pts // 3 + 5, (2 * n_pts) // 3 - 7, n_pts]
+    want = om.lsi_refgrid(q, 64) if mode == "grid" else om.lsi(q)
+    parts = []
+    try:
+        ctx.set_option("lsi_filter", flt)
+        ctx.set_option("sort_queries", 0)
+        ctx.build_index(1 - q, mode, grid_size=64)
+        lsi = rjb.LSI(ctx, mode)
+        lsi.Init(4.0)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            ctx.set_option("lsi_window_begin", a)
+            ctx.set_option("lsi_window_end", b)
+            lsi.Query(q)
+            xs = lsi.get_xsects()
+            p1 = om.p1[q][xs["eid"][:, q]]  # start point of every reported query edge
+            assert ((p1 >= a) & (p1 < b)).all()
+            parts.append(xs)
+    finally:
+        ctx.set_option("lsi_window_begin", 0)
+        ctx.set_option("lsi_window_end", 0)
+        ctx.set_option("lsi_filter", -1)
+    got = sort_xsects(np.concatenate(parts), q)
+    assert len(got[0]) == len(want[0])
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
 def test_cached_query_order_follows_the_map(rjb, oracle):
     """The Morton order of a short-chain query map is computed once and kept with the map: a
     second query reuses it, replacing the map drops it."""

@@ -26,11 +26,18 @@ dev = torch.device("cuda", local)
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 A, B = bench.get_map("R", 1, args.scale), bench.get_map("S", 2, args.scale)
+# first pass: NCCL builds its point-to-point connections lazily (0.3 s on first use of a peer);
+# the timed pass is the steady state of a resident service
+ov, cold = rd.distributed_overlay(dist, [A, B], mode=args.mode, xsect_factor=args.xsect_factor,
+                                  device=local, torch_device=dev, output=None)
+if ov is not None:
+    ov.ctx.close()
 dist.barrier(); torch.cuda.synchronize()
 t = time.perf_counter()
 ov, phases = rd.distributed_overlay(dist, [A, B], mode=args.mode, xsect_factor=args.xsect_factor,
                                     device=local, torch_device=dev,
                                     output=args.output if rank == 0 else None)
+phases["cold_gather_s"] = cold["gather_s"]
 torch.cuda.synchronize(); dist.barrier()
 total = time.perf_counter() - t
 if rank == 0:
