@@ -195,7 +195,7 @@ k_sort_onesweep(const uint64_t* __restrict__ k_in, uint64_t* __restrict__ k_out,
 constexpr int kSortPItems = 16;
 constexpr int kSortPTile = kSortThreads * kSortPItems;  // 4096 words per tile
 
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 4)
 k_sort_onesweep_packed(const uint64_t* __restrict__ w_in, uint64_t* __restrict__ w_out, uint32_t n, int shift,
                        uint32_t mask, const uint32_t* __restrict__ digit_base /* [256] exclusive */,
                        volatile uint32_t* tile_state /* [n_tiles][256], zeroed */,

@@ -47,6 +47,7 @@ if rank == 0:
     if args.check:
         ctx = RJ.Context([A, B], device=local)
         single = RJ.MapOverlay(ctx, args.mode, xsect_factor=args.xsect_factor)
+        single.Run()  # warm-up (first-use allocations)
         t = time.perf_counter(); single.Run(); line["single_gpu_run_s"] = time.perf_counter() - t
         line["single_gpu_phase_ms"] = single.phase_ms
         ref = args.output + ".single"
