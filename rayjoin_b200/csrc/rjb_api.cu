@@ -31,6 +31,14 @@ struct DeviceMap {
   bool edge_order_valid = false;
   DBuf<int32_t> left, right;
   std::vector<int32_t> h_left, h_right;
+  DBuf<uint32_t> block_chain;  // chain of every 256th point (k_load_points)
+  // pinned staging of the small per-chain arrays {left, right, block_chain}: pageable sources
+  // would make every cudaMemcpyAsync of the upload synchronise the stream first
+  int32_t* h_stage = nullptr;
+  size_t h_stage_cap = 0;
+  ~DeviceMap() {
+    if (h_stage) cudaFreeHost(h_stage);
+  }
   // host copy of the source graph kept for the overlay writer (points as
   // given, chains) -- WriteOutputChain reads ctx.get_planar_graph(im)
   std::vector<double> h_xy;
@@ -177,32 +185,54 @@ static int guarded(F&& f) {
 //  * the occupancy descriptor of the edge ENDING at p (edge_desc[p - 1], what
 //    k_lsi_filter streams): the previous vertex comes from the neighbour lane, or is
 //    re-scaled from the raw array -- uploaded already, chunks arrive in order.
-// p_begin is a multiple of 32, so a warp owns whole last_bits words.
+// p_begin is a multiple of 256: a CTA owns 256 consecutive points, a warp whole last_bits words.
+//
+// The chain of a point is found WITHOUT a search per point (a 20-step binary search over
+// row_index for each of 9 M points made this kernel latency bound at 32 % of the HBM
+// roofline): the host hands over the chain of every 256th point (block_chain, one merge pass
+// over the chains while it validates them), the CTA stages the next 258 chain starts in
+// shared memory, a warp finds the chain of its first point there and marks the chain starts
+// among its 32 points in one 32-bit mask (__reduce_or_sync); chain = chain of the first
+// point + popcount of the starts at or before the lane.
 __global__ void __launch_bounds__(256)
 k_load_points(const double2* __restrict__ in, uint32_t p_begin, uint32_t p_end, uint32_t n_points,
               double rx, double ry, double dx, double dy, const uint32_t* __restrict__ row_index,
-              uint32_t n_chains, longlong2* __restrict__ out, uint32_t* __restrict__ edge_desc,
-              uint32_t* __restrict__ point_chain, uint32_t* __restrict__ edge_chain,
-              uint32_t* __restrict__ last_bits) {
-  const uint32_t p = p_begin + blockIdx.x * blockDim.x + threadIdx.x;
+              uint32_t n_chains, const uint32_t* __restrict__ block_chain, longlong2* __restrict__ out,
+              uint32_t* __restrict__ edge_desc, uint32_t* __restrict__ point_chain,
+              uint32_t* __restrict__ edge_chain, uint32_t* __restrict__ last_bits) {
+  __shared__ uint32_t s_ri[258];
+  const uint32_t pb0 = p_begin + blockIdx.x * 256;
+  const uint32_t p = pb0 + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  bool last = false, first = false;
+  const uint32_t c_block = __ldg(&block_chain[pb0 >> 8]);
+  s_ri[threadIdx.x] = __ldg(&row_index[min(c_block + threadIdx.x, n_chains)]);
+  if (threadIdx.x < 2) s_ri[256 + threadIdx.x] = __ldg(&row_index[min(c_block + 256 + threadIdx.x, n_chains)]);
   longlong2 o = make_longlong2(0, 0);
   if (p < p_end) {
     const double2 v = in[p];
     o.x = (long long) fma(v.x, rx, dx);
     o.y = (long long) fma(v.y, ry, dy);
     out[p] = o;
-    // last chain c with row_index[c] <= p
-    uint32_t lo = 0, hi = n_chains;
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (__ldg(&row_index[mid]) <= p) lo = mid; else hi = mid;
-    }
-    point_chain[p] = lo;
-    first = __ldg(&row_index[lo]) == p;
-    last = __ldg(&row_index[lo + 1]) - 1 == p;
-    if (!last) edge_chain[p - lo] = lo;
+  }
+  __syncthreads();
+  const uint32_t pw = pb0 + (threadIdx.x & ~31u);  // first point of the warp
+  // last staged chain whose first point is <= pw (<= 128 chains start inside a CTA: every
+  // chain has at least 2 points); the same search in every lane, no divergence
+  uint32_t lo = 0, hi = 130;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (s_ri[mid] <= pw) lo = mid; else hi = mid;
+  }
+  // chain starts among the warp's points (row_index[n_chains] = n_points acts as one more start)
+  const uint32_t off = s_ri[lo + 1 + lane] - pw;
+  const uint32_t starts = __reduce_or_sync(0xffffffffu, off < 32u ? 1u << off : 0u);
+  const bool start_after = __any_sync(0xffffffffu, off == 32u);
+  const uint32_t chain = c_block + lo + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
+  const bool first = lane == 0 ? s_ri[lo] == pw : (starts >> lane) & 1u;
+  const bool last = p < p_end && (lane < 31 ? (starts >> (lane + 1)) & 1u : start_after);
+  if (p < p_end) {
+    point_chain[p] = chain;
+    if (!last) edge_chain[p - chain] = chain;
   }
   const unsigned m = __ballot_sync(0xffffffffu, last);
   if (lane == 0 && p < p_end) last_bits[p >> 5] = m;
@@ -484,8 +514,15 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     const GridView gv = Bm.grid.view();
     RJB_CUDA(cudaMemsetAsync(ctr, 0, 10 * sizeof(unsigned long long), c->stream));
     RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
-    k_grid_lsi_filter<<<div_up(p_hi - (p_lo & ~31u), 256), 256, 0, c->stream>>>(Q, p_lo, p_hi, gv, work, wcap, wn, big,
-                                                                               wn + 2);
+    // maps of short chains in arbitrary order (polygon soups) are walked in Morton order, so that
+    // neighbouring work items share cells and base vertices (as in the LBVH path)
+    const uint32_t* gorder = windowed ? nullptr : query_order_edges(c, Qm, Q);
+    if (gorder)
+      k_grid_lsi_filter<<<div_up(Q.n_edges, 256), 256, 0, c->stream>>>(Q, gorder, 0, Q.n_edges, gv, work, wcap, wn, big,
+                                                                      wn + 2);
+    else
+      k_grid_lsi_filter<<<div_up(p_hi - (p_lo & ~31u), 256), 256, 0, c->stream>>>(Q, nullptr, p_lo, p_hi, gv, work,
+                                                                                 wcap, wn, big, wn + 2);
     k_grid_lsi_big<<<kNumSMs, 256, 0, c->stream>>>(Q, gv, big, wn + 2, work, wcap, wn);
     RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
     k_grid_lsi_exact<<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, gv, q, work, wn, wcap, xs, cap,
@@ -867,10 +904,25 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
     m.n_edges = (uint32_t) (n_points - n_chains);
     m.h_left.resize(n_chains);
     m.h_right.resize(n_chains);
+    // chain of every 256th point, for the load kernel (one merge pass over the chains)
+    const uint64_t n_blocks = (n_points + 255) / 256;
+    const size_t stage_n = 2 * n_chains + n_blocks + 1;
+    if (m.h_stage_cap < stage_n) {
+      if (m.h_stage) cudaFreeHost(m.h_stage);
+      m.h_stage = nullptr;
+      m.h_stage_cap = 0;
+      RJB_CUDA(cudaHostAlloc((void**) &m.h_stage, (stage_n + stage_n / 8) * sizeof(int32_t), cudaHostAllocDefault));
+      m.h_stage_cap = stage_n + stage_n / 8;
+    }
+    int32_t* h_l = m.h_stage;
+    int32_t* h_r = m.h_stage + n_chains;
+    uint32_t* h_bc = (uint32_t*) (m.h_stage + 2 * n_chains);
+    uint64_t b = 0;
     for (uint64_t i = 0; i < n_chains; i++) {
       RJB_REQUIRE(row_index[i + 1] >= row_index[i] + 2, "rjb_set_map: chain with < 2 points");
-      m.h_left[i] = (int32_t) left[i];
-      m.h_right[i] = (int32_t) right[i];
+      m.h_left[i] = h_l[i] = (int32_t) left[i];
+      m.h_right[i] = h_r[i] = (int32_t) right[i];
+      for (; b < n_blocks && 256 * b < row_index[i + 1]; b++) h_bc[b] = (uint32_t) i;
     }
     if (c->keep_host_graph) {
       m.h_xy.assign(xy, xy + 2 * n_points);
@@ -890,6 +942,7 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
     uint32_t* cc = m.edge_desc.ensure(n_points + 16);
     uint32_t n_words = (uint32_t) (n_points / 32 + 2);
     uint32_t* lb = m.last_bits.ensure(n_words);
+    uint32_t* bc = m.block_chain.ensure(n_blocks ? n_blocks : 1);
     cudaStream_t st = c->stream;
     if (n_points) {
       // Small arrays first, then the vertices in chunks: the copy engine streams chunk
@@ -897,10 +950,9 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
       // edge numbering hide behind the PCIe transfer (which bounds the whole upload).
       RJB_CUDA(cudaMemcpyAsync(ri, row_index, (n_chains + 1) * sizeof(uint32_t),
                                cudaMemcpyHostToDevice, st));
-      RJB_CUDA(cudaMemcpyAsync(l, m.h_left.data(), n_chains * sizeof(int32_t),
-                               cudaMemcpyHostToDevice, st));
-      RJB_CUDA(cudaMemcpyAsync(r, m.h_right.data(), n_chains * sizeof(int32_t),
-                               cudaMemcpyHostToDevice, st));
+      RJB_CUDA(cudaMemcpyAsync(l, h_l, n_chains * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      RJB_CUDA(cudaMemcpyAsync(r, h_r, n_chains * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      RJB_CUDA(cudaMemcpyAsync(bc, h_bc, n_blocks * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
       RJB_CUDA(cudaMemsetAsync(lb + (n_words - 2), 0, 2 * sizeof(uint32_t), st));
       RJB_CUDA(cudaMemsetAsync(cc + n_points, 0xFF, 16 * sizeof(uint32_t), st));
       ensure_load_pipeline(c);
@@ -916,7 +968,7 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
         RJB_CUDA(cudaStreamWaitEvent(c->aux, c->chunk_ev[k], 0));
         k_load_points<<<div_up(p1 - p0, 256), 256, 0, c->aux>>>(
             raw, (uint32_t) p0, p1, m.n_points, c->sc.rx, c->sc.ry, c->sc.deltax, c->sc.deltay, ri,
-            m.n_chains, pts, cc, pc, ec, lb);
+            m.n_chains, bc, pts, cc, pc, ec, lb);
       }
       RJB_CUDA(cudaGetLastError());
       RJB_CUDA(cudaEventRecord(c->chunk_ev[kLoadChunksMax], c->aux));

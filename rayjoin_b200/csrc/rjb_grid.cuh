@@ -327,12 +327,15 @@ static inline void build_grid(Grid& g, const MapView& B, uint32_t gsize, long lo
 constexpr uint32_t kGridSmallCells = 16;
 
 __global__ void __launch_bounds__(256)
-k_grid_lsi_filter(MapView Q, uint32_t p_lo, uint32_t p_hi, GridView g, uint2* __restrict__ work,
-                  uint32_t work_cap, unsigned int* work_n, uint32_t* __restrict__ big_list, unsigned int* big_n) {
+k_grid_lsi_filter(MapView Q, const uint32_t* __restrict__ order, uint32_t p_lo, uint32_t p_hi, GridView g,
+                  uint2* __restrict__ work, uint32_t work_cap, unsigned int* work_n,
+                  uint32_t* __restrict__ big_list, unsigned int* big_n) {
   const int lane = threadIdx.x & 31;
-  const uint32_t tile = p_lo / 32 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  // slots: the start points of the query window [p_lo, p_hi) in map order, or (order != null, no
+  // window) the p_hi = n_edges entries of the map's Morton-ordered edge list
+  const uint32_t tile = (order ? 0u : p_lo / 32) + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (tile * 32 >= p_hi) return;
-  const QTile t = load_tile(Q, nullptr, p_hi, tile, lane, 32, p_lo);  // query window [p_lo, p_hi)
+  const QTile t = load_tile(Q, order, p_hi, tile, lane, 32, order ? 0u : p_lo);
   CellBox c = {0, -1, 0, -1};
   uint32_t hits = 0;  // bit k = k-th cell of the box (column by column) is occupied
   bool big = false;
@@ -468,6 +471,22 @@ static __device__ __forceinline__ void grid_drain(const MapView& Q, const MapVie
 
 constexpr int kGridInLane = 8;  // items of a cell a lane walks itself; longer lists: the whole warp
 
+// box of a query edge relative to cell `bit`, in the steps of the item records: {qx0, qx1, qy0, qy1}
+static __device__ __forceinline__ uint4 grid_query_qbox(const GridView& g, const Seg& e, uint32_t bit) {
+  const int cx = (int) (bit / g.gs), cy = (int) (bit % g.gs);
+  return make_uint4(grid_qx(g, min(e.x1, e.x2), cx), grid_qx(g, max(e.x1, e.x2), cx),
+                    grid_qy(g, min(e.y1, e.y2), cy), grid_qy(g, max(e.y1, e.y2), cy));
+}
+
+// Conservative box test on the item's packed 32-bit box alone: both boxes are clamped into the
+// cell by the same monotone map, so boxes that overlap still overlap.  In dense cells most items
+// end here, without a vertex load or a 64-bit compare.
+static __device__ __forceinline__ bool grid_qbox_overlap(const uint4& q, uint32_t m) {
+  const uint32_t ix0 = m & 63u, ix1 = (m >> 6) & 63u, iy0 = (m >> 14) & 127u;
+  const uint32_t iy1 = (m >> 28) ? 127u : ((m >> 21) & 127u);  // ends in a higher cell: up to the top
+  return ix0 <= q.y && q.x <= ix1 && iy0 <= q.w && q.z <= iy1;
+}
+
 __global__ void __launch_bounds__(kExactThreads)
 k_grid_lsi_exact(MapView Q, MapView B, GridView g, int q, const uint2* __restrict__ work,
                  const unsigned int* __restrict__ work_n_dev, uint32_t work_cap, rjb_xsect* __restrict__ out,
@@ -485,6 +504,7 @@ k_grid_lsi_exact(MapView Q, MapView B, GridView g, int q, const uint2* __restric
     const uint64_t i = i0 + threadIdx.x;
     uint32_t pq = 0, bit = 0, beg = 0, end = 0;
     Seg eq = {0, 0, 0, 0};
+    uint4 qq = make_uint4(1, 0, 1, 0);  // empty
     if (i < n) {
       const uint2 w = work[i];
       pq = w.x;
@@ -492,20 +512,22 @@ k_grid_lsi_exact(MapView Q, MapView B, GridView g, int q, const uint2* __restric
       grid_cell_range(g, bit, beg, end);
       const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
       eq = {a.x, a.y, b.x, b.y};
+      qq = grid_query_qbox(g, eq, bit);
     }
-    // the first kGridInLane items of the lane's own cell: item ids, then vertices, in flight together
-    uint32_t pb[kGridInLane];
+    // the first kGridInLane items of the lane's own cell: the item records in flight together;
+    // vertices are loaded only for the items whose packed box overlaps the query's
+    uint2 it[kGridInLane];
 #pragma unroll
-    for (int k = 0; k < kGridInLane; k++) pb[k] = beg + k < end ? __ldg(&g.items[beg + k].x) : 0xFFFFFFFFu;
+    for (int k = 0; k < kGridInLane; k++) it[k] = beg + k < end ? __ldg(&g.items[beg + k]) : make_uint2(0xFFFFFFFFu, 0);
 #pragma unroll
     for (int k = 0; k < kGridInLane; k++) {
       bool pass = false;
-      if (pb[k] != 0xFFFFFFFFu) {
-        const longlong2 c = __ldg(&B.pts[pb[k]]), d = __ldg(&B.pts[pb[k] + 1]);
+      if (it[k].x != 0xFFFFFFFFu && grid_qbox_overlap(qq, it[k].y)) {
+        const longlong2 c = __ldg(&B.pts[it[k].x]), d = __ldg(&B.pts[it[k].x + 1]);
         const Seg eb = {c.x, c.y, d.x, d.y};
         pass = seg_boxes_overlap(eq, eb) && grid_pair_here(g, eq, eb, bit);
       }
-      exact_push(pass, make_uint2(pq, pb[k]), s_list, &s_n, lane, cand);
+      exact_push(pass, make_uint2(pq, it[k].x), s_list, &s_n, lane, cand);
     }
     // longer lists (dense cells): one lane's cell at a time, the warp strides over its items and
     // tests what passes the boxes at once
@@ -517,15 +539,20 @@ k_grid_lsi_exact(MapView Q, MapView B, GridView g, int q, const uint2* __restric
       const uint32_t spq = __shfl_sync(0xffffffffu, pq, src), sbit = __shfl_sync(0xffffffffu, bit, src);
       const Seg sq = {__shfl_sync(0xffffffffu, eq.x1, src), __shfl_sync(0xffffffffu, eq.y1, src),
                       __shfl_sync(0xffffffffu, eq.x2, src), __shfl_sync(0xffffffffu, eq.y2, src)};
+      const uint4 sqq = make_uint4(__shfl_sync(0xffffffffu, qq.x, src), __shfl_sync(0xffffffffu, qq.y, src),
+                                   __shfl_sync(0xffffffffu, qq.z, src), __shfl_sync(0xffffffffu, qq.w, src));
       for (uint32_t k0 = b0; k0 < e0; k0 += 32) {
         const uint32_t k = k0 + lane;
         bool pass = false;
         uint32_t p = 0;
         if (k < e0) {
-          p = __ldg(&g.items[k].x);
-          const longlong2 c = __ldg(&B.pts[p]), d = __ldg(&B.pts[p + 1]);
-          const Seg eb = {c.x, c.y, d.x, d.y};
-          pass = seg_boxes_overlap(sq, eb) && grid_pair_here(g, sq, eb, sbit);
+          const uint2 item = __ldg(&g.items[k]);
+          p = item.x;
+          if (grid_qbox_overlap(sqq, item.y)) {
+            const longlong2 c = __ldg(&B.pts[p]), d = __ldg(&B.pts[p + 1]);
+            const Seg eb = {c.x, c.y, d.x, d.y};
+            pass = seg_boxes_overlap(sq, eb) && grid_pair_here(g, sq, eb, sbit);
+          }
         }
         cand += __popc(__ballot_sync(0xffffffffu, pass));
         grid_test_emit(Q, B, g, q, pass, make_uint2(spq, p), out, cap, counter, lane);

@@ -120,7 +120,32 @@ static int run_lsi(const Flags& f) {
   uint64_t cap = (uint64_t) ((float) ne * (float) f.d("xsect_factor"));
   std::cerr << "Intersections: " << n << " Queue Load Factor: " << (cap ? (double) n / cap : 0.0)
             << std::endl;
-  if (f.b("profile")) std::cerr << "Total tests: " << cand << std::endl;
+  if (f.b("profile")) {
+    // -profile: the reference prints the stopwatches of its index build sub-stages and, in Debug
+    // builds, "Total tests" (src/grid/uniform_grid.h:134-244, deps/lbvh/lbvh/bvh.cuh:277-474,
+    // src/app/lsi_lbvh.h:83-96); here: device times of the build and of every query kernel
+    std::cerr << "Total tests: " << cand << std::endl;
+    std::cerr << "Build Index (device): " << build_ms << " ms" << std::endl;
+    double st[4] = {0, 0, 0, 0};
+    int layout = 0;
+    ok(rjb_last_stage_ms(ctx, st, &layout), "rjb_last_stage_ms");
+    static const char* names[5][4] = {{"all-pairs kernel", "point pass", "", ""},
+                                      {"k_lsi_filter", "k_lsi_bvh", "k_lsi_exact", "k_lsi_points"},
+                                      {"", "", "", ""},
+                                      {"k_grid_lsi_filter", "k_grid_lsi_exact", "k_lsi_points", ""},
+                                      {"ordering", "query kernel", "", ""}};
+    for (int k = 0; k < 4; k++)
+      if (layout >= 0 && layout <= 4 && names[layout][k][0])
+        std::cerr << " - " << names[layout][k] << ": " << st[k] << " ms" << std::endl;
+    uint64_t stats[8];
+    ok(rjb_last_stats(ctx, stats), "rjb_last_stats");
+    if (mode == RJB_MODE_LBVH)
+      std::cerr << " - filter survivors: " << stats[7] << ", (query edge, leaf) pairs: " << stats[2] << std::endl;
+    uint64_t info[4];
+    ok(rjb_index_info(ctx, 0, mode, info), "rjb_index_info");
+    std::cerr << " - index: " << info[0] << (mode == RJB_MODE_LBVH ? " leaves, " : " edge-cell incidences, ")
+              << info[1] / 1048576.0 << " MiB" << std::endl;
+  }
   std::vector<rjb_xsect> res;
   if (!f.s("output").empty() || (f.b("check") && mode != RJB_MODE_GRID)) res = fetch_xsects(ctx, d, n);
   if (!f.s("output").empty()) {
