@@ -434,6 +434,12 @@ def main():
     ap.add_argument("--filter", type=int, default=-1, help="occupancy pre-filter: -1 auto, 0 off, 1 on")
     ap.add_argument("--cells", type=int, default=0, help="experimental cell-directory candidate path (option lsi_cells)")
     ap.add_argument("--stage-timing", type=int, default=1, help="CUDA event after every kernel of the query")
+    ap.add_argument("--ag", type=int, default=0, help="adaptive leaf grouping (option lbvh_ag)")
+    ap.add_argument("--ag-iter", type=int, default=5)
+    ap.add_argument("--enlarge", type=float, default=3.5)
+    ap.add_argument("--share-chains", type=float, default=0.0,
+                    help="append copies of this fraction of R's chains (every 2nd vertex) to S: shared "
+                         "vertices and near-collinear edges (experiments only)")
     ap.add_argument("--legs", default="", help="lsi,pip,overlay (default: all at N = 1, lsi at N > 1)")
     ap.add_argument("--pip-modes", default="lbvh,grid")
     ap.add_argument("--pip-grid-size", type=int, default=16384)
@@ -477,6 +483,8 @@ def main():
     t0 = time.time()
     R = get_map("R", 1, args.scale)
     S = get_map("S", 2 + rank, args.scale)
+    if args.share_chains > 0:
+        S = synth.share_chains(R, S, frac=args.share_chains, seed=3)
     bbox = synth.US_BBOX  # same scaling on every rank
     log("[rank %d] maps ready in %.1fs: R %d edges / %d chains, S %d edges / %d chains; host cores of this rank: %s"
         % (rank, time.time() - t0, R.n_edges, R.n_chains, S.n_edges, S.n_chains, n_cores))
@@ -489,6 +497,9 @@ def main():
     ctx.set_option("lsi_filter", args.filter)
     ctx.set_option("lsi_cells", args.cells)
     ctx.set_option("stage_timing", args.stage_timing)
+    ctx.set_option("lbvh_ag", args.ag)
+    ctx.set_option("lbvh_ag_iter", args.ag_iter)
+    ctx.set_option("lbvh_enlarge_x1000", int(args.enlarge * 1000))
     ctx.set_bounding_box(*bbox)
     ctx.set_map(0, R)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -676,6 +687,7 @@ def main():
             "vs_baseline": None, "dtype": "int64/int128", "data": "synthetic",
             "config": cfg,
             "engine": {"mode": args.mode, "lbvh_leaf_size": args.leaf_size, "sort_queries": args.sort_queries,
+                       "lbvh_ag": args.ag, "share_chains": args.share_chains,
                        "timing": "CUDA events on the launch stream around the enqueued query (rjb_lsi_launch); "
                                  "max over ranks of the sum of the K step times + the count exchange",
                        "l2": "256 MiB flush write between timed iterations; inputs (S descriptors + survivors' "

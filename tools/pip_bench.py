@@ -19,7 +19,7 @@ ap.add_argument("--modes", default="lbvh,grid")
 ap.add_argument("--grid-size", type=int, default=8192)
 ap.add_argument("--sort", default="0,1")  # PIP: points are ordered only on request
 ap.add_argument("--repeat", type=int, default=3)
-ap.add_argument("--check", type=int, default=200_000)
+ap.add_argument("--check", type=int, default=200_000, help="points checked against the oracle (-1: all of them)")
 ap.add_argument("--stats", type=int, default=0)
 ap.add_argument("--park", default="0", help="option pip_park values to run (A/B), e.g. 0,1")
 args = ap.parse_args()
@@ -72,12 +72,17 @@ for mode in args.modes.split(","):
                                      "lane_leaf": st[5] / w, "max_stack": st[7], "cand_per_point": st[1] / args.points}
             ctx.set_option("stats", 0)
         if args.check:
-            n = min(args.check, args.points)
+            n = args.points if args.check < 0 else min(args.check, args.points)
             eids = ctx.copy_to_host(de, np.empty(args.points, np.uint32))[:n]
             if om_pts is None:
                 om_pts = O.scale_points(sc, R.xy); om_p1, _ = O.build_edges(R.row_index)
+                O.set_num_threads(len(os.sched_getaffinity(0)))
+                t_or = time.perf_counter()
                 want = O.pip_grid(om_pts, om_p1, sc, pts[:n].cpu().numpy(), 1)
-            out["parity_vs_oracle_sample"] = "bit-exact" if np.array_equal(eids, want) else "MISMATCH (%d)" % int((eids != want).sum())
+                t_or = time.perf_counter() - t_or
+            out["oracle_s_%dcores" % O.num_threads()] = t_or
+            out["points_checked"] = n
+            out["parity_vs_oracle"] = "bit-exact" if np.array_equal(eids, want) else "MISMATCH (%d)" % int((eids != want).sum())
             out["hit_fraction"] = float((eids != 0xFFFFFFFF).mean())
         print(json.dumps(out), flush=True)
 ctx.close()
