@@ -432,7 +432,8 @@ def main():
     ap.add_argument("--leaf-size", type=int, default=4)
     ap.add_argument("--sort-queries", type=int, default=-1)
     ap.add_argument("--filter", type=int, default=-1, help="occupancy pre-filter: -1 auto, 0 off, 1 on")
-    ap.add_argument("--cells", type=int, default=0, help="experimental cell-directory candidate path (option lsi_cells)")
+    ap.add_argument("--cells", type=int, default=0, help="cell-directory candidate path for the filter's survivors (option lsi_cells)")
+    ap.add_argument("--tile-filter", type=int, default=1, help="two-level occupancy filter (option lsi_tile_filter)")
     ap.add_argument("--stage-timing", type=int, default=1, help="CUDA event after every kernel of the query")
     ap.add_argument("--ag", type=int, default=0, help="adaptive leaf grouping (option lbvh_ag)")
     ap.add_argument("--ag-iter", type=int, default=5)
@@ -496,6 +497,7 @@ def main():
     ctx.set_option("sort_queries", args.sort_queries)
     ctx.set_option("lsi_filter", args.filter)
     ctx.set_option("lsi_cells", args.cells)
+    ctx.set_option("lsi_tile_filter", args.tile_filter)
     ctx.set_option("stage_timing", args.stage_timing)
     ctx.set_option("lbvh_ag", args.ag)
     ctx.set_option("lbvh_ag_iter", args.ag_iter)

@@ -24,7 +24,7 @@ struct DeviceMap {
   uint32_t n_points = 0, n_edges = 0, n_chains = 0;
   DBuf<double2> raw;
   DBuf<longlong2> pts;
-  DBuf<uint32_t> edge_chain, point_chain, edge_desc, row_index, last_bits;
+  DBuf<uint32_t> edge_chain, point_chain, edge_desc, tile_desc, row_index, last_bits;
   // Morton order of the map's edges as query start points (maps of short chains): computed
   // by the first query that wants it, reused until the map is replaced
   DBuf<uint32_t> edge_order;
@@ -51,6 +51,7 @@ struct DeviceMap {
     v.edge_chain = edge_chain.p;
     v.point_chain = point_chain.p;
     v.edge_desc = edge_desc.p;
+    v.tile_desc = tile_desc.p;
     v.row_index = row_index.p;
     v.last_bits = last_bits.p;
     v.left = left.p;
@@ -93,7 +94,7 @@ struct LsiPending {
   int q = 0, mode = 0, attempt = 0;
   double xsect_factor = 0;
   uint32_t cap = 0, ccap = 0, n_slots = 0;
-  bool lbvh = false, grid = false, filter = false, cells = false;
+  bool lbvh = false, grid = false, filter = false, cells = false, fused = false;
   unsigned launches = 0;  // kernels this attempt put on the stream
 };
 
@@ -103,7 +104,11 @@ struct rjb_ctx {
   // map upload pipeline: the copy runs on `stream`, the per-chunk load kernel on `aux`
   cudaStream_t aux = nullptr;
   cudaEvent_t chunk_ev[kLoadChunksMax + 1] = {};
-  unsigned long long* h_counters = nullptr;  // pinned: the counts a query reads back
+  unsigned long long* h_counters = nullptr;  // pinned + mapped: the counts a query reads back
+  unsigned long long* d_h_counters = nullptr;  // the same buffer as the device sees it
+  DBuf<unsigned int> lsi_ticket;             // k_lsi_resolve: CTAs that have finished (zero between queries)
+  bool ctr_clean = false;                    // the device counters are zero (left so by k_lsi_resolve)
+  int fused = 1;                             // LBVH LSI: exact + point pass in one kernel (option lsi_fused)
   bool have_scaling = false;
   rjb_scaling sc;
   DeviceMap maps[2];
@@ -128,6 +133,7 @@ struct rjb_ctx {
   uint32_t last_survivors = 0, last_long = 0;
   DBuf<uint32_t> long_edges;  // survivors longer than a cell (tree walk)
   uint32_t load_chunk = kLoadChunkPoints;  // points per upload chunk (option load_chunk_points)
+  int tile_filter = 1;    // LSI: two-level occupancy filter (tiles of 32 edges first)
   int use_cells = 0;      // LSI: cell directory for the filter's survivors (experimental, off)
   size_t cand_cap = 0;
   size_t grid_work_cap = 0;
@@ -198,8 +204,9 @@ __global__ void __launch_bounds__(256)
 k_load_points(const double2* __restrict__ in, uint32_t p_begin, uint32_t p_end, uint32_t n_points,
               double rx, double ry, double dx, double dy, const uint32_t* __restrict__ row_index,
               uint32_t n_chains, const uint32_t* __restrict__ block_chain, longlong2* __restrict__ out,
-              uint32_t* __restrict__ edge_desc, uint32_t* __restrict__ point_chain,
-              uint32_t* __restrict__ edge_chain, uint32_t* __restrict__ last_bits) {
+              uint32_t* __restrict__ edge_desc, uint32_t* __restrict__ tile_desc,
+              uint32_t* __restrict__ point_chain, uint32_t* __restrict__ edge_chain,
+              uint32_t* __restrict__ last_bits) {
   __shared__ uint32_t s_ri[258];
   const uint32_t pb0 = p_begin + blockIdx.x * 256;
   const uint32_t p = pb0 + threadIdx.x;
@@ -239,6 +246,8 @@ k_load_points(const double2* __restrict__ in, uint32_t p_begin, uint32_t p_end, 
   longlong2 q;  // vertex p - 1
   q.x = __shfl_up_sync(0xffffffffu, o.x, 1);
   q.y = __shfl_up_sync(0xffffffffu, o.y, 1);
+  // cell box of the edge ending at p (empty when there is none), for the tile descriptor
+  uint32_t bx0 = 0xFFFFFFFFu, by0 = 0xFFFFFFFFu, bx1 = 0, by1 = 0;
   if (p < p_end && p > 0) {
     uint32_t d = kDescNone << 24;
     if (!first) {
@@ -247,11 +256,23 @@ k_load_points(const double2* __restrict__ in, uint32_t p_begin, uint32_t p_end, 
         q.x = (long long) fma(v.x, rx, dx);
         q.y = (long long) fma(v.y, ry, dy);
       }
-      d = edge_desc_of(occ_code(q.x, q.y), occ_code(o.x, o.y));
+      const uint32_t c1 = occ_code(q.x, q.y), c2 = occ_code(o.x, o.y);
+      d = edge_desc_of(c1, c2);
+      const uint32_t x1 = c1 & (kOccDim - 1), x2 = c2 & (kOccDim - 1), y1 = c1 >> kOccBits, y2 = c2 >> kOccBits;
+      bx0 = min(x1, x2); bx1 = max(x1, x2);
+      by0 = min(y1, y2); by1 = max(y1, y2);
     }
     edge_desc[p - 1] = d;
   }
   if (p == n_points - 1) edge_desc[p] = kDescNone << 24;
+  // tile descriptor of the warp's 32 points (tile_desc_of): one word per warp
+  const bool any_edge = __any_sync(0xffffffffu, bx0 != 0xFFFFFFFFu);
+  bx0 = __reduce_min_sync(0xffffffffu, bx0);
+  by0 = __reduce_min_sync(0xffffffffu, by0);
+  bx1 = __reduce_max_sync(0xffffffffu, bx1);
+  by1 = __reduce_max_sync(0xffffffffu, by1);
+  if (lane == 0 && p < p_end) tile_desc[p >> 5] = any_edge ? tile_desc_of(bx0, by0, bx1, by1) : (kTileNone << 24);
+  if (p == n_points - 1) tile_desc[(p >> 5) + 1] = kTileNone << 24;  // the tile after the last one is read too
 }
 
 // scaling alone (query points of rjb_pip_host): fma.rn.f64 then cvt.rzi.s64.f64
@@ -353,7 +374,12 @@ static void ensure_load_pipeline(rjb_ctx* c) {
 }
 
 static void ensure_events(rjb_ctx* c) {
-  if (!c->h_counters) RJB_CUDA(cudaHostAlloc((void**) &c->h_counters, 128 * sizeof(unsigned long long), cudaHostAllocDefault));
+  if (!c->h_counters) {
+    RJB_CUDA(cudaHostAlloc((void**) &c->h_counters, 128 * sizeof(unsigned long long), cudaHostAllocMapped));
+    RJB_CUDA(cudaHostGetDevicePointer((void**) &c->d_h_counters, c->h_counters, 0));
+    unsigned int* t = c->lsi_ticket.ensure(1);
+    RJB_CUDA(cudaMemsetAsync(t, 0, sizeof(unsigned int), c->stream));
+  }
   for (int i = 0; i <= kTimedStages; i++)
     if (!c->ev[i]) RJB_CUDA(cudaEventCreate(&c->ev[i]));
   for (int i = 0; i < 2; i++)
@@ -406,6 +432,7 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
   // [8], [9]: {filter survivors, (query, leaf) pairs, long survivors} as 32-bit counters
   unsigned long long* ctr = c->counters.ensure(128);
   ensure_events(c);
+  if (!(mode == RJB_MODE_LBVH && c->fused && !c->stats)) c->ctr_clean = false;  // the other paths leave their counts
   MapView Q = Qm.view(), B = Bm.view();
   LsiPending& P = c->lsi_pending;
   const int attempt = P.active ? P.attempt : 0;  // a retry keeps its attempt number
@@ -441,12 +468,15 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     // [0] survivors, [1] (query, leaf) pairs, [2] survivors that are longer than a cell
     unsigned int* surv_n = (unsigned int*) (ctr + 8);
     // cell directory instead of the tree walk for the survivors (option lsi_cells)
-    const bool cells = filter && Bm.bvh.have_cells && c->use_cells > 0 && !c->stats;
+    const bool cells = filter && Bm.bvh.have_cells && c->use_cells > 0 && !c->stats && Q.n_points < (1u << kDirectShift);
     uint32_t* long_list = cells ? c->long_edges.ensure(Q.n_points) : nullptr;
     RJB_REQUIRE(c->cand_cap < 0xFFFFFFF0ull, "rjb_lsi: candidate queue exceeds 2^32 entries");
     const uint32_t ccap = (uint32_t) c->cand_cap;
     uint2* cands = c->cands.ensure(ccap);
-    RJB_CUDA(cudaMemsetAsync(ctr, 0, 10 * sizeof(unsigned long long), c->stream));
+    // fused exact + point pass: its last CTA hands the counters to the host and zeroes them
+    const bool fused = c->fused && !c->stats;
+    if (!(fused && c->ctr_clean)) RJB_CUDA(cudaMemsetAsync(ctr, 0, 10 * sizeof(unsigned long long), c->stream));
+    c->ctr_clean = false;  // until lsi_finish has seen this query complete
     RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
     // query slots: point indices (edge = slot, slot + 1), or a list of start points
     // (Morton-sorted edges, or the survivors of the occupancy filter, whose count
@@ -456,8 +486,12 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     const uint32_t* slots = order;
     const unsigned int* n_slots_dev = nullptr;
     if (filter) {
-      k_lsi_filter<<<div_up(p_hi - (p_lo & ~31u), kFilterCtaPoints), kFilterThreads, 0, c->stream>>>(
-          Q, p_lo, p_hi, Bm.bvh.occ.p, surv, surv_n, long_list, surv_n + 2);
+      if (c->tile_filter)
+        k_lsi_filter_tiles<<<div_up(p_hi / 32 - p_lo / 32 + 1, kTfCtaTiles), kTfWarps * 32, 0, c->stream>>>(
+            Q, p_lo, p_hi, Bm.bvh.occ.p, surv, surv_n, long_list, surv_n + 2);
+      else
+        k_lsi_filter<<<div_up(p_hi - (p_lo & ~31u), kFilterCtaPoints), kFilterThreads, 0, c->stream>>>(
+            Q, p_lo, p_hi, Bm.bvh.occ.p, surv, surv_n, long_list, surv_n + 2);
       slots = surv;
       n_slots_dev = surv_n;
       slot_lo = 0;
@@ -482,23 +516,39 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
       // nothing to walk (no long edges last time; a non-empty list triggers the retry in lsi_finish)
     } else if (c->stats)
       k_lsi_bvh<true><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-          Q, B, Bm.bvh.view(), slots, n_slots, slot_lo, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
+          Q, B, Bm.bvh.view(), slots, n_slots, slot_lo, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2, cells);
     else
       k_lsi_bvh<false><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
-          Q, B, Bm.bvh.view(), slots, n_slots, slot_lo, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2);
+          Q, B, Bm.bvh.view(), slots, n_slots, slot_lo, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2, cells);
     RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
-    k_lsi_exact<<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
-                                                   xs, cap, (unsigned int*) ctr, ctr + 1);
-    if (c->stage_timing) RJB_CUDA(cudaEventRecord(c->ev[3], c->stream));
-    k_lsi_points<<<kNumSMs * 3, kPointsThreads, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs, false);
+    if (fused) {
+      const LsiTail tail = {ctr, c->d_h_counters, c->lsi_ticket.p};
+      if (cells)  // pairs in the direct format of the cell directory
+        k_lsi_resolve<true><<<kNumSMs * 3, kExactThreads, 0, c->stream>>>(Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1,
+                                                                         ccap, xs, cap, (unsigned int*) ctr, ctr + 1, tail);
+      else
+        k_lsi_resolve<false><<<kNumSMs * 3, kExactThreads, 0, c->stream>>>(Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1,
+                                                                          ccap, xs, cap, (unsigned int*) ctr, ctr + 1, tail);
+      if (c->stage_timing) RJB_CUDA(cudaEventRecord(c->ev[3], c->stream));
+    } else {
+      if (cells)  // pairs in the direct format of the cell directory
+        k_lsi_exact<true><<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
+                                                                       xs, cap, (unsigned int*) ctr, ctr + 1);
+      else
+        k_lsi_exact<false><<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
+                                                                        xs, cap, (unsigned int*) ctr, ctr + 1);
+      if (c->stage_timing) RJB_CUDA(cudaEventRecord(c->ev[3], c->stream));
+      k_lsi_points<<<kNumSMs * 3, kPointsThreads, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs, false);
+    }
     RJB_CUDA(cudaEventRecord(c->ev[4], c->stream));
     RJB_CUDA(cudaGetLastError());
     P.lbvh = true;
+    P.fused = fused;
     P.filter = filter;
     P.cells = cells;
     P.ccap = ccap;
     P.n_slots = n_slots;
-    P.launches = 3 + (filter ? 1 : 0) + (cells ? 1 : 0) - (blocks == 0 ? 1 : 0);
+    P.launches = (fused ? 2 : 3) + (filter ? 1 : 0) + (cells ? 1 : 0) - (blocks == 0 ? 1 : 0);
     c->timing_pending = 4;
     c->timing_layout = c->stage_timing ? 1 : 2;
   } else if (mode == RJB_MODE_GRID && nonempty) {
@@ -558,9 +608,11 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     c->timing_pending = 2;  // event times are fetched when rjb_last_kernel_ms asks for them
     c->timing_layout = 0;
   }
-  // one read-back into pinned memory: the only host round trip of the query
-  RJB_CUDA(cudaMemcpyAsync(c->h_counters, ctr, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                           c->stream));
+  // one read-back into pinned memory: the only host round trip of the query (the fused LBVH
+  // pipeline writes it from its last kernel)
+  if (!P.fused)
+    RJB_CUDA(cudaMemcpyAsync(c->h_counters, ctr, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             c->stream));
   P.active = true;
 }
 
@@ -578,6 +630,7 @@ static uint64_t lsi_finish(rjb_ctx* c, uint64_t* n_candidates) {
       throw;
     }
     launches += P.launches;
+    if (P.fused) c->ctr_clean = true;  // zeroed by the last CTA of k_lsi_resolve
     memcpy(h, c->h_counters, sizeof(h));
     unsigned int hs[4];
     memcpy(hs, c->h_counters + 8, sizeof(hs));
@@ -680,6 +733,7 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
   constexpr int kPipCtrs = 16 + kCtrSlots;
   unsigned long long* ctr = c->counters.ensure(kPipCtrs);
   ensure_events(c);
+  c->ctr_clean = false;
   RJB_CUDA(cudaMemsetAsync(ctr, 0, kPipCtrs * sizeof(unsigned long long), c->stream));
   MapView B = Bm.view();
   if (mode == RJB_MODE_LBVH && !Bm.bvh.built) throw Error(RJB_ERR_NO_INDEX, "rjb_pip: no LBVH on the base map");
@@ -861,6 +915,10 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
       c->load_chunk = (uint32_t) value;
     } else if (n == "lsi_cells") {
       c->use_cells = (int) value;
+    } else if (n == "lsi_tile_filter") {
+      c->tile_filter = value != 0;
+    } else if (n == "lsi_fused") {
+      c->fused = value != 0;
     } else if (n == "pip_park") {
       c->pip_park = value != 0;
     } else if (n == "stage_timing") {
@@ -940,6 +998,7 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
     uint32_t* pc = m.point_chain.ensure(n_points ? n_points : 1);
     // padded with "no edge" (0xFF bytes: class bits = kDescNone): the filter reads 16 per thread
     uint32_t* cc = m.edge_desc.ensure(n_points + 16);
+    uint32_t* td = m.tile_desc.ensure(n_points / 32 + 2);
     uint32_t n_words = (uint32_t) (n_points / 32 + 2);
     uint32_t* lb = m.last_bits.ensure(n_words);
     uint32_t* bc = m.block_chain.ensure(n_blocks ? n_blocks : 1);
@@ -968,7 +1027,7 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
         RJB_CUDA(cudaStreamWaitEvent(c->aux, c->chunk_ev[k], 0));
         k_load_points<<<div_up(p1 - p0, 256), 256, 0, c->aux>>>(
             raw, (uint32_t) p0, p1, m.n_points, c->sc.rx, c->sc.ry, c->sc.deltax, c->sc.deltay, ri,
-            m.n_chains, bc, pts, cc, pc, ec, lb);
+            m.n_chains, bc, pts, cc, td, pc, ec, lb);
       }
       RJB_CUDA(cudaGetLastError());
       RJB_CUDA(cudaEventRecord(c->chunk_ev[kLoadChunksMax], c->aux));

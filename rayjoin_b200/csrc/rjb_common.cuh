@@ -42,6 +42,7 @@ struct MapView {
   const uint32_t* edge_chain;  // per edge: eid -> chain (start point = eid + chain)
   const uint32_t* point_chain; // per point: p -> chain (eid of the edge starting at p = p - chain)
   const uint32_t* edge_desc;   // per point: occupancy descriptor of the edge starting there (edge_desc_of)
+  const uint32_t* tile_desc;   // per 32 points: cell box of the edges ENDING at them (tile_desc_of)
   const uint32_t* row_index;   // per chain, CSR into pts
   const uint32_t* last_bits;   // bit p set <=> point p is the last of its chain (no edge starts there)
   const int32_t* left;         // per chain
@@ -66,15 +67,15 @@ struct BvhView {
   // edge whose box touches no occupied cell cannot intersect anything.  Followed by the
   // dilated bitmap occ2 (bit (x, y) = OR of occ over {x, x+1} x {y, y+1}), see edge_desc_of.
   const uint32_t* occ;
-  // Cell directory over the OCCUPIED cells (sparse base maps only, else nullptr): cell id =
-  // occ_rank[word] + popcount of the lower bits of the word; the leaves whose box touches
-  // cell id are cell_leaf[cell_begin[id] .. cell_begin[id + 1]).  leaf_box = the quantised
-  // leaf boxes in leaf order.  A short query edge finds its candidate leaves with three
-  // dependent loads instead of a tree walk (k_lsi_cells).
-  const uint32_t* occ_rank;
+  // Cell directory over the OCCUPIED cells (sparse base maps only, else nullptr): occ_dir[word]
+  // = {bitmap word, occupied cells before it}, cell id = rank + popcount of the lower bits; the
+  // leaves whose box touches cell id are cell_item[cell_begin[id] .. cell_begin[id + 1]), each
+  // item = the leaf's quantised box clipped to the cell + its first point and edge count
+  // (cell_item_of).  A short query edge finds its candidate leaves with three dependent loads
+  // and no tree walk (k_lsi_cells).
+  const uint2* occ_dir;
   const uint32_t* cell_begin;
-  const uint32_t* cell_leaf;
-  const int4* leaf_box;
+  const uint4* cell_item;
   int top_levels;          // 3, or 4 for big trees (>= 2^18 leaves): depth 20 resolved in 4 steps
   int4 root_box;
   uint32_t n_leaves;
@@ -117,6 +118,77 @@ static __host__ __device__ __forceinline__ uint32_t edge_desc_of(uint32_t c1, ui
   const uint32_t cls = (ex | ey) == 0 ? kDescSame : (ex <= 1 && ey <= 1) ? kDescSmall : kDescBig;
   return (cls << 24) | (ym << kOccBits) | xm;
 }
+
+// Tile descriptor: the union of the cell boxes of the 32 edges that END at points 32 t .. 32 t + 31
+// (= the edges STARTING at points 32 t - 1 .. 32 t + 30, whose descriptors are
+// edge_desc[32 t - 1 .. 32 t + 30]).  k_lsi_filter_tiles decides a whole tile with ONE look-up
+// in a bitmap dilated to the size of the box, and reads the 32 edge descriptors only of the
+// tiles that survive:
+//   bits 0..23  code of the min corner cell of the box
+//   bits 24..26 class: kTileNone no edge; 1..4 box within 1 / 2 x 2 / 4 x 4 / 8 x 8 cells at the
+//               min corner -> bitmap (class - 1) of the four {occ, occ2, occ4, occ8}, where
+//               occK(x, y) = OR of occ over [x, x + K) x [y, y + K);  kTileBig larger: kept
+constexpr uint32_t kTileNone = 0, kTileBig = 5;
+constexpr int kOccMaps = 4;  // occ, occ2, occ4, occ8: one array, kOccWords words apart
+
+static __host__ __device__ __forceinline__ uint32_t tile_desc_of(uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) {
+  const uint32_t e = (x1 - x0) > (y1 - y0) ? (x1 - x0) : (y1 - y0);
+  const uint32_t cls = e == 0 ? 1u : e <= 1 ? 2u : e <= 3 ? 3u : e <= 7 ? 4u : kTileBig;
+  return (cls << 24) | (y0 << kOccBits) | x0;
+}
+
+// Cell directory items.  Inside ONE cell the quantised coordinates of a box need kOccShift = 19
+// bits each once they are clipped to the cell, so a leaf box, "starts left of / below the cell"
+// flags, the leaf's edge count and its first point fit one 16-byte record:
+//   x = x0 | x1[0..12] << 19      y = y0 | y1[0..12] << 19
+//   z = x1[13..18] | y1[13..18] << 6 | starts_left << 12 | starts_below << 13 | (count - 1) << 14
+//   w = first point of the leaf (eid + chain of its first edge)
+// Two boxes that both touch cell (cx, cy) overlap iff their clipped boxes do (clipping is
+// monotone, and where they do not overlap the separating coordinates lie inside the cell).
+static __host__ __device__ __forceinline__ uint32_t cell_rel(int q, int c) {
+  const long long r = (long long) ((unsigned) q + (1u << 30)) - ((long long) c << kOccShift);
+  const long long hi = (1ll << kOccShift) - 1;
+  return (uint32_t) (r < 0 ? 0 : (r > hi ? hi : r));
+}
+
+struct CellBoxQ {
+  uint32_t x0, y0, x1, y1;
+  bool left, below;  // the box starts left of / below the cell
+};
+
+static __host__ __device__ __forceinline__ CellBoxQ cell_clip(const int4& b, int cx, int cy) {
+  CellBoxQ r;
+  r.x0 = cell_rel(b.x, cx); r.y0 = cell_rel(b.y, cy);
+  r.x1 = cell_rel(b.z, cx); r.y1 = cell_rel(b.w, cy);
+  r.left = occ_cell(b.x) < cx;
+  r.below = occ_cell(b.y) < cy;
+  return r;
+}
+
+static __host__ __device__ __forceinline__ uint4 cell_item_of(const int4& b, int cx, int cy, uint32_t first_point,
+                                                              uint32_t count) {
+  const CellBoxQ r = cell_clip(b, cx, cy);
+  return make_uint4(r.x0 | (r.x1 << 19), r.y0 | (r.y1 << 19),
+                    (r.x1 >> 13) | ((r.y1 >> 13) << 6) | ((r.left ? 1u : 0u) << 12) | ((r.below ? 1u : 0u) << 13) |
+                        ((count - 1) << 14),
+                    first_point);
+}
+
+// item x query box (clipped to the same cell): boxes overlap, and this is the cell that reports
+// the pair -- the one holding the min corner of the intersection of the two cell boxes, i.e. not
+// both boxes start left of it and not both below it
+static __host__ __device__ __forceinline__ bool cell_item_hit(const uint4& it, const CellBoxQ& q) {
+  const uint32_t m19 = (1u << 19) - 1;
+  const uint32_t ix0 = it.x & m19, iy0 = it.y & m19;
+  const uint32_t ix1 = (it.x >> 19) | ((it.z & 63u) << 13), iy1 = (it.y >> 19) | (((it.z >> 6) & 63u) << 13);
+  const bool il = (it.z >> 12) & 1u, ib = (it.z >> 13) & 1u;
+  return ix0 <= q.x1 && q.x0 <= ix1 && iy0 <= q.y1 && q.y0 <= iy1 && !(il && q.left) && !(ib && q.below);
+}
+
+// (query, leaf) pairs handed to the exact pass come in two formats: {query start point, leaf id}
+// from the tree walk, or DIRECT {query start point | (count - 1) << 29, first point of the leaf}
+// from the cell directory (no leaf record to look up; maps of < 2^29 points)
+constexpr uint32_t kDirectShift = 29;
 
 constexpr int kTopOff0 = 0, kTopOff1 = 32, kTopOff2 = 32 + 1024, kTopOff3 = 32 + 1024 + 32768;
 constexpr int kTopSlots3 = kTopOff3, kTopSlots4 = kTopOff3 + 32 * 32768;

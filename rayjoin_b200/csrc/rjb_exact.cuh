@@ -233,16 +233,24 @@ static __host__ __device__ long long lsi_point_axis(const Seg& e1, const Seg& e2
       *deferred = true;
       return 0;
     }
-    // gcd(num, den) = gcd(num - t*den, den) for any integer t: the binary gcd starts
-    // from ~2k-bit operands instead of a ~110-bit numerator
-    const i128 c1 = -(i128) e1.x1 * a1 - (i128) e1.y1 * b1;
-    const i128 c2 = -(i128) e2.x1 * a2 - (i128) e2.y1 * b2;
-    const i128 num = axis == 0 ? (i128) ((u128) c2 * (u128) b1 - (u128) c1 * (u128) b2)
-                               : (i128) ((u128) a2 * (u128) c1 - (u128) a1 * (u128) c2);
-    const i128 g = gcd128(r, denom);
-    const i128 sn = denom < 0 ? -num : num;
-    rn = g == 1 ? sn : sn / g;
-    rd = g == 1 ? aden : aden / g;
+    // gcd(num, den) = gcd(num - t*den, den) for any integer t: the binary gcd starts from
+    // ~2k-bit operands instead of a ~110-bit numerator.  The reduced rational follows from
+    // x = X0 + rs/aden without dividing that numerator either: num/g = X0 * (aden/g) + rs/g
+    // (exact: g divides rs and aden), two 64-bit divisions when aden fits 64 bits -- it does
+    // unless both edges span more than 2^31 units -- instead of two software 128-bit ones.
+    const i128 g = gcd128(rs, aden);
+    if (g == 1) {
+      rd = aden;
+      rn = (i128) X0 * aden + rs;
+    } else if ((aden >> 64) == 0) {
+      const unsigned long long g64 = (unsigned long long) g;
+      const unsigned long long rd64 = (unsigned long long) aden / g64;
+      rd = (i128) (u128) rd64;
+      rn = (i128) X0 * (i128) (u128) rd64 + (i128) (u128) ((unsigned long long) rs / g64);
+    } else {
+      rd = aden / g;
+      rn = (i128) X0 * rd + rs / g;
+    }
   } else {
     if (kDefer) {
       *deferred = true;

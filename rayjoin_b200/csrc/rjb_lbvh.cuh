@@ -32,7 +32,9 @@ struct Bvh {
   DBuf<int4> root_box_d;
   DBuf<int4> top_box;
   DBuf<int> top_code;
-  DBuf<uint32_t> occ, occ_pop, occ_rank, cell_cnt, cell_begin, cell_leaf;
+  DBuf<uint32_t> occ, occ_pop, occ_rank, cell_cnt, cell_begin;
+  DBuf<uint2> occ_dir;
+  DBuf<uint4> cell_item;
   DBuf<unsigned long long> inc_counter;
   bool have_cells = false;
   uint32_t n_occ_cells = 0, n_incidences = 0;
@@ -51,10 +53,9 @@ struct Bvh {
     v.top_box = top_box.p;
     v.top_code = top_code.p;
     v.occ = occ.p;
-    v.occ_rank = have_cells ? occ_rank.p : nullptr;
+    v.occ_dir = have_cells ? occ_dir.p : nullptr;
     v.cell_begin = cell_begin.p;
-    v.cell_leaf = cell_leaf.p;
-    v.leaf_box = leaf_box_s.p;
+    v.cell_item = cell_item.p;
     v.top_levels = top_levels;
     return v;
   }
@@ -62,9 +63,9 @@ struct Bvh {
     uint32_t n_int = n_leaves > 1 ? n_leaves - 1 : 1;
     return (size_t) n_int * (2 * sizeof(int4) + sizeof(int2)) + (size_t) n_leaves * sizeof(uint2) +
            (size_t) (top_levels == 4 ? kTopSlots4 : kTopSlots3) * (sizeof(int4) + sizeof(int)) +
-           2 * (size_t) kOccDim * kOccDim / 8 +
-           (have_cells ? (size_t) (kOccWords + 1) * 4 + (size_t) (n_occ_cells + 1) * 4 +
-                             (size_t) n_incidences * 4 + (size_t) n_leaves * sizeof(int4) : 0);
+           (size_t) kOccMaps * kOccDim * kOccDim / 8 +
+           (have_cells ? (size_t) (kOccWords + 1) * sizeof(uint2) + (size_t) (n_occ_cells + 1) * 4 +
+                             (size_t) n_incidences * sizeof(uint4) : 0);
   }
 };
 
@@ -471,33 +472,49 @@ static __device__ __forceinline__ uint32_t occ_cell_id(const uint32_t* __restric
   return __ldg(&rank[bit >> 5]) + __popc(__ldg(&occ[bit >> 5]) & ((1u << (bit & 31)) - 1));
 }
 
-// cell directory, pass 1 (fill == false): leaves per occupied cell; pass 2: the lists
+// cell directory, pass 1 (fill == false): leaves per occupied cell; pass 2: the item records
 template <bool kFill>
-__global__ void k_cell_lists(const int4* __restrict__ leaf_box, uint32_t n, const uint32_t* __restrict__ occ,
-                             const uint32_t* __restrict__ rank, uint32_t* __restrict__ cnt,
-                             const uint32_t* __restrict__ begin, uint32_t* __restrict__ cell_leaf) {
+__global__ void k_cell_lists(const int4* __restrict__ leaf_box, const uint2* __restrict__ leaf_rec, uint32_t n,
+                             const uint32_t* __restrict__ occ, const uint32_t* __restrict__ rank,
+                             uint32_t* __restrict__ cnt, const uint32_t* __restrict__ begin,
+                             uint4* __restrict__ cell_item) {
   const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= n) return;
   const int4 b = leaf_box[l];
+  uint32_t first_point = 0, count = 1;
+  if (kFill) {
+    const uint2 rec = leaf_rec[l];
+    first_point = rec.x + (rec.y & 0x0FFFFFFFu);
+    count = rec.y >> 28;
+  }
   const int x0 = occ_cell(b.x), x1 = occ_cell(b.z), y0 = occ_cell(b.y), y1 = occ_cell(b.w);
   for (int y = y0; y <= y1; y++)
     for (int x = x0; x <= x1; x++) {
       const uint32_t id = occ_cell_id(occ, rank, (uint32_t) y * kOccDim + x);
       const uint32_t k = atomicAdd(&cnt[id], 1u);
-      if (kFill) cell_leaf[__ldg(&begin[id]) + k] = l;
+      if (kFill) cell_item[__ldg(&begin[id]) + k] = cell_item_of(b, x, y, first_point, count);
     }
 }
 
-// occ2(x, y) = occ(x, y) | occ(x+1, y) | occ(x, y+1) | occ(x+1, y+1), one word per thread
-__global__ void k_occ_dilate(const uint32_t* __restrict__ occ, uint32_t* __restrict__ occ2) {
+// {bitmap word, rank} side by side: one 8-byte load finds a cell
+__global__ void k_occ_dir(const uint32_t* __restrict__ occ, const uint32_t* __restrict__ rank,
+                          uint2* __restrict__ dir) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w <= kOccWords) dir[w] = make_uint2(w < kOccWords ? occ[w] : 0u, rank[w]);
+}
+
+// One doubling step of the dilation: out(x, y) = in(x, y) | in(x+s, y) | in(x, y+s) | in(x+s, y+s),
+// one word per thread.  occ -> occ2 (s = 1) -> occ4 (s = 2) -> occ8 (s = 4): occK(x, y) is the OR
+// of occ over the K x K cells at (x, y), what a box of that size at that min corner can touch.
+__global__ void k_occ_dilate(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int s) {
   constexpr uint32_t kRowWords = kOccDim / 32;
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= kOccWords) return;
   const uint32_t y = w / kRowWords, wx = w % kRowWords;
-  const bool has_row = y + 1 < (uint32_t) kOccDim, has_col = wx + 1 < kRowWords;
-  const uint32_t a = occ[w] | (has_row ? occ[w + kRowWords] : 0u);
-  const uint32_t an = has_col ? (occ[w + 1] | (has_row ? occ[w + 1 + kRowWords] : 0u)) : 0u;
-  occ2[w] = a | (a >> 1) | (an << 31);
+  const bool has_row = y + s < (uint32_t) kOccDim, has_col = wx + 1 < kRowWords;
+  const uint32_t a = in[w] | (has_row ? in[w + s * kRowWords] : 0u);
+  const uint32_t an = has_col ? (in[w + 1] | (has_row ? in[w + 1 + s * kRowWords] : 0u)) : 0u;
+  out[w] = a | (a >> s) | (an << (32 - s));
 }
 
 // ag_iter > 0: adaptive leaf grouping with that many merge rounds (at most 3 take effect) and
@@ -575,14 +592,16 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, int ag_it
   k_top_tree<<<(1u << (5 * b.top_levels)) / 256, 256, 0, st>>>(nbox, nchild, root_d, n,
                                                               5 * b.top_levels, tbox, tcode);
   const uint32_t occ_words = kOccWords;
-  uint32_t* occ = b.occ.ensure(2 * occ_words);  // occ, then the dilated occ2
+  uint32_t* occ = b.occ.ensure((size_t) kOccMaps * occ_words);  // occ, then the dilated occ2, occ4, occ8
   RJB_CUDA(cudaMemsetAsync(occ, 0, occ_words * sizeof(uint32_t), st));
   // [0] (leaf, cell) incidences, [1] cells of the largest box (> 1024 only), [2] big boxes
   unsigned long long* inc = b.inc_counter.ensure(3);
   RJB_CUDA(cudaMemsetAsync(inc, 0, 3 * sizeof(unsigned long long), st));
   k_occ_mark<<<div_up(n, T), T, 0, st>>>(box_s, n, occ, inc, va /* free after the sort */);
   k_occ_mark_big<<<kNumSMs, 256, 0, st>>>(box_s, va, inc, occ);
-  k_occ_dilate<<<div_up(occ_words, T), T, 0, st>>>(occ, occ + occ_words);
+  for (int k = 1; k < kOccMaps; k++)
+    k_occ_dilate<<<div_up(occ_words, T), T, 0, st>>>(occ + (size_t) (k - 1) * occ_words, occ + (size_t) k * occ_words,
+                                                     1 << (k - 1));
   RJB_CUDA(cudaGetLastError());
   uint32_t n_occ = 0;
   unsigned long long n_inc = 0, max_area = 0;
@@ -614,12 +633,14 @@ static inline void build_lbvh(Bvh& b, const MapView& m, int leaf_size, int ag_it
     b.n_incidences = (uint32_t) n_inc;
     uint32_t* ccnt = b.cell_cnt.ensure(n_occ + 1);
     uint32_t* cbeg = b.cell_begin.ensure(n_occ + 1);
-    uint32_t* clist = b.cell_leaf.ensure(n_inc ? n_inc : 1);
+    uint4* clist = b.cell_item.ensure(n_inc ? n_inc : 1);
+    uint2* dir = b.occ_dir.ensure(occ_words + 1);
     RJB_CUDA(cudaMemsetAsync(ccnt, 0, (n_occ + 1) * sizeof(uint32_t), st));
-    k_cell_lists<false><<<div_up(n, T), T, 0, st>>>(box_s, n, occ, rank, ccnt, nullptr, nullptr);
+    k_cell_lists<false><<<div_up(n, T), T, 0, st>>>(box_s, rec_s, n, occ, rank, ccnt, nullptr, nullptr);
     exclusive_scan_u32(ccnt, cbeg, n_occ, b.scan_tmp, st);
     RJB_CUDA(cudaMemsetAsync(ccnt, 0, (n_occ + 1) * sizeof(uint32_t), st));
-    k_cell_lists<true><<<div_up(n, T), T, 0, st>>>(box_s, n, occ, rank, ccnt, cbeg, clist);
+    k_cell_lists<true><<<div_up(n, T), T, 0, st>>>(box_s, rec_s, n, occ, rank, ccnt, cbeg, clist);
+    k_occ_dir<<<div_up(occ_words + 1, T), T, 0, st>>>(occ, rank, dir);
     RJB_CUDA(cudaGetLastError());
     b.have_cells = true;
   }

@@ -69,6 +69,8 @@ struct Emit {
   uint2* __restrict__ out;
   uint32_t cap;
   unsigned int* counter;
+  // non-null: the staged pairs are {query, leaf id} and leave in the DIRECT format (kDirectShift)
+  const uint2* __restrict__ conv_leaf_rec;
 };
 
 static __device__ __forceinline__ void emit_flush(Emit& E, int lane) {
@@ -77,8 +79,14 @@ static __device__ __forceinline__ void emit_flush(Emit& E, int lane) {
   if (lane == 0) base = atomicAdd(E.counter, E.n);
   base = __shfl_sync(0xffffffffu, base, 0);
   __syncwarp();
-  for (unsigned t = lane; t < E.n; t += 32)
-    if (base + t < E.cap) E.out[base + t] = E.buf[t];
+  for (unsigned t = lane; t < E.n; t += 32) {
+    uint2 v = E.buf[t];
+    if (E.conv_leaf_rec) {
+      const uint2 rec = __ldg(&E.conv_leaf_rec[v.y]);
+      v = make_uint2(v.x | (((rec.y >> 28) - 1) << kDirectShift), rec.x + (rec.y & 0x0FFFFFFFu));
+    }
+    if (base + t < E.cap) E.out[base + t] = v;
+  }
   __syncwarp();
   E.n = 0;
 }
@@ -306,19 +314,130 @@ k_lsi_filter(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __restrict
   }
 }
 
+// Two-level variant of the filter (option lsi_tile_filter, default): a warp first decides 32
+// TILES of 32 edges each with one look-up per tile (lane = tile: tile_desc_of, bitmaps dilated
+// to the size of the tile's box), then reads the 32 edge descriptors of the live tiles only,
+// kTfBatch tiles in flight at a time.  On the County x Zipcode-scale workload 29 % of the tiles
+// are live, so the kernel moves a third of the descriptors and executes a third of the rounds.
+// Tile t = the edges starting at points 32 t - 1 .. 32 t + 30 (lane = point again in stage 2).
+// Survivors leave as one map-ordered run per CTA, like k_lsi_filter.
+constexpr int kTfWarps = 4;
+constexpr int kTfBatch = 8;
+constexpr int kTfCtaTiles = kTfWarps * 32;
+
+__global__ void __launch_bounds__(kTfWarps * 32)
+k_lsi_filter_tiles(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __restrict__ occ,
+                   uint32_t* __restrict__ survivors, unsigned int* counter, uint32_t* __restrict__ long_list,
+                   unsigned int* long_counter) {
+  __shared__ unsigned s_mask[kTfWarps][32];  // keep mask (bit = lane) of the k-th live tile of a warp
+  __shared__ unsigned s_wsum[kTfWarps];
+  __shared__ unsigned s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // tiles of the query window: start point p lies in tile (p + 1) / 32
+  const uint32_t t_last = p_hi / 32;  // tile of the last start point p_hi - 1
+  const uint32_t t0 = p_lo / 32 + (blockIdx.x * kTfWarps + warp) * 32;
+  // stage 1: lane = tile
+  uint32_t td = kTileNone << 24;
+  if (t0 + lane <= t_last) td = __ldg(&Q.tile_desc[t0 + lane]);
+  const uint32_t tcls = td >> 24;
+  bool live = tcls == kTileBig;
+  if (tcls >= 1 && tcls < kTileBig) {
+    const uint32_t code = td & 0xFFFFFFu;
+    live = (__ldg(&occ[(tcls - 1) * kOccWords + (code >> 5)]) >> (code & 31u)) & 1u;
+  }
+  const unsigned live_m = __ballot_sync(0xffffffffu, live);
+  const int n_live = __popc(live_m);
+  // stage 2: lane = point, kTfBatch live tiles at a time (warp-uniform control flow)
+  unsigned cnt = 0;
+  unsigned rest = live_m;
+  for (int b0 = 0; b0 < n_live; b0 += kTfBatch) {
+    uint32_t d[kTfBatch], pp[kTfBatch];
+#pragma unroll
+    for (int j = 0; j < kTfBatch; j++) {
+      const int tj = rest ? __ffs(rest) - 1 : -1;
+      rest &= rest - 1;
+      const uint32_t p = (t0 + (uint32_t) tj) * 32 - 1 + lane;  // (tile 0, lane 0: wraps, rejected below)
+      pp[j] = p;
+      const bool in = tj >= 0 && p >= p_lo && p < p_hi;
+      d[j] = in ? __ldg(&Q.edge_desc[p]) : (kDescNone << 24);
+    }
+    uint32_t w[kTfBatch];
+#pragma unroll
+    for (int j = 0; j < kTfBatch; j++)
+      w[j] = __ldg(&occ[((d[j] & 0xFFFFFFu) >> 5) + ((d[j] >> 24) & 1u) * kOccWords]);
+#pragma unroll
+    for (int j = 0; j < kTfBatch; j++) {
+      const uint32_t cls = d[j] >> 24;
+      bool keep = cls < kDescBig && ((w[j] >> (d[j] & 31u)) & 1u);
+      if (__any_sync(0xffffffffu, cls == kDescBig)) {
+        bool within3 = false;
+        bool big = cls == kDescBig && occ_rect(Q, occ, pp[j], &within3);
+        if (long_list) {
+          if (big && within3) {
+            keep = true;
+            big = false;
+          }
+          const unsigned mb = __ballot_sync(0xffffffffu, big);
+          if (mb) {
+            unsigned base = 0;
+            const int leader = __ffs(mb) - 1;
+            if (lane == leader) base = atomicAdd(long_counter, (unsigned) __popc(mb));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (big) long_list[base + __popc(mb & ((1u << lane) - 1))] = pp[j];
+          }
+        } else if (big) {
+          keep = true;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (b0 + j < n_live) {
+        if (lane == 0) s_mask[warp][b0 + j] = m;
+        cnt += __popc(m);
+      }
+    }
+  }
+  if (lane == 0) s_wsum[warp] = cnt;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned sum = lane < kTfWarps ? s_wsum[lane] : 0u;
+    unsigned winc = sum;
+#pragma unroll
+    for (int o = 1; o < kTfWarps; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += v;
+    }
+    if (lane < kTfWarps) s_wsum[lane] = winc - sum;
+    if (lane == kTfWarps - 1) s_base = winc ? atomicAdd(counter, winc) : 0u;
+  }
+  __syncthreads();
+  unsigned pos = s_base + s_wsum[warp];
+  const unsigned lt = (1u << lane) - 1;
+  rest = live_m;
+  for (int k = 0; k < n_live; k++) {
+    const int tj = __ffs(rest) - 1;
+    rest &= rest - 1;
+    const unsigned m = s_mask[warp][k];
+    if ((m >> lane) & 1u) survivors[pos + __popc(m & lt)] = (t0 + (uint32_t) tj) * 32 - 1 + lane;
+    pos += __popc(m);
+  }
+}
+
 // Candidate generation through the cell directory (sparse base maps, short query edges:
 // the survivors of the occupancy filter whose box lies within 3 x 3 cells).  A warp owns 32
-// query edges.  Every lane looks up the cells of ITS edge -- rank, list bounds: two rounds
-// of independent loads for the 2 x 2 cells at the min corner, two more only if some edge
-// spans three cells -- and the warp then works through the
-// concatenation of all the leaf lists with one lane per (query, leaf) item, 128 items at a
-// time: the owner of an item is found by binary search over the prefix sums, the leaf ids
-// and then the leaf boxes of a batch are loaded together.  Five dependent rounds of loads
-// per warp in all, independent of how unevenly the lists are distributed over the lanes
-// (a lane-per-query loop waits for the longest list: 8.1 tests against a mean of 3.4).
+// query edges.  Every lane looks up the cells of ITS edge -- {bitmap word, rank} in one load,
+// then the list bounds: two rounds of independent loads for the 2 x 2 cells at the min corner,
+// two more only if some edge spans three cells -- and the warp then works through the
+// concatenation of all the lists with one lane per (query, item), 128 items at a time: the
+// owner of an item is found by binary search over the prefix sums, and the 16-byte item record
+// (cell_item_of: the leaf's box clipped to the cell, its first point and edge count) decides
+// the pair without touching the leaf.  Four dependent rounds of loads per warp in all
+// (survivor -> vertices -> directory -> bounds -> items) against eight for the tree walk,
+// independent of how unevenly the lists are distributed over the lanes (a lane-per-query loop
+// waits for the longest list: 8.1 tests against a mean of 3.4).
 // A leaf that is listed in several cells of the query's box is reported once: in the cell
 // that holds the min corner of the intersection of the two cell boxes.  The pairs are
-// exactly the ones the tree walk emits (quantised boxes overlap).
+// exactly the ones the tree walk emits (quantised boxes overlap); they leave in the DIRECT
+// format, so the exact pass needs no leaf record either.
 struct CellWork {
   int4 qb[32];           // query boxes of the lanes
   uint32_t p[32];        // query start points
@@ -329,14 +448,18 @@ struct CellWork {
 
 constexpr int kCellBatch = 4;  // items per lane and batch
 
-// list bounds of cell (cx, cy) if it is occupied, else an empty range
-static __device__ __forceinline__ void cell_range(const BvhView& bvh, bool in, int cx, int cy,
-                                                  uint32_t& beg, uint32_t& end) {
+// the directory word of cell (cx, cy): {bitmap word, rank}, first round of loads
+static __device__ __forceinline__ uint2 cell_dir(const BvhView& bvh, bool in, int cx, int cy) {
   const uint32_t bit = in ? (uint32_t) cy * kOccDim + cx : 0u;
-  const uint32_t wd = __ldg(&bvh.occ[bit >> 5]);
-  const uint32_t rk = __ldg(&bvh.occ_rank[bit >> 5]);
-  const bool set = in && ((wd >> (bit & 31)) & 1u);
-  const uint32_t id = set ? rk + __popc(wd & ((1u << (bit & 31)) - 1)) : 0u;
+  return __ldg(&bvh.occ_dir[bit >> 5]);
+}
+
+// list bounds of the cell if it is occupied, else an empty range: second round
+static __device__ __forceinline__ void cell_bounds(const BvhView& bvh, bool in, int cx, int cy, const uint2& dir,
+                                                   uint32_t& beg, uint32_t& end) {
+  const uint32_t bit = in ? (uint32_t) cy * kOccDim + cx : 0u;
+  const bool set = in && ((dir.x >> (bit & 31)) & 1u);
+  const uint32_t id = set ? dir.y + __popc(dir.x & ((1u << (bit & 31)) - 1)) : 0u;
   beg = __ldg(&bvh.cell_begin[id]);
   end = set ? __ldg(&bvh.cell_begin[id + 1]) : beg;
 }
@@ -355,17 +478,28 @@ static __device__ __forceinline__ void cells_tile(const MapView& Q, const BvhVie
   uint32_t lb[9], le[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) lb[k] = le[k] = 0;
+  {
+    uint2 dir[4];
 #pragma unroll
-  for (int k = 0; k < 9; k++) {
-    if (k % 3 == 2 || k / 3 == 2) continue;
-    cell_range(bvh, valid && cx0 + k % 3 <= cx1 && cy0 + k / 3 <= cy1, cx0 + k % 3, cy0 + k / 3, lb[k], le[k]);
+    for (int k = 0; k < 4; k++) {
+      const int dx = k & 1, dy = k >> 1;
+      dir[k] = cell_dir(bvh, valid && cx0 + dx <= cx1 && cy0 + dy <= cy1, cx0 + dx, cy0 + dy);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int dx = k & 1, dy = k >> 1;
+      cell_bounds(bvh, valid && cx0 + dx <= cx1 && cy0 + dy <= cy1, cx0 + dx, cy0 + dy, dir[k], lb[dy * 3 + dx],
+                  le[dy * 3 + dx]);
+    }
   }
   // third column / row: only for the rare edge spanning three cells
   if (__any_sync(0xffffffffu, valid && (cx1 - cx0 == 2 || cy1 - cy0 == 2))) {
 #pragma unroll
     for (int k = 0; k < 9; k++) {
       if (!(k % 3 == 2 || k / 3 == 2)) continue;
-      cell_range(bvh, valid && cx0 + k % 3 <= cx1 && cy0 + k / 3 <= cy1, cx0 + k % 3, cy0 + k / 3, lb[k], le[k]);
+      const bool in = valid && cx0 + k % 3 <= cx1 && cy0 + k / 3 <= cy1;
+      const uint2 dir = cell_dir(bvh, in, cx0 + k % 3, cy0 + k / 3);
+      cell_bounds(bvh, in, cx0 + k % 3, cy0 + k / 3, dir, lb[k], le[k]);
     }
   }
   uint32_t total = 0;
@@ -389,7 +523,8 @@ static __device__ __forceinline__ void cells_tile(const MapView& Q, const BvhVie
   __syncwarp();
   const uint32_t all = W.pre[32];
   for (uint32_t base = 0; base < all; base += 32 * kCellBatch) {
-    uint32_t owner[kCellBatch], cell[kCellBatch], leaf[kCellBatch];
+    uint32_t owner[kCellBatch], cell[kCellBatch];
+    uint4 item[kCellBatch];
     bool act[kCellBatch];
 #pragma unroll
     for (int s2 = 0; s2 < kCellBatch; s2++) {
@@ -414,11 +549,8 @@ static __device__ __forceinline__ void cells_tile(const MapView& Q, const BvhVie
         }
       }
       cell[s2] = k;
-      leaf[s2] = act[s2] ? __ldg(&bvh.cell_leaf[W.beg[lo][k] + (r - before)]) : 0u;
+      item[s2] = act[s2] ? __ldg(&bvh.cell_item[W.beg[lo][k] + (r - before)]) : make_uint4(0, 0, 0, 0);
     }
-    int4 box[kCellBatch];
-#pragma unroll
-    for (int s2 = 0; s2 < kCellBatch; s2++) box[s2] = __ldg(&bvh.leaf_box[leaf[s2]]);
 #pragma unroll
     for (int s2 = 0; s2 < kCellBatch; s2++) {
       bool hit = false;
@@ -426,13 +558,11 @@ static __device__ __forceinline__ void cells_tile(const MapView& Q, const BvhVie
       if (act[s2]) {
         const int4 oq = W.qb[owner[s2]];
         qp = W.p[owner[s2]];
-        if (box_overlap(oq, box[s2])) {
-          const int ox = occ_cell(oq.x), oy = occ_cell(oq.y);
-          hit = max(ox, occ_cell(box[s2].x)) == ox + (int) (cell[s2] % 3u) &&
-                max(oy, occ_cell(box[s2].y)) == oy + (int) (cell[s2] / 3u);
-        }
+        const CellBoxQ qc = cell_clip(oq, occ_cell(oq.x) + (int) (cell[s2] % 3u), occ_cell(oq.y) + (int) (cell[s2] / 3u));
+        hit = cell_item_hit(item[s2], qc);
       }
-      lsi_leaf<false>((int) leaf[s2], hit, qp, E, lane, st);
+      // DIRECT pair: {query start point | (count - 1) << 29, first point of the leaf}
+      lsi_leaf<false>((int) item[s2].w, hit, qp | ((item[s2].z >> 14) << kDirectShift), E, lane, st);
     }
   }
 }
@@ -444,7 +574,7 @@ k_lsi_cells(MapView Q, BvhView bvh, const uint32_t* __restrict__ survivors,
   __shared__ uint2 s_emit[kLsiWarps][kEmitBuf];
   __shared__ CellWork s_work[kLsiWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  Emit E = {s_emit[warp], 0u, out, cap, counter};
+  Emit E = {s_emit[warp], 0u, out, cap, counter, nullptr};
   TravStats st = {0, 0, 0, 0, 0};
   const uint32_t n = *n_survivors_dev;
   const uint32_t n_tiles = (n + 31) / 32;
@@ -483,12 +613,13 @@ __global__ void __launch_bounds__(kLsiWarps * 32)
 k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order, uint32_t n_slots,
           uint32_t p_lo, const unsigned int* __restrict__ n_slots_dev, uint32_t spw,
           uint2* __restrict__ out, uint32_t cap, unsigned int* counter,
-          unsigned long long* stats) {
+          unsigned long long* stats, bool direct) {
   __shared__ int s_stack[kLsiWarps][kStackDepth];
   __shared__ uint2 s_emit[kLsiWarps][kEmitBuf];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* stack = s_stack[warp];
-  Emit E = {s_emit[warp], 0u, out, cap, counter};
+  // direct: the pairs join those of the cell directory, in its format
+  Emit E = {s_emit[warp], 0u, out, cap, counter, direct ? bvh.leaf_rec : nullptr};
   if (n_slots_dev) n_slots = *n_slots_dev;  // survivor count of the pre-filter
   // spw = query slots per warp: 32, or fewer for a list of queries from all over the map
   // (the long edges the cell directory leaves over): a warp follows the clusters of its
@@ -669,6 +800,7 @@ static __device__ __forceinline__ void exact_push(bool pass, uint2 item, uint2* 
   cand += __popc(m);  // counted by every lane alike
 }
 
+template <bool kDirect>
 __global__ void __launch_bounds__(kExactThreads)
 k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ pairs, const uint2* __restrict__ leaf_rec,
             const unsigned int* __restrict__ n_pairs_dev, uint32_t pair_cap,
@@ -691,10 +823,16 @@ k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ pairs, const uint2* 
     for (int k = 0; k < 5; k++) bp[k] = make_longlong2(0, 0);
     if (i < n) {
       const uint2 pr = pairs[i];
-      pq = pr.x;
-      const uint2 rec = __ldg(&leaf_rec[pr.y]);
-      cnt = rec.y >> 28;
-      pb0 = rec.x + (rec.y & 0x0FFFFFFFu);
+      if (kDirect) {
+        pq = pr.x & ((1u << kDirectShift) - 1);
+        cnt = (pr.x >> kDirectShift) + 1;
+        pb0 = pr.y;
+      } else {
+        pq = pr.x;
+        const uint2 rec = __ldg(&leaf_rec[pr.y]);
+        cnt = rec.y >> 28;
+        pb0 = rec.x + (rec.y & 0x0FFFFFFFu);
+      }
       const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
       e1 = {a.x, a.y, b.x, b.y};
 #pragma unroll
@@ -809,6 +947,211 @@ k_lsi_points(MapView Q, MapView B, int query_map_id, const unsigned int* __restr
   }
   __syncthreads();
   points_flush(base_first ? B : Q, base_first ? Q : B, s_list, s_n, out);
+}
+
+// ---- fused exact + point pass (option lsi_fused, default) -----------------------------------
+// k_lsi_exact and k_lsi_points as ONE kernel, and the last kernel of the query: every kernel
+// of this pipeline costs ~20 us beyond its issue time (launch, a chain of dependent loads
+// through a flushed L2, a tail), and the point pass re-loaded everything the predicate had in
+// registers -- the hit list, four vertices and two chain ids per hit.  Here the lane that finds a
+// hit computes both coordinates at once (gcd-free path) and writes the finished record; only
+// the coordinates that need the 128-bit gcd (6 %) are parked in shared memory and worked off
+// densely, like before.  The LAST CTA to finish copies the query's counters straight into
+// mapped pinned host memory and zeroes them for the next query: no memset before and no
+// memcpy after the kernels (each ~3-5 us of stream time on a 0.15 ms query).
+constexpr int kLsiCtrs = 10;  // 64-bit words the host reads back
+
+struct LsiTail {
+  unsigned long long* ctr;   // device counters [0, kLsiCtrs)
+  unsigned long long* host;  // their mapped pinned copy (device pointer), or nullptr: leave them
+  unsigned int* ticket;      // CTAs that have finished; zero before and after the kernel
+};
+
+// (all threads of the CTA)
+static __device__ __forceinline__ void lsi_tail(const LsiTail& T) {
+  __shared__ bool s_last;
+  if (!T.host) return;
+  __syncthreads();  // the CTA's own atomics are issued
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(T.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < kLsiCtrs) {
+    T.host[threadIdx.x] = ((volatile unsigned long long*) T.ctr)[threadIdx.x];
+    T.ctr[threadIdx.x] = 0;
+  }
+  if (threadIdx.x == 0) *T.ticket = 0;
+}
+
+constexpr int kResolveDefer = 3 * kExactThreads;  // < kExactThreads before a drain, <= 2 per thread added
+
+// deferred coordinates of the CTA: the full (gcd) path, one item per thread
+static __device__ __forceinline__ void resolve_flush(const MapView& Q, const MapView& B, const DeferItem* list,
+                                                     unsigned n_list, rjb_xsect* __restrict__ out) {
+  for (unsigned t = threadIdx.x; t < n_list; t += kExactThreads) {
+    const DeferItem it = list[t];
+    const longlong2 a = __ldg(&Q.pts[it.pq]), b = __ldg(&Q.pts[it.pq + 1]);
+    const longlong2 c = __ldg(&B.pts[it.pb]), d = __ldg(&B.pts[it.pb + 1]);
+    const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
+    const long long v = lsi_point_axis<false>(e1, e2, (int) it.axis, nullptr);
+    if (it.axis == 0) out[it.i].x = v; else out[it.i].y = v;
+  }
+}
+
+// intersect_test over the CTA's list of box-overlapping pairs, every lane busy; a hit becomes a
+// finished rjb_xsect record at once (deferred coordinates: s_defer, flushed whenever a CTA's
+// worth has gathered).  Called by ALL threads with the same n_list; contains barriers.
+static __device__ __forceinline__ void resolve_drain(const MapView& Q, const MapView& B, int query_map_id,
+                                                     const uint2* list, unsigned n_list, DeferItem* s_defer,
+                                                     unsigned* s_nd, rjb_xsect* __restrict__ out, uint32_t cap,
+                                                     unsigned int* counter) {
+  const int lane = threadIdx.x & 31;
+  for (unsigned r0 = 0; r0 < n_list; r0 += kExactThreads) {  // block-uniform trip count (barriers inside)
+    const unsigned t = r0 + threadIdx.x;
+    bool found = false;
+    uint2 it = make_uint2(0, 0);
+    Seg e1 = {0, 0, 0, 0}, e2 = {0, 0, 0, 0};
+    uint32_t cq = 0, cb = 0;
+    if (t < n_list) {
+      it = list[t];
+      const longlong2 a = __ldg(&Q.pts[it.x]), b = __ldg(&Q.pts[it.x + 1]);
+      const longlong2 c = __ldg(&B.pts[it.y]), d = __ldg(&B.pts[it.y + 1]);
+      cq = __ldg(&Q.point_chain[it.x]);  // with the vertices: no dependent round trip for the hits
+      cb = __ldg(&B.point_chain[it.y]);
+      e1 = {a.x, a.y, b.x, b.y};
+      e2 = {c.x, c.y, d.x, d.y};
+      found = lsi_intersect(e1, e2);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, found);
+    unsigned base = 0;
+    const int leader = __ffs(m) - 1;
+    if (m && lane == leader) base = atomicAdd(counter, (unsigned) __popc(m));
+    if (m) base = __shfl_sync(0xffffffffu, base, leader);
+    if (found) {
+      const unsigned pos = base + __popc(m & ((1u << lane) - 1));
+      if (pos < cap) {
+        bool dx = false, dy = false;
+        rjb_xsect r;
+        r.x = lsi_point_axis<true>(e1, e2, 0, &dx);
+        r.y = lsi_point_axis<true>(e1, e2, 1, &dy);
+        if (dx) s_defer[atomicAdd(s_nd, 1u)] = {pos, it.x, it.y, 0u};
+        if (dy) s_defer[atomicAdd(s_nd, 1u)] = {pos, it.x, it.y, 1u};
+        const uint32_t eq = it.x - cq, eb = it.y - cb;
+        r.eid[0] = query_map_id == 0 ? eq : eb;
+        r.eid[1] = query_map_id == 0 ? eb : eq;
+        r.mid_point_polygon_id = RJB_DONTKNOW;
+        r._pad = 0;
+        out[pos] = r;
+      }
+    }
+    // <= 2 deferred coordinates per thread and round: the list never exceeds kResolveDefer
+    __syncthreads();
+    if (*s_nd >= kExactThreads) {
+      resolve_flush(Q, B, s_defer, *s_nd, out);
+      __syncthreads();
+      if (threadIdx.x == 0) *s_nd = 0;
+      __syncthreads();
+    }
+  }
+}
+
+template <bool kDirect>
+__global__ void __launch_bounds__(kExactThreads)
+k_lsi_resolve(MapView Q, MapView B, int query_map_id, const uint2* __restrict__ pairs,
+              const uint2* __restrict__ leaf_rec, const unsigned int* __restrict__ n_pairs_dev, uint32_t pair_cap,
+              rjb_xsect* __restrict__ out, uint32_t cap, unsigned int* counter, unsigned long long* n_cand,
+              LsiTail tail) {
+  __shared__ uint2 s_list[kExactList];
+  __shared__ DeferItem s_defer[kResolveDefer];
+  __shared__ unsigned s_n, s_nd;
+  if (threadIdx.x == 0) s_n = s_nd = 0;
+  __syncthreads();
+  const uint32_t n = min(*n_pairs_dev, pair_cap);
+  const int lane = threadIdx.x & 31;
+  unsigned cand = 0;
+  // block-uniform trip count: every thread reaches the barriers
+  for (uint64_t i0 = (uint64_t) blockIdx.x * kExactThreads; i0 < n; i0 += (uint64_t) gridDim.x * kExactThreads) {
+    const uint64_t i = i0 + threadIdx.x;
+    uint32_t pq = 0, pb0 = 0, cnt = 0;
+    Seg e1 = {0, 0, 0, 0};
+    longlong2 bp[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) bp[k] = make_longlong2(0, 0);
+    if (i < n) {
+      const uint2 pr = pairs[i];
+      if (kDirect) {
+        pq = pr.x & ((1u << kDirectShift) - 1);
+        cnt = (pr.x >> kDirectShift) + 1;
+        pb0 = pr.y;
+      } else {
+        pq = pr.x;
+        const uint2 rec = __ldg(&leaf_rec[pr.y]);
+        cnt = rec.y >> 28;
+        pb0 = rec.x + (rec.y & 0x0FFFFFFFu);
+      }
+      const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
+      e1 = {a.x, a.y, b.x, b.y};
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+        if ((uint32_t) k <= cnt) bp[k] = __ldg(&B.pts[pb0 + k]);
+    }
+    // the <= 4 edges of the leaf in ONE push: a single shared-memory atomic per warp and round
+    unsigned pass_m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const Seg e2 = {bp[k].x, bp[k].y, bp[k + 1].x, bp[k + 1].y};
+      if ((uint32_t) k < cnt && seg_boxes_overlap(e1, e2)) pass_m |= 1u << k;
+    }
+    if (__any_sync(0xffffffffu, cnt > 4)) {  // leaves of 5..8 edges (lbvh_leaf_size > 4)
+      longlong2 p1 = bp[4];
+      for (uint32_t k = 4; k < 8; k++) {
+        if (k < cnt) {
+          const longlong2 p2 = __ldg(&B.pts[pb0 + k + 1]);
+          const Seg e2 = {p1.x, p1.y, p2.x, p2.y};
+          if (seg_boxes_overlap(e1, e2)) pass_m |= 1u << k;
+          p1 = p2;
+        }
+      }
+    }
+    {
+      const unsigned mine = __popc(pass_m);
+      unsigned inc = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+      if (total) {
+        unsigned base = 0;
+        if (lane == 31) base = atomicAdd(&s_n, total);
+        base = __shfl_sync(0xffffffffu, base, 31) + inc - mine;
+        while (pass_m) {
+          const uint32_t k = __ffs(pass_m) - 1;
+          pass_m &= pass_m - 1;
+          s_list[base++] = make_uint2(pq, pb0 + k);
+        }
+        cand += total;  // counted by every lane alike
+      }
+    }
+    __syncthreads();
+    const unsigned n_list = s_n;
+    if (n_list >= kExactThreads) {
+      resolve_drain(Q, B, query_map_id, s_list, n_list, s_defer, &s_nd, out, cap, counter);
+      __syncthreads();
+      if (threadIdx.x == 0) s_n = 0;
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  resolve_drain(Q, B, query_map_id, s_list, s_n, s_defer, &s_nd, out, cap, counter);
+  __syncthreads();
+  resolve_flush(Q, B, s_defer, s_nd, out);
+  if (lane == 0 && cand) atomicAdd(n_cand, (unsigned long long) cand);
+  lsi_tail(tail);
 }
 
 // All |Q| x |B| pairs, no index: pins the exact arithmetic (RJB_MODE_BRUTE).

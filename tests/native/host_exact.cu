@@ -57,6 +57,34 @@ unsigned hx_edge_desc(long long x1, long long y1, long long x2, long long y2) {
   return edge_desc_of(occ_code(x1, y1), occ_code(x2, y2));
 }
 int hx_occ_cell_of_quant(long long v) { return occ_cell((int) (v >> kQuantShift)); }
+unsigned hx_tile_desc(unsigned x0, unsigned y0, unsigned x1, unsigned y1) { return tile_desc_of(x0, y0, x1, y1); }
+
+// Cell-directory items (k_cell_lists / k_lsi_cells): for n pairs of quantised boxes {x0, y0, x1, y1}
+// (leaf box, query box) counts in how many cells of the query's cell box, among the cells the
+// leaf is registered in, cell_item_hit fires (out_hits) and records the last such cell.
+void hx_cell_item_batch(const int* leaf, const int* query, unsigned long long n, unsigned* out_hits,
+                        unsigned* out_cell, unsigned* out_first, unsigned* out_count) {
+  for (unsigned long long i = 0; i < n; i++) {
+    const int4 lb = make_int4(leaf[4 * i], leaf[4 * i + 1], leaf[4 * i + 2], leaf[4 * i + 3]);
+    const int4 qb = make_int4(query[4 * i], query[4 * i + 1], query[4 * i + 2], query[4 * i + 3]);
+    unsigned hits = 0, cell = 0, first = 0, count = 0;
+    for (int cy = occ_cell(qb.y); cy <= occ_cell(qb.w); cy++)
+      for (int cx = occ_cell(qb.x); cx <= occ_cell(qb.z); cx++) {
+        if (cx < occ_cell(lb.x) || cx > occ_cell(lb.z) || cy < occ_cell(lb.y) || cy > occ_cell(lb.w)) continue;
+        const uint4 it = cell_item_of(lb, cx, cy, 1000u + (unsigned) i, 1u + (unsigned) (i % 8));
+        if (cell_item_hit(it, cell_clip(qb, cx, cy))) {
+          hits++;
+          cell = (unsigned) cy * kOccDim + (unsigned) cx;
+          first = it.w;
+          count = (it.z >> 14) + 1;
+        }
+      }
+    out_hits[i] = hits;
+    out_cell[i] = cell;
+    out_first[i] = first;
+    out_count[i] = count;
+  }
+}
 
 // PIP: the update rule scanned over all edges in eid order for a batch of points
 // (edges: nb x 4 int64 {x1, y1, x2, y2}; out: chosen edge index or 0xFFFFFFFF)

@@ -136,6 +136,57 @@ def test_edge_descriptor_covers_the_edge_box(hx):
     assert seen == {0, 1, 2}
 
 
+def test_tile_descriptor_classes(hx):
+    """Tile descriptor of the two-level LSI filter: class k promises that the box lies within the
+    2^(k-1) x 2^(k-1) cells at its min corner (the area the k-th dilated bitmap covers)."""
+    hx.hx_tile_desc.restype = C.c_uint32
+    rng = np.random.default_rng(5)
+    for _ in range(5000):
+        x0, y0 = (int(v) for v in rng.integers(0, 4000, 2))
+        ex, ey = (int(v) for v in rng.integers(0, 12, 2))
+        d = hx.hx_tile_desc(x0, y0, x0 + ex, y0 + ey)
+        cls, corner = d >> 24, d & 0xFFFFFF
+        assert corner == (y0 << 12 | x0)
+        e = max(ex, ey)
+        assert cls == (1 if e == 0 else 2 if e <= 1 else 3 if e <= 3 else 4 if e <= 7 else 5)
+
+
+def test_cell_directory_items_report_each_overlap_exactly_once(hx):
+    """k_lsi_cells decides a (query, leaf) pair from the leaf's 16-byte item record (box clipped to
+    the cell) and the query box clipped to the same cell.  Over all common cells of the two cell
+    boxes it must fire exactly once when the quantised boxes overlap -- in the cell holding the
+    min corner of the intersection of the cell boxes -- and never otherwise; the record must
+    give back the leaf's first point and edge count."""
+    rng = np.random.default_rng(11)
+    n = 300000
+    cell = 1 << 19
+    # leaf boxes of 0..3 cells, query boxes of 0..2 cells, near each other; some exactly touching
+    l0 = rng.integers(-2**30, 2**30 - 4 * cell, size=(n, 2))
+    lsz = (rng.integers(0, 3 * cell, size=(n, 2)) >> rng.integers(0, 19, size=(n, 1)))
+    q0 = l0 + rng.integers(-2 * cell, 3 * cell, size=(n, 2)) // rng.choice([1, 1, 7, 4096], size=(n, 1))
+    qsz = (rng.integers(0, 2 * cell, size=(n, 2)) >> rng.integers(0, 19, size=(n, 1)))
+    touch = rng.random(n) < 0.1
+    q0[touch, 0] = (l0 + lsz)[touch, 0]  # query starts where the leaf ends (closed boxes: overlap)
+    q0 = np.clip(q0, -2**30, 2**30 - 3 * cell)
+    leaf = np.ascontiguousarray(np.concatenate([l0, l0 + lsz], axis=1).astype(np.int32))
+    query = np.ascontiguousarray(np.concatenate([q0, q0 + qsz], axis=1).astype(np.int32))
+    hits, cellid, first, count = (np.zeros(n, np.uint32) for _ in range(4))
+    u32p = C.POINTER(C.c_uint32)
+    hx.hx_cell_item_batch(leaf.ctypes.data_as(C.POINTER(C.c_int)), query.ctypes.data_as(C.POINTER(C.c_int)),
+                          C.c_uint64(n), hits.ctypes.data_as(u32p), cellid.ctypes.data_as(u32p),
+                          first.ctypes.data_as(u32p), count.ctypes.data_as(u32p))
+    L, Q = leaf.astype(np.int64), query.astype(np.int64)
+    overlap = (L[:, 0] <= Q[:, 2]) & (Q[:, 0] <= L[:, 2]) & (L[:, 1] <= Q[:, 3]) & (Q[:, 1] <= L[:, 3])
+    assert 0.1 < overlap.mean() < 0.9
+    assert np.array_equal(hits, overlap.astype(np.uint32))
+    occ = lambda v: ((v + 2**30) >> 19) & 4095
+    want_cell = np.maximum(occ(L[:, 1]), occ(Q[:, 1])) * 4096 + np.maximum(occ(L[:, 0]), occ(Q[:, 0]))
+    assert np.array_equal(cellid[overlap], want_cell[overlap].astype(np.uint32))
+    idx = np.arange(n)
+    assert np.array_equal(first[overlap], (1000 + idx[overlap]).astype(np.uint32))
+    assert np.array_equal(count[overlap], (1 + idx[overlap] % 8).astype(np.uint32))
+
+
 @pytest.mark.parametrize("q", [0, 1])
 def test_pip_update_rule_matches_oracle(hx, oracle, q):
     """The kernels' pip_update (closest edge above, src/algo/pip.h:27-96) scanned in eid order

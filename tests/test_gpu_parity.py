@@ -127,8 +127,10 @@ def test_lsi_cell_directory_path(rjb, loaded, name, q):
     want = om.lsi(q)
     counts = {}
     try:
-        for cells in (0, 1):
+        for cells, tiles, fused in ((0, 1, 1), (1, 1, 1), (0, 0, 1), (1, 0, 1), (0, 1, 0), (1, 1, 0)):
             ctx.set_option("lsi_cells", cells)
+            ctx.set_option("lsi_tile_filter", tiles)
+            ctx.set_option("lsi_fused", fused)  # exact + point pass as one kernel, or as two
             ctx.set_option("lsi_filter", 1)
             ctx.set_option("sort_queries", 0)
             ctx.build_index(1 - q, "lbvh")
@@ -140,7 +142,11 @@ def test_lsi_cell_directory_path(rjb, loaded, name, q):
                 assert n == len(want[0])
                 for g, w in zip(got, want):
                     assert np.array_equal(g, w)
-            counts[cells] = lsi.n_candidates
+            counts[(cells, tiles, fused)] = lsi.n_candidates
+            surv = counts.setdefault(("survivors", cells), ctx.last_stats()[7])
+            # (the tile test is at least as tight as the edge test: a Small descriptor looks at the
+            # whole 2 x 2 block, the tile box only at the cells its edges touch)
+            assert ctx.last_stats()[7] <= surv if tiles else ctx.last_stats()[7] >= surv
             st = ctx.last_stats()
             # the directory is only built where leaves are small against the cells
             assert st[5] in (0, cells)
@@ -148,11 +154,13 @@ def test_lsi_cell_directory_path(rjb, loaded, name, q):
                 assert st[7] > 0 and st[5] == cells  # filter on, and the path that was asked for
     finally:
         ctx.set_option("lsi_cells", 0)
+        ctx.set_option("lsi_tile_filter", 1)
+        ctx.set_option("lsi_fused", 1)
         ctx.set_option("lsi_filter", -1)
-    assert counts[0] == counts[1]
+    assert len({counts[k] for k in counts if k[0] != "survivors"}) == 1
 
 
-@pytest.mark.parametrize("mode,flt", [("lbvh", 1), ("lbvh", 0), ("grid", 0)])
+@pytest.mark.parametrize("mode,flt", [("lbvh", 1), ("lbvh", 2), ("lbvh", 3), ("lbvh", 0), ("grid", 0)])
 @pytest.mark.parametrize("name", ["voronoi", "shared", "soup"])
 def test_lsi_query_window(rjb, loaded, name, mode, flt):
     """Options lsi_window_begin / lsi_window_end: the query edges starting in a window of the
@@ -165,7 +173,10 @@ def test_lsi_query_window(rjb, loaded, name, mode, flt):
     want = om.lsi_refgrid(q, 64) if mode == "grid" else om.lsi(q)
     parts = []
     try:
-        ctx.set_option("lsi_filter", flt)
+        # flt 1: two-level filter (tiles, then edges); 2: one-level filter; 3: two-level + cell directory
+        ctx.set_option("lsi_filter", min(flt, 1))
+        ctx.set_option("lsi_tile_filter", 0 if flt == 2 else 1)
+        ctx.set_option("lsi_cells", 1 if flt == 3 else 0)
         ctx.set_option("sort_queries", 0)
         ctx.build_index(1 - q, mode, grid_size=64)
         lsi = rjb.LSI(ctx, mode)
@@ -182,6 +193,8 @@ def test_lsi_query_window(rjb, loaded, name, mode, flt):
         ctx.set_option("lsi_window_begin", 0)
         ctx.set_option("lsi_window_end", 0)
         ctx.set_option("lsi_filter", -1)
+        ctx.set_option("lsi_tile_filter", 1)
+        ctx.set_option("lsi_cells", 0)
     got = sort_xsects(np.concatenate(parts), q)
     assert len(got[0]) == len(want[0])
     for g, w in zip(got, want):

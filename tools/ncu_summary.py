@@ -32,12 +32,19 @@ def raw(path):
                           for a, b in st])
 
 
-def src(path, top=40):
+def src(path, top=40, only=None):
+    """per kernel: source lines by warp-stall samples (where the warps wait) with their share of
+    the executed warp instructions"""
+    csv.field_size_limit(10 ** 9)
     rows = list(csv.reader(open(path)))
-    cur, hdr, agg, tot = None, None, {}, 0
+    cur, fn, hdr = None, None, None
+    agg = {}
     for r in rows:
         if len(r) == 2 and r[0] == "File Path":
             cur = r[1]
+            continue
+        if len(r) == 2 and r[0] == "Function Name":
+            fn = re.sub(r"\(.*", "", r[1]).replace("rjb::", "").replace("void ", "")
             continue
         if len(r) > 3 and r[0] == "Line No":
             hdr = r
@@ -47,20 +54,28 @@ def src(path, top=40):
                 ln = int(r[0])
             except ValueError:
                 continue
-            ie, te = r[hdr.index("Instructions Executed")], r[hdr.index("Thread Instructions Executed")]
+            ie = r[hdr.index("Instructions Executed")]
             if ie == "":
                 continue
-            a = agg.setdefault((cur.split("/")[-1], ln, r[1].strip()[:100]), [0, 0])
+            te = r[hdr.index("Thread Instructions Executed")] if "Thread Instructions Executed" in hdr else "0"
+            ss = r[hdr.index("Warp Stall Sampling (All Samples)")] if "Warp Stall Sampling (All Samples)" in hdr else "0"
+            a = agg.setdefault(fn, {}).setdefault((cur.split("/")[-1], ln, r[1].strip()[:100]), [0, 0, 0])
             a[0] += int(ie)
-            a[1] += int(te)
-            tot += int(ie)
-    print("total warp instructions", tot)
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-        print("%6.2f%%  thr/inst %5.1f  %s:%d  %s" % (100 * v[0] / tot, v[1] / max(1, v[0]), k[0], k[1], k[2]))
+            a[1] += int(te or 0)
+            a[2] += int(ss or 0)
+    for fn, d in agg.items():
+        if only and only not in fn:
+            continue
+        tot = sum(v[0] for v in d.values()) or 1
+        tots = sum(v[2] for v in d.values()) or 1
+        print("== %s: %d warp instructions, %d stall samples" % (fn, tot, tots))
+        for k, v in sorted(d.items(), key=lambda kv: -kv[1][2])[:top]:
+            print("  stall %5.1f%%  inst %5.1f%%  thr/inst %5.1f  %s:%d  %s"
+                  % (100 * v[2] / tots, 100 * v[0] / tot, v[1] / max(1, v[0]), k[0], k[1], k[2]))
 
 
 if __name__ == "__main__":
     if sys.argv[1] == "raw":
         raw(sys.argv[2])
     else:
-        src(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40)
+        src(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40, sys.argv[4] if len(sys.argv) > 4 else None)
