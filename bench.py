@@ -432,8 +432,9 @@ def main():
     ap.add_argument("--leaf-size", type=int, default=4)
     ap.add_argument("--sort-queries", type=int, default=-1)
     ap.add_argument("--filter", type=int, default=-1, help="occupancy pre-filter: -1 auto, 0 off, 1 on")
-    ap.add_argument("--cells", type=int, default=0, help="cell-directory candidate path for the filter's survivors (option lsi_cells)")
-    ap.add_argument("--tile-filter", type=int, default=1, help="two-level occupancy filter (option lsi_tile_filter)")
+    ap.add_argument("--cells", type=int, default=1, help="cell-directory candidate path for the filter's survivors (option lsi_cells)")
+    ap.add_argument("--tile-filter", type=int, default=0, help="two-level occupancy filter (option lsi_tile_filter)")
+    ap.add_argument("--fused", type=int, default=1, help="exact + point pass as one kernel (option lsi_fused)")
     ap.add_argument("--stage-timing", type=int, default=1, help="CUDA event after every kernel of the query")
     ap.add_argument("--ag", type=int, default=0, help="adaptive leaf grouping (option lbvh_ag)")
     ap.add_argument("--ag-iter", type=int, default=5)
@@ -498,6 +499,7 @@ def main():
     ctx.set_option("lsi_filter", args.filter)
     ctx.set_option("lsi_cells", args.cells)
     ctx.set_option("lsi_tile_filter", args.tile_filter)
+    ctx.set_option("lsi_fused", args.fused)
     ctx.set_option("stage_timing", args.stage_timing)
     ctx.set_option("lbvh_ag", args.ag)
     ctx.set_option("lbvh_ag_iter", args.ag_iter)
@@ -659,18 +661,35 @@ def main():
             #  exact    : the pair list, per distinct leaf its record and <= 5 vertices, per distinct
             #             query edge its two vertices, 8 B per hit out
             #  points   : per hit 8 B in, four vertices, two chain ids, 32 B record out
-            tree_bytes = idx["bytes"] - 2 * (4096 * 4096 // 8) - 8 * n_leaves
+            n_maps = 4  # occupancy bitmaps: occ and its 2 x 2 / 4 x 4 / 8 x 8 dilations (2 MiB each)
+            cells_on = bool(lst[5]) and args.cells > 0
+            # (the cell directory = what k_lsi_cells reads instead of the tree: {word, rank} pairs,
+            # list bounds per occupied cell, 16-byte item records)
+            dir_bytes = idx.get("cell_directory_bytes", 0)
+            tree_bytes = idx["bytes"] - n_maps * (4096 * 4096 // 8) - 8 * n_leaves - dir_bytes
+            pair_in = 8 * ql_pairs
+            # exact pass: per distinct leaf <= 5 vertices (+ its 8-byte record unless the pairs are
+            # direct), per distinct query edge two vertices; point pass: four vertices, two chain
+            # ids, the 32-byte record
+            exact_b = pair_in + (80 if cells_on else 88) * min(ql_pairs, n_leaves) + 32 * min(ql_pairs, surv)
+            points_b = (64 + 8 + 32) * n_pairs
             kern = [
                 ("k_lsi_filter", f_ms, 4 * S.n_points + 2 * (4096 * 4096 // 8) + 4 * surv),
-                ("k_lsi_bvh", t_ms, 20 * surv + tree_bytes + 8 * ql_pairs),
-                ("k_lsi_exact", x_ms, 8 * ql_pairs + 88 * min(ql_pairs, n_leaves) + 32 * min(ql_pairs, surv) + 8 * n_pairs),
-                ("k_lsi_points", p_ms, (8 + 64 + 8 + 32) * n_pairs),
+                ("k_lsi_cells" if cells_on else "k_lsi_bvh", t_ms,
+                 20 * surv + (dir_bytes if cells_on else tree_bytes) + 8 * ql_pairs),
             ]
+            if args.fused and p_ms < 0.005:  # k_lsi_resolve = exact + point pass in one kernel
+                kern.append(("k_lsi_resolve", x_ms + p_ms, exact_b + points_b))
+            else:
+                kern += [("k_lsi_exact", x_ms, exact_b + 8 * n_pairs), ("k_lsi_points", p_ms, 8 * n_pairs + points_b)]
             if not lst[7]:
                 kern = kern[1:]
                 kern[0] = ("k_lsi_bvh", t_ms, 4 * S.n_edges + 16 * S.n_points + tree_bytes + 8 * ql_pairs)
             # whole query, SURVEY 8(d): every S vertex, every S edge id, the index and every R vertex once
-            alg_query = 16 * S.n_points + 4 * S.n_edges + idx["bytes"] + 16 * R.n_points + 8 * n_pairs
+            # ("the index" = what this query path reads of it: the two bitmaps of the filter and the
+            # cell directory, or the tree -- not both, and not the dilated bitmaps it does not use)
+            idx_read = 2 * (4096 * 4096 // 8) + (dir_bytes if cells_on else tree_bytes + 8 * n_leaves)
+            alg_query = 16 * S.n_points + 4 * S.n_edges + idx_read + 16 * R.n_points + 8 * n_pairs
         else:
             kern = [("k_lsi_grid", f_ms, 16 * S.n_points + 4 * S.n_edges + idx["bytes"] + 16 * R.n_points + 8 * n_pairs),
                     ("k_xsect_points_dyn", t_ms, (8 + 64 + 8 + 32) * n_pairs)]
@@ -689,7 +708,8 @@ def main():
             "vs_baseline": None, "dtype": "int64/int128", "data": "synthetic",
             "config": cfg,
             "engine": {"mode": args.mode, "lbvh_leaf_size": args.leaf_size, "sort_queries": args.sort_queries,
-                       "lbvh_ag": args.ag, "share_chains": args.share_chains,
+                       "lbvh_ag": args.ag, "share_chains": args.share_chains, "lsi_cells": args.cells,
+                       "lsi_fused": args.fused, "lsi_tile_filter": args.tile_filter,
                        "timing": "CUDA events on the launch stream around the enqueued query (rjb_lsi_launch); "
                                  "max over ranks of the sum of the K step times + the count exchange",
                        "l2": "256 MiB flush write between timed iterations; inputs (S descriptors + survivors' "

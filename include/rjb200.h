@@ -141,10 +141,17 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
  *                     < 32 edges per chain; points only on request)
  *   "lsi_filter"      LBVH LSI occupancy pre-filter: -1 auto (default: on when the
  *                     base map occupies < 25 % of a 4096^2 bitmap), 0 off, 1 on
- *   "lsi_cells"       LBVH LSI, experimental: 1 = the filter's survivors look their candidate
- *                     leaves up in a directory of the occupied cells, built with the index
- *                     (edges longer than a cell still walk the tree); 0 (default) = every
+ *   "lsi_cells"       LBVH LSI: 1 = the filter's survivors look their candidate leaves up in a
+ *                     directory of the occupied cells, built with the index (+0.15 ms and
+ *                     +48 MB on a 4 M-edge map; edges longer than 3 x 3 cells still walk the
+ *                     tree) and the exact pass reads no leaf records; 0 (default) = every
  *                     survivor walks the tree.  Set it before rjb_build_index.
+ *   "lsi_fused"       LBVH LSI: 1 (default) = exact pass and point pass are one kernel whose last
+ *                     CTA hands the counters to the host (no memset / memcpy around a query);
+ *                     0 = two kernels (k_lsi_exact, k_lsi_points)
+ *   "lsi_tile_filter" LBVH LSI: 1 = two-level occupancy filter (tiles of 32 edges first); same
+ *                     result, measured no faster; 0 (default)
+ *   "lsi_resolve_ctas" CTAs per SM of the fused kernel; 0 (default) = one resident wave
  *   "load_chunk_points" points per upload chunk of rjb_set_map (multiple of 1024, default 2^20):
  *                     the load kernel of chunk k runs while chunk k+1 is copied
  *   "pip_park"        LBVH PIP: 1 (default) = lanes park the leaf their ray meets and the
@@ -246,7 +253,8 @@ int rjb_overlay_write(rjb_ctx* ctx, const char* path);
  * -profile sub-stage timers (src/util/stopwatch.h).                            */
 int rjb_last_kernel_ms(const rjb_ctx* ctx, double out[2]);
 /* per-kernel device times (ms) of the last query, by *layout:
- *   1  LBVH LSI : {k_lsi_filter, k_lsi_bvh (+ k_lsi_cells), k_lsi_exact, k_lsi_points}
+ *   1  LBVH LSI : {k_lsi_filter, k_lsi_bvh (+ k_lsi_cells), k_lsi_exact, k_lsi_points};
+ *                 with lsi_fused: {filter, bvh / cells, k_lsi_resolve, ~0}
  *                 (option "stage_timing" = 0: one event per phase only,
  *                  {filter + traversal, 0, exact + points, 0})
  *   3  grid LSI : {k_grid_lsi_filter (+ big), k_grid_lsi_exact, k_lsi_points, 0}
@@ -266,7 +274,8 @@ int rjb_last_stats(const rjb_ctx* ctx, uint64_t out[8]);
 /* number of kernels the last completed rjb_lsi / rjb_pip put on the stream (all attempts) */
 int rjb_last_launches(const rjb_ctx* ctx, uint32_t* out);
 /* index of map_id: out[0] = leaves (LBVH) / edge-cell incidences (grid),
- * out[1] = bytes of the index, out[2] = leaf size / grid size, out[3] = 0      */
+ * out[1] = bytes of the index, out[2] = leaf size / grid size,
+ * out[3] = bytes of the LBVH's cell directory (part of out[1]; 0 if none)     */
 int rjb_index_info(const rjb_ctx* ctx, int map_id, int mode, uint64_t out[4]);
 
 /* test hook: the engine's onesweep radix sort on host (key, value) pairs, key

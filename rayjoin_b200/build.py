@@ -32,7 +32,8 @@ def _sources():
 def build(force=False, verbose=False):
     deps = _sources()
     if force or _newer(LIB, deps):
-        cmd = [NVCC] + ARCH + COMMON + ["-Xcompiler", "-fPIC,-pthread", "-shared", "-o", LIB,
+        cmd = [NVCC] + ARCH + COMMON + os.environ.get("RJB_DEFINES", "").split() + \
+              ["-Xcompiler", "-fPIC,-pthread", "-shared", "-o", os.environ.get("RJB_LIB_OUT", LIB),
                                         os.path.join(HERE, "csrc", "rjb_api.cu"),
                                         os.path.join(HERE, "host", "cdb.cc")]
         if verbose:

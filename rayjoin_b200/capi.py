@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librjb200.so")
+LIB_PATH = os.environ.get("RJB_LIB", os.path.join(_HERE, "librjb200.so"))  # (RJB_LIB: tuning builds)
 
 MODE_GRID, MODE_LBVH, MODE_BRUTE = 0, 1, 2
 MODES = {"grid": MODE_GRID, "lbvh": MODE_LBVH, "brute": MODE_BRUTE}
@@ -275,7 +275,7 @@ class Context:
     def index_info(self, map_id, mode):
         out = (C.c_uint64 * 4)()
         _check(self.lib.rjb_index_info(self._h, C.c_int(map_id), C.c_int(MODES.get(mode, mode)), out))
-        return {"units": out[0], "bytes": out[1], "param": out[2]}
+        return {"units": out[0], "bytes": out[1], "param": out[2], "cell_directory_bytes": out[3]}
 
     def last_kernel_ms(self):
         out = (C.c_double * 2)()

@@ -108,6 +108,8 @@ struct rjb_ctx {
   unsigned long long* d_h_counters = nullptr;  // the same buffer as the device sees it
   DBuf<unsigned int> lsi_ticket;             // k_lsi_resolve: CTAs that have finished (zero between queries)
   bool ctr_clean = false;                    // the device counters are zero (left so by k_lsi_resolve)
+  int resolve_ctas_per_sm = 0;               // grid of k_lsi_resolve: 0 = what is resident at once (occupancy API)
+  int resolve_resident = 0;
   int fused = 1;                             // LBVH LSI: exact + point pass in one kernel (option lsi_fused)
   bool have_scaling = false;
   rjb_scaling sc;
@@ -133,7 +135,7 @@ struct rjb_ctx {
   uint32_t last_survivors = 0, last_long = 0;
   DBuf<uint32_t> long_edges;  // survivors longer than a cell (tree walk)
   uint32_t load_chunk = kLoadChunkPoints;  // points per upload chunk (option load_chunk_points)
-  int tile_filter = 1;    // LSI: two-level occupancy filter (tiles of 32 edges first)
+  int tile_filter = 0;    // LSI: two-level occupancy filter (tiles of 32 edges first): no faster, see rjb_lsi.cuh
   int use_cells = 0;      // LSI: cell directory for the filter's survivors (experimental, off)
   size_t cand_cap = 0;
   size_t grid_work_cap = 0;
@@ -523,11 +525,19 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
     if (fused) {
       const LsiTail tail = {ctr, c->d_h_counters, c->lsi_ticket.p};
+      // one resident wave: every CTA ends with a gcd tail, a second wave would pay it twice
+      if (!c->resolve_resident) {
+        int a = 0, b = 0;
+        RJB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_lsi_resolve<true>, kResolveThreads, 0));
+        RJB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_lsi_resolve<false>, kResolveThreads, 0));
+        c->resolve_resident = std::max(1, std::min(a, b));
+      }
+      const unsigned resolve_ctas = kNumSMs * (unsigned) (c->resolve_ctas_per_sm ? c->resolve_ctas_per_sm : c->resolve_resident);
       if (cells)  // pairs in the direct format of the cell directory
-        k_lsi_resolve<true><<<kNumSMs * 3, kExactThreads, 0, c->stream>>>(Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1,
+        k_lsi_resolve<true><<<resolve_ctas, kResolveThreads, 0, c->stream>>>(Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1,
                                                                          ccap, xs, cap, (unsigned int*) ctr, ctr + 1, tail);
       else
-        k_lsi_resolve<false><<<kNumSMs * 3, kExactThreads, 0, c->stream>>>(Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1,
+        k_lsi_resolve<false><<<resolve_ctas, kResolveThreads, 0, c->stream>>>(Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1,
                                                                           ccap, xs, cap, (unsigned int*) ctr, ctr + 1, tail);
       if (c->stage_timing) RJB_CUDA(cudaEventRecord(c->ev[3], c->stream));
     } else {
@@ -816,6 +826,19 @@ const char* rjb_last_error(void) { return g_last_error.c_str(); }
 void rjb__set_error(const char* msg) { g_last_error = msg ? msg : ""; }
 const char* rjb_version(void) { return "rjb200 0.1 (sm_100a)"; }
 
+#ifdef RJB_TRACE
+// development builds only (-DRJB_TRACE): the phase trace of the last k_lsi_resolve launch
+int rjb_debug_trace(rjb_ctx* c, unsigned long long* out, int n_words) {
+  return guarded([&] {
+    RJB_CUDA(cudaStreamSynchronize(c->stream));
+    if (n_words > 4096 * 16)  // the per-warp trace
+      RJB_CUDA(cudaMemcpyFromSymbol(out, rjb::g_trace_w, (size_t) n_words * sizeof(unsigned long long)));
+    else
+      RJB_CUDA(cudaMemcpyFromSymbol(out, rjb::g_trace, (size_t) n_words * sizeof(unsigned long long)));
+  });
+}
+#endif
+
 int rjb_create(int device, rjb_ctx** out) {
   return guarded([&] {
     RJB_REQUIRE(out != nullptr, "rjb_create: out is NULL");
@@ -917,6 +940,9 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
       c->use_cells = (int) value;
     } else if (n == "lsi_tile_filter") {
       c->tile_filter = value != 0;
+    } else if (n == "lsi_resolve_ctas") {
+      RJB_REQUIRE(value >= 0 && value <= 64, "lsi_resolve_ctas must be in 0..64");
+      c->resolve_ctas_per_sm = (int) value;
     } else if (n == "lsi_fused") {
       c->fused = value != 0;
     } else if (n == "pip_park") {
@@ -1272,6 +1298,7 @@ int rjb_index_info(const rjb_ctx* c, int map_id, int mode, uint64_t out[4]) {
       out[0] = m.bvh.n_leaves;
       out[1] = m.bvh.index_bytes();
       out[2] = m.bvh.leaf_size;
+      out[3] = m.bvh.cell_directory_bytes();  // part of out[1]
     } else if (mode == RJB_MODE_GRID && m.grid.built) {
       out[0] = m.grid.n_items;
       out[1] = m.grid.index_bytes();
@@ -1307,7 +1334,7 @@ int rjb_debug_intersect_batch(rjb_ctx* c, const int64_t* h_pts, uint64_t n, int 
                               int64_t* h_x, int64_t* h_y) {
   return guarded([&] {
     RJB_REQUIRE(c && (n == 0 || (h_pts && h_flags && h_x && h_y)), "NULL argument");
-    RJB_REQUIRE(mode == 0 || mode == 1, "mode must be 0 or 1");
+    RJB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
     RJB_CUDA(cudaSetDevice(c->device));
     if (n == 0) return;
     DBuf<long long> pts, x, y;

@@ -10,7 +10,8 @@ namespace rjb {
 
 // pts: n x 8 int64 {e1.x1, e1.y1, e1.x2, e1.y2, e2.x1, e2.y1, e2.x2, e2.y2}; e1 = query side.
 // mode 0: lsi_intersect + lsi_point_axis<false> (always through the gcd);
-// mode 1: the path of k_lsi_points: lsi_point_axis<true>, deferred coordinates re-run with <false>.
+// mode 1: the path of k_lsi_points: lsi_point_axis<true>, deferred coordinates re-run with <false>;
+// mode 2: the path of k_lsi_resolve: lsi_point_both, parked states through lsi_point_finish.
 // flags[i]: bit 0 = intersects, bit 1 / 2 = x / y was deferred.
 __global__ void k_debug_intersect(const long long* __restrict__ pts, uint64_t n, int mode,
                                   unsigned char* __restrict__ flags, long long* __restrict__ ox,
@@ -25,6 +26,18 @@ __global__ void k_debug_intersect(const long long* __restrict__ pts, uint64_t n,
     if (mode == 0) {
       x = lsi_point_axis<false>(e1, e2, 0, nullptr);
       y = lsi_point_axis<false>(e1, e2, 1, nullptr);
+    } else if (mode == 2) {
+      long long out[2];
+      int code[2];
+      PointState st[2];
+      lsi_point_both(e1, e2, out, code, st);
+      for (int axis = 0; axis < 2; axis++) {
+        if (code[axis] != kPointDone) f |= 2 << axis;
+        if (code[axis] == kPointGcd) out[axis] = lsi_point_finish(st[axis]);
+        if (code[axis] == kPointRedo) out[axis] = lsi_point_axis<false>(e1, e2, axis, nullptr);
+      }
+      x = out[0];
+      y = out[1];
     } else {
       bool dx = false, dy = false;
       x = lsi_point_axis<true>(e1, e2, 0, &dx);

@@ -268,7 +268,82 @@ static __host__ __device__ long long lsi_point_axis(const Seg& e1, const Seg& e2
   return (long long) ((double) rn / (double) rd);
 }
 
+// ---- both coordinates at once, deferred coordinates with their state ------------------------
+// The fused kernel (k_lsi_resolve) computes x and y of a hit together: edge equations, the
+// denominator and e2's constant term are shared between the axes (a third of the
+// instructions of two lsi_point_axis calls), and a coordinate that needs the gcd is parked
+// WITH what has been computed -- x = X0 + rs / aden -- so that the dense pass starts at the gcd
+// instead of re-loading four vertices and re-deriving everything.  Same values as
+// lsi_point_axis (the CPU and GPU tests run both against the oracle).
+struct PointState {
+  long long X0;
+  unsigned long long rs, aden;  // 0 < rs < aden < 2^64
+};
+
+constexpr int kPointDone = 0, kPointGcd = 1, kPointRedo = 2;
+
+// the gcd path from a parked state: reduce rs / aden, assemble num/g = X0 * (aden/g) + rs/g
+static RJB_HD long long lsi_point_finish(const PointState& st) {
+  const unsigned long long g = gcd64(st.rs, st.aden);
+  const unsigned long long rd = g == 1 ? st.aden : st.aden / g;
+  const unsigned long long rr = g == 1 ? st.rs : st.rs / g;
+  const i128 rn = (i128) st.X0 * (i128) (u128) rd + (i128) (u128) rr;
+  return (long long) ((double) rn / (double) (i128) (u128) rd);
+}
+
+// out[axis] = the coordinate when code[axis] == kPointDone; kPointGcd: st[axis] is filled, finish
+// with lsi_point_finish; kPointRedo: long edges (or a 65+ bit denominator), run lsi_point_axis<false>
+static __host__ __device__ void lsi_point_both(const Seg& e1, const Seg& e2, long long out[2], int code[2],
+                                               PointState st[2]) {
+  long long a1l, b1l, a2l, b2l;
+  edge_ab(e1, a1l, b1l);
+  edge_ab(e2, a2l, b2l);
+  const long long lim = 1ll << 38;
+  if (!(a1l > -lim && a1l < lim && b1l < lim && a2l > -lim && a2l < lim && b2l < lim)) {
+    code[0] = code[1] = kPointRedo;
+    out[0] = out[1] = 0;
+    return;
+  }
+  const i128 denom = (i128) a1l * b2l - (i128) a2l * b1l;  // < 2^77: nothing wraps here
+  const i128 aden = iabs128(denom);
+  const i128 c2p = -((i128) (e2.x1 - e1.x1) * a2l + (i128) (e2.y1 - e1.y1) * b2l);
+  const double dden = (double) denom;
+#pragma unroll
+  for (int axis = 0; axis < 2; axis++) {
+    const long long lo = axis == 0 ? min4ll(e1.x1, e1.x2, e2.x1, e2.x2) : min4ll(e1.y1, e1.y2, e2.y1, e2.y2);
+    const long long hi = axis == 0 ? max4ll(e1.x1, e1.x2, e2.x1, e2.x2) : max4ll(e1.y1, e1.y2, e2.y1, e2.y2);
+    const i128 np = axis == 0 ? c2p * b1l : -c2p * a1l;
+    const long long q = (long long) rint((double) np / dden);
+    const i128 r = np - (i128) q * denom;
+    long long X0 = (axis == 0 ? e1.x1 : e1.y1) + q;
+    i128 rs = denom < 0 ? -r : r;
+    while (rs < 0) { rs += aden; X0--; }
+    while (rs >= aden) { rs -= aden; X0++; }
+    code[axis] = kPointDone;
+    if (X0 < lo) out[axis] = lo;
+    else if (X0 > hi || (X0 == hi && rs != 0)) out[axis] = hi;
+    else if (rs == 0) out[axis] = X0;
+    else if (32 * rs >= aden && 32 * (aden - rs) >= aden && lo >= -(1ll << 46) && hi <= (1ll << 46))
+      out[axis] = X0 >= 0 ? X0 : X0 + 1;
+    else if ((aden >> 64) == 0) {
+      out[axis] = 0;
+      code[axis] = kPointGcd;
+      st[axis].X0 = X0;
+      st[axis].rs = (unsigned long long) rs;
+      st[axis].aden = (unsigned long long) aden;
+    } else {
+      out[axis] = 0;
+      code[axis] = kPointRedo;
+    }
+  }
+}
+
 static __host__ __device__ long long lsi_point_axis(const Seg& e1, const Seg& e2, int axis) {
+  return lsi_point_axis<false>(e1, e2, axis, nullptr);
+}
+
+// out of line: the rare "redo" path of the fused kernel (long edges) must not bloat its hot code
+static __host__ __device__ __noinline__ long long lsi_point_axis_slow(const Seg& e1, const Seg& e2, int axis) {
   return lsi_point_axis<false>(e1, e2, axis, nullptr);
 }
 

@@ -59,13 +59,15 @@ struct Bvh {
     v.top_levels = top_levels;
     return v;
   }
+  size_t cell_directory_bytes() const {
+    return have_cells ? (size_t) (kOccWords + 1) * sizeof(uint2) + (size_t) (n_occ_cells + 1) * 4 +
+                            (size_t) n_incidences * sizeof(uint4) : 0;
+  }
   size_t index_bytes() const {
     uint32_t n_int = n_leaves > 1 ? n_leaves - 1 : 1;
     return (size_t) n_int * (2 * sizeof(int4) + sizeof(int2)) + (size_t) n_leaves * sizeof(uint2) +
            (size_t) (top_levels == 4 ? kTopSlots4 : kTopSlots3) * (sizeof(int4) + sizeof(int)) +
-           (size_t) kOccMaps * kOccDim * kOccDim / 8 +
-           (have_cells ? (size_t) (kOccWords + 1) * sizeof(uint2) + (size_t) (n_occ_cells + 1) * 4 +
-                             (size_t) n_incidences * sizeof(uint4) : 0);
+           (size_t) kOccMaps * kOccDim * kOccDim / 8 + cell_directory_bytes();
   }
 };
 

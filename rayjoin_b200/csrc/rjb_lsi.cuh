@@ -314,11 +314,14 @@ k_lsi_filter(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __restrict
   }
 }
 
-// Two-level variant of the filter (option lsi_tile_filter, default): a warp first decides 32
-// TILES of 32 edges each with one look-up per tile (lane = tile: tile_desc_of, bitmaps dilated
+// Two-level variant of the filter (option lsi_tile_filter, off by default): a warp first decides
+// 32 TILES of 32 edges each with one look-up per tile (lane = tile: tile_desc_of, bitmaps dilated
 // to the size of the tile's box), then reads the 32 edge descriptors of the live tiles only,
-// kTfBatch tiles in flight at a time.  On the County x Zipcode-scale workload 29 % of the tiles
-// are live, so the kernel moves a third of the descriptors and executes a third of the rounds.
+// kTfBatch tiles in flight at a time.  MEASURED: no gain on the County x Zipcode-scale workload
+// (35.3 us against 34.5 us).  With the TIGHT box of a tile 29 % of the tiles are live, but 61 % of
+// the tiles span more than 8 x 8 cells (a third hold a chain end, and 32 edges are ~9 cells
+// long), which the largest dilated bitmap cannot decide: 72 % stay live.  Tiles of 16 edges
+// would leave 35 % live (CPU experiment, tools/micro notes in DESIGN.md section 8).
 // Tile t = the edges starting at points 32 t - 1 .. 32 t + 30 (lane = point again in stage 2).
 // Survivors leave as one map-ordered run per CTA, like k_lsi_filter.
 constexpr int kTfWarps = 4;
@@ -961,6 +964,26 @@ k_lsi_points(MapView Q, MapView B, int query_map_id, const unsigned int* __restr
 // memcpy after the kernels (each ~3-5 us of stream time on a 0.15 ms query).
 constexpr int kLsiCtrs = 10;  // 64-bit words the host reads back
 
+// Optional phase trace (build with -DRJB_TRACE; rjb_debug_trace reads it): thread 0 of every
+// CTA notes %globaltimer at the phase boundaries of k_lsi_resolve.
+#ifdef RJB_TRACE
+constexpr int kTraceSlots = 16;
+__device__ unsigned long long g_trace[4096 * kTraceSlots];
+__device__ unsigned long long g_trace_w[4096 * 4 * kTraceSlots];  // lane 0 of every warp
+static __device__ __forceinline__ void trace_mark(int& k) {
+  if ((threadIdx.x & 31) == 0 && blockIdx.x < 4096 && k < kTraceSlots) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (threadIdx.x == 0) g_trace[blockIdx.x * kTraceSlots + k] = t;
+    g_trace_w[(blockIdx.x * 4 + (threadIdx.x >> 5 & 3)) * kTraceSlots + k] = t;
+  }
+  k++;
+}
+#define RJB_MARK(k) trace_mark(k)
+#else
+#define RJB_MARK(k)
+#endif
+
 struct LsiTail {
   unsigned long long* ctr;   // device counters [0, kLsiCtrs)
   unsigned long long* host;  // their mapped pinned copy (device pointer), or nullptr: leave them
@@ -971,10 +994,16 @@ struct LsiTail {
 static __device__ __forceinline__ void lsi_tail(const LsiTail& T) {
   __shared__ bool s_last;
   if (!T.host) return;
+#ifdef RJB_TRACE
+  int tk = 6;  // slots 6..9 (the rounds rarely get that far)
+#endif
   __syncthreads();  // the CTA's own atomics are issued
+  RJB_MARK(tk);  // 6: barrier B passed
   if (threadIdx.x == 0) {
     __threadfence();
+    RJB_MARK(tk);  // 7: fence done
     s_last = atomicAdd(T.ticket, 1u) == gridDim.x - 1;
+    RJB_MARK(tk);  // 8: ticket back
   }
   __syncthreads();
   if (!s_last) return;
@@ -986,30 +1015,80 @@ static __device__ __forceinline__ void lsi_tail(const LsiTail& T) {
   if (threadIdx.x == 0) *T.ticket = 0;
 }
 
-constexpr int kResolveDefer = 3 * kExactThreads;  // < kExactThreads before a drain, <= 2 per thread added
+// Build-time variants, measured on the B200 (k_lsi_resolve on the bench workload, us):
+//   defaults below                                                   47.4
+//   RJB_RESOLVE_JOINT=1  both axes at once (lsi_point_both), parked state   53.0  (88 registers)
+//   RJB_RESOLVE_INL=__noinline__  one copy of drain / flush (72 KB code)    51.0  (240 B stack)
+//   RJB_RESOLVE_ROT=1    flush warp rotates with the CTA                     49.1
+//   RJB_RESOLVE_THREADS=128  twice as many, smaller CTAs                     49.1
+// (tools/trace_resolve.py with -DRJB_TRACE shows the phases: 3 box rounds of 2 us, 2-3 drains
+// of 6-9 us, a final flush of 15 us of which the gcd itself is 3.5 us.)
+#ifndef RJB_RESOLVE_INL
+#define RJB_RESOLVE_INL __forceinline__
+#endif
+#ifndef RJB_RESOLVE_ROT
+#define RJB_RESOLVE_ROT 0
+#endif
+#ifndef RJB_RESOLVE_JOINT
+#define RJB_RESOLVE_JOINT 0
+#endif
+#ifndef RJB_RESOLVE_THREADS
+#define RJB_RESOLVE_THREADS 256
+#endif
+#ifndef RJB_RESOLVE_MIN_CTAS
+#define RJB_RESOLVE_MIN_CTAS 1
+#endif
+constexpr int kResolveThreads = RJB_RESOLVE_THREADS;  // small CTAs: the gcd tail of one overlaps the others' work
+constexpr int kResolveList = 9 * kResolveThreads;
+constexpr int kResolveDefer = 3 * kResolveThreads;  // < kResolveThreads before a drain, <= 2 per thread added
 
-// deferred coordinates of the CTA: the full (gcd) path, one item per thread
-static __device__ __forceinline__ void resolve_flush(const MapView& Q, const MapView& B, const DeferItem* list,
+// a parked coordinate: where it goes, and the state the gcd path continues from (or, for long
+// edges, the pair to redo from scratch)
+struct ResolveDefer {
+  uint32_t i;       // result slot
+  uint32_t axis;    // 0 / 1, + 2 when the item must be redone with lsi_point_axis<false>
+  PointState st;    // (redo: X0 = query start point | base start point << 32)
+};
+
+// deferred coordinates of the CTA: the gcd path, one item per thread.  A flush usually has a
+// dozen items, i.e. ONE busy warp per CTA running a ~1400-instruction dependent chain.  Warp w of
+// every CTA sits on sub-partition w % 4, so with the items in warp 0 the flushes of the six
+// CTAs of an SM all queued on one scheduler (ncu / %globaltimer trace: 15 us per flush against
+// 3.5 us for the same code alone); the warp that takes the first items rotates with the CTA.
+// (ONE copy of the code: the kernel calls it from two places, and a 170 KB kernel does not stay in
+// the instruction cache)
+static __device__ RJB_RESOLVE_INL void resolve_flush(const MapView& Q, const MapView& B, const ResolveDefer* list,
                                                      unsigned n_list, rjb_xsect* __restrict__ out) {
-  for (unsigned t = threadIdx.x; t < n_list; t += kExactThreads) {
-    const DeferItem it = list[t];
-    const longlong2 a = __ldg(&Q.pts[it.pq]), b = __ldg(&Q.pts[it.pq + 1]);
-    const longlong2 c = __ldg(&B.pts[it.pb]), d = __ldg(&B.pts[it.pb + 1]);
-    const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
-    const long long v = lsi_point_axis<false>(e1, e2, (int) it.axis, nullptr);
-    if (it.axis == 0) out[it.i].x = v; else out[it.i].y = v;
+  const unsigned rot = RJB_RESOLVE_ROT ? 32u * ((blockIdx.x / kNumSMs + blockIdx.x) % (kResolveThreads / 32)) : 0u;
+  for (unsigned t = (threadIdx.x + kResolveThreads - rot) % kResolveThreads; t < n_list; t += kResolveThreads) {
+    const ResolveDefer it = list[t];
+    long long v;
+    if (it.axis & 2u) {
+      const uint32_t pq = (uint32_t) (unsigned long long) it.st.X0, pb = (uint32_t) ((unsigned long long) it.st.X0 >> 32);
+      const longlong2 a = __ldg(&Q.pts[pq]), b = __ldg(&Q.pts[pq + 1]);
+      const longlong2 c = __ldg(&B.pts[pb]), d = __ldg(&B.pts[pb + 1]);
+      const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
+      v = lsi_point_axis_slow(e1, e2, (int) (it.axis & 1u));
+    } else {
+#ifdef RJB_EXP_NOGCD
+      v = it.st.X0;
+#else
+      v = lsi_point_finish(it.st);
+#endif
+    }
+    if ((it.axis & 1u) == 0) out[it.i].x = v; else out[it.i].y = v;
   }
 }
 
 // intersect_test over the CTA's list of box-overlapping pairs, every lane busy; a hit becomes a
 // finished rjb_xsect record at once (deferred coordinates: s_defer, flushed whenever a CTA's
 // worth has gathered).  Called by ALL threads with the same n_list; contains barriers.
-static __device__ __forceinline__ void resolve_drain(const MapView& Q, const MapView& B, int query_map_id,
-                                                     const uint2* list, unsigned n_list, DeferItem* s_defer,
+static __device__ RJB_RESOLVE_INL void resolve_drain(const MapView& Q, const MapView& B, int query_map_id,
+                                                     const uint2* list, unsigned n_list, ResolveDefer* s_defer,
                                                      unsigned* s_nd, rjb_xsect* __restrict__ out, uint32_t cap,
                                                      unsigned int* counter) {
   const int lane = threadIdx.x & 31;
-  for (unsigned r0 = 0; r0 < n_list; r0 += kExactThreads) {  // block-uniform trip count (barriers inside)
+  for (unsigned r0 = 0; r0 < n_list; r0 += kResolveThreads) {  // block-uniform trip count (barriers inside)
     const unsigned t = r0 + threadIdx.x;
     bool found = false;
     uint2 it = make_uint2(0, 0);
@@ -1033,12 +1112,37 @@ static __device__ __forceinline__ void resolve_drain(const MapView& Q, const Map
     if (found) {
       const unsigned pos = base + __popc(m & ((1u << lane) - 1));
       if (pos < cap) {
-        bool dx = false, dy = false;
+        long long xy[2];
+        int code[2];
+        PointState st[2];
+#if RJB_RESOLVE_JOINT
+        lsi_point_both(e1, e2, xy, code, st);
+#else
+        for (int axis = 0; axis < 2; axis++) {
+          bool def = false;
+          xy[axis] = lsi_point_axis<true>(e1, e2, axis, &def);
+          code[axis] = def ? kPointRedo : kPointDone;
+        }
+#endif
         rjb_xsect r;
-        r.x = lsi_point_axis<true>(e1, e2, 0, &dx);
-        r.y = lsi_point_axis<true>(e1, e2, 1, &dy);
-        if (dx) s_defer[atomicAdd(s_nd, 1u)] = {pos, it.x, it.y, 0u};
-        if (dy) s_defer[atomicAdd(s_nd, 1u)] = {pos, it.x, it.y, 1u};
+        r.x = xy[0];
+        r.y = xy[1];
+#pragma unroll
+        for (int axis = 0; axis < 2; axis++)
+#ifdef RJB_EXP_INLINE_GCD
+          if (code[axis] == kPointGcd) {
+            const long long v = lsi_point_finish(st[axis]);
+            if (axis == 0) r.x = v; else r.y = v;
+          } else
+#endif
+          if (code[axis] != kPointDone) {
+            ResolveDefer d;
+            d.i = pos;
+            d.axis = (uint32_t) axis | (code[axis] == kPointRedo ? 2u : 0u);
+            d.st = st[axis];
+            if (code[axis] == kPointRedo) d.st.X0 = (long long) ((unsigned long long) it.x | ((unsigned long long) it.y << 32));
+            s_defer[atomicAdd(s_nd, 1u)] = d;
+          }
         const uint32_t eq = it.x - cq, eb = it.y - cb;
         r.eid[0] = query_map_id == 0 ? eq : eb;
         r.eid[1] = query_map_id == 0 ? eb : eq;
@@ -1049,7 +1153,7 @@ static __device__ __forceinline__ void resolve_drain(const MapView& Q, const Map
     }
     // <= 2 deferred coordinates per thread and round: the list never exceeds kResolveDefer
     __syncthreads();
-    if (*s_nd >= kExactThreads) {
+    if (*s_nd >= kResolveThreads) {
       resolve_flush(Q, B, s_defer, *s_nd, out);
       __syncthreads();
       if (threadIdx.x == 0) *s_nd = 0;
@@ -1059,21 +1163,28 @@ static __device__ __forceinline__ void resolve_drain(const MapView& Q, const Map
 }
 
 template <bool kDirect>
-__global__ void __launch_bounds__(kExactThreads)
+__global__ void __launch_bounds__(kResolveThreads, RJB_RESOLVE_MIN_CTAS)
 k_lsi_resolve(MapView Q, MapView B, int query_map_id, const uint2* __restrict__ pairs,
               const uint2* __restrict__ leaf_rec, const unsigned int* __restrict__ n_pairs_dev, uint32_t pair_cap,
               rjb_xsect* __restrict__ out, uint32_t cap, unsigned int* counter, unsigned long long* n_cand,
               LsiTail tail) {
-  __shared__ uint2 s_list[kExactList];
-  __shared__ DeferItem s_defer[kResolveDefer];
+  __shared__ uint2 s_list[kResolveList];
+  __shared__ ResolveDefer s_defer[kResolveDefer];
   __shared__ unsigned s_n, s_nd;
   if (threadIdx.x == 0) s_n = s_nd = 0;
+#ifdef RJB_TRACE
+  int tk = 0;
+  if (threadIdx.x == 0 && blockIdx.x < 4096)
+    for (int z = 0; z < kTraceSlots; z++) g_trace[blockIdx.x * kTraceSlots + z] = 0;
+#endif
+  RJB_MARK(tk);  // 0: start
   __syncthreads();
   const uint32_t n = min(*n_pairs_dev, pair_cap);
   const int lane = threadIdx.x & 31;
   unsigned cand = 0;
+  RJB_MARK(tk);  // 1: count read
   // block-uniform trip count: every thread reaches the barriers
-  for (uint64_t i0 = (uint64_t) blockIdx.x * kExactThreads; i0 < n; i0 += (uint64_t) gridDim.x * kExactThreads) {
+  for (uint64_t i0 = (uint64_t) blockIdx.x * kResolveThreads; i0 < n; i0 += (uint64_t) gridDim.x * kResolveThreads) {
     const uint64_t i = i0 + threadIdx.x;
     uint32_t pq = 0, pb0 = 0, cnt = 0;
     Seg e1 = {0, 0, 0, 0};
@@ -1138,20 +1249,38 @@ k_lsi_resolve(MapView Q, MapView B, int query_map_id, const uint2* __restrict__ 
       }
     }
     __syncthreads();
+    RJB_MARK(tk);  // after the box stage of a round
     const unsigned n_list = s_n;
-    if (n_list >= kExactThreads) {
+    if (n_list >= kResolveThreads) {
       resolve_drain(Q, B, query_map_id, s_list, n_list, s_defer, &s_nd, out, cap, counter);
       __syncthreads();
       if (threadIdx.x == 0) s_n = 0;
       __syncthreads();
+      RJB_MARK(tk);  // after a drain
     }
   }
   __syncthreads();
+#ifdef RJB_TRACE
+  tk = 10;
+#endif
+  RJB_MARK(tk);  // 10: loop done
   resolve_drain(Q, B, query_map_id, s_list, s_n, s_defer, &s_nd, out, cap, counter);
   __syncthreads();
+  RJB_MARK(tk);  // 11: final drain done
   resolve_flush(Q, B, s_defer, s_nd, out);
+#ifdef RJB_TRACE
+  { int k2 = 14; RJB_MARK(k2); }  // 14: back from the flush
+#endif
+#ifndef RJB_EXP_NOCAND
   if (lane == 0 && cand) atomicAdd(n_cand, (unsigned long long) cand);
+#endif
+#ifdef RJB_TRACE
+  { int k2 = 15; RJB_MARK(k2); }  // 15: atomic issued
+#endif
+  __syncthreads();
+  RJB_MARK(tk);  // 12: final flush done
   lsi_tail(tail);
+  RJB_MARK(tk);  // 13: end
 }
 
 // All |Q| x |B| pairs, no index: pins the exact arithmetic (RJB_MODE_BRUTE).

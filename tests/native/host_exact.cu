@@ -18,6 +18,20 @@ void hx_intersect_batch(const long long* pts, unsigned long long n, int mode, un
     hit[i] = lsi_intersect(e1, e2) ? 1 : 0;
     ox[i] = oy[i] = 0;
     if (!hit[i]) continue;
+    if (mode == 2) {  // the path of k_lsi_resolve: both axes at once, parked states finished afterwards
+      long long out[2];
+      int code[2];
+      PointState st[2];
+      lsi_point_both(e1, e2, out, code, st);
+      for (int axis = 0; axis < 2; axis++) {
+        if (code[axis] != kPointDone) nd++;
+        if (code[axis] == kPointGcd) out[axis] = lsi_point_finish(st[axis]);
+        if (code[axis] == kPointRedo) out[axis] = lsi_point_axis<false>(e1, e2, axis, nullptr);
+      }
+      ox[i] = out[0];
+      oy[i] = out[1];
+      continue;
+    }
     for (int axis = 0; axis < 2; axis++) {
       long long v;
       if (mode == 0) {

@@ -58,7 +58,7 @@ def crossing(rng, n, span_bits, off_bits=46):
     return e.reshape(n, 8)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_product_arithmetic_matches_reference_golden(hx, mode):
     z = np.load(os.path.join(GOLD, "lsi_kat.npz"))
     hit, x, y, _ = run(hx, z["pts"], mode)
@@ -74,7 +74,7 @@ def test_gcd_free_point_path_is_bit_exact(hx, oracle, span_bits):
     hit, x, y = oracle.intersect_batch(pts)
     m = hit == 1
     assert m.sum() > 30000
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         h2, x2, y2, nd = run(hx, pts, mode)
         assert np.array_equal(hit, h2)
         assert np.array_equal(x[m], x2[m]) and np.array_equal(y[m], y2[m])
@@ -100,7 +100,7 @@ def test_gcd_free_point_path_special_cases(hx, oracle):
     for pts in sets:
         hit, x, y = oracle.intersect_batch(pts)
         m = hit == 1
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             h2, x2, y2, _ = run(hx, pts, mode)
             assert np.array_equal(hit, h2)
             assert np.array_equal(x[m], x2[m]) and np.array_equal(y[m], y2[m])

@@ -31,7 +31,7 @@ def ctx(rjb):
     c.close()
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_reference_golden_vectors_on_device(ctx, mode):
     z = np.load(os.path.join(GOLD, "lsi_kat.npz"))
     flags, x, y = ctx.debug_intersect_batch(z["pts"], mode)
@@ -50,7 +50,7 @@ def test_device_points_match_oracle_for_every_span(ctx, oracle, span_bits):
     hit, x, y = oracle.intersect_batch(pts)
     m = hit == 1
     assert m.sum() > 80000
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         flags, gx, gy = ctx.debug_intersect_batch(pts, mode)
         assert np.array_equal(flags & 1, hit)
         assert np.array_equal(gx[m], x[m]) and np.array_equal(gy[m], y[m])
@@ -71,7 +71,7 @@ def test_device_degenerate_cases_match_oracle(ctx, oracle):
     for pts in sets:
         hit, x, y = oracle.intersect_batch(pts)
         m = hit == 1
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             flags, gx, gy = ctx.debug_intersect_batch(pts, mode)
             assert np.array_equal(flags & 1, hit)
             assert np.array_equal(gx[m], x[m]) and np.array_equal(gy[m], y[m])

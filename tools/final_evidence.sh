@@ -12,8 +12,8 @@ tail -2 gpurun_out/bench_${TAG}.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_bench_lbvh.csv \
   python bench.py --legs lsi --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launch.log 2>&1
 # full captures of the query kernels (one launch each, after warm-up launches are skipped)
-ncu --set full --clock-control none --import-source on -k regex:"k_lsi_filter|k_lsi_bvh|k_lsi_exact|k_lsi_points" \
-  --launch-skip 8 -c 4 -o gpurun_out/${TAG}_lsi_full python bench.py --legs lsi --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/${TAG}_ncu_lsi.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_lsi_filter|k_lsi_bvh|k_lsi_cells|k_lsi_resolve|k_lsi_exact|k_lsi_points" \
+  --launch-skip 6 -c 3 -o gpurun_out/${TAG}_lsi_full python bench.py --legs lsi --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/${TAG}_ncu_lsi.log 2>&1
 ncu -i gpurun_out/${TAG}_lsi_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_full_lsi_kernels_raw.csv 2>/dev/null
 ncu --set full --clock-control none --import-source on -k regex:"k_pip_grid|k_pip_bvh|k_sort_onesweep_packed|k_grid_lsi" \
   -c 6 -o gpurun_out/${TAG}_pip_full python tools/pip_bench.py --points 50000000 --modes grid,lbvh --sort 1 --park 1 --check 0 --repeat 1 --grid-size 16384 > gpurun_out/${TAG}_ncu_pip.log 2>&1
