@@ -135,6 +135,7 @@ struct rjb_ctx {
   uint32_t last_survivors = 0, last_long = 0;
   DBuf<uint32_t> long_edges;  // survivors longer than a cell (tree walk)
   uint32_t load_chunk = kLoadChunkPoints;  // points per upload chunk (option load_chunk_points)
+  int pip_sort_bits = 24; // grid PIP: key bits the points are ordered by (the high ones: column first)
   int tile_filter = 0;    // LSI: two-level occupancy filter (tiles of 32 edges first): no faster, see rjb_lsi.cuh
   int use_cells = 0;      // LSI: cell directory for the filter's survivors (experimental, off)
   size_t cand_cap = 0;
@@ -762,8 +763,9 @@ static void do_pip(rjb_ctx* c, int q, int mode, const longlong2* d_pts, uint32_t
       k_query_keys_points_grid<<<div_up(n, 256), 256, 0, c->stream>>>(d_pts, n, gv, ka);
       int bits = 1;
       while (bits < 32 && (((uint64_t) gv.gx * gv.gs) >> bits)) bits++;
-      // the low (row) bits beyond 24 key bits buy nothing: three radix passes at most
-      const int lo = bits > 24 ? bits - 24 : 0;
+      // the low (row) bits beyond pip_sort_bits (default 24) key bits buy nothing: three radix
+      // passes at most
+      const int lo = bits > c->pip_sort_bits ? bits - c->pip_sort_bits : 0;
       order = sort_packed(ka, kb, n, lo, bits, c->ord_sort, c->stream);
       launches += 3 + (bits - lo + 7) / 8;
     } else {
@@ -940,6 +942,9 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
       c->use_cells = (int) value;
     } else if (n == "lsi_tile_filter") {
       c->tile_filter = value != 0;
+    } else if (n == "pip_sort_bits") {
+      RJB_REQUIRE(value >= 1 && value <= 32, "pip_sort_bits must be in 1..32");
+      c->pip_sort_bits = (int) value;
     } else if (n == "lsi_resolve_ctas") {
       RJB_REQUIRE(value >= 0 && value <= 64, "lsi_resolve_ctas must be in 0..64");
       c->resolve_ctas_per_sm = (int) value;

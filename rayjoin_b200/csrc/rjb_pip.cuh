@@ -172,8 +172,11 @@ static __device__ __forceinline__ int lowest_slot(unsigned m, int ymin, int lane
   return __ffs(__ballot_sync(0xffffffffu, key == best && ((m >> lane) & 1u))) - 1;
 }
 
+#ifndef RJB_PIP_MIN_CTAS
+#define RJB_PIP_MIN_CTAS 8
+#endif
 template <bool kStats, bool kPark>
-__global__ void __launch_bounds__(kLsiWarps * 32, 8)
+__global__ void __launch_bounds__(kLsiWarps * 32, RJB_PIP_MIN_CTAS)
 k_pip_bvh(const longlong2* __restrict__ pts, uint32_t n_pts, const uint64_t* __restrict__ order,
           MapView B, BvhView bvh, int query_map_id, uint32_t* __restrict__ out_eid,
           int32_t* __restrict__ out_face, uint2* __restrict__ out_packed, unsigned long long* counters) {

@@ -22,6 +22,7 @@ ap.add_argument("--repeat", type=int, default=3)
 ap.add_argument("--check", type=int, default=200_000, help="points checked against the oracle (-1: all of them)")
 ap.add_argument("--stats", type=int, default=0)
 ap.add_argument("--park", default="0", help="option pip_park values to run (A/B), e.g. 0,1")
+ap.add_argument("--sort-bits", default="24", help="option pip_sort_bits values to run (grid mode)")
 args = ap.parse_args()
 
 t0 = time.time()
@@ -51,19 +52,23 @@ torch.cuda.synchronize()
 om_pts = None
 for mode in args.modes.split(","):
     build = min(ctx.build_index(0, mode, args.grid_size) for _ in range(2))
-    for sq, park in [(int(x), int(y)) for x in args.sort.split(",") for y in args.park.split(",")]:
+    for sq, park, sbits in [(int(x), int(y), int(z)) for x in args.sort.split(",") for y in args.park.split(",")
+                            for z in (args.sort_bits.split(",") if mode == "grid" else ["24"])]:
+        if sq == 0 and sbits != int(args.sort_bits.split(",")[0]):
+            continue
         ctx.set_option("sort_queries", sq)
+        ctx.set_option("pip_sort_bits", sbits)
         ctx.set_option("pip_park", park if mode == "lbvh" else 0)
         times, kms = [], []
         for it in range(args.repeat + 1):
             torch.cuda.synchronize(); t = time.perf_counter()
             de, df, cand = ctx.pip_device(1, mode, pts.data_ptr(), args.points)
             dt = time.perf_counter() - t
-            if it: times.append(dt * 1e3); kms.append(ctx.last_kernel_ms()[0])
-        out = {"query": "pip", "mode": mode, "sort_queries": sq, "pip_park": park, "points": args.points,
+            if it: times.append(dt * 1e3); kms.append(ctx.last_kernel_ms()[0]); stg = ctx.last_stage_ms()[0]
+        out = {"query": "pip", "mode": mode, "sort_queries": sq, "pip_park": park, "pip_sort_bits": sbits, "points": args.points,
                "edges": R.n_edges, "build_ms": build, "query_ms": float(np.min(times)),
                "kernel_ms": float(np.min(kms)), "points_per_s": args.points / (np.min(times) / 1e3),
-               "candidates": cand}
+               "order_ms": stg[0], "candidates": cand}
         if args.stats:
             ctx.set_option("stats", 1)
             ctx.pip_device(1, mode, pts.data_ptr(), args.points)
