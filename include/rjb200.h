@@ -152,12 +152,19 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
  *   "lsi_tile_filter" LBVH LSI: 1 = two-level occupancy filter (tiles of 32 edges first); same
  *                     result, measured no faster; 0 (default)
  *   "lsi_resolve_ctas" CTAs per SM of the fused kernel; 0 (default) = one resident wave
+ *   "lsi_pdl"         LBVH LSI: 1 = the kernels of a query are launched as programmatic dependents
+ *                     (griddepcontrol); measured slower (early CTAs of the next kernel take the
+ *                     registers the running one needs); 0 (default; 1 needs a -DRJB_PDL build)
+ *   "pip_sort_bits"   grid PIP with ordered points: how many (high) bits of the cell key the
+ *                     points are ordered by, default 24 = three radix passes
  *   "load_chunk_points" points per upload chunk of rjb_set_map (multiple of 1024, default 2^20):
  *                     the load kernel of chunk k runs while chunk k+1 is copied
  *   "pip_park"        LBVH PIP: 1 (default) = lanes park the leaf their ray meets and the
  *                     warp opens the parked leaves together; 0 = open a leaf when reached
  *   "stage_timing"    LBVH LSI: 1 (default) = a CUDA event after every kernel
- *                     (rjb_last_stage_ms), 0 = after every phase only
+ *                     (rjb_last_stage_ms), 0 = after every phase only, -1 = none (the times of
+ *                     rjb_last_kernel_ms / rjb_last_stage_ms are 0 then; every event record
+ *                     costs 2-3 us of stream time, ~8 % of a 0.13 ms query)
  *   "stats"           1 = collect traversal statistics (rjb_last_stats; slower)
  *   "keep_host_graph" 0 = rjb_set_map keeps no host copy of the source graph
  *                     (saves a memcpy; rjb_overlay_write then refuses)     */

@@ -110,6 +110,7 @@ struct rjb_ctx {
   bool ctr_clean = false;                    // the device counters are zero (left so by k_lsi_resolve)
   int resolve_ctas_per_sm = 0;               // grid of k_lsi_resolve: 0 = what is resident at once (occupancy API)
   int resolve_resident = 0;
+  int pdl = 0;                               // programmatic dependent launch of the query's kernels: measured slower
   int fused = 1;                             // LBVH LSI: exact + point pass in one kernel (option lsi_fused)
   bool have_scaling = false;
   rjb_scaling sc;
@@ -268,14 +269,18 @@ k_load_points(const double2* __restrict__ in, uint32_t p_begin, uint32_t p_end, 
     edge_desc[p - 1] = d;
   }
   if (p == n_points - 1) edge_desc[p] = kDescNone << 24;
-  // tile descriptor of the warp's 32 points (tile_desc_of): one word per warp
-  const bool any_edge = __any_sync(0xffffffffu, bx0 != 0xFFFFFFFFu);
-  bx0 = __reduce_min_sync(0xffffffffu, bx0);
-  by0 = __reduce_min_sync(0xffffffffu, by0);
-  bx1 = __reduce_max_sync(0xffffffffu, bx1);
-  by1 = __reduce_max_sync(0xffffffffu, by1);
-  if (lane == 0 && p < p_end) tile_desc[p >> 5] = any_edge ? tile_desc_of(bx0, by0, bx1, by1) : (kTileNone << 24);
-  if (p == n_points - 1) tile_desc[(p >> 5) + 1] = kTileNone << 24;  // the tile after the last one is read too
+  // tile descriptors of the warp's 32 points (tile_desc_of): one word per group of kTileT lanes
+  {
+    const unsigned gmask = (kTileT == 32 ? 0xffffffffu : ((1u << kTileT) - 1u)) << (lane & ~(kTileT - 1));
+    const bool any_edge = (__ballot_sync(0xffffffffu, bx0 != 0xFFFFFFFFu) & gmask) != 0;
+    bx0 = __reduce_min_sync(gmask, bx0);
+    by0 = __reduce_min_sync(gmask, by0);
+    bx1 = __reduce_max_sync(gmask, bx1);
+    by1 = __reduce_max_sync(gmask, by1);
+    if ((lane & (kTileT - 1)) == 0 && p < p_end)
+      tile_desc[p / kTileT] = any_edge ? tile_desc_of(bx0, by0, bx1, by1) : (kTileNone << 24);
+    if (p == n_points - 1) tile_desc[p / kTileT + 1] = kTileNone << 24;  // the tile after the last one is read too
+  }
 }
 
 // scaling alone (query points of rjb_pip_host): fma.rn.f64 then cvt.rzi.s64.f64
@@ -356,6 +361,22 @@ static const uint32_t* query_order_edges(rjb_ctx* c, DeviceMap& Qm, const MapVie
   k_unpack_low<<<div_up(n, 256), 256, 0, c->stream>>>(sorted, n, keep);
   Qm.edge_order_valid = true;
   return keep;
+}
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait in rjb_lsi.cuh)
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  RJB_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
 }
 
 // Wait for the stream by polling (yielding the core between polls): a blocking cudaStreamSynchronize wakes the host tens of
@@ -480,7 +501,8 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     const bool fused = c->fused && !c->stats;
     if (!(fused && c->ctr_clean)) RJB_CUDA(cudaMemsetAsync(ctr, 0, 10 * sizeof(unsigned long long), c->stream));
     c->ctr_clean = false;  // until lsi_finish has seen this query complete
-    RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    const bool timed = c->stage_timing >= 0;  // (-1: no events at all: each costs 2-3 us of stream time)
+    if (timed) RJB_CUDA(cudaEventRecord(c->ev[0], c->stream));
     // query slots: point indices (edge = slot, slot + 1), or a list of start points
     // (Morton-sorted edges, or the survivors of the occupancy filter, whose count
     // stays on the device)
@@ -490,7 +512,7 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     const unsigned int* n_slots_dev = nullptr;
     if (filter) {
       if (c->tile_filter)
-        k_lsi_filter_tiles<<<div_up(p_hi / 32 - p_lo / 32 + 1, kTfCtaTiles), kTfWarps * 32, 0, c->stream>>>(
+        k_lsi_filter_tiles<<<div_up(p_hi / kTileT - p_lo / kTileT + 1, kTfCtaTiles), kTfWarps * 32, 0, c->stream>>>(
             Q, p_lo, p_hi, Bm.bvh.occ.p, surv, surv_n, long_list, surv_n + 2);
       else
         k_lsi_filter<<<div_up(p_hi - (p_lo & ~31u), kFilterCtaPoints), kFilterThreads, 0, c->stream>>>(
@@ -501,11 +523,15 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
       // grid for the worst case; warps beyond the survivor count exit at once
       n_slots = c->last_survivors ? min(Q.n_points, c->last_survivors + c->last_survivors / 4 + 4096) : Q.n_points;
     }
-    if (c->stage_timing) RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    if (c->stage_timing > 0) RJB_CUDA(cudaEventRecord(c->ev[1], c->stream));
     if (cells) {
       // survivors: cell directory; the long ones (usually none) walk the tree
-      k_lsi_cells<<<kNumSMs * 48, kLsiWarps * 32, 0, c->stream>>>(Q, Bm.bvh.view(), surv, surv_n, cands, ccap,
-                                                                surv_n + 1);
+      if (c->pdl)
+        launch_pdl(k_lsi_cells, kNumSMs * 48, kLsiWarps * 32, c->stream, Q, Bm.bvh.view(), (const uint32_t*) surv,
+                   (const unsigned int*) surv_n, cands, ccap, surv_n + 1);
+      else
+        k_lsi_cells<<<kNumSMs * 48, kLsiWarps * 32, 0, c->stream>>>(Q, Bm.bvh.view(), surv, surv_n, cands, ccap,
+                                                                  surv_n + 1);
       slots = long_list;
       n_slots_dev = surv_n + 2;
       slot_lo = 0;
@@ -520,10 +546,13 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     } else if (c->stats)
       k_lsi_bvh<true><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
           Q, B, Bm.bvh.view(), slots, n_slots, slot_lo, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2, cells);
+    else if (c->pdl)
+      launch_pdl(k_lsi_bvh<false>, blocks, kLsiWarps * 32, c->stream, Q, B, Bm.bvh.view(), slots, n_slots, slot_lo,
+                 n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2, cells);
     else
       k_lsi_bvh<false><<<blocks, kLsiWarps * 32, 0, c->stream>>>(
           Q, B, Bm.bvh.view(), slots, n_slots, slot_lo, n_slots_dev, spw, cands, ccap, surv_n + 1, ctr + 2, cells);
-    RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    if (timed) RJB_CUDA(cudaEventRecord(c->ev[2], c->stream));
     if (fused) {
       const LsiTail tail = {ctr, c->d_h_counters, c->lsi_ticket.p};
       // one resident wave: every CTA ends with a gcd tail, a second wave would pay it twice
@@ -534,13 +563,22 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
         c->resolve_resident = std::max(1, std::min(a, b));
       }
       const unsigned resolve_ctas = kNumSMs * (unsigned) (c->resolve_ctas_per_sm ? c->resolve_ctas_per_sm : c->resolve_resident);
-      if (cells)  // pairs in the direct format of the cell directory
-        k_lsi_resolve<true><<<resolve_ctas, kResolveThreads, 0, c->stream>>>(Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1,
-                                                                         ccap, xs, cap, (unsigned int*) ctr, ctr + 1, tail);
+      if (!c->pdl) {
+        if (cells)  // pairs in the direct format of the cell directory
+          k_lsi_resolve<true><<<resolve_ctas, kResolveThreads, 0, c->stream>>>(
+              Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap, xs, cap, (unsigned int*) ctr, ctr + 1, tail);
+        else
+          k_lsi_resolve<false><<<resolve_ctas, kResolveThreads, 0, c->stream>>>(
+              Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap, xs, cap, (unsigned int*) ctr, ctr + 1, tail);
+      } else if (cells)
+        launch_pdl(k_lsi_resolve<true>, resolve_ctas, kResolveThreads, c->stream, Q, B, q, (const uint2*) cands,
+                   (const uint2*) Bm.bvh.leaf_rec.p, (const unsigned int*) (surv_n + 1), ccap, xs, cap,
+                   (unsigned int*) ctr, ctr + 1, tail);
       else
-        k_lsi_resolve<false><<<resolve_ctas, kResolveThreads, 0, c->stream>>>(Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1,
-                                                                          ccap, xs, cap, (unsigned int*) ctr, ctr + 1, tail);
-      if (c->stage_timing) RJB_CUDA(cudaEventRecord(c->ev[3], c->stream));
+        launch_pdl(k_lsi_resolve<false>, resolve_ctas, kResolveThreads, c->stream, Q, B, q, (const uint2*) cands,
+                   (const uint2*) Bm.bvh.leaf_rec.p, (const unsigned int*) (surv_n + 1), ccap, xs, cap,
+                   (unsigned int*) ctr, ctr + 1, tail);
+      if (c->stage_timing > 0) RJB_CUDA(cudaEventRecord(c->ev[3], c->stream));
     } else {
       if (cells)  // pairs in the direct format of the cell directory
         k_lsi_exact<true><<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
@@ -548,10 +586,10 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
       else
         k_lsi_exact<false><<<kNumSMs * 4, kExactThreads, 0, c->stream>>>(Q, B, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap,
                                                                         xs, cap, (unsigned int*) ctr, ctr + 1);
-      if (c->stage_timing) RJB_CUDA(cudaEventRecord(c->ev[3], c->stream));
+      if (c->stage_timing > 0) RJB_CUDA(cudaEventRecord(c->ev[3], c->stream));
       k_lsi_points<<<kNumSMs * 3, kPointsThreads, 0, c->stream>>>(Q, B, q, (const unsigned int*) ctr, cap, xs, false);
     }
-    RJB_CUDA(cudaEventRecord(c->ev[4], c->stream));
+    if (timed) RJB_CUDA(cudaEventRecord(c->ev[4], c->stream));
     RJB_CUDA(cudaGetLastError());
     P.lbvh = true;
     P.fused = fused;
@@ -560,8 +598,10 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     P.ccap = ccap;
     P.n_slots = n_slots;
     P.launches = (fused ? 2 : 3) + (filter ? 1 : 0) + (cells ? 1 : 0) - (blocks == 0 ? 1 : 0);
-    c->timing_pending = 4;
-    c->timing_layout = c->stage_timing ? 1 : 2;
+    c->timing_pending = timed ? 4 : 0;
+    c->timing_layout = c->stage_timing > 0 ? 1 : 2;
+    if (!timed)
+      for (int k = 0; k < kTimedStages; k++) c->last_ms[k] = 0;
   } else if (mode == RJB_MODE_GRID && nonempty) {
     // cell filter -> (query edge, occupied cell) work items -> dense exact pass -> point pass.
     // Reference semantics of LSIGrid: intersect_test(map-0 edge, map-1 edge) whatever the query
@@ -948,12 +988,19 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
     } else if (n == "lsi_resolve_ctas") {
       RJB_REQUIRE(value >= 0 && value <= 64, "lsi_resolve_ctas must be in 0..64");
       c->resolve_ctas_per_sm = (int) value;
+    } else if (n == "lsi_pdl") {
+#ifdef RJB_PDL
+      c->pdl = value != 0;
+#else
+      RJB_REQUIRE(value == 0, "lsi_pdl: this build has no programmatic dependent launch (-DRJB_PDL)");
+#endif
     } else if (n == "lsi_fused") {
       c->fused = value != 0;
     } else if (n == "pip_park") {
       c->pip_park = value != 0;
     } else if (n == "stage_timing") {
-      c->stage_timing = value != 0;
+      RJB_REQUIRE(value >= -1 && value <= 1, "stage_timing must be -1, 0 or 1");
+      c->stage_timing = (int) value;
     } else if (n == "stats") {
       c->stats = value != 0;
     } else if (n == "keep_host_graph") {
@@ -1029,7 +1076,7 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
     uint32_t* pc = m.point_chain.ensure(n_points ? n_points : 1);
     // padded with "no edge" (0xFF bytes: class bits = kDescNone): the filter reads 16 per thread
     uint32_t* cc = m.edge_desc.ensure(n_points + 16);
-    uint32_t* td = m.tile_desc.ensure(n_points / 32 + 2);
+    uint32_t* td = m.tile_desc.ensure(n_points / kTileT + 2);
     uint32_t n_words = (uint32_t) (n_points / 32 + 2);
     uint32_t* lb = m.last_bits.ensure(n_words);
     uint32_t* bc = m.block_chain.ensure(n_blocks ? n_blocks : 1);

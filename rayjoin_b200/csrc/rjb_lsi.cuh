@@ -9,6 +9,27 @@
 
 namespace rjb {
 
+// Programmatic dependent launch: the kernels of a query are launched with the "programmatic
+// stream serialization" attribute, so the next kernel's CTAs may be scheduled (and run their
+// prologue) while the previous kernel drains; pdl_wait() blocks until the previous grid has
+// completed and its writes are visible, pdl_launch_dependents() lets the next grid start early.
+// MEASURED (B200, bench workload): slower, 0.155 against 0.124 ms per query -- the early CTAs of
+// the next kernel take the registers the running one still needs -- and even the bare
+// griddepcontrol instructions in normally launched kernels cost (k_lsi_cells 47 -> 67 us), so
+// the whole mechanism is compiled in only with -DRJB_PDL (option lsi_pdl then switches it on).
+// (Under PDL the counts the previous kernel left must be read with volatile loads -- a const
+// __restrict__ load may be hoisted above the wait, which lost pairs -- and those loads are not
+// free: every warp of the grid then goes to ONE L2 sector, k_lsi_cells 47 -> 67 us.)
+#ifdef RJB_PDL
+static __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+static __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+static __device__ __forceinline__ unsigned int load_count(const unsigned int* p) { return *(volatile const unsigned int*) p; }
+#else
+static __device__ __forceinline__ void pdl_wait() {}
+static __device__ __forceinline__ void pdl_launch_dependents() {}
+static __device__ __forceinline__ unsigned int load_count(const unsigned int* p) { return *p; }
+#endif
+
 constexpr int kLsiWarps = 4;     // warps per CTA (small CTAs: a slow warp holds few others)
 constexpr int kStackDepth = 96;  // >= max LBVH depth (64 key bits + 32 index bits)
 
@@ -208,6 +229,10 @@ constexpr int kFilterCtaPoints = kFilterThreads * kFilterPerThread;
 // edge longer than a cell (rare): every cell of its box, a bitmap word at a time.  A box of
 // more than 4096 words is kept without looking (the tree walk deals with it): the loop of
 // one thread stays bounded whatever the map contains.
+#ifndef RJB_OCC_RECT_MAX
+#define RJB_OCC_RECT_MAX 4096
+#endif
+constexpr uint32_t kOccRectMaxWords = RJB_OCC_RECT_MAX;
 static __device__ __noinline__ bool occ_rect(const MapView& Q, const uint32_t* __restrict__ occ, uint32_t p,
                                              bool* within3) {
   const longlong2 a = __ldg(&Q.pts[p]), b = __ldg(&Q.pts[p + 1]);
@@ -217,7 +242,7 @@ static __device__ __noinline__ bool occ_rect(const MapView& Q, const uint32_t* _
   const uint32_t y0 = min(c1 >> kOccBits, c2 >> kOccBits), y1 = max(c1 >> kOccBits, c2 >> kOccBits);
   *within3 = x1 - x0 <= 2 && y1 - y0 <= 2;
   const uint32_t w0 = x0 >> 5, w1 = x1 >> 5;
-  if ((w1 - w0 + 1) * (y1 - y0 + 1) > 4096u) return true;
+  if ((w1 - w0 + 1) * (y1 - y0 + 1) > kOccRectMaxWords) return true;
   for (uint32_t y = y0; y <= y1; y++)
     for (uint32_t w = w0; w <= w1; w++) {
       const uint32_t lo = max(x0, 32 * w), hi = min(x1, 32 * w + 31);
@@ -240,6 +265,7 @@ k_lsi_filter(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __restrict
   constexpr int kWarps = kFilterThreads / 32;
   __shared__ unsigned s_wsum[kWarps];
   __shared__ unsigned s_base;
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // point of (round e, lane) = w0 + 32 * e + lane; only start points in the query window
   // [p_lo, p_hi) are looked at (a shard of the query map; the whole map by default)
@@ -314,88 +340,105 @@ k_lsi_filter(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __restrict
   }
 }
 
-// Two-level variant of the filter (option lsi_tile_filter, off by default): a warp first decides
-// 32 TILES of 32 edges each with one look-up per tile (lane = tile: tile_desc_of, bitmaps dilated
-// to the size of the tile's box), then reads the 32 edge descriptors of the live tiles only,
-// kTfBatch tiles in flight at a time.  MEASURED: no gain on the County x Zipcode-scale workload
-// (35.3 us against 34.5 us).  With the TIGHT box of a tile 29 % of the tiles are live, but 61 % of
-// the tiles span more than 8 x 8 cells (a third hold a chain end, and 32 edges are ~9 cells
-// long), which the largest dilated bitmap cannot decide: 72 % stay live.  Tiles of 16 edges
-// would leave 35 % live (CPU experiment, tools/micro notes in DESIGN.md section 8).
-// Tile t = the edges starting at points 32 t - 1 .. 32 t + 30 (lane = point again in stage 2).
-// Survivors leave as one map-ordered run per CTA, like k_lsi_filter.
-constexpr int kTfWarps = 4;
-constexpr int kTfBatch = 8;
-constexpr int kTfCtaTiles = kTfWarps * 32;
+// Two-level variant of the filter (option lsi_tile_filter): a warp first decides 32 TILES of
+// kTileT edges each with one look-up per tile (lane = tile: tile_desc_of, bitmaps dilated to the
+// size of the tile's box), then reads the edge descriptors of the live tiles only: the live tiles
+// of the warp are compacted into a list, and every look-up instruction of stage 2 serves
+// 32 / kTileT of them (lane = point of a tile).  Survivors leave as one map-ordered run per CTA,
+// like k_lsi_filter.  (With tiles of 32 edges 72 % of the tiles stayed live and nothing was
+// gained; see tile_desc_of.)
+#ifndef RJB_TF_ROUNDS
+#define RJB_TF_ROUNDS 4
+#endif
+constexpr int kTfWarps = 8;
+constexpr int kTfRounds = RJB_TF_ROUNDS;   // super-rounds of 32 tiles per warp: fewer, larger CTAs = fewer
+                                           // atomics on the one survivor counter
+constexpr int kTfCtaTiles = kTfWarps * kTfRounds * 32;
+constexpr int kTfGroup = 32 / kTileT;      // tiles per stage-2 instruction
+constexpr int kTfSlots = 32 / kTfGroup;    // stage-2 rounds per super-round at most (all 32 tiles live)
+constexpr int kTfBatch = 2;                // stage-2 rounds in flight together
 
 __global__ void __launch_bounds__(kTfWarps * 32)
 k_lsi_filter_tiles(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __restrict__ occ,
                    uint32_t* __restrict__ survivors, unsigned int* counter, uint32_t* __restrict__ long_list,
                    unsigned int* long_counter) {
-  __shared__ unsigned s_mask[kTfWarps][32];  // keep mask (bit = lane) of the k-th live tile of a warp
+  __shared__ unsigned s_mask[kTfWarps][kTfRounds][kTfSlots];  // keep mask (bit = lane) per stage-2 round
+  __shared__ uint32_t s_live[kTfWarps][kTfRounds][32];        // live tiles of a super-round, compacted
+  __shared__ unsigned char s_nlive[kTfWarps][kTfRounds];
   __shared__ unsigned s_wsum[kTfWarps];
   __shared__ unsigned s_base;
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // tiles of the query window: start point p lies in tile (p + 1) / 32
-  const uint32_t t_last = p_hi / 32;  // tile of the last start point p_hi - 1
-  const uint32_t t0 = p_lo / 32 + (blockIdx.x * kTfWarps + warp) * 32;
-  // stage 1: lane = tile
-  uint32_t td = kTileNone << 24;
-  if (t0 + lane <= t_last) td = __ldg(&Q.tile_desc[t0 + lane]);
-  const uint32_t tcls = td >> 24;
-  bool live = tcls == kTileBig;
-  if (tcls >= 1 && tcls < kTileBig) {
-    const uint32_t code = td & 0xFFFFFFu;
-    live = (__ldg(&occ[(tcls - 1) * kOccWords + (code >> 5)]) >> (code & 31u)) & 1u;
-  }
-  const unsigned live_m = __ballot_sync(0xffffffffu, live);
-  const int n_live = __popc(live_m);
-  // stage 2: lane = point, kTfBatch live tiles at a time (warp-uniform control flow)
+#ifdef RJB_EXP_NULL_FILTER
+  if (p_hi) return;
+#endif
+  // tiles of the query window: start point p lies in tile (p + 1) / kTileT
+  const uint32_t t_last = p_hi / kTileT;  // tile of the last start point p_hi - 1
+  const int sub = lane / kTileT, off = lane % kTileT;
   unsigned cnt = 0;
-  unsigned rest = live_m;
-  for (int b0 = 0; b0 < n_live; b0 += kTfBatch) {
-    uint32_t d[kTfBatch], pp[kTfBatch];
-#pragma unroll
-    for (int j = 0; j < kTfBatch; j++) {
-      const int tj = rest ? __ffs(rest) - 1 : -1;
-      rest &= rest - 1;
-      const uint32_t p = (t0 + (uint32_t) tj) * 32 - 1 + lane;  // (tile 0, lane 0: wraps, rejected below)
-      pp[j] = p;
-      const bool in = tj >= 0 && p >= p_lo && p < p_hi;
-      d[j] = in ? __ldg(&Q.edge_desc[p]) : (kDescNone << 24);
+  for (int r = 0; r < kTfRounds; r++) {
+    const uint32_t t0 = p_lo / kTileT + ((blockIdx.x * kTfWarps + warp) * kTfRounds + r) * 32;
+    // stage 1: lane = tile
+    uint32_t td = kTileNone << 24;
+    if (t0 + lane <= t_last) td = __ldg(&Q.tile_desc[t0 + lane]);
+    const uint32_t tcls = td >> 24;
+    bool live = tcls == kTileBig;
+    if (tcls >= 1 && tcls < kTileBig) {
+      const uint32_t code = td & 0xFFFFFFu;
+      live = (__ldg(&occ[(tcls - 1) * kOccWords + (code >> 5)]) >> (code & 31u)) & 1u;
     }
-    uint32_t w[kTfBatch];
+    const unsigned live_m = __ballot_sync(0xffffffffu, live);
+    const int n_live = __popc(live_m);
+    if (live) s_live[warp][r][__popc(live_m & ((1u << lane) - 1))] = t0 + lane;
+    if (lane == 0) s_nlive[warp][r] = (unsigned char) n_live;
+    __syncwarp();
+    // stage 2: lane = point of one of kTfGroup live tiles per round, kTfBatch rounds in flight
+    // together and only as many rounds as there are live tiles (warp-uniform trip count)
+    const int n_slots = (n_live + kTfGroup - 1) / kTfGroup;
+    for (int k0 = 0; k0 < n_slots; k0 += kTfBatch) {
+      uint32_t d[kTfBatch], pp[kTfBatch];
 #pragma unroll
-    for (int j = 0; j < kTfBatch; j++)
-      w[j] = __ldg(&occ[((d[j] & 0xFFFFFFu) >> 5) + ((d[j] >> 24) & 1u) * kOccWords]);
-#pragma unroll
-    for (int j = 0; j < kTfBatch; j++) {
-      const uint32_t cls = d[j] >> 24;
-      bool keep = cls < kDescBig && ((w[j] >> (d[j] & 31u)) & 1u);
-      if (__any_sync(0xffffffffu, cls == kDescBig)) {
-        bool within3 = false;
-        bool big = cls == kDescBig && occ_rect(Q, occ, pp[j], &within3);
-        if (long_list) {
-          if (big && within3) {
-            keep = true;
-            big = false;
-          }
-          const unsigned mb = __ballot_sync(0xffffffffu, big);
-          if (mb) {
-            unsigned base = 0;
-            const int leader = __ffs(mb) - 1;
-            if (lane == leader) base = atomicAdd(long_counter, (unsigned) __popc(mb));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (big) long_list[base + __popc(mb & ((1u << lane) - 1))] = pp[j];
-          }
-        } else if (big) {
-          keep = true;
-        }
+      for (int j = 0; j < kTfBatch; j++) {
+        const int idx = (k0 + j) * kTfGroup + sub;
+        const bool have = idx < n_live;
+        const uint32_t p = (have ? s_live[warp][r][idx] : 0u) * kTileT - 1 + off;  // (tile 0, point 0: wraps, rejected)
+        pp[j] = p;
+        const bool in = have && p >= p_lo && p < p_hi;
+        d[j] = in ? __ldg(&Q.edge_desc[p]) : (kDescNone << 24);
       }
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (b0 + j < n_live) {
-        if (lane == 0) s_mask[warp][b0 + j] = m;
-        cnt += __popc(m);
+      uint32_t w[kTfBatch];
+#pragma unroll
+      for (int j = 0; j < kTfBatch; j++)
+        w[j] = __ldg(&occ[((d[j] & 0xFFFFFFu) >> 5) + ((d[j] >> 24) & 1u) * kOccWords]);
+#pragma unroll
+      for (int j = 0; j < kTfBatch; j++) {
+        const uint32_t cls = d[j] >> 24;
+        bool keep = cls < kDescBig && ((w[j] >> (d[j] & 31u)) & 1u);
+        if (__any_sync(0xffffffffu, cls == kDescBig)) {
+          bool within3 = false;
+          bool big = cls == kDescBig && occ_rect(Q, occ, pp[j], &within3);
+          if (long_list) {
+            if (big && within3) {
+              keep = true;
+              big = false;
+            }
+            const unsigned mb = __ballot_sync(0xffffffffu, big);
+            if (mb) {
+              unsigned base = 0;
+              const int leader = __ffs(mb) - 1;
+              if (lane == leader) base = atomicAdd(long_counter, (unsigned) __popc(mb));
+              base = __shfl_sync(0xffffffffu, base, leader);
+              if (big) long_list[base + __popc(mb & ((1u << lane) - 1))] = pp[j];
+            }
+          } else if (big) {
+            keep = true;
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (k0 + j < n_slots) {
+          if (lane == 0) s_mask[warp][r][k0 + j] = m;
+          cnt += __popc(m);
+        }
       }
     }
   }
@@ -415,13 +458,15 @@ k_lsi_filter_tiles(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __re
   __syncthreads();
   unsigned pos = s_base + s_wsum[warp];
   const unsigned lt = (1u << lane) - 1;
-  rest = live_m;
-  for (int k = 0; k < n_live; k++) {
-    const int tj = __ffs(rest) - 1;
-    rest &= rest - 1;
-    const unsigned m = s_mask[warp][k];
-    if ((m >> lane) & 1u) survivors[pos + __popc(m & lt)] = (t0 + (uint32_t) tj) * 32 - 1 + lane;
-    pos += __popc(m);
+  for (int r = 0; r < kTfRounds; r++) {
+    const int n_live = s_nlive[warp][r];
+    const int n_slots = (n_live + kTfGroup - 1) / kTfGroup;
+    for (int k = 0; k < n_slots; k++) {
+      const unsigned m = s_mask[warp][r][k];
+      const int idx = k * kTfGroup + sub;
+      if ((m >> lane) & 1u) survivors[pos + __popc(m & lt)] = s_live[warp][r][idx] * kTileT - 1 + off;
+      pos += __popc(m);
+    }
   }
 }
 
@@ -579,7 +624,9 @@ k_lsi_cells(MapView Q, BvhView bvh, const uint32_t* __restrict__ survivors,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Emit E = {s_emit[warp], 0u, out, cap, counter, nullptr};
   TravStats st = {0, 0, 0, 0, 0};
-  const uint32_t n = *n_survivors_dev;
+  pdl_wait();  // the filter's survivors
+  pdl_launch_dependents();
+  const uint32_t n = load_count(n_survivors_dev);
   const uint32_t n_tiles = (n + 31) / 32;
   for (uint32_t tile = blockIdx.x * kLsiWarps + warp; tile < n_tiles; tile += gridDim.x * kLsiWarps) {
     const uint32_t slot = tile * 32 + lane;
@@ -623,7 +670,9 @@ k_lsi_bvh(MapView Q, MapView B, BvhView bvh, const uint32_t* __restrict__ order,
   int* stack = s_stack[warp];
   // direct: the pairs join those of the cell directory, in its format
   Emit E = {s_emit[warp], 0u, out, cap, counter, direct ? bvh.leaf_rec : nullptr};
-  if (n_slots_dev) n_slots = *n_slots_dev;  // survivor count of the pre-filter
+  pdl_wait();  // the filter's survivors / the cell kernel's long list
+  pdl_launch_dependents();
+  if (n_slots_dev) n_slots = load_count(n_slots_dev);  // survivor count of the pre-filter
   // spw = query slots per warp: 32, or fewer for a list of queries from all over the map
   // (the long edges the cell directory leaves over): a warp follows the clusters of its
   // queries one after the other, and 32 unrelated queries are 32 clusters
@@ -812,8 +861,9 @@ k_lsi_exact(MapView Q, MapView B, const uint2* __restrict__ pairs, const uint2* 
   __shared__ uint2 s_list[kExactList];
   __shared__ unsigned s_n;
   if (threadIdx.x == 0) s_n = 0;
+  pdl_wait();
   __syncthreads();
-  const uint32_t n = min(*n_pairs_dev, pair_cap);
+  const uint32_t n = min(load_count(n_pairs_dev), pair_cap);
   const int lane = threadIdx.x & 31;
   unsigned cand = 0;
   // block-uniform trip count: every thread reaches the barriers
@@ -1178,8 +1228,9 @@ k_lsi_resolve(MapView Q, MapView B, int query_map_id, const uint2* __restrict__ 
     for (int z = 0; z < kTraceSlots; z++) g_trace[blockIdx.x * kTraceSlots + z] = 0;
 #endif
   RJB_MARK(tk);  // 0: start
+  pdl_wait();  // the (query, leaf) pairs
   __syncthreads();
-  const uint32_t n = min(*n_pairs_dev, pair_cap);
+  const uint32_t n = min(load_count(n_pairs_dev), pair_cap);
   const int lane = threadIdx.x & 31;
   unsigned cand = 0;
   RJB_MARK(tk);  // 1: count read
