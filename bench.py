@@ -433,7 +433,7 @@ def main():
     ap.add_argument("--sort-queries", type=int, default=-1)
     ap.add_argument("--filter", type=int, default=-1, help="occupancy pre-filter: -1 auto, 0 off, 1 on")
     ap.add_argument("--cells", type=int, default=1, help="cell-directory candidate path for the filter's survivors (option lsi_cells)")
-    ap.add_argument("--tile-filter", type=int, default=0, help="two-level occupancy filter (option lsi_tile_filter)")
+    ap.add_argument("--tile-filter", type=int, default=1, help="two-level occupancy filter (option lsi_tile_filter)")
     ap.add_argument("--fused", type=int, default=1, help="exact + point pass as one kernel (option lsi_fused)")
     ap.add_argument("--stage-timing", type=int, default=-1, help="engine-internal CUDA events during the headline loop: -1 none (default), 0 per phase, 1 per kernel; the per-kernel times always come from a separate pass")
     ap.add_argument("--ag", type=int, default=0, help="adaptive leaf grouping (option lbvh_ag)")

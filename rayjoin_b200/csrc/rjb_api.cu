@@ -137,7 +137,7 @@ struct rjb_ctx {
   DBuf<uint32_t> long_edges;  // survivors longer than a cell (tree walk)
   uint32_t load_chunk = kLoadChunkPoints;  // points per upload chunk (option load_chunk_points)
   int pip_sort_bits = 24; // grid PIP: key bits the points are ordered by (the high ones: column first)
-  int tile_filter = 0;    // LSI: two-level occupancy filter (tiles of 32 edges first): no faster, see rjb_lsi.cuh
+  int tile_filter = 1;    // LSI: two-level occupancy filter (tiles of 8 edges first, k_lsi_filter_tiles)
   int use_cells = 0;      // LSI: cell directory for the filter's survivors (experimental, off)
   size_t cand_cap = 0;
   size_t grid_work_cap = 0;

@@ -340,31 +340,39 @@ k_lsi_filter(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __restrict
   }
 }
 
-// Two-level variant of the filter (option lsi_tile_filter): a warp first decides 32 TILES of
-// kTileT edges each with one look-up per tile (lane = tile: tile_desc_of, bitmaps dilated to the
-// size of the tile's box), then reads the edge descriptors of the live tiles only: the live tiles
-// of the warp are compacted into a list, and every look-up instruction of stage 2 serves
-// 32 / kTileT of them (lane = point of a tile).  Survivors leave as one map-ordered run per CTA,
-// like k_lsi_filter.  (With tiles of 32 edges 72 % of the tiles stayed live and nothing was
-// gained; see tile_desc_of.)
+// Two-level variant of the filter (option lsi_tile_filter, default): a warp first decides
+// kTfRounds x 32 TILES of kTileT edges each with one look-up per tile (lane = tile: tile_desc_of,
+// bitmaps dilated to the size of the tile's box), then reads the edge descriptors of the live
+// tiles only: the live tiles of the warp are compacted into a list, and every look-up
+// instruction of stage 2 serves 32 / kTileT of them (lane = point of a tile).  What makes it
+// faster than the one-level filter is not the smaller volume (12 MB instead of 36 MB: neither
+// is near the bandwidth) but the SHAPE: all loads of a level are issued together, so a warp pays
+// four round trips to memory for 2048 edges, and the whole grid is one resident wave.  Survivors
+// leave as one map-ordered run per CTA, like k_lsi_filter.  (History: tiles of 32 edges: 72 %
+// live, no gain; tiles of 8, one 32-tile group per warp and round trip: no gain either, 35 us.)
+// (measured, filter stage incl. its launch: 8 warps x 4 / 8 / 12 / 16 groups: 28.7 / 25.4 / 27.4 / 27.2 us;
+// one group per warp, one warp-wide memory round trip per level and group: 35.6 us = the one-level filter)
 #ifndef RJB_TF_ROUNDS
-#define RJB_TF_ROUNDS 4
+#define RJB_TF_ROUNDS 8
 #endif
-constexpr int kTfWarps = 8;
-constexpr int kTfRounds = RJB_TF_ROUNDS;   // super-rounds of 32 tiles per warp: fewer, larger CTAs = fewer
-                                           // atomics on the one survivor counter
+#ifndef RJB_TF_WARPS
+#define RJB_TF_WARPS 8
+#endif
+constexpr int kTfWarps = RJB_TF_WARPS;
+constexpr int kTfRounds = RJB_TF_ROUNDS;   // 32-tile groups per warp, decided TOGETHER: every level of the
+                                           // chain tile_desc -> bitmap -> edge_desc -> bitmap is one round
+                                           // trip to memory per warp, whatever the number of groups
 constexpr int kTfCtaTiles = kTfWarps * kTfRounds * 32;
 constexpr int kTfGroup = 32 / kTileT;      // tiles per stage-2 instruction
-constexpr int kTfSlots = 32 / kTfGroup;    // stage-2 rounds per super-round at most (all 32 tiles live)
-constexpr int kTfBatch = 2;                // stage-2 rounds in flight together
+constexpr int kTfMaxSlots = kTfRounds * 32 / kTfGroup;  // stage-2 rounds of a warp at most (every tile live)
+constexpr int kTfBatch = 8;                // stage-2 rounds in flight together
 
 __global__ void __launch_bounds__(kTfWarps * 32)
 k_lsi_filter_tiles(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __restrict__ occ,
                    uint32_t* __restrict__ survivors, unsigned int* counter, uint32_t* __restrict__ long_list,
                    unsigned int* long_counter) {
-  __shared__ unsigned s_mask[kTfWarps][kTfRounds][kTfSlots];  // keep mask (bit = lane) per stage-2 round
-  __shared__ uint32_t s_live[kTfWarps][kTfRounds][32];        // live tiles of a super-round, compacted
-  __shared__ unsigned char s_nlive[kTfWarps][kTfRounds];
+  __shared__ unsigned s_mask[kTfWarps][kTfMaxSlots];      // keep mask (bit = lane) per stage-2 round
+  __shared__ uint32_t s_live[kTfWarps][kTfRounds * 32];   // the warp's live tiles, compacted, in map order
   __shared__ unsigned s_wsum[kTfWarps];
   __shared__ unsigned s_base;
   pdl_launch_dependents();
@@ -374,71 +382,79 @@ k_lsi_filter_tiles(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __re
 #endif
   // tiles of the query window: start point p lies in tile (p + 1) / kTileT
   const uint32_t t_last = p_hi / kTileT;  // tile of the last start point p_hi - 1
+  const uint32_t t0 = p_lo / kTileT + (blockIdx.x * kTfWarps + warp) * (kTfRounds * 32);
   const int sub = lane / kTileT, off = lane % kTileT;
-  unsigned cnt = 0;
+  // stage 1: lane = tile, kTfRounds groups of 32 tiles; all descriptor loads, then all look-ups
+  uint32_t td[kTfRounds];
+#pragma unroll
   for (int r = 0; r < kTfRounds; r++) {
-    const uint32_t t0 = p_lo / kTileT + ((blockIdx.x * kTfWarps + warp) * kTfRounds + r) * 32;
-    // stage 1: lane = tile
-    uint32_t td = kTileNone << 24;
-    if (t0 + lane <= t_last) td = __ldg(&Q.tile_desc[t0 + lane]);
-    const uint32_t tcls = td >> 24;
-    bool live = tcls == kTileBig;
-    if (tcls >= 1 && tcls < kTileBig) {
-      const uint32_t code = td & 0xFFFFFFu;
-      live = (__ldg(&occ[(tcls - 1) * kOccWords + (code >> 5)]) >> (code & 31u)) & 1u;
+    const uint32_t t = t0 + r * 32 + lane;
+    td[r] = t <= t_last ? __ldg(&Q.tile_desc[t]) : (kTileNone << 24);
+  }
+  uint32_t tw[kTfRounds];
+#pragma unroll
+  for (int r = 0; r < kTfRounds; r++) {
+    const uint32_t cls = td[r] >> 24;
+    const uint32_t code = td[r] & 0xFFFFFFu;
+    tw[r] = (cls >= 1 && cls < kTileBig) ? __ldg(&occ[(cls - 1) * kOccWords + (code >> 5)]) : 0u;
+  }
+  int n_live = 0;
+#pragma unroll
+  for (int r = 0; r < kTfRounds; r++) {
+    const uint32_t cls = td[r] >> 24;
+    const bool live = cls == kTileBig || (cls >= 1 && cls < kTileBig && ((tw[r] >> (td[r] & 31u)) & 1u));
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if (live) s_live[warp][n_live + __popc(m & ((1u << lane) - 1))] = t0 + r * 32 + lane;
+    n_live += __popc(m);
+  }
+  __syncwarp();
+  // stage 2: lane = point of one of kTfGroup live tiles per round, kTfBatch rounds in flight
+  // together and only as many rounds as there are live tiles (warp-uniform trip count)
+  const int n_slots = (n_live + kTfGroup - 1) / kTfGroup;
+  unsigned cnt = 0;
+  for (int k0 = 0; k0 < n_slots; k0 += kTfBatch) {
+    uint32_t d[kTfBatch], pp[kTfBatch];
+#pragma unroll
+    for (int j = 0; j < kTfBatch; j++) {
+      const int idx = (k0 + j) * kTfGroup + sub;
+      const bool have = idx < n_live;
+      const uint32_t p = (have ? s_live[warp][idx] : 0u) * kTileT - 1 + off;  // (tile 0, point 0: wraps, rejected)
+      pp[j] = p;
+      const bool in = have && p >= p_lo && p < p_hi;
+      d[j] = in ? __ldg(&Q.edge_desc[p]) : (kDescNone << 24);
     }
-    const unsigned live_m = __ballot_sync(0xffffffffu, live);
-    const int n_live = __popc(live_m);
-    if (live) s_live[warp][r][__popc(live_m & ((1u << lane) - 1))] = t0 + lane;
-    if (lane == 0) s_nlive[warp][r] = (unsigned char) n_live;
-    __syncwarp();
-    // stage 2: lane = point of one of kTfGroup live tiles per round, kTfBatch rounds in flight
-    // together and only as many rounds as there are live tiles (warp-uniform trip count)
-    const int n_slots = (n_live + kTfGroup - 1) / kTfGroup;
-    for (int k0 = 0; k0 < n_slots; k0 += kTfBatch) {
-      uint32_t d[kTfBatch], pp[kTfBatch];
+    uint32_t w[kTfBatch];
 #pragma unroll
-      for (int j = 0; j < kTfBatch; j++) {
-        const int idx = (k0 + j) * kTfGroup + sub;
-        const bool have = idx < n_live;
-        const uint32_t p = (have ? s_live[warp][r][idx] : 0u) * kTileT - 1 + off;  // (tile 0, point 0: wraps, rejected)
-        pp[j] = p;
-        const bool in = have && p >= p_lo && p < p_hi;
-        d[j] = in ? __ldg(&Q.edge_desc[p]) : (kDescNone << 24);
-      }
-      uint32_t w[kTfBatch];
+    for (int j = 0; j < kTfBatch; j++)
+      w[j] = __ldg(&occ[((d[j] & 0xFFFFFFu) >> 5) + ((d[j] >> 24) & 1u) * kOccWords]);
 #pragma unroll
-      for (int j = 0; j < kTfBatch; j++)
-        w[j] = __ldg(&occ[((d[j] & 0xFFFFFFu) >> 5) + ((d[j] >> 24) & 1u) * kOccWords]);
-#pragma unroll
-      for (int j = 0; j < kTfBatch; j++) {
-        const uint32_t cls = d[j] >> 24;
-        bool keep = cls < kDescBig && ((w[j] >> (d[j] & 31u)) & 1u);
-        if (__any_sync(0xffffffffu, cls == kDescBig)) {
-          bool within3 = false;
-          bool big = cls == kDescBig && occ_rect(Q, occ, pp[j], &within3);
-          if (long_list) {
-            if (big && within3) {
-              keep = true;
-              big = false;
-            }
-            const unsigned mb = __ballot_sync(0xffffffffu, big);
-            if (mb) {
-              unsigned base = 0;
-              const int leader = __ffs(mb) - 1;
-              if (lane == leader) base = atomicAdd(long_counter, (unsigned) __popc(mb));
-              base = __shfl_sync(0xffffffffu, base, leader);
-              if (big) long_list[base + __popc(mb & ((1u << lane) - 1))] = pp[j];
-            }
-          } else if (big) {
+    for (int j = 0; j < kTfBatch; j++) {
+      const uint32_t cls = d[j] >> 24;
+      bool keep = cls < kDescBig && ((w[j] >> (d[j] & 31u)) & 1u);
+      if (__any_sync(0xffffffffu, cls == kDescBig)) {
+        bool within3 = false;
+        bool big = cls == kDescBig && occ_rect(Q, occ, pp[j], &within3);
+        if (long_list) {
+          if (big && within3) {
             keep = true;
+            big = false;
           }
+          const unsigned mb = __ballot_sync(0xffffffffu, big);
+          if (mb) {
+            unsigned base = 0;
+            const int leader = __ffs(mb) - 1;
+            if (lane == leader) base = atomicAdd(long_counter, (unsigned) __popc(mb));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (big) long_list[base + __popc(mb & ((1u << lane) - 1))] = pp[j];
+          }
+        } else if (big) {
+          keep = true;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (k0 + j < n_slots) {
-          if (lane == 0) s_mask[warp][r][k0 + j] = m;
-          cnt += __popc(m);
-        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (k0 + j < n_slots) {
+        if (lane == 0) s_mask[warp][k0 + j] = m;
+        cnt += __popc(m);
       }
     }
   }
@@ -458,15 +474,10 @@ k_lsi_filter_tiles(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __re
   __syncthreads();
   unsigned pos = s_base + s_wsum[warp];
   const unsigned lt = (1u << lane) - 1;
-  for (int r = 0; r < kTfRounds; r++) {
-    const int n_live = s_nlive[warp][r];
-    const int n_slots = (n_live + kTfGroup - 1) / kTfGroup;
-    for (int k = 0; k < n_slots; k++) {
-      const unsigned m = s_mask[warp][r][k];
-      const int idx = k * kTfGroup + sub;
-      if ((m >> lane) & 1u) survivors[pos + __popc(m & lt)] = s_live[warp][r][idx] * kTileT - 1 + off;
-      pos += __popc(m);
-    }
+  for (int k = 0; k < n_slots; k++) {
+    const unsigned m = s_mask[warp][k];
+    if ((m >> lane) & 1u) survivors[pos + __popc(m & lt)] = s_live[warp][k * kTfGroup + sub] * kTileT - 1 + off;
+    pos += __popc(m);
   }
 }
 
