@@ -689,7 +689,8 @@ def main():
             exact_b = pair_in + (80 if cells_on else 88) * min(ql_pairs, n_leaves) + 32 * min(ql_pairs, surv)
             points_b = (64 + 8 + 32) * n_pairs
             kern = [
-                ("k_lsi_filter", f_ms, 4 * S.n_points + 2 * (4096 * 4096 // 8) + 4 * surv),
+                ("k_lsi_filter_tiles" if args.tile_filter else "k_lsi_filter", f_ms,
+                 4 * S.n_points + 2 * (4096 * 4096 // 8) + 4 * surv),
                 ("k_lsi_cells" if cells_on else "k_lsi_bvh", t_ms,
                  20 * surv + (dir_bytes if cells_on else tree_bytes) + 8 * ql_pairs),
             ]
