@@ -152,6 +152,8 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
  *   "lsi_tile_filter" LBVH LSI: 1 (default) = two-level occupancy filter (tiles of 8 edges decided
  *                     first, 25 us instead of 35 us on the bench workload); 0 = one level
  *   "lsi_resolve_ctas" CTAs per SM of the fused kernel; 0 (default) = one resident wave
+ *   "lsi_resolve_warp" LBVH LSI: 1 = the fused kernel with warp-private lists (no CTA barrier);
+ *                     measured no faster; 0 (default)
  *   "lsi_pdl"         LBVH LSI: 1 = the kernels of a query are launched as programmatic dependents
  *                     (griddepcontrol); measured slower (early CTAs of the next kernel take the
  *                     registers the running one needs); 0 (default; 1 needs a -DRJB_PDL build)

@@ -109,7 +109,8 @@ struct rjb_ctx {
   DBuf<unsigned int> lsi_ticket;             // k_lsi_resolve: CTAs that have finished (zero between queries)
   bool ctr_clean = false;                    // the device counters are zero (left so by k_lsi_resolve)
   int resolve_ctas_per_sm = 0;               // grid of k_lsi_resolve: 0 = what is resident at once (occupancy API)
-  int resolve_resident = 0;
+  int resolve_resident = 0, resolve_resident_w = 0;
+  int resolve_warp = 0;                      // k_lsi_resolve_w (warp-private lists) instead of k_lsi_resolve
   int pdl = 0;                               // programmatic dependent launch of the query's kernels: measured slower
   int fused = 1;                             // LBVH LSI: exact + point pass in one kernel (option lsi_fused)
   bool have_scaling = false;
@@ -412,6 +413,9 @@ static void ensure_events(rjb_ctx* c) {
     RJB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_lsi_resolve<true>, kResolveThreads, 0));
     RJB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_lsi_resolve<false>, kResolveThreads, 0));
     c->resolve_resident = std::max(1, std::min(a, b));
+    RJB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_lsi_resolve_w<true>, kResolveThreads, 0));
+    RJB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_lsi_resolve_w<false>, kResolveThreads, 0));
+    c->resolve_resident_w = std::max(1, std::min(a, b));
   }
   for (int i = 0; i <= kTimedStages; i++)
     if (!c->ev[i]) RJB_CUDA(cudaEventCreate(&c->ev[i]));
@@ -567,9 +571,17 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     if (fused) {
       const LsiTail tail = {ctr, c->d_h_counters, c->lsi_ticket.p};
       // one resident wave: every CTA ends with a gcd tail, a second wave would pay it twice
-      const unsigned resolve_ctas = kNumSMs * (unsigned) (c->resolve_ctas_per_sm ? c->resolve_ctas_per_sm : c->resolve_resident);
+      const unsigned resolve_ctas = kNumSMs * (unsigned) (c->resolve_ctas_per_sm ? c->resolve_ctas_per_sm
+                                                                                  : (c->resolve_warp ? c->resolve_resident_w : c->resolve_resident));
       if (!c->pdl) {
-        if (cells)  // pairs in the direct format of the cell directory
+        if (c->resolve_warp) {  // warp-private lists, no CTA barrier before the end
+          if (cells)
+            k_lsi_resolve_w<true><<<resolve_ctas, kResolveThreads, 0, c->stream>>>(
+                Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap, xs, cap, (unsigned int*) ctr, ctr + 1, tail);
+          else
+            k_lsi_resolve_w<false><<<resolve_ctas, kResolveThreads, 0, c->stream>>>(
+                Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap, xs, cap, (unsigned int*) ctr, ctr + 1, tail);
+        } else if (cells)  // pairs in the direct format of the cell directory
           k_lsi_resolve<true><<<resolve_ctas, kResolveThreads, 0, c->stream>>>(
               Q, B, q, cands, Bm.bvh.leaf_rec.p, surv_n + 1, ccap, xs, cap, (unsigned int*) ctr, ctr + 1, tail);
         else
@@ -994,6 +1006,8 @@ int rjb_set_option(rjb_ctx* c, const char* name, int64_t value) {
     } else if (n == "lsi_resolve_ctas") {
       RJB_REQUIRE(value >= 0 && value <= 64, "lsi_resolve_ctas must be in 0..64");
       c->resolve_ctas_per_sm = (int) value;
+    } else if (n == "lsi_resolve_warp") {
+      c->resolve_warp = value != 0;
     } else if (n == "lsi_pdl") {
 #ifdef RJB_PDL
       c->pdl = value != 0;
