@@ -127,10 +127,13 @@ def test_lsi_cell_directory_path(rjb, loaded, name, q):
     want = om.lsi(q)
     counts = {}
     try:
-        for cells, tiles, fused in ((0, 1, 1), (1, 1, 1), (0, 0, 1), (1, 0, 1), (0, 1, 0), (1, 1, 0)):
+        # fused: 1 = exact + point pass as one kernel, 2 = its warp-private variant, 0 = two kernels
+        for cells, tiles, fused in ((0, 1, 1), (1, 1, 1), (0, 0, 1), (1, 0, 1), (0, 1, 0), (1, 1, 0), (1, 1, 2), (0, 0, 2)):
             ctx.set_option("lsi_cells", cells)
             ctx.set_option("lsi_tile_filter", tiles)
-            ctx.set_option("lsi_fused", fused)  # exact + point pass as one kernel, or as two
+            ctx.set_option("lsi_fused", min(fused, 1))
+            ctx.set_option("lsi_resolve_warp", 1 if fused == 2 else 0)
+            ctx.set_option("stage_timing", -1 if fused == 2 else 1)  # (also the event-free query)
             ctx.set_option("lsi_filter", 1)
             ctx.set_option("sort_queries", 0)
             ctx.build_index(1 - q, "lbvh")
@@ -156,6 +159,8 @@ def test_lsi_cell_directory_path(rjb, loaded, name, q):
         ctx.set_option("lsi_cells", 0)
         ctx.set_option("lsi_tile_filter", 1)
         ctx.set_option("lsi_fused", 1)
+        ctx.set_option("lsi_resolve_warp", 0)
+        ctx.set_option("stage_timing", 1)
         ctx.set_option("lsi_filter", -1)
     assert len({counts[k] for k in counts if k[0] != "survivors"}) == 1
 
