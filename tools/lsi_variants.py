@@ -10,9 +10,10 @@ from rayjoin_b200 import synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--share-chains", type=float, default=0.0)
+ap.add_argument("--s-seed", type=int, default=2, help="seed of the query map (bench rank r uses 2 + r)")
 ap.add_argument("variants", nargs="+")
 args = ap.parse_args()
-R, S = bench.get_map("R", 1), bench.get_map("S", 2)
+R, S = bench.get_map("R", 1), bench.get_map("S", args.s_seed)
 if args.share_chains > 0:
     S = synth.share_chains(R, S, frac=args.share_chains, seed=3)
 dev = torch.device("cuda:0")
