@@ -145,7 +145,10 @@ int rjb_build_index(rjb_ctx* ctx, int map_id, int mode, uint32_t grid_size,
  *                     directory of the occupied cells, built with the index (+0.15 ms and
  *                     +48 MB on a 4 M-edge map; edges longer than 3 x 3 cells still walk the
  *                     tree) and the exact pass reads no leaf records; 0 (default) = every
- *                     survivor walks the tree.  Set it before rjb_build_index.
+ *                     survivor walks the tree; 2 = like 1, and keep the directory even when a query
+ *                     found edges too long for it (1 falls back to the walk for that query map:
+ *                     their separate walk costs more than the directory saves).  Set it before
+ *                     rjb_build_index.
  *   "lsi_fused"       LBVH LSI: 1 (default) = exact pass and point pass are one kernel whose last
  *                     CTA hands the counters to the host (no memset / memcpy around a query);
  *                     0 = two kernels (k_lsi_exact, k_lsi_points)

@@ -139,6 +139,9 @@ struct rjb_ctx {
   // off only where few edges survive (bench direction: 8 %; the overlay's direction: 23 %, where
   // it measured 80 us against 41 us for the one-level filter)
   uint32_t dir_survivors[2] = {0, 0};
+  // the cell directory left long edges to a tree walk of their own last time (per query map): that
+  // extra kernel costs more than the directory saves (0.130 vs 0.123 ms), so the walk takes everything
+  bool dir_long[2] = {false, false};
   DBuf<uint32_t> long_edges;  // survivors longer than a cell (tree walk)
   uint32_t load_chunk = kLoadChunkPoints;  // points per upload chunk (option load_chunk_points)
   int pip_sort_bits = 24; // grid PIP: key bits the points are ordered by (the high ones: column first)
@@ -505,7 +508,8 @@ static void lsi_enqueue(rjb_ctx* c, int q, int mode, double xsect_factor) {
     // [0] survivors, [1] (query, leaf) pairs, [2] survivors that are longer than a cell
     unsigned int* surv_n = (unsigned int*) (ctr + 8);
     // cell directory instead of the tree walk for the survivors (option lsi_cells)
-    const bool cells = filter && Bm.bvh.have_cells && c->use_cells > 0 && !c->stats && Q.n_points < (1u << kDirectShift);
+    const bool cells = filter && Bm.bvh.have_cells && c->use_cells > 0 && !c->stats && Q.n_points < (1u << kDirectShift) &&
+                       !(c->use_cells == 1 && c->dir_long[q]);  // (lsi_cells = 2: the directory regardless)
     uint32_t* long_list = cells ? c->long_edges.ensure(Q.n_points) : nullptr;
     RJB_REQUIRE(c->cand_cap < 0xFFFFFFF0ull, "rjb_lsi: candidate queue exceeds 2^32 entries");
     const uint32_t ccap = (uint32_t) c->cand_cap;
@@ -725,7 +729,10 @@ static uint64_t lsi_finish(rjb_ctx* c, uint64_t* n_candidates) {
     if (!P.lbvh) break;
     // launches sized from the last query
     const bool grid_too_small = P.cells ? hs[2] > P.n_slots : (P.filter && hs[0] > P.n_slots);
-    if (P.cells) c->last_long = hs[2];
+    if (P.cells) {
+      c->last_long = hs[2];
+      if (hs[2]) c->dir_long[P.q] = true;
+    }
     if (P.filter) {
       c->last_survivors = hs[0];
       c->dir_survivors[P.q] = hs[0] ? hs[0] : 1;
@@ -1050,6 +1057,7 @@ int rjb_set_map(rjb_ctx* c, int map_id, const double* xy, uint64_t n_points,
     c->ov.n_xsects = 0;
     c->filter_useless = false;  // new data: let the occupancy filter prove itself again
     c->dir_survivors[0] = c->dir_survivors[1] = 0;
+    c->dir_long[0] = c->dir_long[1] = false;
     if (n_chains > 0) {
       RJB_REQUIRE(row_index[0] == 0 && row_index[n_chains] == n_points,
                   "rjb_set_map: row_index must span [0, n_points]");

@@ -129,7 +129,7 @@ def test_lsi_cell_directory_path(rjb, loaded, name, q):
     try:
         # fused: 1 = exact + point pass as one kernel, 2 = its warp-private variant, 0 = two kernels
         for cells, tiles, fused in ((0, 1, 1), (1, 1, 1), (0, 0, 1), (1, 0, 1), (0, 1, 0), (1, 1, 0), (1, 1, 2), (0, 0, 2)):
-            ctx.set_option("lsi_cells", cells)
+            ctx.set_option("lsi_cells", 2 * cells)  # (2: keep the directory whatever the query finds)
             ctx.set_option("lsi_tile_filter", tiles)
             ctx.set_option("lsi_fused", min(fused, 1))
             ctx.set_option("lsi_resolve_warp", 1 if fused == 2 else 0)
@@ -181,7 +181,7 @@ def test_lsi_query_window(rjb, loaded, name, mode, flt):
         # flt 1: two-level filter (tiles, then edges); 2: one-level filter; 3: two-level + cell directory
         ctx.set_option("lsi_filter", min(flt, 1))
         ctx.set_option("lsi_tile_filter", 0 if flt == 2 else 1)
-        ctx.set_option("lsi_cells", 1 if flt == 3 else 0)
+        ctx.set_option("lsi_cells", 2 if flt == 3 else 0)
         ctx.set_option("sort_queries", 0)
         ctx.build_index(1 - q, mode, grid_size=64)
         lsi = rjb.LSI(ctx, mode)
