@@ -377,9 +377,6 @@ k_lsi_filter_tiles(MapView Q, uint32_t p_lo, uint32_t p_hi, const uint32_t* __re
   __shared__ unsigned s_base;
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#ifdef RJB_EXP_NULL_FILTER
-  if (p_hi) return;
-#endif
   // tiles of the query window: start point p lies in tile (p + 1) / kTileT
   const uint32_t t_last = p_hi / kTileT;  // tile of the last start point p_hi - 1
   const uint32_t t0 = p_lo / kTileT + (blockIdx.x * kTfWarps + warp) * (kTfRounds * 32);
@@ -1131,11 +1128,7 @@ static __device__ RJB_RESOLVE_INL void resolve_flush(const MapView& Q, const Map
       const Seg e1 = {a.x, a.y, b.x, b.y}, e2 = {c.x, c.y, d.x, d.y};
       v = lsi_point_axis_slow(e1, e2, (int) (it.axis & 1u));
     } else {
-#ifdef RJB_EXP_NOGCD
-      v = it.st.X0;
-#else
       v = lsi_point_finish(it.st);
-#endif
     }
     if ((it.axis & 1u) == 0) out[it.i].x = v; else out[it.i].y = v;
   }
@@ -1190,12 +1183,6 @@ static __device__ RJB_RESOLVE_INL void resolve_drain(const MapView& Q, const Map
         r.y = xy[1];
 #pragma unroll
         for (int axis = 0; axis < 2; axis++)
-#ifdef RJB_EXP_INLINE_GCD
-          if (code[axis] == kPointGcd) {
-            const long long v = lsi_point_finish(st[axis]);
-            if (axis == 0) r.x = v; else r.y = v;
-          } else
-#endif
           if (code[axis] != kPointDone) {
             ResolveDefer d;
             d.i = pos;
@@ -1333,9 +1320,7 @@ k_lsi_resolve(MapView Q, MapView B, int query_map_id, const uint2* __restrict__ 
 #ifdef RJB_TRACE
   { int k2 = 14; RJB_MARK(k2); }  // 14: back from the flush
 #endif
-#ifndef RJB_EXP_NOCAND
   if (lane == 0 && cand) atomicAdd(n_cand, (unsigned long long) cand);
-#endif
 #ifdef RJB_TRACE
   { int k2 = 15; RJB_MARK(k2); }  // 15: atomic issued
 #endif
