@@ -151,6 +151,67 @@ def test_tile_descriptor_classes(hx):
         assert cls == (1 if e == 0 else 2 if e <= 1 else 3 if e <= 3 else 4 if e <= 7 else 5)
 
 
+def test_two_level_filter_never_drops_a_kept_edge(hx):
+    """The invariant behind k_lsi_filter_tiles: if the edge-level test keeps an edge (its descriptor's
+    bit is set in occ / occ2), the tile-level test keeps the tile that holds it -- the tile descriptor
+    covers the cell boxes of its 8 edges, and bitmap K is the K x K dilation.  Random chains of short
+    and long edges against random sparse occupancy bitmaps, everything restated with numpy."""
+    hx.hx_occ_code.restype = C.c_uint32
+    hx.hx_edge_desc.restype = C.c_uint32
+    hx.hx_tile_desc.restype = C.c_uint32
+    rng = np.random.default_rng(21)
+    G = 4096
+    occ = np.zeros((G, G), bool)  # [y, x]
+    pts0 = rng.integers(0, G, size=(3000, 2))
+    occ[pts0[:, 1], pts0[:, 0]] = True
+
+    def dilate(a, k):  # bit (x, y) = OR over [x, x + k) x [y, y + k)
+        out = np.zeros_like(a)
+        for dy in range(k):
+            for dx in range(k):
+                out[:G - dy, :G - dx] |= a[dy:, dx:]
+        return out
+    maps = {1: occ, 2: dilate(occ, 2), 3: dilate(occ, 4), 4: dilate(occ, 8)}
+    cell = 1 << 35  # coordinate units per occupancy cell
+    kept_edges = live_tiles = 0
+    for trial in range(60):
+        # a chain of 9 points = 8 edges = one tile; steps from a fraction of a cell to several cells
+        scale = int(rng.choice([cell // 8, cell // 2, cell, 3 * cell]))
+        p = np.cumsum(np.vstack([rng.integers(-2**46 + 40 * cell, 2**46 - 40 * cell, size=(1, 2)),
+                                 rng.integers(-scale, scale + 1, size=(8, 2))]), axis=0)
+        codes = [hx.hx_occ_code(C.c_longlong(int(x)), C.c_longlong(int(y))) for x, y in p]
+        cx = np.array([c & 4095 for c in codes]); cy = np.array([c >> 12 for c in codes])
+        # plant an occupied cell near the chain in half of the trials, so that edges are kept
+        if trial % 2 == 0:
+            j = int(rng.integers(0, 9))
+            occ2 = occ.copy(); occ2[cy[j], cx[j]] = True
+            m = {1: occ2, 2: dilate(occ2, 2), 3: dilate(occ2, 4), 4: dilate(occ2, 8)}
+        else:
+            m = maps
+        keep_any = False
+        for e in range(8):
+            d = hx.hx_edge_desc(*(C.c_longlong(int(v)) for v in (p[e, 0], p[e, 1], p[e + 1, 0], p[e + 1, 1])))
+            cls, code = d >> 24, d & 0xFFFFFF
+            ex0, ey0 = code & 4095, code >> 12
+            if cls == 0:
+                keep = m[1][ey0, ex0]
+            elif cls == 1:
+                keep = m[2][ey0, ex0]
+            else:  # longer edge: rectangle test (occ_rect), exact over its cell box
+                x0, x1 = sorted((cx[e], cx[e + 1])); y0, y1 = sorted((cy[e], cy[e + 1]))
+                keep = m[1][y0:y1 + 1, x0:x1 + 1].any()
+            keep_any |= bool(keep)
+            kept_edges += bool(keep)
+        t = hx.hx_tile_desc(int(cx.min()), int(cy.min()), int(cx.max()), int(cy.max()))
+        tcls, tcode = t >> 24, t & 0xFFFFFF
+        live = True if tcls == 5 else bool(m[tcls][tcode >> 12, tcode & 4095])
+        live_tiles += live
+        assert tcls in (1, 2, 3, 4, 5)
+        if keep_any:
+            assert live
+    assert kept_edges > 20 and live_tiles < 60  # both outcomes occurred
+
+
 def test_cell_directory_items_report_each_overlap_exactly_once(hx):
     """k_lsi_cells decides a (query, leaf) pair from the leaf's 16-byte item record (box clipped to
     the cell) and the query box clipped to the same cell.  Over all common cells of the two cell
