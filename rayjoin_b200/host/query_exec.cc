@@ -130,7 +130,8 @@ static int run_lsi(const Flags& f) {
     int layout = 0;
     ok(rjb_last_stage_ms(ctx, st, &layout), "rjb_last_stage_ms");
     static const char* names[5][4] = {{"all-pairs kernel", "point pass", "", ""},
-                                      {"k_lsi_filter", "k_lsi_bvh", "k_lsi_exact", "k_lsi_points"},
+                                      {"occupancy filter (k_lsi_filter[_tiles])", "candidates (k_lsi_bvh / k_lsi_cells)",
+                                       "exact pass (k_lsi_resolve, or k_lsi_exact)", "point pass (k_lsi_points; 0 when fused)"},
                                       {"", "", "", ""},
                                       {"k_grid_lsi_filter", "k_grid_lsi_exact", "k_lsi_points", ""},
                                       {"ordering", "query kernel", "", ""}};
