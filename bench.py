@@ -181,16 +181,48 @@ def ncu_traffic(kernel):
         return None
 
 
+def gpu_cpu_sets(n_gpus, allowed):
+    """Per local GPU: the allowed host cores NVML names as close to it (its NUMA node), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = [int(v) for v in vis.split(",")] if vis and all(v.strip().isdigit() for v in vis.split(",")) else None
+        words = (max(os.cpu_count() or 1, max(allowed) + 1) + 63) // 64
+        out = []
+        for i in range(n_gpus):
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys[i] if phys else i)
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            near = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+            out.append(sorted(near & set(allowed)))
+        return out
+    except Exception:
+        return None
+
+
 def pin_to_cores(local_rank, world):
     """Each rank gets its own slice of the host cores: the completion wait polls the
     stream, and eight unpinned pollers next to each other showed up as single steps of
-    1-2 ms (round 1, N = 8)."""
+    1-2 ms (round 1, N = 8).  The slice is taken from the cores NEAR the rank's GPU (NVML CPU
+    affinity = its NUMA node), shared evenly among the ranks whose GPUs sit on the same node, so
+    that the pinned upload buffers -- allocated after this call -- are node-local to the GPU that
+    reads them; without NVML: equal slices of the allowed cores in rank order."""
     try:
         cpus = sorted(os.sched_getaffinity(0))
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
-        per = len(cpus) // max(1, local_world)
-        if local_world > 1 and per >= 1:
-            os.sched_setaffinity(0, cpus[local_rank * per:(local_rank + 1) * per])
+        if local_world > 1:
+            sets = gpu_cpu_sets(local_world, cpus)
+            mine = sets[local_rank] if sets else None
+            if mine and len(mine) < len(cpus):  # (one node for everything: nothing to choose)
+                peers = [i for i in range(local_world) if sets[i] == mine]
+                per = len(mine) // len(peers)
+                if per >= 1:
+                    k = peers.index(local_rank)
+                    os.sched_setaffinity(0, mine[k * per:(k + 1) * per])
+                    return len(os.sched_getaffinity(0))
+            per = len(cpus) // max(1, local_world)
+            if per >= 1:
+                os.sched_setaffinity(0, cpus[local_rank * per:(local_rank + 1) * per])
         return len(os.sched_getaffinity(0))
     except Exception:
         return None
@@ -488,8 +520,9 @@ def main():
     if args.share_chains > 0:
         S = synth.share_chains(R, S, frac=args.share_chains, seed=3)
     bbox = synth.US_BBOX  # same scaling on every rank
-    log("[rank %d] maps ready in %.1fs: R %d edges / %d chains, S %d edges / %d chains; host cores of this rank: %s"
-        % (rank, time.time() - t0, R.n_edges, R.n_chains, S.n_edges, S.n_chains, n_cores))
+    log("[rank %d] maps ready in %.1fs: R %d edges / %d chains, S %d edges / %d chains; host cores of this rank: %s %s"
+        % (rank, time.time() - t0, R.n_edges, R.n_chains, S.n_edges, S.n_chains, n_cores,
+           sorted(os.sched_getaffinity(0)) if world > 1 else ""))
 
     stream = torch.cuda.Stream(device=dev)
     ctx = RJ.Context(device=local_rank, stream=stream.cuda_stream)
